@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the h_octree trace path on B200.
+
+Metric (BASELINE.json): Mrays/s on the depth-12 (4096^3) synthetic terrain DAG, 3840x2160 primary rays.
+A *step* = one pass over the camera poses A, B, C = 3 frames = 24 883 200 rays per
+GPU.  At N GPUs every step holds 3*N frames; each frame is cut into cyclic 8-row tile strips, rank r
+tracing tiles r, r+N, ... of every frame with its own replica of the DAG (weak scaling: per-GPU work is
+fixed, no data-path collective).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # product (CUDA, libort_b200.so)
+    python bench.py --impl reference [...]                         # the reference's own CPU sse_trace
+
+One JSON line on stdout (rank 0).  `value`: device-resident throughput (outputs stay in HBM; L2 is
+flushed before every frame).  `e2e`: the same frames through the public host-buffer entry point
+(ort_trace_frame: camera in, voxel/face/t out to pinned host memory, copies inside the timed region).
+`roofline`: algorithmic bytes (32 B per child-slot load + 9 B of output per ray) over the
+measured kernel time against the measured HBM copy peak.  `cpu_baseline`: the reference's CPU trace
+(oracle/_ref when present, else the oracle port) on the host cores, same rays.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+DEPTH, LOG2CAP = 12, 24
+W, H = 3840, 2160
+TILE_ROWS = 8
+POSE_NAMES = ("A", "B", "C")
+METRIC = "Mrays/s, depth-12 terrain DAG, 3840x2160 primary rays"
+WORKLOAD = "h_octree<24,12> simplex terrain (no tunnels), 3840x2160, poses A/B/C per step"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self.active = False
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+            }
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+            while not self._stop.is_set():
+                if self.active:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = get_reasons(h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                time.sleep(0.002)
+        except Exception as e:  # NVML missing: report nothing rather than fail the bench
+            self.error = repr(e)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+def physical_gpu_index(local_rank: int) -> int:
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_rank])
+        except Exception:
+            return local_rank
+    return local_rank
+
+
+def rank_tiles(rank: int, n: int):
+    tiles = list(range(rank, H // TILE_ROWS, n))
+    return tiles, len(tiles) * TILE_ROWS
+
+
+# ------------------------------------------------------------------------------------------------
+# product arm
+# ------------------------------------------------------------------------------------------------
+
+def run_product(args):
+    import torch
+    import torch.distributed as dist
+    import octree_ray_tracing_b200 as ort
+    from octree_ray_tracing_b200 import harness
+
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if world != args.gpus:
+        log(f"note: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU trace)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    t0 = time.time()
+    tree = ort.HOctree(LOG2CAP, DEPTH, device=local_rank, node_capacity=1 << 21)
+    harness.build_terrain(tree)
+    n_up, _ = tree.sync()
+    ctx = tree.ctx
+    log(f"[rank {rank}] DAG built + uploaded in {time.time() - t0:.1f}s: {n_up} nodes ({n_up * 32 / 2**20:.1f} MiB)")
+
+    poses = [harness.POSES[p] for p in POSE_NAMES]
+    cams = [(np.array(p[0], np.float32),) + ort.camera_coeffs(p[1], p[2]) for p in poses]
+    tiles, rows = rank_tiles(rank, world)
+    n_local = rows * W
+    y0 = rank * TILE_ROWS
+    frames_per_step = len(cams) * world
+    rays_per_step_total = frames_per_step * W * H          # all ranks together
+    rays_per_step_local = frames_per_step * n_local
+
+    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    dv = torch.empty(n_local, dtype=torch.int32, device="cuda")
+    df = torch.empty(n_local, dtype=torch.uint8, device="cuda")
+    dt = torch.empty(n_local, dtype=torch.float32, device="cuda")
+    dn = torch.empty(n_local, dtype=torch.int16, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+
+    def frame(cam, npush=None):
+        ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, world, dv, df, dt, npush)
+
+    # algorithmic bytes: PUSH counts from an (untimed) counting pass -- identical to the oracle's counts (tests)
+    pushes = 0
+    hits = 0
+    with torch.cuda.stream(stream):
+        for cam in cams:
+            frame(cam, dn)
+            stream.synchronize()
+            pushes += int((dn.to(torch.int64) & 0xFFFF).sum().item())
+            hits += int((dv != 0).sum().item())
+    pushes_per_step_local = pushes * world
+    bytes_per_step_local = 32 * pushes_per_step_local + 9 * rays_per_step_local
+
+    def timed_loop(steps, do_flush):
+        evs = []
+        with torch.cuda.stream(stream):
+            for _ in range(steps):
+                for _rep in range(world):
+                    for cam in cams:
+                        if do_flush:
+                            flush.zero_()
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        frame(cam)
+                        b.record(stream)
+                        evs.append((a, b))
+        return evs
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local_rank))
+    sampler.start()
+
+    launches0 = ctx.launch_count
+    timed_loop(args.warmup, True)
+    barrier()
+    launches0 = ctx.launch_count
+    sampler.active = True
+    wall0 = time.perf_counter()
+    evs = timed_loop(args.steps, True)
+    barrier()
+    wall = time.perf_counter() - wall0
+    sampler.active = False
+    launches = ctx.launch_count - launches0
+    kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    # same loop without the flush (steady state of a real frame loop: DAG stays L2-resident)
+    timed_loop(1, False)
+    barrier()
+    evs_w = timed_loop(args.steps, False)
+    barrier()
+    warm_ms = sum(a.elapsed_time(b) for a, b in evs_w)
+
+    # end to end through the host-buffer entry point: pinned outputs, D2H inside the timed region
+    hv = torch.empty(n_local, dtype=torch.int32).pin_memory()
+    hf = torch.empty(n_local, dtype=torch.uint8).pin_memory()
+    ht = torch.empty(n_local, dtype=torch.float32).pin_memory()
+    out = (hv.numpy().view(np.uint32), hf.numpy(), ht.numpy(), None)
+
+    def e2e_step():
+        for _rep in range(world):
+            for cam in cams:
+                ctx.trace_frame(cam[0], cam[1], cam[2], W, H, y0=y0, rows=rows, tile_rows=TILE_ROWS, tile_step=world, out=out)
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        e2e_step()
+    barrier()
+    e0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - e0
+    e2e_check = int((out[0] != 0).sum())
+
+    clocks = sampler.stop()
+
+    # max over ranks
+    if world > 1:
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        kernel_ms, warm_ms, e2e_s, wall = (float(x) for x in tt.tolist())
+        cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        launches_all = int(cnt[0].item())
+    else:
+        launches_all = launches
+
+    result = None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        ms_per_step = kernel_ms / args.steps
+        value = rays_per_step_total / (ms_per_step * 1e-3) / 1e6
+        n_launch_local = args.steps * frames_per_step
+        avg_launch_s = kernel_ms * 1e-3 / n_launch_local
+        achieved = (bytes_per_step_local / frames_per_step) / avg_launch_s / 1e9
+        e2e_val = rays_per_step_total * e2e_steps / e2e_s / 1e6
+        result = {
+            "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD, "frames_per_step": frames_per_step, "rays_per_step": rays_per_step_total,
+                "partition": f"cyclic {TILE_ROWS}-row tile strips over {world} GPU(s), DAG replicated",
+                "l2": "flushed before every frame (256 MiB memset outside the timed events)",
+                "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
+                "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3),
+                "hit_fraction": round(hits / (len(cams) * n_local), 4),
+                "timing": "sum of CUDA-event intervals around each frame launch on the launching stream, max over ranks",
+            },
+            "warm_l2": {"value": round(rays_per_step_total / (warm_ms / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s",
+                        "note": "same loop without the L2 flush (DAG stays L2-resident between frames)"},
+            "e2e": {"value": round(e2e_val, 2), "unit": "Mrays/s", "h2d_bytes_per_step": frames_per_step * 52,
+                    "d2h_bytes_per_step": frames_per_step * n_local * 9, "steps": e2e_steps,
+                    "api": "ort_trace_frame (host buffers, pinned; chunked D2H overlapped with the kernel)", "hits_last_frame": e2e_check},
+            "gpu_launches": launches_all,
+            "roofline": {
+                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
+                "traffic": None, "peak_source": peak_src, "kernel": "ort::trace_frame_kernel",
+                "algorithmic_bytes_per_launch": int(bytes_per_step_local / frames_per_step),
+                "avg_launch_ms": round(avg_launch_s * 1e3, 4),
+                "note": "32 B per child-slot load (PUSH) + 9 B output per ray; DAG is L2-resident so HBM is not the binding limit (latency/divergence bound)",
+            },
+            "clocks": clocks,
+            "wall_s_timed_region": round(wall, 3),
+        }
+        if world == 1 and not args.no_cpu:
+            result["cpu_baseline"] = cpu_baseline(tree, sample_tiles=4)
+        print(json.dumps(result), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (the reference's own sse_trace where oracle/_ref exists, else the oracle port)
+# ------------------------------------------------------------------------------------------------
+
+def cpu_tracer(nodes8, root):
+    """Returns (kind, fn(o, d, nthreads) -> (vox, face, t))."""
+    from oracle import oracle as oc
+    if oc.have_ref():
+        R = oc.RefTree(LOG2CAP, DEPTH)
+        R.import_compact(nodes8, root)
+        return "reference", lambda o, d, nt: R.trace(o, d, nthreads=nt)
+    return "port", lambda o, d, nt: oc.trace_rays(nodes8, root, DEPTH, o, d, nthreads=nt)
+
+
+def sample_rays(sample_tiles: int):
+    """Every `sample_tiles`-th 8-row tile of each pose's 4K frame: (origin, directions) per pose."""
+    from oracle import oracle as oc
+    from octree_ray_tracing_b200 import harness
+    out = []
+    for p in POSE_NAMES:
+        pos, yaw, pitch = harness.POSES[p]
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        d = np.concatenate([oc.gen_rays(rot, fov, W, H, t * TILE_ROWS, (t + 1) * TILE_ROWS) for t in range(0, H // TILE_ROWS, sample_tiles)])
+        out.append((np.array(pos, np.float32), d))
+    return out
+
+
+def cpu_baseline(tree, sample_tiles: int):
+    nodes8, root, _ = tree.flatten()
+    kind, fn = cpu_tracer(nodes8, root)
+    cores = os.cpu_count() or 1
+    rays = sample_rays(sample_tiles)
+    n = sum(d.shape[0] for _, d in rays)
+    fn(rays[0][0], rays[0][1][:100000], cores)          # warm-up
+    t0 = time.perf_counter()
+    for o, d in rays:
+        fn(o, d, cores)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    fn(rays[1][0], rays[1][1][: 1 << 20], 1)
+    one = (1 << 20) / (time.perf_counter() - t1) / 1e6
+    return {"value": round(n / dt / 1e6, 2), "unit": "Mrays/s", "cores": cores, "kind": kind,
+            "sample": f"every {sample_tiles}th 8-row tile of the 3 poses' 4K frames ({n} rays), {cores} threads",
+            "one_thread_mrays": round(one, 2)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    from octree_ray_tracing_b200 import harness
+    import octree_ray_tracing_b200 as ort
+    tree = ort.HOctree(LOG2CAP, DEPTH, device=None)        # host table only: this arm never touches the GPU
+    harness.build_terrain(tree)
+    nodes8, root, _ = tree.flatten()
+    kind, fn = cpu_tracer(nodes8, root)
+    cores = os.cpu_count() or 1
+    sample_tiles = 4
+    rays = sample_rays(sample_tiles)
+    n = sum(d.shape[0] for _, d in rays)
+
+    def step():
+        for o, d in rays:
+            fn(o, d, cores)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt / 1e6
+    sample = f"every {sample_tiles}th 8-row tile of the 3 poses' 4K frames ({n} rays per step), {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32+u32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample, "rays_per_step": n},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_product(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,190 @@
+/* ort_b200.h -- C ABI of the B200-native h_octree trace path (libort_b200.so).
+ *
+ * Drop-in boundary for the ONE hot path of AlexanderRipar/Octree_Ray_Tracing: the adapted
+ * Laine-Karras traversal behind och::h_octree<L,D>::sse_trace and the node store it reads.
+ * The reference has no FFI of its own; its boundary is the C++ member API of och::h_octree
+ * (och_h_octree.h:17-452) plus the call sites in test_och_h_octree.cpp.  Every entry point
+ * below names the reference interface it replaces (paths relative to
+ * /root/reference/Octree_Ray_Tracing/).  include/och_h_octree_b200.hpp rebuilds the
+ * reference's C++ class on top of this ABI; INTEGRATION.md shows the binding.
+ *
+ * Conventions: opaque handles, plain pointers and sizes, int error codes (0 = ORT_OK), no
+ * exceptions cross the boundary, no CPU fallback -- every trace entry point fails with
+ * ORT_ERR_CUDA / ORT_ERR_NO_DEVICE when no sm_100 device is usable.  A handle is driven by one
+ * host thread at a time; different handles may be driven concurrently.
+ */
+#ifndef ORT_B200_H
+#define ORT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ort_ctx  ort_ctx;   /* device side: node mirror + streams of ONE GPU                */
+typedef struct ort_tree ort_tree;  /* host side:   the reference's node_hashtable, re-implemented  */
+
+enum
+{
+	ORT_OK = 0,
+	ORT_ERR_INVALID = 1,     /* bad argument                                                      */
+	ORT_ERR_CUDA = 2,        /* a CUDA call failed; see ort_last_error()                          */
+	ORT_ERR_NO_DEVICE = 3,   /* no CUDA device / not an sm_100 part                               */
+	ORT_ERR_TABLE_FULL = 4,  /* host table above 93.75 % fill (reference: printf + exit(0), och_h_octree.h:112-116) */
+	ORT_ERR_CAPACITY = 5,    /* device mirror too small for this upload                           */
+	ORT_ERR_NOT_ATTACHED = 6 /* tree operation needs a device context                             */
+};
+
+/* face codes = och::direction (och_tree_helper.h:7-18) */
+enum
+{
+	ORT_FACE_X_POS = 0, ORT_FACE_Y_POS = 1, ORT_FACE_Z_POS = 2,
+	ORT_FACE_X_NEG = 3, ORT_FACE_Y_NEG = 4, ORT_FACE_Z_NEG = 5,
+	ORT_FACE_EXIT = 6, ORT_FACE_INSIDE = 7, ORT_FACE_ERROR = 8
+};
+
+const char* ort_version(void);
+/* message of the last failing call on this thread (ctx may be NULL) */
+const char* ort_last_error(const ort_ctx* ctx);
+
+/* ================================================================================================
+ * Device context
+ * ============================================================================================== */
+
+/* Replaces: construction of the table the tracer reads (och_h_octree.h:93).  Allocates the
+ * device node mirror (node_capacity nodes of 32 B, 16-B aligned halves) on `device` and loads
+ * the built-in reciprocal table.  depth = tree depth D (1..16). */
+int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity);
+int ort_destroy(ort_ctx* ctx);
+
+/* Replaces: the CPU's RCPPS used at och_h_octree.h:316.  tab has 1<<log2n entries (log2n 1..23):
+ * the RCPPS result bit patterns for 1.0 <= x < 2.0 indexed by the top log2n mantissa bits; other
+ * exponents, zeros, infinities follow the rule documented at oc_rcp_table_bits.
+ * The built-in default is the 2048-entry table of Intel's RCPPS (csrc/ort_rcp_table.h). */
+int ort_set_rcp_table(ort_ctx* ctx, const uint32_t* tab, int log2n);
+
+/* Replaces: the tracer's view of table->nodes[] / root_idx (och_h_octree.h:82, :95, :344).
+ * nodes8 = n_nodes * 8 uint32 in COMPACT numbering: node id i (1-based) is row i-1; interior
+ * children are compact ids, children of level-`depth` nodes are voxel payloads; 0 = empty.
+ * root = compact id of the root, 0 = empty tree (every ray then misses, as the reference's
+ * callers arrange: test_och_h_octree.cpp:443, :535).  Host or device pointers. */
+int ort_upload_full(ort_ctx* ctx, const uint32_t* nodes8, size_t n_nodes, uint32_t root);
+/* Replaces: the writes at och_h_octree.h:155 between two frames.  Scatters n nodes to compact
+ * ids ids[i] (1-based) and installs the new root. */
+int ort_upload_delta(ort_ctx* ctx, const uint32_t* ids, const uint32_t* nodes8, size_t n, uint32_t root);
+
+/* Replaces: N calls of sse_trace(ox,oy,oz,dx,dy,dz, direction&, uint32_t&, float&) const
+ * (och_h_octree.h:292-447).  o3: origins, 3 floats each, o_stride = 3, or ONE shared origin with
+ * o_stride = 0.  d3: n directions.  Outputs per ray: voxel = hit_voxel, face = hit_direction,
+ * t = hit_time.  All pointers may be host (pageable or pinned) or device pointers; host buffers
+ * are staged through pinned memory and overlapped with the kernel.  npush (optional, may be
+ * NULL) receives each ray's number of child-slot loads (PUSH evaluations), saturated to 65535. */
+int ort_trace_rays(ort_ctx* ctx, const float* o3, int o_stride, const float* d3, size_t n,
+                   uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush);
+
+/* Replaces: tree_camera::update_position + the update_image pixel loop
+ * (test_och_h_octree.cpp:87-138, :437-457) for rows of a W x H frame: rays are generated in the
+ * kernel from pos / rot[9] (t_x_fx .. t_z_fz, :107-115) / fov_factor (:97) and traced.
+ * Rows: local row r (0 <= r < rows) is frame row  y0 + (r / tile_rows) * tile_rows * tile_step
+ * + r % tile_rows  -- tile_step = 1 gives the contiguous strip [y0, y0+rows); tile_step = N with
+ * y0 = rank * tile_rows gives rank's share of a cyclic strip partition over N GPUs.
+ * Outputs are rows * W entries in local row order, pixel index = x + r * W.  npush as above. */
+int ort_trace_frame(ort_ctx* ctx, const float pos[3], const float rot[9], float fov_factor,
+                    int W, int H, int y0, int rows, int tile_rows, int tile_step,
+                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush);
+
+/* Enqueue-only form for device output buffers: no synchronisation, no staging; work is queued on
+ * the context's stream (see ort_stream).  Same semantics otherwise. */
+int ort_trace_frame_async(ort_ctx* ctx, const float pos[3], const float rot[9], float fov_factor,
+                          int W, int H, int y0, int rows, int tile_rows, int tile_step,
+                          uint32_t* d_voxel, uint8_t* d_face, float* d_t, uint16_t* d_npush);
+int ort_trace_rays_async(ort_ctx* ctx, const float* d_o3, int o_stride, const float* d_d3, size_t n,
+                         uint32_t* d_voxel, uint8_t* d_face, float* d_t, uint16_t* d_npush);
+
+int   ort_sync(ort_ctx* ctx);
+void* ort_stream(ort_ctx* ctx);                 /* the cudaStream_t all work of ctx is queued on */
+int   ort_device(const ort_ctx* ctx);
+uint32_t ort_node_count(const ort_ctx* ctx);    /* highest compact id in use on the device */
+uint32_t ort_root(const ort_ctx* ctx);
+/* number of kernels of this library launched on ctx since creation (bench.py's gpu_launches) */
+uint64_t ort_launch_count(const ort_ctx* ctx);
+/* Kernel selection knobs (tuning / profiling): key in {"variant","smem_levels","block"}. */
+int ort_set_option(ort_ctx* ctx, const char* key, int value);
+
+/* pinned host memory for callers that want zero staging */
+int ort_host_alloc(void** out, size_t bytes);
+int ort_host_free(void* p);
+
+/* rot[9], fov_factor from yaw (dir.x) and pitch (dir.y) exactly as update_position computes
+ * them on the host (test_och_h_octree.cpp:95-115). */
+void ort_camera_coeffs(float yaw, float pitch, float rot[9], float* fov_factor);
+
+/* ================================================================================================
+ * Host node store -- och::h_octree<Log2_table_capacity, Depth> (och_h_octree.h:17-288)
+ * ============================================================================================== */
+
+int      ort_tree_create(ort_tree** out, int log2_table_capacity, int depth);
+void     ort_tree_destroy(ort_tree* tree);
+/* register_node (:110-160): returns slot+1, or 0 with the table-full flag set */
+uint32_t ort_tree_register_node(ort_tree* tree, const uint32_t children[8]);
+void     ort_tree_remove_node(ort_tree* tree, uint32_t idx);                               /* :162-174 */
+void     ort_tree_set(ort_tree* tree, uint16_t x, uint16_t y, uint16_t z, uint32_t v);     /* :176-237 */
+/* n x (x, y, z, v) uint32 quadruples applied in order */
+void     ort_tree_set_many(ort_tree* tree, const uint32_t* xyzv, size_t n);
+/* the T / Z edit (test_och_h_octree.cpp:408-413, :427-432): set() over the box
+ * [cx-ext/2, cx+(ext+1)/2) x ... in the reference's z, y, x loop order, uint16 wrap-around included */
+void     ort_tree_set_box(ort_tree* tree, uint16_t cx, uint16_t cy, uint16_t cz, int ext, uint32_t v);
+uint32_t ort_tree_at(const ort_tree* tree, int x, int y, int z);                           /* :239-258 */
+void     ort_tree_set_root(ort_tree* tree, uint32_t idx);                                  /* :260-263 */
+uint32_t ort_tree_get_root(const ort_tree* tree);                                          /* :265-268 */
+uint32_t ort_tree_get_fillcnt(const ort_tree* tree);                                       /* :270-273 */
+uint32_t ort_tree_get_nodecnt(const ort_tree* tree);                                       /* :275-278 */
+uint32_t ort_tree_get_max_refcnt(const ort_tree* tree);                                    /* :280-283 */
+void     ort_tree_clear(ort_tree* tree);                                                   /* :285-288 */
+int      ort_tree_table_full(const ort_tree* tree);
+int      ort_tree_depth(const ort_tree* tree);
+int      ort_tree_log2_capacity(const ort_tree* tree);
+/* raw views of the table (cap*8 uint32, cap bytes, cap uint32) for inspection / parity tests */
+const uint32_t* ort_tree_nodes(const ort_tree* tree);
+const uint8_t*  ort_tree_cashes(const ort_tree* tree);
+const uint32_t* ort_tree_refcounts(const ort_tree* tree);
+
+/* Flatten the live DAG into compact, level-ordered numbering (root = id 1, then level 2, ...).
+ * Returns the node count; *nodes8 (n*8 uint32) stays owned by the tree and is valid until the
+ * next flatten/sync.  level_offsets (optional, depth+1 entries) receives the first id of each
+ * level (entry depth = n+1).  Pure host code. */
+size_t   ort_tree_flatten(ort_tree* tree, const uint32_t** nodes8, uint32_t* root, uint32_t* level_offsets);
+
+/* Bind a device context: subsequent ort_tree_sync() calls mirror the table into it. */
+int      ort_tree_attach(ort_tree* tree, ort_ctx* ctx);
+/* Bring the device mirror up to date with the host table: a full level-ordered upload the first
+ * time (or when more than half of the live nodes changed), otherwise a delta holding only the
+ * nodes created since the last sync.  Cheap when nothing changed. */
+int      ort_tree_sync(ort_tree* tree);
+/* statistics of the last ort_tree_sync: nodes uploaded, 1 if it was a full upload */
+void     ort_tree_sync_stats(const ort_tree* tree, uint64_t* nodes_uploaded, int* was_full);
+/* Build the pending delta WITHOUT a device (for multi-GPU broadcast and CPU tests): returns n and
+ * pointers (owned by the tree) to ids[n], nodes8[n*8] and the new compact root; is_full = 1 means
+ * the buffers hold a full flatten instead.  The delta is consumed (marked as applied). */
+size_t   ort_tree_take_delta(ort_tree* tree, const uint32_t** ids, const uint32_t** nodes8, uint32_t* root, int* is_full);
+
+/* ================================================================================================
+ * Headless harness fixtures (replaces initialize_h_octree and friends,
+ * test_och_h_octree.cpp:561-598, :651-695, :767-787)
+ * ============================================================================================== */
+
+/* heights[y*dim+x] = get_terrain_heigth(x, y) with och::simplex_n(0.5F) (:561-566) */
+void ort_fixture_heightmap(int depth, uint16_t* heights, int nthreads);
+/* Same voxel content as initialize_h_octree (solid stone below the heightmap, grass/dark-grass
+ * top chosen by grass[y*dim+x], two dirt layers, optional simplex tunnels) but built bottom-up
+ * with memoisation, so depth 12-14 take seconds.  The DAG is canonical, so it equals the
+ * reference's up to slot numbering.  Returns ORT_OK or ORT_ERR_TABLE_FULL. */
+int  ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uint8_t* grass, int tunnels, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ORT_B200_H */

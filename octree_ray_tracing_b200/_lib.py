@@ -1,0 +1,102 @@
+"""ctypes loader for libort_b200.so -- the C ABI declared in include/ort_b200.h.
+
+There is no fallback: if the library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libort_b200.so")
+
+_vp = C.c_void_p
+_u32p = C.POINTER(C.c_uint32)
+
+ORT_OK, ORT_ERR_INVALID, ORT_ERR_CUDA, ORT_ERR_NO_DEVICE, ORT_ERR_TABLE_FULL, ORT_ERR_CAPACITY, ORT_ERR_NOT_ATTACHED = range(7)
+
+
+class OrtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"ort error {code}: {msg}")
+        self.code = code
+
+
+_SIGS = {
+    "ort_version": (C.c_char_p, []),
+    "ort_last_error": (C.c_char_p, [_vp]),
+    "ort_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32]),
+    "ort_destroy": (C.c_int, [_vp]),
+    "ort_set_rcp_table": (C.c_int, [_vp, _vp, C.c_int]),
+    "ort_upload_full": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32]),
+    "ort_upload_delta": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32]),
+    "ort_trace_rays": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    "ort_trace_frame": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "ort_trace_frame_async": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "ort_trace_rays_async": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    "ort_sync": (C.c_int, [_vp]),
+    "ort_stream": (_vp, [_vp]),
+    "ort_device": (C.c_int, [_vp]),
+    "ort_node_count": (C.c_uint32, [_vp]),
+    "ort_root": (C.c_uint32, [_vp]),
+    "ort_launch_count": (C.c_uint64, [_vp]),
+    "ort_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int]),
+    "ort_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "ort_host_free": (C.c_int, [_vp]),
+    "ort_camera_coeffs": (None, [C.c_float, C.c_float, _vp, C.POINTER(C.c_float)]),
+    "ort_tree_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int]),
+    "ort_tree_destroy": (None, [_vp]),
+    "ort_tree_register_node": (C.c_uint32, [_vp, _vp]),
+    "ort_tree_remove_node": (None, [_vp, C.c_uint32]),
+    "ort_tree_set": (None, [_vp, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint32]),
+    "ort_tree_set_many": (None, [_vp, _vp, C.c_size_t]),
+    "ort_tree_set_box": (None, [_vp, C.c_uint16, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32]),
+    "ort_tree_at": (C.c_uint32, [_vp, C.c_int, C.c_int, C.c_int]),
+    "ort_tree_set_root": (None, [_vp, C.c_uint32]),
+    "ort_tree_get_root": (C.c_uint32, [_vp]),
+    "ort_tree_get_fillcnt": (C.c_uint32, [_vp]),
+    "ort_tree_get_nodecnt": (C.c_uint32, [_vp]),
+    "ort_tree_get_max_refcnt": (C.c_uint32, [_vp]),
+    "ort_tree_clear": (None, [_vp]),
+    "ort_tree_table_full": (C.c_int, [_vp]),
+    "ort_tree_depth": (C.c_int, [_vp]),
+    "ort_tree_log2_capacity": (C.c_int, [_vp]),
+    "ort_tree_nodes": (_u32p, [_vp]),
+    "ort_tree_cashes": (C.POINTER(C.c_uint8), [_vp]),
+    "ort_tree_refcounts": (_u32p, [_vp]),
+    "ort_tree_flatten": (C.c_size_t, [_vp, C.POINTER(_u32p), _u32p, _vp]),
+    "ort_tree_attach": (C.c_int, [_vp, _vp]),
+    "ort_tree_sync": (C.c_int, [_vp]),
+    "ort_tree_sync_stats": (None, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
+    "ort_tree_take_delta": (C.c_size_t, [_vp, C.POINTER(_u32p), C.POINTER(_u32p), _u32p, C.POINTER(C.c_int)]),
+    "ort_fixture_heightmap": (None, [C.c_int, _vp, C.c_int]),
+    "ort_fixture_build_terrain": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library (raises if libort_b200.so has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise OSError(f"{LIB_PATH} is missing: run `python -m octree_ray_tracing_b200.build` "
+                          "(there is no CPU or PyTorch fallback for the trace path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGS)
+
+
+def check(rc: int, ctx=None):
+    if rc != ORT_OK:
+        msg = lib().ort_last_error(ctx)
+        raise OrtError(rc, msg.decode() if msg else "?")

@@ -1,0 +1,63 @@
+"""Build libort_b200.so (hand-written CUDA for sm_100a + the C++ host side) in-tree with nvcc.
+
+    python -m octree_ray_tracing_b200.build [--force] [--verbose]
+
+The library is the product: there is no JIT, no torch extension and no CPU fallback.  nvcc
+cross-compiles without a GPU, so this also runs in CPU-only containers.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libort_b200.so")
+SOURCES = ["ort_device.cu", "ort_host_tree.cpp", "ort_fixture.cpp"]
+HEADERS = ["ort_internal.h", "ort_trace.cuh", "ort_rcp_table.h", os.path.join("..", "..", "include", "ort_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",                      # a*b+c is only ever fused where the source says __fmaf_rn
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall",
+    "-Xptxas", "-v",
+    "-shared", "-cudart", "static",
+]
+
+
+def nvcc() -> str:
+    for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libort_b200.so cannot be built")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    cmd = [nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    log = out.stdout + out.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if verbose or out.returncode:
+        print(log)
+    if out.returncode:
+        raise RuntimeError("nvcc failed building libort_b200.so")
+    return LIB
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="--verbose" in sys.argv or "-v" in sys.argv)
+    print(LIB)

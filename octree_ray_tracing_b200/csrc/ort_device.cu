@@ -1,0 +1,602 @@
+// ort_device.cu -- device context, kernels and the trace entry points of libort_b200.so (sm_100a).
+//
+// What lives on the GPU: the live DAG as ONE compact array of 32-byte nodes (two 16-byte halves,
+// 16-B aligned) in level order -- root = id 1, then level 2, ... -- so the whole depth-12 terrain
+// (~44 MiB) sits contiguously in the 126 MB L2 and the top levels are a contiguous prefix.  The host
+// table (ort_host_tree.cpp) stays the owner; edits arrive as (id, node) deltas and are scattered.
+#include "ort_internal.h"
+#include "ort_rcp_table.h"
+#include "ort_trace.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+
+struct ort_ctx
+{
+	int device = 0;
+	int depth = 0;
+	cudaStream_t stream = nullptr;      // all kernels + uploads
+	cudaStream_t copy_stream = nullptr; // D2H of finished chunks, overlapped with the next chunk's kernel
+	cudaEvent_t  ev_chunk[2] = { nullptr, nullptr };
+	cudaEvent_t  ev_copied[2] = { nullptr, nullptr };
+
+	uint32_t* d_nodes = nullptr;        // cap_nodes * 8
+	uint32_t  cap_nodes = 0;
+	uint32_t  n_nodes = 0;              // highest compact id in use
+	uint32_t  root = 0;
+
+	uint32_t* d_rcp = nullptr;
+	int       rcp_log2n = 0;
+
+	// staging (grown on demand)
+	void*  d_stage = nullptr;  size_t d_stage_bytes = 0;   // device side of host-pointer calls
+	void*  h_stage = nullptr;  size_t h_stage_bytes = 0;   // pinned
+
+	uint64_t launches = 0;
+	int opt_variant = 0;
+	int opt_smem_levels = -1;
+	int opt_block = 256;
+	int sm_count = 0;
+	std::string last_error;
+};
+
+int ort_fail(ort_ctx* ctx, int code, const char* fmt, ...)
+{
+	char buf[512];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	if (ctx) ctx->last_error = buf;
+	return code;
+}
+
+#define ORT_CUDA(ctx, call)                                                                                  \
+	do {                                                                                                     \
+		cudaError_t e_ = (call);                                                                             \
+		if (e_ != cudaSuccess)                                                                               \
+			return ort_fail(ctx, ORT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+	} while (0)
+
+namespace {
+
+struct DeviceGuard
+{
+	int prev = -1;
+	explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+	~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+bool is_device_ptr(const void* p)
+{
+	if (!p) return false;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+int ensure_dstage(ort_ctx* c, size_t bytes)
+{
+	if (bytes <= c->d_stage_bytes) return ORT_OK;
+	if (c->d_stage) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); cudaFree(c->d_stage); c->d_stage = nullptr; c->d_stage_bytes = 0; }
+	ORT_CUDA(c, cudaMalloc(&c->d_stage, bytes));
+	c->d_stage_bytes = bytes;
+	return ORT_OK;
+}
+
+int ensure_hstage(ort_ctx* c, size_t bytes)
+{
+	if (bytes <= c->h_stage_bytes) return ORT_OK;
+	if (c->h_stage) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_bytes = 0; }
+	ORT_CUDA(c, cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocDefault));
+	c->h_stage_bytes = bytes;
+	return ORT_OK;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+
+namespace ort {
+
+// delta upload: one thread per 16-byte half node
+__global__ void scatter_nodes_kernel(uint4* __restrict__ nodes, const uint32_t* __restrict__ ids, const uint4* __restrict__ src, uint32_t n)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < 2u * n)
+		nodes[2u * (ids[i >> 1] - 1u) + (i & 1u)] = src[i];
+}
+
+__global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush, size_t n)
+{
+	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n)
+	{
+		voxel[i] = 0;
+		face[i] = 6;
+		t[i] = __uint_as_float(0x7F800000u);
+		if (npush) npush[i] = 0;
+	}
+}
+
+// explicit rays: thread i traces ray i
+__global__ void __launch_bounds__(256)
+trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt,
+                  const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, size_t n,
+                  uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float* o = o3 + i * static_cast<size_t>(o_stride);
+	const float* d = d3 + i * 3;
+	const Ray r = ray_setup(rt, __ldg(o), __ldg(o + 1), __ldg(o + 2), __ldg(d), __ldg(d + 1), __ldg(d + 2));
+	const Hit h = traverse(nodes, root, depth, r);
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+	if (npush) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
+struct FrameRows
+{
+	int W, H;
+	int y0, rows, tile_rows, tile_step;
+};
+
+// camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
+// a 256-thread block a 16 x 16 pixel tile
+__global__ void __launch_bounds__(256)
+trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt, Camera cam, FrameRows fr,
+                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	const int y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	const Hit h = traverse(nodes, root, depth, ray);
+
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+	if (npush) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
+}  // namespace ort
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+const char* ort_version(void) { return "ort_b200 0.1 (sm_100a)"; }
+
+const char* ort_last_error(const ort_ctx* ctx)
+{
+	if (ctx && !ctx->last_error.empty()) return ctx->last_error.c_str();
+	return g_last_error.c_str();
+}
+
+int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
+{
+	if (!out || depth < 1 || depth > ort::kMaxDepth)
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_create: depth must be 1..%d", ort::kMaxDepth);
+
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+	{
+		cudaGetLastError();
+		return ort_fail(nullptr, ORT_ERR_NO_DEVICE, "ort_create: no CUDA device is visible; this library has no CPU path");
+	}
+	if (device < 0 || device >= ndev)
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_create: device %d out of range (%d visible)", device, ndev);
+
+	cudaDeviceProp prop;
+	ORT_CUDA(nullptr, cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10)
+		return ort_fail(nullptr, ORT_ERR_NO_DEVICE, "ort_create: device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+
+	DeviceGuard g(device);
+	ort_ctx* c = new (std::nothrow) ort_ctx;
+	if (!c) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_create: out of host memory");
+	c->device = device;
+	c->depth = depth;
+	c->sm_count = prop.multiProcessorCount;
+
+	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i)
+	{
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+	}
+
+	if (node_capacity < 64) node_capacity = 64;
+	ORT_CUDA(nullptr, cudaMalloc(&c->d_nodes, static_cast<size_t>(node_capacity) * 32));
+	c->cap_nodes = node_capacity;
+
+	*out = c;
+	const int rc = ort_set_rcp_table(c, ort_rcp_table_default, ORT_RCP_TABLE_LOG2N);
+	if (rc != ORT_OK) { *out = nullptr; ort_destroy(c); }
+	return rc;
+}
+
+int ort_destroy(ort_ctx* c)
+{
+	if (!c) return ORT_OK;
+	DeviceGuard g(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+	cudaFree(c->d_nodes);
+	cudaFree(c->d_rcp);
+	cudaFree(c->d_stage);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
+	for (int i = 0; i < 2; ++i)
+	{
+		if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
+	}
+	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	delete c;
+	return ORT_OK;
+}
+
+int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
+{
+	if (!c || !tab || log2n < 1 || log2n > 23)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_set_rcp_table: need a table of 2^1..2^23 entries");
+	DeviceGuard g(c->device);
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (c->rcp_log2n != log2n)
+	{
+		cudaFree(c->d_rcp);
+		c->d_rcp = nullptr;
+		ORT_CUDA(c, cudaMalloc(&c->d_rcp, sizeof(uint32_t) << log2n));
+		c->rcp_log2n = log2n;
+	}
+	ORT_CUDA(c, cudaMemcpy(c->d_rcp, tab, sizeof(uint32_t) << log2n, cudaMemcpyDefault));
+	return ORT_OK;
+}
+
+int ort_upload_full(ort_ctx* c, const uint32_t* nodes8, size_t n, uint32_t root)
+{
+	if (!c || (n && !nodes8) || root > n || n > 0xFFFFFFF0u)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_full: bad arguments (n=%zu root=%u)", n, root);
+	DeviceGuard g(c->device);
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	if (n > c->cap_nodes)
+	{
+		// grow with head-room for the deltas that will follow
+		size_t want = n + n / 4 + 4096;
+		if (want > 0xFFFFFFF0u) want = 0xFFFFFFF0u;
+		cudaFree(c->d_nodes);
+		c->d_nodes = nullptr;
+		c->cap_nodes = 0;
+		ORT_CUDA(c, cudaMalloc(&c->d_nodes, want * 32));
+		c->cap_nodes = static_cast<uint32_t>(want);
+	}
+	if (n)
+		ORT_CUDA(c, cudaMemcpyAsync(c->d_nodes, nodes8, n * 32, cudaMemcpyDefault, c->stream));
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));   // the source may be reused by the caller right away
+	c->n_nodes = static_cast<uint32_t>(n);
+	c->root = root;
+	return ORT_OK;
+}
+
+int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, size_t n, uint32_t root)
+{
+	if (!c || (n && (!ids || !nodes8)))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: bad arguments");
+	DeviceGuard g(c->device);
+
+	uint32_t max_id = c->n_nodes;
+	const bool dev_src = n && is_device_ptr(ids);
+	if (n && !dev_src)
+		for (size_t i = 0; i < n; ++i)
+		{
+			if (ids[i] == 0) return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: id 0 at entry %zu", i);
+			if (ids[i] > max_id) max_id = ids[i];
+		}
+	if (max_id > c->cap_nodes || root > c->cap_nodes)
+		return ort_fail(c, ORT_ERR_CAPACITY, "ort_upload_delta: id %u exceeds the mirror capacity %u", max_id, c->cap_nodes);
+
+	if (n)
+	{
+		const uint32_t* d_ids = ids;
+		const uint32_t* d_src = nodes8;
+		if (!dev_src)
+		{
+			// [ids | pad to 16 B | nodes] through the device staging buffer
+			const size_t off = align_up(n * 4, 16);
+			int rc = ensure_dstage(c, off + n * 32);
+			if (rc != ORT_OK) return rc;
+			char* base = static_cast<char*>(c->d_stage);
+			ORT_CUDA(c, cudaMemcpyAsync(base, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
+			ORT_CUDA(c, cudaMemcpyAsync(base + off, nodes8, n * 32, cudaMemcpyHostToDevice, c->stream));
+			d_ids = reinterpret_cast<const uint32_t*>(base);
+			d_src = reinterpret_cast<const uint32_t*>(base + off);
+		}
+		const uint32_t threads = 256, blocks = static_cast<uint32_t>((2 * n + threads - 1) / threads);
+		ort::scatter_nodes_kernel<<<blocks, threads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_nodes), d_ids, reinterpret_cast<const uint4*>(d_src), static_cast<uint32_t>(n));
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		if (!dev_src)
+			ORT_CUDA(c, cudaStreamSynchronize(c->stream));   // pageable sources may be reused by the caller
+	}
+	c->n_nodes = max_id;
+	c->root = root;
+	return ORT_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trace
+// ------------------------------------------------------------------------------------------------
+
+static ort::Camera make_camera(const float pos[3], const float rot[9], float fov_factor, int W, int H)
+{
+	ort::Camera cam;
+	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
+	for (int i = 0; i < 9; ++i) cam.r[i] = rot[i];
+	cam.fov = fov_factor;
+	cam.aspect = static_cast<float>(W) / static_cast<float>(H);   // test_och_h_octree.cpp:89
+	cam.vfx = 2.0F / static_cast<float>(W);                       // :91
+	cam.vfy = 2.0F / static_cast<float>(H);                       // :93
+	return cam;
+}
+
+static int launch_miss(ort_ctx* c, size_t n, uint32_t* v, uint8_t* f, float* t, uint16_t* np)
+{
+	if (!n) return ORT_OK;
+	ort::fill_miss_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(v, f, t, np, n);
+	++c->launches;
+	ORT_CUDA(c, cudaGetLastError());
+	return ORT_OK;
+}
+
+int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float* d3, size_t n,
+                         uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
+{
+	if (!c || (n && (!o3 || !d3 || !voxel || !face || !t)) || (o_stride != 0 && o_stride != 3))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_rays: bad arguments");
+	if (!n) return ORT_OK;
+	DeviceGuard g(c->device);
+	if (c->root == 0)
+		return launch_miss(c, n, voxel, face, t, npush);
+	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
+	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+	ort::trace_rays_kernel<<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush);
+	++c->launches;
+	ORT_CUDA(c, cudaGetLastError());
+	return ORT_OK;
+}
+
+int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
+                          int W, int H, int y0, int rows, int tile_rows, int tile_step,
+                          uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
+{
+	if (!c || !pos || !rot || W <= 0 || H <= 0 || rows < 0 || tile_rows <= 0 || tile_step <= 0 || y0 < 0 || (rows && (!voxel || !face || !t)))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: bad arguments");
+	if (!rows) return ORT_OK;
+	DeviceGuard g(c->device);
+	const size_t n = static_cast<size_t>(rows) * W;
+	if (c->root == 0)
+		return launch_miss(c, n, voxel, face, t, npush);
+	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
+	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
+	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
+	ort::trace_frame_kernel<<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush);
+	++c->launches;
+	ORT_CUDA(c, cudaGetLastError());
+	return ORT_OK;
+}
+
+// Device layout of one staged result block of n rays: voxel[n] | t[n] | npush[n] | face[n], each 256-B aligned.
+struct StageLayout
+{
+	size_t off_v, off_t, off_np, off_f, total;
+	explicit StageLayout(size_t n)
+	{
+		off_v = 0;
+		off_t = align_up(off_v + n * 4, 256);
+		off_np = align_up(off_t + n * 4, 256);
+		off_f = align_up(off_np + n * 2, 256);
+		total = align_up(off_f + n, 256);
+	}
+};
+
+int ort_trace_rays(ort_ctx* c, const float* o3, int o_stride, const float* d3, size_t n,
+                   uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
+{
+	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_trace_rays: null context");
+	if (!n) return ORT_OK;
+	if (!o3 || !d3 || !voxel || !face || !t || (o_stride != 0 && o_stride != 3))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_rays: bad arguments");
+	DeviceGuard g(c->device);
+
+	const bool in_dev = is_device_ptr(d3), out_dev = is_device_ptr(voxel);
+	if (in_dev && out_dev)
+	{
+		int rc = ort_trace_rays_async(c, o3, o_stride, d3, n, voxel, face, t, npush);
+		if (rc != ORT_OK) return rc;
+		ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+		return ORT_OK;
+	}
+
+	// host buffers: stage in -> kernel -> stage out
+	const StageLayout L(n);
+	const size_t off_d = L.total, off_o = align_up(off_d + n * 12, 256);
+	const size_t o_bytes = o_stride ? n * 12 : 12;
+	int rc = ensure_dstage(c, off_o + align_up(o_bytes, 256));
+	if (rc != ORT_OK) return rc;
+	char* base = static_cast<char*>(c->d_stage);
+
+	const float* dd = d3;
+	const float* dorg = o3;
+	if (!in_dev)
+	{
+		ORT_CUDA(c, cudaMemcpyAsync(base + off_d, d3, n * 12, cudaMemcpyHostToDevice, c->stream));
+		ORT_CUDA(c, cudaMemcpyAsync(base + off_o, o3, o_bytes, cudaMemcpyHostToDevice, c->stream));
+		dd = reinterpret_cast<const float*>(base + off_d);
+		dorg = reinterpret_cast<const float*>(base + off_o);
+	}
+	uint32_t* dv = out_dev ? voxel : reinterpret_cast<uint32_t*>(base + L.off_v);
+	float*    dt = out_dev ? t : reinterpret_cast<float*>(base + L.off_t);
+	uint8_t*  df = out_dev ? face : reinterpret_cast<uint8_t*>(base + L.off_f);
+	uint16_t* dn = !npush ? nullptr : (out_dev ? npush : reinterpret_cast<uint16_t*>(base + L.off_np));
+
+	rc = ort_trace_rays_async(c, dorg, o_stride, dd, n, dv, df, dt, dn);
+	if (rc != ORT_OK) return rc;
+	if (!out_dev)
+	{
+		ORT_CUDA(c, cudaMemcpyAsync(voxel, dv, n * 4, cudaMemcpyDeviceToHost, c->stream));
+		ORT_CUDA(c, cudaMemcpyAsync(t, dt, n * 4, cudaMemcpyDeviceToHost, c->stream));
+		ORT_CUDA(c, cudaMemcpyAsync(face, df, n, cudaMemcpyDeviceToHost, c->stream));
+		if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush, dn, n * 2, cudaMemcpyDeviceToHost, c->stream));
+	}
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	return ORT_OK;
+}
+
+int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
+                    int W, int H, int y0, int rows, int tile_rows, int tile_step,
+                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
+{
+	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: null context");
+	if (rows == 0) return ORT_OK;
+	if (!voxel || !face || !t || W <= 0 || rows < 0)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: bad arguments");
+	DeviceGuard g(c->device);
+
+	if (is_device_ptr(voxel))
+	{
+		int rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, voxel, face, t, npush);
+		if (rc != ORT_OK) return rc;
+		ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+		return ORT_OK;
+	}
+
+	// Host outputs.  The frame is cut into row chunks (multiples of 16 rows and of tile_rows); chunk k's
+	// results travel to the host on copy_stream while chunk k+1 is traced on stream.  Two staging slots.
+	int chunk_rows = (rows + 7) / 8;
+	const int q = tile_rows > 16 ? tile_rows : 16;
+	chunk_rows = (chunk_rows + q - 1) / q * q;
+	if (tile_rows > 1 && chunk_rows % tile_rows) chunk_rows = (chunk_rows / tile_rows + 1) * tile_rows;
+	const size_t chunk_n = static_cast<size_t>(chunk_rows) * W;
+	const StageLayout L(chunk_n);
+	int rc = ensure_dstage(c, 2 * L.total);
+	if (rc != ORT_OK) return rc;
+	char* base = static_cast<char*>(c->d_stage);
+
+	int slot = 0;
+	bool used[2] = { false, false };
+	for (int r0 = 0; r0 < rows; r0 += chunk_rows, slot ^= 1)
+	{
+		const int nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
+		const size_t n = static_cast<size_t>(nr) * W, first = static_cast<size_t>(r0) * W;
+		char* s = base + slot * L.total;
+		uint32_t* dv = reinterpret_cast<uint32_t*>(s + L.off_v);
+		float*    dt = reinterpret_cast<float*>(s + L.off_t);
+		uint8_t*  df = reinterpret_cast<uint8_t*>(s + L.off_f);
+		uint16_t* dn = npush ? reinterpret_cast<uint16_t*>(s + L.off_np) : nullptr;
+
+		if (used[slot])
+			ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));   // slot's previous results have left
+		// rows r0.. of this call: same mapping with the chunk's first frame row as origin
+		const int cy0 = y0 + (r0 / tile_rows) * tile_rows * tile_step;
+		rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, cy0, nr, tile_rows, tile_step, dv, df, dt, dn);
+		if (rc != ORT_OK) return rc;
+		ORT_CUDA(c, cudaEventRecord(c->ev_chunk[slot], c->stream));
+		ORT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[slot], 0));
+		ORT_CUDA(c, cudaMemcpyAsync(voxel + first, dv, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+		ORT_CUDA(c, cudaMemcpyAsync(t + first, dt, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+		ORT_CUDA(c, cudaMemcpyAsync(face + first, df, n, cudaMemcpyDeviceToHost, c->copy_stream));
+		if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush + first, dn, n * 2, cudaMemcpyDeviceToHost, c->copy_stream));
+		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+		used[slot] = true;
+	}
+	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	return ORT_OK;
+}
+
+int ort_sync(ort_ctx* c)
+{
+	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_sync: null context");
+	DeviceGuard g(c->device);
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	return ORT_OK;
+}
+
+void*    ort_stream(ort_ctx* c) { return c ? c->stream : nullptr; }
+int      ort_device(const ort_ctx* c) { return c ? c->device : -1; }
+uint32_t ort_node_count(const ort_ctx* c) { return c ? c->n_nodes : 0; }
+uint32_t ort_root(const ort_ctx* c) { return c ? c->root : 0; }
+uint64_t ort_launch_count(const ort_ctx* c) { return c ? c->launches : 0; }
+
+int ort_set_option(ort_ctx* c, const char* key, int value)
+{
+	if (!c || !key) return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: bad arguments");
+	if (!std::strcmp(key, "variant")) c->opt_variant = value;
+	else if (!std::strcmp(key, "smem_levels")) c->opt_smem_levels = value;
+	else if (!std::strcmp(key, "block")) c->opt_block = value;
+	else return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: unknown key '%s'", key);
+	return ORT_OK;
+}
+
+int ort_host_alloc(void** out, size_t bytes)
+{
+	if (!out) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_host_alloc: null out");
+	ORT_CUDA(nullptr, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+	return ORT_OK;
+}
+
+int ort_host_free(void* p)
+{
+	if (p) ORT_CUDA(nullptr, cudaFreeHost(p));
+	return ORT_OK;
+}
+
+void ort_camera_coeffs(float yaw, float pitch, float rot[9], float* fov_factor)
+{
+	// test_och_h_octree.cpp:95-115; roll (a) is fixed at 0 there, so sin_a = 0 and cos_a = 1
+	const float fov = 1.25F;
+	if (fov_factor) *fov_factor = 1 / tanf(fov / 2);
+	const float sa = 0, ca = 1;
+	const float sb = sinf(yaw), cb = cosf(yaw);
+	const float sc = sinf(pitch), cc = cosf(pitch);
+	rot[0] = ca * cb;
+	rot[1] = ca * sb * sc - sa * cc;
+	rot[2] = ca * sb * cc + sa * sc;
+	rot[3] = sa * cb;
+	rot[4] = sa * sb * sc + ca * cc;
+	rot[5] = sa * sb * cc - ca * sc;
+	rot[6] = -sb;
+	rot[7] = cb * sc;
+	rot[8] = cb * cc;
+}
+
+}  // extern "C"

@@ -1,0 +1,566 @@
+// ort_host_tree.cpp -- host side of the drop-in: the reference's reference-counted,
+// hash-deduplicated node store (och::h_octree<L,D>, och_h_octree.h:17-288) re-implemented, plus
+// what the GPU path adds to it: dirty-slot tracking at the single place the table is written,
+// flattening of the live DAG into the compact level-ordered array the kernel reads, and delta
+// extraction after edits.  Pure host C++; no CUDA calls except through the C ABI in ort_b200.h.
+//
+// Slot layout, hash, tag ("cash") rule, probe order, gravestone reuse and refcount arithmetic follow
+// the reference exactly, so the ids returned by register_node() and the table contents are the
+// same as the reference's for the same call sequence (tests/test_host_tree.py checks this
+// slot-for-slot against the oracle).
+#include "ort_internal.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+namespace {
+
+inline uint32_t fnv1a_signed(const uint32_t* c8)
+{
+	// och_h_octree.h:52-65 -- the bytes are read through `const char*`, i.e. SIGNED on x86, so
+	// bytes >= 0x80 flip the upper 24 hash bits as well.
+	const int8_t* b = reinterpret_cast<const int8_t*>(c8);
+	uint32_t h = 2166136261u;
+	for (int i = 0; i < 32; ++i)
+		h = (static_cast<uint32_t>(static_cast<int32_t>(b[i])) ^ h) * 16777619u;
+	return h;
+}
+
+inline bool same_node(const uint32_t* a, const uint32_t* b)
+{
+	return std::memcmp(a, b, 32) == 0;
+}
+
+inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z)
+{
+	// och::z_encode_16 (och_z_order.cpp:191-196): x -> bits 0,3,6.., y -> 1,4,7.., z -> 2,5,8..
+	auto spread = [](uint64_t v) {
+		v &= 0xFFFFu;
+		v = (v | (v << 32)) & 0x001F00000000FFFFull;
+		v = (v | (v << 16)) & 0x001F0000FF0000FFull;
+		v = (v | (v << 8)) & 0x100F00F00F00F00Full;
+		v = (v | (v << 4)) & 0x10C30C30C30C30C3ull;
+		v = (v | (v << 2)) & 0x1249249249249249ull;
+		return v;
+	};
+	return spread(x) | (spread(y) << 1) | (spread(z) << 2);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// construction
+// ------------------------------------------------------------------------------------------------
+
+ort_tree::ort_tree(int log2cap_, int depth_)
+	: log2cap(log2cap_), depth(depth_), cap(1u << log2cap_), idx_mask(((cap - 1u) >> 4) << 4)
+{
+	tags = static_cast<uint8_t*>(std::calloc(cap, 1));
+	refcounts = static_cast<uint32_t*>(std::calloc(cap, 4));
+	nodes = static_cast<uint32_t*>(std::aligned_alloc(64, static_cast<size_t>(cap) * 32));
+	if (nodes) std::memset(nodes, 0, static_cast<size_t>(cap) * 32);
+	dirty_bits = static_cast<uint64_t*>(std::calloc((cap + 63) / 64, 8));
+	id_interior = static_cast<uint32_t*>(std::calloc(cap, 4));
+	id_leaf = static_cast<uint32_t*>(std::calloc(cap, 4));
+}
+
+ort_tree::~ort_tree()
+{
+	std::free(tags);
+	std::free(refcounts);
+	std::free(nodes);
+	std::free(dirty_bits);
+	std::free(id_interior);
+	std::free(id_leaf);
+}
+
+// ------------------------------------------------------------------------------------------------
+// table operations (och_h_octree.h:110-288)
+// ------------------------------------------------------------------------------------------------
+
+inline void ort_tree::mark_dirty(uint32_t slot)
+{
+	uint64_t& w = dirty_bits[slot >> 6];
+	const uint64_t bit = 1ull << (slot & 63);
+	if (!(w & bit))
+	{
+		w |= bit;
+		dirty.push_back(slot);
+	}
+}
+
+// Probe for `n`.  Returns the slot holding an equal node (found = true) or the slot an insert
+// must use (found = false): the LAST gravestone seen on the probe path if any, else the
+// terminating empty slot (och_h_octree.h:129-151).
+inline uint32_t ort_tree::probe(const uint32_t* n, uint8_t& tag, bool& found) const
+{
+	const uint32_t h = fnv1a_signed(n);
+	uint32_t i = h & idx_mask;                                   // :120 (start slot is 16-aligned)
+	tag = static_cast<uint8_t>(h >> log2cap);                    // :122
+	if (tag == 0) tag = 1;                                       // :124-127
+	else if (tag == 0xFF) tag = 0x7F;
+
+	uint32_t grave = UINT32_MAX;
+	for (uint8_t t; (t = tags[i]) != 0; i = (i + 1) & (cap - 1))
+	{
+		if (t == 0xFF)
+			grave = i;
+		else if (t == tag && same_node(nodes + 8 * static_cast<size_t>(i), n))
+		{
+			found = true;
+			return i;
+		}
+	}
+	found = false;
+	return grave != UINT32_MAX ? grave : i;
+}
+
+uint32_t ort_tree::register_node(const uint32_t* n)
+{
+	if (fillcnt > static_cast<uint32_t>(static_cast<float>(cap) * 0.9375F))   // :112
+	{
+		table_full = true;    // the reference prints and exit(0)s here (:114-115); a library reports instead
+		return 0;
+	}
+
+	uint8_t tag;
+	bool found;
+	const uint32_t slot = probe(n, tag, found);
+
+	++nodecnt;
+	if (found)
+	{
+		uint32_t& rc = refcounts[slot];
+		if (rc != UINT32_MAX) ++rc;                              // saturating (depth >= 13 fixtures); the reference wraps
+		return slot + 1;
+	}
+
+	++fillcnt;
+	tags[slot] = tag;
+	std::memcpy(nodes + 8 * static_cast<size_t>(slot), n, 32);  // :155 -- the ONLY write to nodes[] => the delta hook
+	refcounts[slot] = 1;
+	mark_dirty(slot);
+	return slot + 1;
+}
+
+// insert-or-find without reference counting; counts are assigned by assign_instance_counts()
+uint32_t ort_tree::intern_node(const uint32_t* n)
+{
+	if (fillcnt > static_cast<uint32_t>(static_cast<float>(cap) * 0.9375F))
+	{
+		table_full = true;
+		return 0;
+	}
+	uint8_t tag;
+	bool found;
+	const uint32_t slot = probe(n, tag, found);
+	if (!found)
+	{
+		++fillcnt;
+		tags[slot] = tag;
+		std::memcpy(nodes + 8 * static_cast<size_t>(slot), n, 32);
+		refcounts[slot] = 0;
+		mark_dirty(slot);
+	}
+	return slot + 1;
+}
+
+void ort_tree::remove_node(uint32_t idx)
+{
+	uint32_t& rc = refcounts[idx - 1];
+	--nodecnt;
+	if (rc == UINT32_MAX)
+		return;                                                  // saturated counts are sticky
+	if (--rc == 0)
+	{
+		--fillcnt;
+		tags[idx - 1] = 0xFF;                                    // gravestone (:172)
+		mark_dirty(idx - 1);                                     // its compact id can be recycled at the next sync
+	}
+}
+
+void ort_tree::set(uint16_t x, uint16_t y, uint16_t z, uint32_t v)
+{
+	if (static_cast<uint32_t>(x | y | z) >= (1u << depth))      // :178
+		return;
+
+	const uint64_t key = morton3(x, y, z);
+	uint32_t path[16];                                           // path[d] = node whose child index is key's digit d
+	int d = depth - 1;
+
+	for (uint32_t cur = root; cur != 0 && d >= 0; --d)           // :188-195
+	{
+		path[d] = cur;
+		cur = nodes[8 * static_cast<size_t>(cur - 1) + ((key >> (3 * d)) & 7)];
+	}
+
+	const int first_existing = d + 1;                            // digits below this have no node yet
+	uint32_t child = v;
+
+	if (first_existing != 0)                                     // :202-217
+	{
+		if (v == 0)
+			return;                                              // removing a voxel that is not there
+		for (int k = 0; k < first_existing; ++k)
+		{
+			uint32_t n[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+			n[(key >> (3 * k)) & 7] = child;
+			child = register_node(n);
+		}
+	}
+
+	for (int k = first_existing; k < depth; ++k)                 // :220-234 path copy-on-write, bottom-up
+	{
+		remove_node(path[k]);
+		uint32_t n[8];
+		std::memcpy(n, nodes + 8 * static_cast<size_t>(path[k] - 1), 32);
+		n[(key >> (3 * k)) & 7] = child;
+		const bool empty = !(n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7]);
+		child = empty ? 0 : register_node(n);
+	}
+
+	root = child;                                                // :236
+}
+
+uint32_t ort_tree::at(int x, int y, int z) const
+{
+	if (root == 0)                                               // the reference dereferences nodes[-1] here (UB); 0 = air
+		return 0;
+	const uint64_t key = morton3(static_cast<uint16_t>(x), static_cast<uint16_t>(y), static_cast<uint16_t>(z));
+	uint32_t cur = root;
+	for (int d = depth - 1; d != 0; --d)
+	{
+		cur = nodes[8 * static_cast<size_t>(cur - 1) + ((key >> (3 * d)) & 7)];
+		if (cur == 0)
+			return 0;
+	}
+	return nodes[8 * static_cast<size_t>(cur - 1) + (key & 7)];
+}
+
+void ort_tree::clear()
+{
+	// :285-288 zeroes only the tags -- root, counters and refcounts keep their values.
+	std::memset(tags, 0, cap);
+	invalidate_mirror();
+}
+
+// ------------------------------------------------------------------------------------------------
+// flatten / delta
+// ------------------------------------------------------------------------------------------------
+
+void ort_tree::invalidate_mirror()
+{
+	mirror_valid = false;
+}
+
+void ort_tree::reset_ids()
+{
+	for (uint32_t s : id_owner)
+	{
+		id_interior[s & 0x7FFFFFFFu] = 0;
+		id_leaf[s & 0x7FFFFFFFu] = 0;
+	}
+	id_owner.clear();
+	free_ids.clear();
+	next_id = 1;
+}
+
+void ort_tree::clear_dirty()
+{
+	for (uint32_t s : dirty) dirty_bits[s >> 6] = 0;
+	dirty.clear();
+}
+
+// Level-ordered (BFS) flatten: ids are handed out in discovery order, so each level occupies a
+// contiguous id range, the root is id 1 and the upper levels form a prefix the kernel can stage
+// in shared memory.  A slot reached both as an interior node and as a level-`depth` node gets two
+// ids (its children mean different things in the two roles).
+size_t ort_tree::flatten(uint32_t* level_offsets)
+{
+	reset_ids();
+	flat.clear();
+	flat_root = 0;
+
+	if (level_offsets)
+		for (int l = 0; l <= depth; ++l) level_offsets[l] = 1;
+
+	if (root == 0)
+		return 0;
+
+	std::vector<uint32_t> cur, next;
+	auto give_id = [&](uint32_t slot, bool leaf) {
+		uint32_t& id = (leaf ? id_leaf : id_interior)[slot];
+		id = next_id++;
+		id_owner.push_back(slot | (leaf ? 0x80000000u : 0u));
+		return id;
+	};
+
+	cur.push_back(root - 1);
+	give_id(root - 1, depth == 1);
+	flat_root = 1;
+
+	for (int level = 1; level <= depth; ++level)
+	{
+		if (level_offsets) level_offsets[level - 1] = static_cast<uint32_t>(flat.size() / 8 + 1);
+		const bool leaf = level == depth;
+		const bool child_leaf = level + 1 == depth;
+		next.clear();
+		flat.resize(flat.size() + cur.size() * 8);
+		uint32_t* out = flat.data() + flat.size() - cur.size() * 8;
+
+		for (uint32_t slot : cur)
+		{
+			const uint32_t* n = nodes + 8 * static_cast<size_t>(slot);
+			if (leaf)
+				std::memcpy(out, n, 32);
+			else
+				for (int c = 0; c < 8; ++c)
+				{
+					uint32_t id = 0;
+					if (n[c])
+					{
+						id = (child_leaf ? id_leaf : id_interior)[n[c] - 1];
+						if (!id)
+						{
+							id = give_id(n[c] - 1, child_leaf);
+							next.push_back(n[c] - 1);
+						}
+					}
+					out[c] = id;
+				}
+			out += 8;
+		}
+		cur.swap(next);
+	}
+	if (level_offsets) level_offsets[depth] = static_cast<uint32_t>(flat.size() / 8 + 1);
+
+	return flat.size() / 8;
+}
+
+uint32_t ort_tree::delta_visit(uint32_t slot, int level)
+{
+	const bool leaf = level == depth;
+	uint32_t* ids = leaf ? id_leaf : id_interior;
+	if (ids[slot])
+		return ids[slot];
+
+	uint32_t id;
+	if (!free_ids.empty()) { id = free_ids.back(); free_ids.pop_back(); }
+	else id = next_id++;
+	ids[slot] = id;
+	id_owner.push_back(slot | (leaf ? 0x80000000u : 0u));
+
+	const size_t at = delta_nodes.size();
+	delta_ids.push_back(id);
+	delta_nodes.resize(at + 8);
+
+	const uint32_t* n = nodes + 8 * static_cast<size_t>(slot);
+	if (leaf)
+		std::memcpy(delta_nodes.data() + at, n, 32);
+	else
+		for (int c = 0; c < 8; ++c)
+		{
+			const uint32_t cid = n[c] ? delta_visit(n[c] - 1, level + 1) : 0;
+			delta_nodes[at + c] = cid;   // (delta_nodes may have been reallocated by the recursion)
+		}
+	return id;
+}
+
+// Collect the nodes the device does not have yet.  Invariant used: a node is live iff it is
+// reachable from the root (refcount = number of instances in the expanded tree), every insert and
+// every death marks its slot dirty, and a changed node implies changed ancestors -- so a walk from
+// the root that stops at nodes which still own a compact id visits exactly the new nodes.
+bool ort_tree::build_delta()
+{
+	delta_ids.clear();
+	delta_nodes.clear();
+
+	if (!mirror_valid)
+		return false;
+
+	// 1. slots written or killed since the last sync lose their compact ids
+	for (uint32_t s : dirty)
+	{
+		if (id_interior[s]) { free_ids.push_back(id_interior[s]); id_interior[s] = 0; }
+		if (id_leaf[s]) { free_ids.push_back(id_leaf[s]); id_leaf[s] = 0; }
+	}
+	const size_t n_dirty = dirty.size();
+	clear_dirty();
+
+	// 2. walk
+	delta_root = root ? delta_visit(root - 1, 1) : 0;
+
+	// id_owner grows by one entry per visit; compact it now and then so it stays O(live)
+	if (id_owner.size() > 4 * static_cast<size_t>(fillcnt) + 1024)
+	{
+		std::vector<uint32_t> keep;
+		keep.reserve(fillcnt * 2);
+		for (uint32_t e : id_owner)
+			if ((e & 0x80000000u ? id_leaf : id_interior)[e & 0x7FFFFFFFu]) keep.push_back(e);
+		std::sort(keep.begin(), keep.end());
+		keep.erase(std::unique(keep.begin(), keep.end()), keep.end());
+		id_owner.swap(keep);
+	}
+
+	(void)n_dirty;
+	// a delta that replaces most of the tree is better sent as a fresh level-ordered flatten
+	if (delta_ids.size() > 1024 && delta_ids.size() * 2 > static_cast<size_t>(fillcnt))
+		return false;
+	return true;
+}
+
+size_t ort_tree::take_delta(const uint32_t** ids, const uint32_t** nodes8, uint32_t* root_out, int* is_full)
+{
+	if (build_delta())
+	{
+		*ids = delta_ids.data();
+		*nodes8 = delta_nodes.data();
+		*root_out = delta_root;
+		*is_full = 0;
+		return delta_ids.size();
+	}
+	const size_t n = flatten(nullptr);
+	clear_dirty();
+	mirror_valid = true;
+	*ids = nullptr;
+	*nodes8 = flat.data();
+	*root_out = flat_root;
+	*is_full = 1;
+	return n;
+}
+
+int ort_tree::sync()
+{
+	if (!ctx)
+		return ORT_ERR_NOT_ATTACHED;
+	if (table_full)
+		return ORT_ERR_TABLE_FULL;
+
+	if (mirror_valid && dirty.empty() && synced_root_slot == root)
+	{
+		last_sync_nodes = 0;
+		last_sync_full = 0;
+		return ORT_OK;
+	}
+
+	const uint32_t *ids, *n8;
+	uint32_t r;
+	int full;
+	const size_t n = take_delta(&ids, &n8, &r, &full);
+	int rc;
+	if (full)
+		rc = ort_upload_full(ctx, n8, n, r);
+	else
+	{
+		rc = ort_upload_delta(ctx, ids, n8, n, r);
+		if (rc == ORT_ERR_CAPACITY)
+		{
+			// out of mirror space: re-flatten (drops garbage) and let upload_full grow the mirror
+			const size_t m = flatten(nullptr);
+			full = 1;
+			rc = ort_upload_full(ctx, flat.data(), m, flat_root);
+			last_sync_nodes = m;
+			last_sync_full = 1;
+			if (rc == ORT_OK) synced_root_slot = root; else mirror_valid = false;
+			return rc;
+		}
+	}
+	last_sync_nodes = n;
+	last_sync_full = full;
+	if (rc == ORT_OK) synced_root_slot = root; else mirror_valid = false;
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int ort_tree_create(ort_tree** out, int log2cap, int depth)
+{
+	if (!out || log2cap < 4 || log2cap > 30 || depth < 1 || depth > 16)
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_create: log2_table_capacity in 4..30 and depth in 1..16 required");
+	ort_tree* t = new (std::nothrow) ort_tree(log2cap, depth);
+	if (!t || !t->tags || !t->refcounts || !t->nodes || !t->dirty_bits || !t->id_interior || !t->id_leaf)
+	{
+		delete t;
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_create: out of host memory");
+	}
+	*out = t;
+	return ORT_OK;
+}
+
+void ort_tree_destroy(ort_tree* t) { delete t; }
+
+uint32_t ort_tree_register_node(ort_tree* t, const uint32_t c[8]) { return t->register_node(c); }
+void     ort_tree_remove_node(ort_tree* t, uint32_t idx) { t->remove_node(idx); }
+void     ort_tree_set(ort_tree* t, uint16_t x, uint16_t y, uint16_t z, uint32_t v) { t->set(x, y, z, v); }
+
+void ort_tree_set_many(ort_tree* t, const uint32_t* q, size_t n)
+{
+	for (size_t i = 0; i < n; ++i)
+		t->set(static_cast<uint16_t>(q[4 * i]), static_cast<uint16_t>(q[4 * i + 1]), static_cast<uint16_t>(q[4 * i + 2]), q[4 * i + 3]);
+}
+
+void ort_tree_set_box(ort_tree* t, uint16_t cx, uint16_t cy, uint16_t cz, int ext, uint32_t v)
+{
+	// test_och_h_octree.cpp:408-413 / :427-432: int offsets added to uint16 coordinates, then
+	// narrowed back to uint16 by set()'s parameters (so boxes poking out of the cube wrap to >= dim
+	// and are ignored by set()'s range check at depth < 16).
+	for (int z = -ext / 2; z < (ext + 1) / 2; ++z)
+		for (int y = -ext / 2; y < (ext + 1) / 2; ++y)
+			for (int x = -ext / 2; x < (ext + 1) / 2; ++x)
+				t->set(static_cast<uint16_t>(cx + x), static_cast<uint16_t>(cy + y), static_cast<uint16_t>(cz + z), v);
+}
+
+uint32_t ort_tree_at(const ort_tree* t, int x, int y, int z) { return t->at(x, y, z); }
+void     ort_tree_set_root(ort_tree* t, uint32_t idx) { t->root = idx; }
+uint32_t ort_tree_get_root(const ort_tree* t) { return t->root; }
+uint32_t ort_tree_get_fillcnt(const ort_tree* t) { return t->fillcnt; }
+uint32_t ort_tree_get_nodecnt(const ort_tree* t) { return t->nodecnt; }
+uint32_t ort_tree_get_max_refcnt(const ort_tree* t) { return t->max_refcnt; }   // never written by the reference either (:99)
+void     ort_tree_clear(ort_tree* t) { t->clear(); }
+int      ort_tree_table_full(const ort_tree* t) { return t->table_full; }
+int      ort_tree_depth(const ort_tree* t) { return t->depth; }
+int      ort_tree_log2_capacity(const ort_tree* t) { return t->log2cap; }
+const uint32_t* ort_tree_nodes(const ort_tree* t) { return t->nodes; }
+const uint8_t*  ort_tree_cashes(const ort_tree* t) { return t->tags; }
+const uint32_t* ort_tree_refcounts(const ort_tree* t) { return t->refcounts; }
+
+size_t ort_tree_flatten(ort_tree* t, const uint32_t** nodes8, uint32_t* root, uint32_t* level_offsets)
+{
+	const size_t n = t->flatten(level_offsets);
+	// a bare flatten re-numbers the ids, so whatever the device holds is stale afterwards
+	t->clear_dirty();
+	t->invalidate_mirror();
+	if (nodes8) *nodes8 = t->flat.data();
+	if (root) *root = t->flat_root;
+	return n;
+}
+
+int ort_tree_attach(ort_tree* t, ort_ctx* ctx)
+{
+	t->ctx = ctx;
+	t->invalidate_mirror();
+	return ORT_OK;
+}
+
+int ort_tree_sync(ort_tree* t) { return t->sync(); }
+
+void ort_tree_sync_stats(const ort_tree* t, uint64_t* n, int* full)
+{
+	if (n) *n = t->last_sync_nodes;
+	if (full) *full = t->last_sync_full;
+}
+
+size_t ort_tree_take_delta(ort_tree* t, const uint32_t** ids, const uint32_t** nodes8, uint32_t* root, int* is_full)
+{
+	const size_t n = t->take_delta(ids, nodes8, root, is_full);
+	t->synced_root_slot = t->root;
+	return n;
+}
+
+}  // extern "C"

@@ -1,0 +1,193 @@
+// ort_trace.cuh -- the per-ray DAG traversal, device side (sm_100a).
+//
+// Computes exactly what och::h_octree<L,D>::sse_trace computes (och_h_octree.h:292-447): an adapted
+// Laine-Karras traversal with (i) the "dimension bit" -- one float-mantissa bit OR-ed into / masked
+// out of the position instead of a scale pair -- and (ii) the early POP branch taken before any
+// position update, so no overstep correction exists.  Everything that is an integer trick on float
+// bit patterns in the SSE original is integer arithmetic here; the three float operations that
+// decide results keep their exact IEEE form:
+//     coef  = RCPPS(d)            -> table model (ort_rcp_model), bit-exact with the CPU instruction
+//     bias  = -(coef * o)         -> __fmul_rn, never contracted
+//     t     = fma(pos, coef, bias)-> __fmaf_rn (single rounding, like _mm_fmadd_ps)
+// NaN results (axis-parallel rays: coef = -inf, bias = +inf) are canonicalised to x86's default NaN
+// 0xFFC00000 because the reference orders t values by their raw bits as UNSIGNED integers (:384-406).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace ort {
+
+constexpr int kMaxDepth = 16;
+
+struct RcpTable
+{
+	const uint32_t* tab;   // 1 << log2n entries
+	int shift;             // 23 - log2n
+};
+
+__device__ __forceinline__ uint32_t rcp_model(const RcpTable rt, uint32_t x)
+{
+	const uint32_t sign = x & 0x80000000u;
+	const uint32_t e = (x >> 23) & 0xFFu;
+	const uint32_t m = x & 0x7FFFFFu;
+	if (e == 255u) return m ? (x | 0x00400000u) : sign;      // NaN stays NaN, inf -> 0
+	if (e == 0u) return sign | 0x7F800000u;                  // 0 and denormals -> inf
+	const uint32_t r = __ldg(rt.tab + (m >> rt.shift));
+	const int re = static_cast<int>(r >> 23) - (static_cast<int>(e) - 127);
+	if (re <= 0) return sign;                                // would be denormal -> 0
+	return sign | (static_cast<uint32_t>(re) << 23) | (r & 0x7FFFFFu);
+}
+
+// x86 orders NaN (default NaN 0xFFC00000) after every number when t bits are compared as unsigned
+__device__ __forceinline__ uint32_t t_bits(float t)
+{
+	const uint32_t b = __float_as_uint(t);
+	return (b & 0x7FFFFFFFu) > 0x7F800000u ? 0xFFC00000u : b;
+}
+
+struct Ray
+{
+	float cx, cy, cz;        // coef
+	float bx, by, bz;        // bias
+	uint32_t px, py, pz;     // pos (float bit patterns in [1,2))
+	uint32_t inv;            // inv_signs
+	uint32_t idx;
+};
+
+__device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, int a, float& coef, float& bias, uint32_t& pos, uint32_t& inv, uint32_t& idx)
+{
+	const bool sg = 0.0f < d;                                                  // :310
+	inv |= static_cast<uint32_t>(sg) << a;                                     // :322
+	const uint32_t dn = __float_as_uint(d) | 0x80000000u;                      // :312
+	const float oa = fabsf(__fsub_rn(sg ? 3.0f : 0.0f, o));                    // :314
+	coef = __uint_as_float(rcp_model(rt, dn));                                 // :316
+	bias = __uint_as_float(__float_as_uint(__fmul_rn(coef, oa)) ^ 0x80000000u); // :318
+	pos = __float_as_uint(oa) & 0x3FC00000u;                                   // :320
+	idx |= static_cast<uint32_t>(pos == 0x3FC00000u) << a;                     // :324
+}
+
+__device__ __forceinline__ Ray ray_setup(const RcpTable rt, float ox, float oy, float oz, float dx, float dy, float dz)
+{
+	Ray r;
+	r.inv = 0;
+	r.idx = 0;
+	ray_axis(rt, ox, dx, 0, r.cx, r.bx, r.px, r.inv, r.idx);
+	ray_axis(rt, oy, dy, 1, r.cy, r.by, r.py, r.inv, r.idx);
+	ray_axis(rt, oz, dz, 2, r.cz, r.bz, r.pz, r.inv, r.idx);
+	return r;
+}
+
+struct Hit
+{
+	uint32_t voxel;
+	uint32_t face;
+	float    t;
+	uint32_t npush;
+};
+
+// nodes: compact array, id i (1-based) at nodes[8*(i-1) .. 8*(i-1)+7]; root != 0.
+// Baseline variant: one thread walks one ray from start to end, parent stack in local memory.
+__device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r)
+{
+	uint32_t stack[kMaxDepth];
+	uint32_t node = root;
+	uint32_t dim = 1u << 22;                                                   // :326
+	int      level = 1;                                                        // :334
+	uint32_t mti = 8;                                                          // :336
+	float    tmin = 0.0f;                                                      // :338
+	uint32_t idx = r.idx;
+	uint32_t px = r.px, py = r.py, pz = r.pz;
+	Hit h;
+	h.npush = 0;
+
+	for (;;)
+	{
+		// PUSH (:342-376)
+		++h.npush;
+		const uint32_t child = __ldg(nodes + (static_cast<size_t>(node - 1) << 3) + ((idx ^ r.inv) & 7u));
+
+		if (child)
+		{
+			if (level == depth)                                                // :346 HIT
+			{
+				h.voxel = child;
+				h.face = (mti >> 1) + 3u * ((r.inv & mti) == 0u);
+				h.t = tmin;
+				return h;
+			}
+			stack[level - 1] = node;                                           // :357
+			++level;
+			node = child;
+			dim >>= 1;                                                         // :361
+			const float tx = __fmaf_rn(__uint_as_float(px | dim), r.cx, r.bx); // :363-365
+			const float ty = __fmaf_rn(__uint_as_float(py | dim), r.cy, r.by);
+			const float tz = __fmaf_rn(__uint_as_float(pz | dim), r.cz, r.bz);
+			const bool ux = tx >= tmin, uy = ty >= tmin, uz = tz >= tmin;      // :367 ordered compare, false on NaN
+			idx = static_cast<uint32_t>(ux) | (static_cast<uint32_t>(uy) << 1) | (static_cast<uint32_t>(uz) << 2);
+			px |= ux ? dim : 0u;                                               // :371-373
+			py |= uy ? dim : 0u;
+			pz |= uz ? dim : 0u;
+			continue;
+		}
+
+		for (;;)
+		{
+			// STEP (:378-419)
+			const uint32_t tx = t_bits(__fmaf_rn(__uint_as_float(px), r.cx, r.bx));
+			const uint32_t ty = t_bits(__fmaf_rn(__uint_as_float(py), r.cy, r.by));
+			const uint32_t tz = t_bits(__fmaf_rn(__uint_as_float(pz), r.cz, r.bz));
+			const uint32_t tm = min(tx, min(ty, tz));                          // :388-406: unsigned argmin, ties -> x, y, z
+			mti = tx == tm ? 1u : (ty == tm ? 2u : 4u);
+			tmin = __uint_as_float(tm);
+
+			if (idx & mti)                                                     // :410-419 step to the sibling
+			{
+				px &= ~(mti & 1u ? dim : 0u);
+				py &= ~(mti & 2u ? dim : 0u);
+				pz &= ~(mti & 4u ? dim : 0u);
+				idx ^= mti;
+				break;
+			}
+
+			// POP (:421-446)
+			if (--level == 0)                                                  // :423 MISS
+			{
+				h.voxel = 0;
+				h.face = 6;
+				h.t = __uint_as_float(0x7F800000u);
+				return h;
+			}
+			node = stack[level - 1];                                           // :434
+			px &= ~dim; py &= ~dim; pz &= ~dim;                                // :436
+			dim <<= 1;                                                         // :438
+			idx = static_cast<uint32_t>((px & dim) != 0u) | (static_cast<uint32_t>((py & dim) != 0u) << 1) | (static_cast<uint32_t>((pz & dim) != 0u) << 2); // :440-444
+		}
+	}
+}
+
+// Camera ray of pixel (x, y) -- tree_camera::update_position (test_och_h_octree.cpp:119-137) with
+// every operation rounded separately, in source order.
+struct Camera
+{
+	float ox, oy, oz;
+	float r[9];
+	float fov;
+	float aspect, vfx, vfy;
+};
+
+__device__ __forceinline__ void camera_ray(const Camera& c, int x, int y, float& dx, float& dy, float& dz)
+{
+	const float u = __fmul_rn(c.aspect, __fsub_rn(__fmul_rn(c.vfx, static_cast<float>(x)), 1.0f));   // :123
+	const float v = __fsub_rn(__fmul_rn(c.vfy, static_cast<float>(y)), 1.0f);                        // :125
+	const float ru = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[0]), __fmul_rn(v, c.r[1])), __fmul_rn(c.fov, c.r[2])); // :129-131
+	const float rv = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[3]), __fmul_rn(v, c.r[4])), __fmul_rn(c.fov, c.r[5]));
+	const float rw = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[6]), __fmul_rn(v, c.r[7])), __fmul_rn(c.fov, c.r[8]));
+	const float s = __fadd_rn(__fadd_rn(__fmul_rn(ru, ru), __fmul_rn(rv, rv)), __fmul_rn(rw, rw));
+	const float rm = __fdiv_rn(1.0f, __fsqrt_rn(s));                                                  // :133
+	dx = __fmul_rn(rw, rm);                                                                           // :135
+	dy = __fmul_rn(ru, rm);
+	dz = __fmul_rn(-rv, rm);
+}
+
+}  // namespace ort

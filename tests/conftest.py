@@ -1,0 +1,61 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def oc():
+    """The CPU oracle (test infrastructure)."""
+    from oracle import oracle
+    oracle.lib()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def ort():
+    """The product package; builds libort_b200.so if it is not there yet."""
+    import octree_ray_tracing_b200 as pkg
+    from octree_ray_tracing_b200 import build
+    if not os.path.exists(pkg.LIB_PATH):
+        build.build()
+    pkg.lib()
+    return pkg
+
+
+@pytest.fixture(scope="session")
+def golden():
+    def load(name):
+        return np.load(os.path.join(GOLDEN, name + ".npz"))
+    return load
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a)
+    b = np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype.itemsize == b.dtype.itemsize and np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
+def assert_same_hits(got, want, what=""):
+    """voxel ids and faces bit-exact; t bit-exact too (stricter than north_star's 1e-5 relative)."""
+    gv, gf, gt = got[:3]
+    wv, wf, wt = want[:3]
+    bad_v = np.flatnonzero(np.asarray(gv, np.uint32) != np.asarray(wv, np.uint32))
+    assert bad_v.size == 0, f"{what}: {bad_v.size} voxel mismatches, first at ray {bad_v[:5]}"
+    bad_f = np.flatnonzero(np.asarray(gf, np.uint8) != np.asarray(wf, np.uint8))
+    assert bad_f.size == 0, f"{what}: {bad_f.size} face mismatches, first at ray {bad_f[:5]}"
+    gtb = np.ascontiguousarray(gt, np.float32).view(np.uint32)
+    wtb = np.ascontiguousarray(wt, np.float32).view(np.uint32)
+    bad_t = np.flatnonzero(gtb != wtb)
+    assert bad_t.size == 0, f"{what}: {bad_t.size} hit-time mismatches (bitwise), first at ray {bad_t[:5]}"

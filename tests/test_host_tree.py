@@ -1,0 +1,188 @@
+"""CPU tests of the product's host side (C++ node store, flatten/delta, fixture builder, camera)
+against the oracle.  No GPU needed: nothing here calls a trace entry point."""
+import numpy as np
+import pytest
+
+from conftest import assert_same_hits, same_bits
+
+
+def live_mask(tags):
+    return (tags != 0) & (tags != 0xFF)
+
+
+def test_table_matches_oracle_slot_for_slot(ort, oc):
+    rs = np.random.RandomState(3)
+    a, p = oc.OracleTree(16, 6), ort.HOctree(16, 6, device=None)
+    for rnd in range(4):
+        ops = np.concatenate([rs.randint(0, 70, (15000, 3)), rs.randint(0, 4, (15000, 1))], 1).astype(np.uint32)
+        a.set_many(ops)
+        p.set_many(ops)
+        assert (a.root, a.fillcnt, a.nodecnt) == (p.get_root(), p.get_fillcnt(), p.get_nodecnt())
+        assert np.array_equal(a.cashes(), p.cashes())
+        assert np.array_equal(a.refcounts(), p.refcounts())
+        lm = live_mask(a.cashes())
+        assert np.array_equal(a.nodes()[lm], p.nodes()[lm])
+    pts = rs.randint(-2, 66, (3000, 3))
+    pts = pts[(pts >= 0).all(1) & (pts < 64).all(1)]
+    assert [a.at(*q) for q in pts] == [p.at(*q) for q in pts]
+
+
+def test_register_remove_api(ort, oc):
+    a, p = oc.OracleTree(12, 4), ort.HOctree(12, 4, device=None)
+    rs = np.random.RandomState(5)
+    ids = []
+    for _ in range(300):
+        n = rs.randint(0, 3, 8).astype(np.uint32)
+        if not n.any():
+            n[0] = 1
+        i, j = a.register_node(n), p.register_node(n)
+        assert i == j
+        ids.append(i)
+    for i in ids[::2]:
+        a.remove_node(i)
+        p.remove_node(i)
+    assert np.array_equal(a.cashes(), p.cashes()) and np.array_equal(a.refcounts(), p.refcounts())
+    assert (a.fillcnt, a.nodecnt) == (p.get_fillcnt(), p.get_nodecnt())
+    # re-registering reuses gravestones the same way
+    for _ in range(200):
+        n = rs.randint(0, 3, 8).astype(np.uint32)
+        n[7] = 5
+        assert a.register_node(n) == p.register_node(n)
+    assert np.array_equal(a.cashes(), p.cashes())
+    assert p.get_max_refcnt() == 0      # never maintained by the reference (och_h_octree.h:99)
+
+
+def test_set_edge_cases(ort):
+    t = ort.HOctree(12, 4, device=None)
+    assert t.get_root() == 0 and t.at(1, 2, 3) == 0
+    t.set(1, 2, 3, 0)                     # removing from an empty tree: no-op
+    assert t.get_root() == 0 and t.get_fillcnt() == 0
+    t.set(16, 0, 0, 1)                    # out of range (dim = 16): ignored (och_h_octree.h:178)
+    t.set(0, 65535, 0, 1)
+    assert t.get_root() == 0
+    t.set(1, 2, 3, 9)
+    assert t.at(1, 2, 3) == 9 and t.get_fillcnt() == 4
+    t.set(1, 2, 3, 0)                     # last voxel removed: collapses to the empty tree
+    assert t.get_root() == 0 and t.get_fillcnt() == 0 and t.get_nodecnt() == 0
+    t.set(15, 15, 15, 2)
+    t.clear()                             # clear() only zeroes the tags (och_h_octree.h:285-288)
+    assert t.get_root() != 0 and not t.cashes().any()
+
+
+def test_set_box_is_the_reference_loop(ort, oc):
+    a, p = oc.OracleTree(16, 6), ort.HOctree(16, 6, device=None)
+    for (cx, cy, cz, ext, v) in ((30, 30, 30, 10, 1), (2, 60, 33, 9, 3), (30, 30, 28, 6, 0)):
+        ops = [((cx + x) & 0xFFFF, (cy + y) & 0xFFFF, (cz + z) & 0xFFFF, v)
+               for z in range(-(ext // 2), (ext + 1) // 2) for y in range(-(ext // 2), (ext + 1) // 2) for x in range(-(ext // 2), (ext + 1) // 2)]
+        a.set_many(np.array(ops, np.uint32))
+        p.set_box(cx, cy, cz, ext, v)
+        assert np.array_equal(a.cashes(), p.cashes()) and a.root == p.get_root()
+
+
+def test_camera_coeffs_and_fixture_heightmap(ort, oc):
+    for yaw, pitch in ((0.0, 0.0), (0.7, -0.6), (0.785, -0.3), (-2.5, 1.2)):
+        r1, f1 = ort.camera_coeffs(yaw, pitch)
+        r2, f2 = oc.camera_coeffs(yaw, pitch)
+        assert same_bits(r1, r2) and f1 == f2
+    for d in (4, 6, 8):
+        assert np.array_equal(ort.harness.heightmap(d, 3), oc.heightmap(d))
+
+
+@pytest.mark.parametrize("depth,log2cap,tunnels", [(6, 16, False), (6, 16, True), (8, 19, False), (8, 19, True)])
+def test_fixture_builder_gives_the_canonical_dag(ort, oc, depth, log2cap, tunnels):
+    """The memoising builder and the straight restatement of initialize_h_octree end in the same
+    content-addressed DAG: same node count, instance counts, voxels, and traced image."""
+    h, g = oc.heightmap(depth), oc.grass_bits(depth)
+    A = oc.OracleTree(log2cap, depth)
+    A.initialize_terrain(h, g, tunnels)
+    T = ort.HOctree(log2cap, depth, device=None)
+    ort.harness.build_terrain(T, h, g, tunnels=tunnels)
+    assert (A.fillcnt, A.nodecnt) == (T.get_fillcnt(), T.get_nodecnt())
+    assert np.array_equal(np.sort(A.refcounts()[live_mask(A.cashes())]), np.sort(T.refcounts()[live_mask(T.cashes())]))
+    rs = np.random.RandomState(1)
+    for q in rs.randint(0, 1 << depth, (4000, 3)):
+        assert A.at(*q) == T.at(*q)
+    nodes8, root, lo = T.flatten()
+    assert nodes8.shape[0] == A.fillcnt and root == 1 and lo[0] == 1 and lo[-1] == nodes8.shape[0] + 1
+    rot, fov = oc.camera_coeffs(0.7, -0.6)
+    d = oc.gen_rays(rot, fov, 160, 90)
+    o = np.array([1.5, 1.5, 1.5], np.float32)
+    assert_same_hits(oc.trace_rays(nodes8, root, depth, o, d), A.trace(o, d), "flattened vs hashed table")
+    # edits after a memoised build keep the table consistent (refcounts were real instance counts)
+    ops = np.concatenate([rs.randint(0, 1 << depth, (3000, 3)), rs.randint(0, 3, (3000, 1))], 1).astype(np.uint32)
+    A.set_many(ops)
+    T.set_many(ops)
+    assert (A.fillcnt, A.nodecnt) == (T.get_fillcnt(), T.get_nodecnt())
+    n2, r2, _ = T.flatten()
+    assert n2.shape[0] == T.get_fillcnt()
+    assert_same_hits(oc.trace_rays(n2, r2, depth, o, d), A.trace(o, d), "after edits")
+
+
+def apply_delta(mirror, ids, nodes8):
+    need = int(ids.max()) if ids.size else 0
+    if need > mirror.shape[0]:
+        mirror = np.concatenate([mirror, np.zeros((need - mirror.shape[0], 8), np.uint32)])
+    mirror[ids - 1] = nodes8
+    return mirror
+
+
+def test_delta_stream_keeps_a_mirror_traceable(ort, oc):
+    """Simulated device mirror on the CPU: full flatten once, then only deltas after each burst of
+    edits (single voxels and 40^3-style boxes).  The oracle traced over the mirror must always
+    equal the oracle traced over a straight oracle table that saw the same edits."""
+    depth, log2cap = 6, 16
+    h, g = oc.heightmap(depth), oc.grass_bits(depth)
+    A = oc.OracleTree(log2cap, depth)
+    A.initialize_terrain(h, g, False)
+    T = ort.HOctree(log2cap, depth, device=None)
+    ort.harness.build_terrain(T, h, g)
+    ids, nodes8, root, full = T.take_delta()
+    assert full and ids is None
+    mirror = nodes8.copy()
+    rs = np.random.RandomState(9)
+    rot, fov = oc.camera_coeffs(0.3, -0.9)
+    d = oc.gen_rays(rot, fov, 96, 54)
+    o = np.array([1.5, 1.5, 1.8], np.float32)
+    total_delta = 0
+    for step in range(30):
+        if step % 3 == 2:
+            cx, cy, cz = (int(v) for v in rs.randint(8, 56, 3))
+            ext, v = int(rs.randint(3, 12)), int(rs.randint(0, 2))
+            ops = np.array([((cx + x) & 0xFFFF, (cy + y) & 0xFFFF, (cz + z) & 0xFFFF, v)
+                            for z in range(-(ext // 2), (ext + 1) // 2) for y in range(-(ext // 2), (ext + 1) // 2)
+                            for x in range(-(ext // 2), (ext + 1) // 2)], np.uint32)
+            T.set_box(cx, cy, cz, ext, v)
+        else:
+            ops = np.concatenate([rs.randint(0, 64, (40, 3)), rs.randint(0, 5, (40, 1))], 1).astype(np.uint32)
+            T.set_many(ops)
+        A.set_many(ops)
+        ids, nodes8, root, full = T.take_delta()
+        if full:
+            mirror = nodes8.copy()
+        else:
+            mirror = apply_delta(mirror, ids, nodes8)
+            total_delta += ids.size
+        assert_same_hits(oc.trace_rays(mirror, root, depth, o, d), A.trace(o, d), f"step {step}")
+        assert mirror.shape[0] < 4 * max(T.get_fillcnt(), 256)       # freed ids are recycled
+    assert total_delta > 0
+    # nothing pending -> empty delta, same root
+    ids, nodes8, root2, full = T.take_delta()
+    assert not full and ids.size == 0 and root2 == root
+    # emptying the tree gives root 0
+    for z in range(64):
+        T.set_box(32, 32, z, 64, 0)
+    ids, nodes8, root3, full = T.take_delta()
+    assert T.get_root() == 0 and root3 == 0
+
+
+def test_flatten_is_level_ordered(ort, oc):
+    T = ort.HOctree(19, 8, device=None)
+    ort.harness.build_terrain(T, oc.heightmap(8), oc.grass_bits(8))
+    nodes8, root, lo = T.flatten()
+    assert root == 1 and list(lo) == sorted(lo)
+    for level in range(1, 8):                        # interior children point into the next level's id range
+        rows = nodes8[lo[level - 1] - 1: lo[level] - 1]
+        ch = rows[rows != 0]
+        assert ch.min() >= lo[level] and ch.max() < lo[level + 1]
+    leaf = nodes8[lo[7] - 1:]
+    assert leaf.max() <= 4                           # voxel payloads, untranslated
