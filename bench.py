@@ -60,7 +60,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self.active = False
 
     def run(self):
@@ -77,7 +77,7 @@ class ClockSampler(threading.Thread):
                 getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
             }
             get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
-            while not self._stop.is_set():
+            while not self._halt.is_set():
                 if self.active:
                     self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                     r = get_reasons(h)
@@ -89,7 +89,7 @@ class ClockSampler(threading.Thread):
             self.error = repr(e)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         s = sorted(self.samples)
         return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
@@ -136,6 +136,11 @@ def run_product(args):
     harness.build_terrain(tree)
     n_up, _ = tree.sync()
     ctx = tree.ctx
+    if args.variant is not None:
+        ctx.set_option("variant", args.variant)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     log(f"[rank {rank}] DAG built + uploaded in {time.time() - t0:.1f}s: {n_up} nodes ({n_up * 32 / 2**20:.1f} MiB)")
 
     poses = [harness.POSES[p] for p in POSE_NAMES]
@@ -194,18 +199,24 @@ def run_product(args):
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
 
-    launches0 = ctx.launch_count
+    sampler.active = True          # warm-up, timed loop, warm-L2 loop and e2e are all load
     timed_loop(args.warmup, True)
     barrier()
     launches0 = ctx.launch_count
-    sampler.active = True
     wall0 = time.perf_counter()
     evs = timed_loop(args.steps, True)
     barrier()
     wall = time.perf_counter() - wall0
-    sampler.active = False
     launches = ctx.launch_count - launches0
     kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
+
+    if args.quick:
+        sampler.stop()
+        ms = kernel_ms / args.steps
+        print(json.dumps({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
+                          "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
+                          "per_frame_ms": [round(a.elapsed_time(b), 4) for a, b in evs[-3 * world:]]}), flush=True)
+        return None
 
     # same loop without the flush (steady state of a real frame loop: DAG stays L2-resident)
     timed_loop(1, False)
@@ -389,6 +400,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--quick", action="store_true", help="profiling aid: only the device-resident timed loop (no warm-L2 loop, no e2e, no CPU leg)")
+    ap.add_argument("--variant", type=int, default=None, help="kernel variant (ort_set_option 'variant')")
+    ap.add_argument("--opt", action="append", default=[], help="key=value passed to ort_set_option")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

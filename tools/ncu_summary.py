@@ -1,0 +1,64 @@
+"""Summarise an .ncu-rep (read with `ncu -i ... --page raw --csv`) into the handful of metrics
+DESIGN.md argues from.  Usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/xxx.md"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = [
+    ("gpu__time_duration.sum", "kernel time"),
+    ("launch__registers_per_thread", "registers/thread"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads per warp instruction (of 32)"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue slots busy %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+    ("sm__inst_executed_pipe_cbu.avg.pct_of_peak_sustained_active", "CBU (branch) pipe %"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 sector hit %"),
+    ("lts__t_sector_hit_rate.pct", "L2 sector hit %"),
+    ("l1tex__t_bytes.sum", "L1 bytes"),
+    ("lts__t_bytes.sum", "L2 bytes"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 throughput %"),
+    ("dram__bytes_read.sum", "DRAM read"),
+    ("dram__bytes_write.sum", "DRAM write"),
+    ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "DRAM throughput %"),
+    ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps / cycle / SMSP"),
+    ("smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "stall: math pipe throttle"),
+    ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall: not selected"),
+    ("smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio", "stall: long scoreboard (L1/L2/HBM)"),
+    ("smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "stall: short scoreboard (smem/local)"),
+    ("smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "stall: wait (fixed latency)"),
+    ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall: branch resolving"),
+    ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall: barrier"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall: lg throttle"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall: mio throttle"),
+    ("smsp__sass_average_branch_targets_threads_uniform.pct", "uniform branch targets %"),
+    ("sass__inst_executed_local_loads", "local loads (warp instr)"),
+    ("sass__inst_executed_local_stores", "local stores (warp instr)"),
+    ("sass__inst_executed_shared_loads", "shared loads (warp instr)"),
+]
+
+
+def main():
+    rep = sys.argv[1]
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    name_i = hdr.index("Kernel Name")
+    print(f"# ncu summary of `{rep}`\n")
+    print("launches: " + "; ".join(f"#{i} {r[name_i].split('(')[0]}" for i, r in enumerate(data)) + "\n")
+    print("| metric | unit | " + " | ".join(f"launch {i}" for i in range(len(data))) + " |")
+    print("|---|---|" + "---|" * len(data))
+    for k, label in KEYS:
+        if k in hdr:
+            i = hdr.index(k)
+            print(f"| {label} (`{k}`) | {units[i]} | " + " | ".join(r[i] for r in data) + " |")
+
+
+if __name__ == "__main__":
+    main()
