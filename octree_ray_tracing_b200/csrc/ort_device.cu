@@ -43,7 +43,7 @@ struct ort_ctx
 	void*  h_stage = nullptr;  size_t h_stage_bytes = 0;   // pinned
 
 	uint64_t launches = 0;
-	int opt_variant = 0;
+	int opt_variant = 1;                // 0 = baseline traverse(), 1 = traverse_fast() with fall-back
 	int opt_smem_levels = -1;
 	int opt_block = 256;
 	int sm_count = 0;
@@ -135,6 +135,7 @@ __global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restri
 }
 
 // explicit rays: thread i traces ray i
+template<int VARIANT>
 __global__ void __launch_bounds__(256)
 trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt,
                   const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, size_t n,
@@ -144,8 +145,9 @@ trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, 
 	if (i >= n) return;
 	const float* o = o3 + i * static_cast<size_t>(o_stride);
 	const float* d = d3 + i * 3;
-	const Ray r = ray_setup(rt, __ldg(o), __ldg(o + 1), __ldg(o + 2), __ldg(d), __ldg(d + 1), __ldg(d + 2));
-	const Hit h = traverse(nodes, root, depth, r);
+	const float ox = __ldg(o), oy = __ldg(o + 1), oz = __ldg(o + 2);
+	const Ray r = ray_setup(rt, ox, oy, oz, __ldg(d), __ldg(d + 1), __ldg(d + 2));
+	const Hit h = traverse_variant<VARIANT>(nodes, root, depth, ox, oy, oz, r);
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
@@ -160,6 +162,7 @@ struct FrameRows
 
 // camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
 // a 256-thread block a 16 x 16 pixel tile
+template<int VARIANT>
 __global__ void __launch_bounds__(256)
 trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt, Camera cam, FrameRows fr,
                    uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
@@ -173,7 +176,7 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth,
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
 	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	const Hit h = traverse(nodes, root, depth, ray);
+	const Hit h = traverse_variant<VARIANT>(nodes, root, depth, cam.ox, cam.oy, cam.oz, ray);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
@@ -282,7 +285,7 @@ int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
 
 int ort_upload_full(ort_ctx* c, const uint32_t* nodes8, size_t n, uint32_t root)
 {
-	if (!c || (n && !nodes8) || root > n || n > 0xFFFFFFF0u)
+	if (!c || (n && !nodes8) || root > n || n > ort::kIdMask)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_full: bad arguments (n=%zu root=%u)", n, root);
 	DeviceGuard g(c->device);
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -290,7 +293,7 @@ int ort_upload_full(ort_ctx* c, const uint32_t* nodes8, size_t n, uint32_t root)
 	{
 		// grow with head-room for the deltas that will follow
 		size_t want = n + n / 4 + 4096;
-		if (want > 0xFFFFFFF0u) want = 0xFFFFFFF0u;
+		if (want > ort::kIdMask) want = ort::kIdMask;   // compact ids are 29-bit (3 bits of each stack entry carry the child index)
 		cudaFree(c->d_nodes);
 		c->d_nodes = nullptr;
 		c->cap_nodes = 0;
@@ -386,7 +389,10 @@ int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float*
 		return launch_miss(c, n, voxel, face, t, npush);
 	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
 	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-	ort::trace_rays_kernel<<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush);
+	if (c->opt_variant == 0)
+		ort::trace_rays_kernel<0><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush);
+	else
+		ort::trace_rays_kernel<1><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush);
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
@@ -407,7 +413,10 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
-	ort::trace_frame_kernel<<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush);
+	if (c->opt_variant == 0)
+		ort::trace_frame_kernel<0><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush);
+	else
+		ort::trace_frame_kernel<1><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush);
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;

@@ -166,6 +166,141 @@ __device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint
 	}
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Fast variant.  Same decisions, same FMAs, different bookkeeping -- chosen from the ncu profile of the
+// baseline (profiles/r1_v1_ncu_full.md: ALU pipe 81 % busy, FMA pipe 17 %):
+//   * the position stays in FLOAT registers.  OR-ing the level's mantissa bit into a position whose lower
+//     bits are clear is an exact float add of the cell size (and AND-NOT an exact subtract), so the bit
+//     masks of the SSE original become FADDs on the idle FMA pipe -- valid because the origin is in [1,2)
+//     (callers outside that domain are routed to traverse(), which is exact for any bit pattern);
+//   * axes with d == +-0 or denormal (coef = -inf) would produce NaN t values, which x86 orders LAST as
+//     unsigned bits (0xFFC00000).  Such an axis gets coef = 0, bias = -inf instead: t = -inf = 0xFF800000,
+//     still after every finite value in unsigned order and still failing `t >= tmin`, so every decision is
+//     unchanged and the per-STEP NaN canonicalisation disappears.  (A ray with all three components
+//     degenerate would see tmin = -inf; it is routed to traverse() as well.);
+//   * the child index of the level being left rides in the top 3 bits of the parent-stack entry (compact
+//     ids stay below 2^29), so POP restores idx with one shift instead of three bit tests.
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t kIdMask = 0x1FFFFFFFu;
+
+__device__ __forceinline__ bool in_unit_cube(float ox, float oy, float oz)
+{
+	// all three in [1, 2): exponent field 127, sign 0
+	return ((__float_as_uint(ox) >> 23) == 127u) & ((__float_as_uint(oy) >> 23) == 127u) & ((__float_as_uint(oz) >> 23) == 127u);
+}
+
+__device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r)
+{
+	uint32_t stack[kMaxDepth];
+	uint32_t node = root;
+	int      level = 1;
+	uint32_t idx = r.idx;
+	const uint32_t inv = r.inv;
+	float px = __uint_as_float(r.px), py = __uint_as_float(r.py), pz = __uint_as_float(r.pz);
+	float dimf = 0.5f;               // size of the children of the current node = value of the dimension bit
+	float tmin = 0.0f;
+	uint32_t mti = 8;
+	Hit h;
+	h.npush = 0;
+
+	// degenerate axes (see above)
+	float cx = r.cx, cy = r.cy, cz = r.cz, bx = r.bx, by = r.by, bz = r.bz;
+	const float ninf = __uint_as_float(0xFF800000u);
+	if (cx == ninf) { cx = 0.0f; bx = ninf; }
+	if (cy == ninf) { cy = 0.0f; by = ninf; }
+	if (cz == ninf) { cz = 0.0f; bz = ninf; }
+
+	const uint32_t* nodes_m1 = nodes - 8;
+
+	for (;;)
+	{
+		++h.npush;
+		const uint32_t child = __ldg(nodes_m1 + (static_cast<size_t>(node) << 3) + ((idx ^ inv) & 7u));
+
+		if (child)
+		{
+			if (level == depth)
+			{
+				h.voxel = child;
+				h.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
+				h.t = tmin;
+				break;
+			}
+			stack[level - 1] = node | (idx << 29);
+			++level;
+			node = child;
+			dimf *= 0.5f;
+			const float mx = px + dimf, my = py + dimf, mz = pz + dimf;          // exact
+			const float tx = __fmaf_rn(mx, cx, bx);
+			const float ty = __fmaf_rn(my, cy, by);
+			const float tz = __fmaf_rn(mz, cz, bz);
+			idx = 0;
+			if (tx >= tmin) { px = mx; idx += 1u; }
+			if (ty >= tmin) { py = my; idx += 2u; }
+			if (tz >= tmin) { pz = mz; idx += 4u; }
+			continue;
+		}
+
+		for (;;)
+		{
+			const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
+			const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
+			const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
+			const uint32_t tm = min(tx, min(ty, tz));
+			tmin = __uint_as_float(tm);
+			const bool ax = tx == tm;
+			const bool ay = !ax && ty == tm;
+			mti = ax ? 1u : (ay ? 2u : 4u);
+
+			if (idx & mti)
+			{
+				if (ax) px -= dimf;                                             // exact: the bit is set
+				else if (ay) py -= dimf;
+				else pz -= dimf;
+				idx ^= mti;
+				break;
+			}
+
+			if (--level == 0)
+			{
+				h.voxel = 0;
+				h.face = 6;
+				h.t = __uint_as_float(0x7F800000u);
+				return h;
+			}
+			if (idx & 1u) px -= dimf;                                           // back to the parent's corner
+			if (idx & 2u) py -= dimf;
+			if (idx & 4u) pz -= dimf;
+			dimf += dimf;
+			const uint32_t e = stack[level - 1];
+			node = e & kIdMask;
+			idx = e >> 29;
+		}
+	}
+
+	return h;
+}
+
+// the fast path's preconditions: origin inside [1,2)^3 and at least one non-degenerate direction component
+__device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const Ray& r)
+{
+	const uint32_t ninf = 0xFF800000u;
+	const bool all_degenerate = (__float_as_uint(r.cx) == ninf) & (__float_as_uint(r.cy) == ninf) & (__float_as_uint(r.cz) == ninf);
+	return in_unit_cube(ox, oy, oz) & !all_degenerate;
+}
+
+template<int VARIANT>
+__device__ __forceinline__ Hit traverse_variant(const uint32_t* __restrict__ nodes, uint32_t root, int depth, float ox, float oy, float oz, const Ray& r)
+{
+	if (VARIANT == 0)
+		return traverse(nodes, root, depth, r);
+	if (fast_path_ok(ox, oy, oz, r))
+		return traverse_fast(nodes, root, depth, r);
+	return traverse(nodes, root, depth, r);
+}
+
 // Camera ray of pixel (x, y) -- tree_camera::update_position (test_och_h_octree.cpp:119-137) with
 // every operation rounded separately, in source order.
 struct Camera
