@@ -263,6 +263,40 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 				break;
 			}
 
+			if (((tx | ty | tz) & 0x80000000u) == 0u)
+			{
+				// Multi-level POP.  The reference pops ONE level and re-runs STEP at the parent's corner.  While
+				// every t is a non-negative float (unsigned bit order == float order) that re-run cannot change
+				// anything: on the exit axis a* the parent's corner coordinate is the child's (its idx bit is 0),
+				// on the other axes the corner only moves towards smaller coordinates, i.e. t only grows, and a
+				// lower-indexed axis that lost strictly keeps losing.  So tmin and a* are fixed and the chain of
+				// POPs runs exactly until an ancestor whose idx bit on a* is 1 -- the lowest set mantissa bit of
+				// pos[a*] above the current level.  One FLO replaces the loop; rays with a negative or -inf t in
+				// play take the one-level path below, which is the reference's sequence verbatim.
+				const uint32_t pa = __float_as_uint(ax ? px : (ay ? py : pz));
+				const uint32_t anc = (pa & 0x7FFFFFu) >> (24 - level);          // idx bits of levels level-1, level-2, .. on axis a*
+				if (anc == 0u)
+				{
+					h.voxel = 0;                                                    // popped through the root: MISS
+					h.face = 6;
+					h.t = __uint_as_float(0x7F800000u);
+					return h;
+				}
+				level -= __ffs(static_cast<int>(anc));
+				const uint32_t keep = 0xFFFFFFFFu << (23 - level);              // drop the position bits of the levels left
+				px = __uint_as_float(__float_as_uint(px) & keep);
+				py = __uint_as_float(__float_as_uint(py) & keep);
+				pz = __uint_as_float(__float_as_uint(pz) & keep);
+				dimf = __uint_as_float(static_cast<uint32_t>(127 - level) << 23);
+				const uint32_t e = stack[level - 1];
+				node = e & kIdMask;
+				idx = (e >> 29) ^ mti;                                          // (bit a* is set there) -> step to the sibling
+				if (ax) px -= dimf;
+				else if (ay) py -= dimf;
+				else pz -= dimf;
+				break;
+			}
+
 			if (--level == 0)
 			{
 				h.voxel = 0;
