@@ -135,7 +135,7 @@ __global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restri
 }
 
 // explicit rays: thread i traces ray i
-template<int VARIANT>
+template<int VARIANT, bool COUNT>
 __global__ void __launch_bounds__(256)
 trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt,
                   const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, size_t n,
@@ -147,11 +147,11 @@ trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, 
 	const float* d = d3 + i * 3;
 	const float ox = __ldg(o), oy = __ldg(o + 1), oz = __ldg(o + 2);
 	const Ray r = ray_setup(rt, ox, oy, oz, __ldg(d), __ldg(d + 1), __ldg(d + 2));
-	const Hit h = traverse_variant<VARIANT>(nodes, root, depth, ox, oy, oz, r);
+	const Hit h = traverse_variant<VARIANT, COUNT>(nodes, root, depth, ox, oy, oz, r);
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
-	if (npush) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
 struct FrameRows
@@ -162,7 +162,7 @@ struct FrameRows
 
 // camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
 // a 256-thread block a 16 x 16 pixel tile
-template<int VARIANT>
+template<int VARIANT, bool COUNT>
 __global__ void __launch_bounds__(256)
 trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt, Camera cam, FrameRows fr,
                    uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
@@ -171,18 +171,20 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth,
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	const int y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	int y = fr.y0 + r;                                                 // contiguous strip
+	if (fr.tile_step != 1)                                             // cyclic tile strips (uniform branch)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
 	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	const Hit h = traverse_variant<VARIANT>(nodes, root, depth, cam.ox, cam.oy, cam.oz, ray);
+	const Hit h = traverse_variant<VARIANT, COUNT>(nodes, root, depth, cam.ox, cam.oy, cam.oz, ray);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
-	if (npush) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
 }  // namespace ort
@@ -389,10 +391,10 @@ int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float*
 		return launch_miss(c, n, voxel, face, t, npush);
 	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
 	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-	if (c->opt_variant == 0)
-		ort::trace_rays_kernel<0><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush);
-	else
-		ort::trace_rays_kernel<1><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush);
+#define ORT_LAUNCH_RAYS(V, C) ort::trace_rays_kernel<V, C><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush)
+	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_RAYS(0, true); else ORT_LAUNCH_RAYS(0, false); }
+	else { if (npush) ORT_LAUNCH_RAYS(1, true); else ORT_LAUNCH_RAYS(1, false); }
+#undef ORT_LAUNCH_RAYS
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
@@ -413,10 +415,10 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
-	if (c->opt_variant == 0)
-		ort::trace_frame_kernel<0><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush);
-	else
-		ort::trace_frame_kernel<1><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush);
+#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush)
+	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); }
+	else { if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); }
+#undef ORT_LAUNCH_FRAME
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;

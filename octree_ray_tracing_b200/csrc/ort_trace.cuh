@@ -31,6 +31,14 @@ __device__ __forceinline__ uint32_t rcp_model(const RcpTable rt, uint32_t x)
 	const uint32_t sign = x & 0x80000000u;
 	const uint32_t e = (x >> 23) & 0xFFu;
 	const uint32_t m = x & 0x7FFFFFu;
+	if (e - 1u < 252u)
+	{
+		// common case: the result exponent field (>= 126 - 125 = 1 for Intel's table) cannot underflow
+		const uint32_t r = __ldg(rt.tab + (m >> rt.shift));
+		const int re = static_cast<int>(r >> 23) - (static_cast<int>(e) - 127);
+		if (re > 0) return sign | (r - ((e - 127u) << 23));
+		return sign;
+	}
 	if (e == 255u) return m ? (x | 0x00400000u) : sign;      // NaN stays NaN, inf -> 0
 	if (e == 0u) return sign | 0x7F800000u;                  // 0 and denormals -> inf
 	const uint32_t r = __ldg(rt.tab + (m >> rt.shift));
@@ -191,6 +199,7 @@ __device__ __forceinline__ bool in_unit_cube(float ox, float oy, float oz)
 	return ((__float_as_uint(ox) >> 23) == 127u) & ((__float_as_uint(oy) >> 23) == 127u) & ((__float_as_uint(oz) >> 23) == 127u);
 }
 
+template<bool COUNT>
 __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r)
 {
 	uint32_t stack[kMaxDepth];
@@ -212,12 +221,12 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 	if (cy == ninf) { cy = 0.0f; by = ninf; }
 	if (cz == ninf) { cz = 0.0f; bz = ninf; }
 
-	const uint32_t* nodes_m1 = nodes - 8;
+	const uint32_t* const nodes_m1 = nodes - 8;      // ids are 1-based
 
 	for (;;)
 	{
-		++h.npush;
-		const uint32_t child = __ldg(nodes_m1 + (static_cast<size_t>(node) << 3) + ((idx ^ inv) & 7u));
+		if (COUNT) ++h.npush;
+		const uint32_t child = __ldg(nodes_m1 + (node * 8u + (idx ^ inv)));      // id < 2^29: the word index fits 32 bits
 
 		if (child)
 		{
@@ -226,7 +235,7 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 				h.voxel = child;
 				h.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
 				h.t = tmin;
-				break;
+				return h;
 			}
 			stack[level - 1] = node | (idx << 29);
 			++level;
@@ -243,6 +252,8 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 			continue;
 		}
 
+		// the child slot is empty: leave this cell through its nearest exit plane
+		bool ax, ay;
 		for (;;)
 		{
 			const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
@@ -250,18 +261,12 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 			const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
 			const uint32_t tm = min(tx, min(ty, tz));
 			tmin = __uint_as_float(tm);
-			const bool ax = tx == tm;
-			const bool ay = !ax && ty == tm;
+			ax = tx == tm;
+			ay = !ax && ty == tm;
 			mti = ax ? 1u : (ay ? 2u : 4u);
 
 			if (idx & mti)
-			{
-				if (ax) px -= dimf;                                             // exact: the bit is set
-				else if (ay) py -= dimf;
-				else pz -= dimf;
-				idx ^= mti;
-				break;
-			}
+				break;                                                          // a sibling lies that way
 
 			if (((tx | ty | tz) & 0x80000000u) == 0u)
 			{
@@ -274,15 +279,16 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 				// pos[a*] above the current level.  One FLO replaces the loop; rays with a negative or -inf t in
 				// play take the one-level path below, which is the reference's sequence verbatim.
 				const uint32_t pa = __float_as_uint(ax ? px : (ay ? py : pz));
-				const uint32_t anc = (pa & 0x7FFFFFu) >> (24 - level);          // idx bits of levels level-1, level-2, .. on axis a*
-				if (anc == 0u)
+				// bits of levels level-1, level-2, .. on axis a*; the exponent (127, odd) lands right above them,
+				// so "no ancestor bit set" shows up as level reaching 0
+				level -= __ffs(static_cast<int>(pa >> (24 - level)));
+				if (level == 0)
 				{
 					h.voxel = 0;                                                    // popped through the root: MISS
 					h.face = 6;
 					h.t = __uint_as_float(0x7F800000u);
 					return h;
 				}
-				level -= __ffs(static_cast<int>(anc));
 				const uint32_t keep = 0xFFFFFFFFu << (23 - level);              // drop the position bits of the levels left
 				px = __uint_as_float(__float_as_uint(px) & keep);
 				py = __uint_as_float(__float_as_uint(py) & keep);
@@ -290,10 +296,7 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 				dimf = __uint_as_float(static_cast<uint32_t>(127 - level) << 23);
 				const uint32_t e = stack[level - 1];
 				node = e & kIdMask;
-				idx = (e >> 29) ^ mti;                                          // (bit a* is set there) -> step to the sibling
-				if (ax) px -= dimf;
-				else if (ay) py -= dimf;
-				else pz -= dimf;
+				idx = e >> 29;                                                  // bit a* is set there
 				break;
 			}
 
@@ -312,9 +315,13 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 			node = e & kIdMask;
 			idx = e >> 29;
 		}
-	}
 
-	return h;
+		// step to the sibling across the exit plane (exact: the bit is set)
+		if (ax) px -= dimf;
+		else if (ay) py -= dimf;
+		else pz -= dimf;
+		idx ^= mti;
+	}
 }
 
 // the fast path's preconditions: origin inside [1,2)^3 and at least one non-degenerate direction component
@@ -325,13 +332,13 @@ __device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const
 	return in_unit_cube(ox, oy, oz) & !all_degenerate;
 }
 
-template<int VARIANT>
+template<int VARIANT, bool COUNT>
 __device__ __forceinline__ Hit traverse_variant(const uint32_t* __restrict__ nodes, uint32_t root, int depth, float ox, float oy, float oz, const Ray& r)
 {
 	if (VARIANT == 0)
 		return traverse(nodes, root, depth, r);
 	if (fast_path_ok(ox, oy, oz, r))
-		return traverse_fast(nodes, root, depth, r);
+		return traverse_fast<COUNT>(nodes, root, depth, r);
 	return traverse(nodes, root, depth, r);
 }
 
