@@ -110,7 +110,9 @@ uint32_t ort_node_count(const ort_ctx* ctx);    /* highest compact id in use on 
 uint32_t ort_root(const ort_ctx* ctx);
 /* number of kernels of this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t ort_launch_count(const ort_ctx* ctx);
-/* Kernel selection knobs (tuning / profiling): key in {"variant","smem_levels","block"}. */
+/* Kernel selection knobs (tuning / profiling): key in {"variant" (frames: 0 baseline, 1 fast, 2 persistent
+ * lane-refill), "rays_variant" (explicit rays: 1 one thread per ray, 2 persistent lane-refill), "low_water",
+ * "smem_levels", "block"}. */
 int ort_set_option(ort_ctx* ctx, const char* key, int value);
 
 /* pinned host memory for callers that want zero staging */

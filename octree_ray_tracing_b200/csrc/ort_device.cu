@@ -42,10 +42,15 @@ struct ort_ctx
 	void*  d_stage = nullptr;  size_t d_stage_bytes = 0;   // device side of host-pointer calls
 	void*  h_stage = nullptr;  size_t h_stage_bytes = 0;   // pinned
 
+	unsigned long long* d_counter = nullptr; // work counter of the persistent kernels
+	int max_blocks_rays = 0, max_blocks_frame = 0;
+
 	uint64_t launches = 0;
 	int opt_variant = 1;                // 0 = baseline traverse(), 1 = traverse_fast() with fall-back
 	int opt_smem_levels = -1;
 	int opt_block = 256;
+	int opt_low_water = 20;             // persistent kernels refill when <= this many lanes are busy
+	int opt_rays_variant = 2;           // explicit rays: 2 = persistent refill
 	int sm_count = 0;
 	std::string last_error;
 };
@@ -187,6 +192,127 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth,
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Persistent warps with lane refill ("warp-level ray compaction").
+//
+// A fixed grid (one resident wave) walks the ray list: each warp draws batches of ray indices from a global
+// counter and keeps its 32 lanes busy -- when a lane's ray ends, the lane writes its result and goes idle;
+// once the number of busy lanes (ballot + popc) falls to `low_water` and rays remain, the idle lanes are
+// refilled before traversal continues.  This trades a ballot per traversal round and scattered result
+// writes for lanes that no longer wait on the slowest ray of their warp: worth little on coherent camera
+// rays, a lot on incoherent rays (BASELINE config 3: 10 PUSHes on average, 600 worst case).
+// FRAME = true enumerates the pixels of the strip in 8x4 tile order (index = 32 * tile + lane-in-tile) so
+// that consecutive indices stay spatially coherent.
+// ------------------------------------------------------------------------------------------------
+
+constexpr unsigned kBatch = 128;    // ray indices a warp draws per atomicAdd
+
+template<bool COUNT, bool FRAME>
+__global__ void __launch_bounds__(256)
+trace_persistent_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt,
+                        const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, Camera cam, FrameRows fr,
+                        unsigned long long n, unsigned long long* __restrict__ counter, int low_water,
+                        uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	const unsigned lane = threadIdx.x & 31u;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const uint32_t* const nodes_m1 = nodes - 8;
+	const unsigned tiles_x = FRAME ? (fr.W + 7) / 8 : 0;
+
+	uint32_t stack[kMaxDepth];
+	FastWalker<COUNT> w;
+	bool active = false;
+	size_t out = 0;                              // where this lane's result goes
+	unsigned long long next = 0, end = 0;        // the warp's current batch (uniform)
+	bool exhausted = false;                      // (uniform)
+
+	auto store = [&](size_t i, const Hit& h) {
+		voxel[i] = h.voxel;
+		face[i] = static_cast<uint8_t>(h.face);
+		t[i] = h.t;
+		if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+	};
+
+	for (;;)
+	{
+		// ---- refill idle lanes ---------------------------------------------------------------
+		unsigned idle = __ballot_sync(0xFFFFFFFFu, !active);
+		while (idle != 0u && !exhausted)
+		{
+			if (next == end)
+			{
+				unsigned long long b = 0;
+				if (lane == 0) b = atomicAdd(counter, static_cast<unsigned long long>(kBatch));
+				b = __shfl_sync(0xFFFFFFFFu, b, 0);
+				if (b >= n) { exhausted = true; break; }
+				next = b;
+				end = b + kBatch < n ? b + kBatch : n;
+			}
+			const unsigned long long left = end - next;
+			const unsigned n_idle = __popc(idle);
+			const unsigned avail = left < n_idle ? static_cast<unsigned>(left) : n_idle;
+			const unsigned rank = __popc(idle & lt_mask);
+			if (!active && rank < avail)
+			{
+				const unsigned long long i = next + rank;
+				float ox, oy, oz, dx, dy, dz;
+				bool valid = true;
+				if (FRAME)
+				{
+					const unsigned tile = static_cast<unsigned>(i >> 5), l = static_cast<unsigned>(i) & 31u;
+					const int x = static_cast<int>(tile % tiles_x) * 8 + static_cast<int>(l & 7u);
+					const int r = static_cast<int>(tile / tiles_x) * 4 + static_cast<int>(l >> 3);
+					valid = x < fr.W && r < fr.rows;
+					int y = fr.y0 + r;
+					if (fr.tile_step != 1)
+						y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+					ox = cam.ox; oy = cam.oy; oz = cam.oz;
+					camera_ray(cam, x, y, dx, dy, dz);
+					out = static_cast<size_t>(r) * fr.W + x;
+				}
+				else
+				{
+					const float* o = o3 + i * static_cast<unsigned long long>(o_stride);
+					const float* d = d3 + i * 3ull;
+					ox = __ldg(o); oy = __ldg(o + 1); oz = __ldg(o + 2);
+					dx = __ldg(d); dy = __ldg(d + 1); dz = __ldg(d + 2);
+					out = static_cast<size_t>(i);
+				}
+				if (valid)
+				{
+					const Ray ray = ray_setup(rt, ox, oy, oz, dx, dy, dz);
+					if (fast_path_ok(ox, oy, oz, ray))
+					{
+						w.start(root, ray);
+						active = true;
+					}
+					else
+						store(out, traverse(nodes, root, depth, ray, stack));       // out-of-domain ray: the generic walk, right away
+				}
+			}
+			next += avail;
+			idle = __ballot_sync(0xFFFFFFFFu, !active);
+		}
+
+		if (__ballot_sync(0xFFFFFFFFu, active) == 0u)
+			break;
+
+		// ---- traverse until too few lanes are busy ---------------------------------------------
+		for (;;)
+		{
+			if (active && w.iterate(nodes_m1, depth, stack))
+			{
+				store(out, w.hit);
+				active = false;
+			}
+			const unsigned busy = __ballot_sync(0xFFFFFFFFu, active);
+			if (busy == 0u || (!exhausted && __popc(busy) <= low_water))
+				break;
+		}
+	}
+}
+
 }  // namespace ort
 
 // ------------------------------------------------------------------------------------------------
@@ -241,6 +367,15 @@ int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
 	ORT_CUDA(nullptr, cudaMalloc(&c->d_nodes, static_cast<size_t>(node_capacity) * 32));
 	c->cap_nodes = node_capacity;
 
+	ORT_CUDA(nullptr, cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+	{
+		int b = 0;
+		ORT_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ort::trace_persistent_kernel<false, false>, 256, 0));
+		c->max_blocks_rays = b * c->sm_count;
+		ORT_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ort::trace_persistent_kernel<false, true>, 256, 0));
+		c->max_blocks_frame = b * c->sm_count;
+	}
+
 	*out = c;
 	const int rc = ort_set_rcp_table(c, ort_rcp_table_default, ORT_RCP_TABLE_LOG2N);
 	if (rc != ORT_OK) { *out = nullptr; ort_destroy(c); }
@@ -255,6 +390,7 @@ int ort_destroy(ort_ctx* c)
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_nodes);
 	cudaFree(c->d_rcp);
+	cudaFree(c->d_counter);
 	cudaFree(c->d_stage);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	for (int i = 0; i < 2; ++i)
@@ -391,6 +527,21 @@ int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float*
 		return launch_miss(c, n, voxel, face, t, npush);
 	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
 	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+	if (c->opt_rays_variant == 2 && c->opt_variant != 0)
+	{
+		ORT_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+		const unsigned long long need = (n + 255) / 256;
+		const unsigned pblocks = static_cast<unsigned>(need < static_cast<unsigned long long>(c->max_blocks_rays) ? need : c->max_blocks_rays);
+		const ort::Camera cam0{};
+		const ort::FrameRows fr0{};
+		if (npush)
+			ort::trace_persistent_kernel<true, false><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		else
+			ort::trace_persistent_kernel<false, false><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
 #define ORT_LAUNCH_RAYS(V, C) ort::trace_rays_kernel<V, C><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush)
 	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_RAYS(0, true); else ORT_LAUNCH_RAYS(0, false); }
 	else { if (npush) ORT_LAUNCH_RAYS(1, true); else ORT_LAUNCH_RAYS(1, false); }
@@ -415,6 +566,20 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
+	if (c->opt_variant == 2)
+	{
+		ORT_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+		const unsigned long long tiles = static_cast<unsigned long long>((W + 7) / 8) * ((rows + 3) / 4);
+		const unsigned long long np = tiles * 32ull, need = (np + 255) / 256;
+		const unsigned pblocks = static_cast<unsigned>(need < static_cast<unsigned long long>(c->max_blocks_frame) ? need : c->max_blocks_frame);
+		if (npush)
+			ort::trace_persistent_kernel<true, true><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		else
+			ort::trace_persistent_kernel<false, true><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
 #define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush)
 	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); }
 	else { if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); }
@@ -509,23 +674,39 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
 		return ORT_OK;
 	}
 
-	// Host outputs.  The frame is cut into row chunks (multiples of 16 rows and of tile_rows); chunk k's
-	// results travel to the host on copy_stream while chunk k+1 is traced on stream.  Two staging slots.
-	int chunk_rows = (rows + 7) / 8;
-	const int q = tile_rows > 16 ? tile_rows : 16;
-	chunk_rows = (chunk_rows + q - 1) / q * q;
-	if (tile_rows > 1 && chunk_rows % tile_rows) chunk_rows = (chunk_rows / tile_rows + 1) * tile_rows;
-	const size_t chunk_n = static_cast<size_t>(chunk_rows) * W;
-	const StageLayout L(chunk_n);
+	// Host outputs.  The rows are cut into chunks (multiples of 16 rows and of tile_rows); chunk k's results
+	// travel to the host on copy_stream while chunk k+1 is traced on stream (two staging slots).  PCIe, not
+	// the kernel, is the slow side (9 B per ray at ~57 GB/s vs > 10 Grays/s), so the schedule is geometric:
+	// a small first chunk gets the copy engine going early, later chunks grow (each kernel still finishes
+	// before the previous chunk's copy does) and the number of DMA pieces stays small.
+	int gcd_ = 16, b_ = tile_rows;
+	while (b_) { const int r_ = gcd_ % b_; gcd_ = b_; b_ = r_; }
+	const int q = 16 / gcd_ * tile_rows;                              // lcm(16, tile_rows): chunk borders fall on tile and block borders
+	static const int kParts[] = { 1, 2, 5, 8 };                    // sixteenths of the rows
+	int bounds[5] = { 0, 0, 0, 0, rows };
+	{
+		int acc = 0;
+		for (int k = 0; k < 3; ++k)
+		{
+			acc += kParts[k];
+			int r = static_cast<int>(static_cast<long long>(rows) * acc / 16);
+			r = r / q * q;
+			bounds[k + 1] = r < bounds[k] ? bounds[k] : r;
+		}
+	}
+	int max_rows = 0;
+	for (int k = 0; k < 4; ++k) max_rows = bounds[k + 1] - bounds[k] > max_rows ? bounds[k + 1] - bounds[k] : max_rows;
+	const StageLayout L(static_cast<size_t>(max_rows) * W);
 	int rc = ensure_dstage(c, 2 * L.total);
 	if (rc != ORT_OK) return rc;
 	char* base = static_cast<char*>(c->d_stage);
 
 	int slot = 0;
 	bool used[2] = { false, false };
-	for (int r0 = 0; r0 < rows; r0 += chunk_rows, slot ^= 1)
+	for (int k = 0; k < 4; ++k)
 	{
-		const int nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows;
+		const int r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
+		if (nr <= 0) continue;
 		const size_t n = static_cast<size_t>(nr) * W, first = static_cast<size_t>(r0) * W;
 		char* s = base + slot * L.total;
 		uint32_t* dv = reinterpret_cast<uint32_t*>(s + L.off_v);
@@ -535,7 +716,7 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
 
 		if (used[slot])
 			ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));   // slot's previous results have left
-		// rows r0.. of this call: same mapping with the chunk's first frame row as origin
+		// rows r0.. of this call: same mapping with the chunk's first frame row as origin (r0 is a multiple of tile_rows)
 		const int cy0 = y0 + (r0 / tile_rows) * tile_rows * tile_step;
 		rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, cy0, nr, tile_rows, tile_step, dv, df, dt, dn);
 		if (rc != ORT_OK) return rc;
@@ -547,6 +728,7 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
 		if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush + first, dn, n * 2, cudaMemcpyDeviceToHost, c->copy_stream));
 		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
 		used[slot] = true;
+		slot ^= 1;
 	}
 	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -574,6 +756,8 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	if (!std::strcmp(key, "variant")) c->opt_variant = value;
 	else if (!std::strcmp(key, "smem_levels")) c->opt_smem_levels = value;
 	else if (!std::strcmp(key, "block")) c->opt_block = value;
+	else if (!std::strcmp(key, "low_water")) c->opt_low_water = value;
+	else if (!std::strcmp(key, "rays_variant")) c->opt_rays_variant = value;
 	else return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: unknown key '%s'", key);
 	return ORT_OK;
 }

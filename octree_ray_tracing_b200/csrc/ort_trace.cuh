@@ -96,9 +96,8 @@ struct Hit
 
 // nodes: compact array, id i (1-based) at nodes[8*(i-1) .. 8*(i-1)+7]; root != 0.
 // Baseline variant: one thread walks one ray from start to end, parent stack in local memory.
-__device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r)
+__device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r, uint32_t* stack)
 {
-	uint32_t stack[kMaxDepth];
 	uint32_t node = root;
 	uint32_t dim = 1u << 22;                                                   // :326
 	int      level = 1;                                                        // :334
@@ -199,43 +198,59 @@ __device__ __forceinline__ bool in_unit_cube(float ox, float oy, float oz)
 	return ((__float_as_uint(ox) >> 23) == 127u) & ((__float_as_uint(oy) >> 23) == 127u) & ((__float_as_uint(oz) >> 23) == 127u);
 }
 
+// State of one ray in flight.  iterate() runs ONE round of the reference's PUSH label (one child-slot load)
+// plus whatever STEP/POP work follows it, and returns true when the ray is finished (result in `hit`).
+// Kept as a resumable object so that the persistent kernel can interleave lane refills with traversal.
 template<bool COUNT>
-__device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r)
+struct FastWalker
 {
-	uint32_t stack[kMaxDepth];
-	uint32_t node = root;
-	int      level = 1;
-	uint32_t idx = r.idx;
-	const uint32_t inv = r.inv;
-	float px = __uint_as_float(r.px), py = __uint_as_float(r.py), pz = __uint_as_float(r.pz);
-	float dimf = 0.5f;               // size of the children of the current node = value of the dimension bit
-	float tmin = 0.0f;
-	uint32_t mti = 8;
-	Hit h;
-	h.npush = 0;
+	uint32_t node, idx, inv, mti;
+	int      level;
+	float    px, py, pz, dimf, tmin;
+	float    cx, cy, cz, bx, by, bz;
+	Hit      hit;
 
-	// degenerate axes (see above)
-	float cx = r.cx, cy = r.cy, cz = r.cz, bx = r.bx, by = r.by, bz = r.bz;
-	const float ninf = __uint_as_float(0xFF800000u);
-	if (cx == ninf) { cx = 0.0f; bx = ninf; }
-	if (cy == ninf) { cy = 0.0f; by = ninf; }
-	if (cz == ninf) { cz = 0.0f; bz = ninf; }
-
-	const uint32_t* const nodes_m1 = nodes - 8;      // ids are 1-based
-
-	for (;;)
+	__device__ __forceinline__ void start(uint32_t root, const Ray& r)
 	{
-		if (COUNT) ++h.npush;
+		node = root;
+		level = 1;
+		idx = r.idx;
+		inv = r.inv;
+		px = __uint_as_float(r.px); py = __uint_as_float(r.py); pz = __uint_as_float(r.pz);
+		dimf = 0.5f;                 // size of the children of the current node = value of the dimension bit
+		tmin = 0.0f;
+		mti = 8;
+		hit.npush = 0;
+		// degenerate axes (see above)
+		cx = r.cx; cy = r.cy; cz = r.cz; bx = r.bx; by = r.by; bz = r.bz;
+		const float ninf = __uint_as_float(0xFF800000u);
+		if (cx == ninf) { cx = 0.0f; bx = ninf; }
+		if (cy == ninf) { cy = 0.0f; by = ninf; }
+		if (cz == ninf) { cz = 0.0f; bz = ninf; }
+	}
+
+	__device__ __forceinline__ void miss()
+	{
+		hit.voxel = 0;
+		hit.face = 6;
+		hit.t = __uint_as_float(0x7F800000u);
+	}
+
+	// nodes_m1 = nodes - 8 (ids are 1-based); stack = this ray's parent stack (kMaxDepth entries, caller-owned so
+	// that it stays a plain local array)
+	__device__ __forceinline__ bool iterate(const uint32_t* __restrict__ nodes_m1, int depth, uint32_t* stack)
+	{
+		if (COUNT) ++hit.npush;
 		const uint32_t child = __ldg(nodes_m1 + (node * 8u + (idx ^ inv)));      // id < 2^29: the word index fits 32 bits
 
 		if (child)
 		{
 			if (level == depth)
 			{
-				h.voxel = child;
-				h.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
-				h.t = tmin;
-				return h;
+				hit.voxel = child;
+				hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
+				hit.t = tmin;
+				return true;
 			}
 			stack[level - 1] = node | (idx << 29);
 			++level;
@@ -249,7 +264,7 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 			if (tx >= tmin) { px = mx; idx += 1u; }
 			if (ty >= tmin) { py = my; idx += 2u; }
 			if (tz >= tmin) { pz = mz; idx += 4u; }
-			continue;
+			return false;
 		}
 
 		// the child slot is empty: leave this cell through its nearest exit plane
@@ -284,10 +299,8 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 				level -= __ffs(static_cast<int>(pa >> (24 - level)));
 				if (level == 0)
 				{
-					h.voxel = 0;                                                    // popped through the root: MISS
-					h.face = 6;
-					h.t = __uint_as_float(0x7F800000u);
-					return h;
+					miss();                                                         // popped through the root
+					return true;
 				}
 				const uint32_t keep = 0xFFFFFFFFu << (23 - level);              // drop the position bits of the levels left
 				px = __uint_as_float(__float_as_uint(px) & keep);
@@ -302,10 +315,8 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 
 			if (--level == 0)
 			{
-				h.voxel = 0;
-				h.face = 6;
-				h.t = __uint_as_float(0x7F800000u);
-				return h;
+				miss();
+				return true;
 			}
 			if (idx & 1u) px -= dimf;                                           // back to the parent's corner
 			if (idx & 2u) py -= dimf;
@@ -321,7 +332,18 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes,
 		else if (ay) py -= dimf;
 		else pz -= dimf;
 		idx ^= mti;
+		return false;
 	}
+};
+
+template<bool COUNT>
+__device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes, uint32_t root, int depth, const Ray& r, uint32_t* stack)
+{
+	FastWalker<COUNT> w;
+	w.start(root, r);
+	const uint32_t* const nodes_m1 = nodes - 8;
+	while (!w.iterate(nodes_m1, depth, stack)) {}
+	return w.hit;
 }
 
 // the fast path's preconditions: origin inside [1,2)^3 and at least one non-degenerate direction component
@@ -335,11 +357,12 @@ __device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const
 template<int VARIANT, bool COUNT>
 __device__ __forceinline__ Hit traverse_variant(const uint32_t* __restrict__ nodes, uint32_t root, int depth, float ox, float oy, float oz, const Ray& r)
 {
+	uint32_t stack[kMaxDepth];       // parent stack, local memory (dynamically indexed)
 	if (VARIANT == 0)
-		return traverse(nodes, root, depth, r);
+		return traverse(nodes, root, depth, r, stack);
 	if (fast_path_ok(ox, oy, oz, r))
-		return traverse_fast<COUNT>(nodes, root, depth, r);
-	return traverse(nodes, root, depth, r);
+		return traverse_fast<COUNT>(nodes, root, depth, r, stack);
+	return traverse(nodes, root, depth, r, stack);
 }
 
 // Camera ray of pixel (x, y) -- tree_camera::update_position (test_och_h_octree.cpp:119-137) with

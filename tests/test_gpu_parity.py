@@ -241,3 +241,34 @@ def test_depth12_4k_properties(ort, oc, ncpu):
     coord = (p[np.arange(len(ax)), ax] - 1.0) * (1 << depth)
     assert np.abs(coord - np.round(coord)).max() < 0.6       # RCPPS-grade t: well within one voxel of a cell plane
     assert set(np.unique(v)) <= {0, 1, 2, 3, 4}
+
+
+def test_kernel_variants_agree(ort, golden):
+    """Baseline walk (variant 0), fast walk (1) and persistent lane-refill (2) are the same function."""
+    g = golden("d8_tunnels")
+    ctx = ort.TraceContext(8)
+    ctx.upload_full(g["nodes8"], int(g["root"]))
+    W, H = 333, 217                                    # not multiples of the 8x4 tile
+    pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
+    ref = None
+    for variant in (0, 1, 2):
+        ctx.set_option("variant", variant)
+        got = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
+        part = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=64, tile_rows=8, tile_step=3)
+        rows = np.concatenate([np.arange(8 + 24 * k, 16 + 24 * k) for k in range(8)])
+        if ref is None:
+            ref = got
+        assert_same_hits(got, ref, f"frame variant {variant}")
+        assert np.array_equal(got[3], ref[3]), f"npush differs in variant {variant}"
+        assert_same_hits(part, [x.reshape(H, W)[rows].ravel() for x in ref[:3]], f"tiles variant {variant}")
+    ctx.set_option("variant", 1)
+    for k in ("rand", "edge"):
+        outs = []
+        for rv in (1, 2):
+            ctx.set_option("rays_variant", rv)
+            for lw in ((20,) if rv == 1 else (0, 12, 31)):
+                ctx.set_option("low_water", lw)
+                outs.append(ctx.trace_rays(g[f"{k}_o"], g[f"{k}_d"], want_npush=True))
+        for o in outs:
+            assert_same_hits(o, (g[f"{k}_vox"], g[f"{k}_face"], g[f"{k}_t"]), k)
+            assert np.array_equal(o[3], outs[0][3])
