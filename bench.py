@@ -105,11 +105,6 @@ def physical_gpu_index(local_rank: int) -> int:
     return local_rank
 
 
-def rank_tiles(rank: int, n: int):
-    tiles = list(range(rank, H // TILE_ROWS, n))
-    return tiles, len(tiles) * TILE_ROWS
-
-
 # ------------------------------------------------------------------------------------------------
 # product arm
 # ------------------------------------------------------------------------------------------------
@@ -131,23 +126,31 @@ def run_product(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
+    from octree_ray_tracing_b200 import multi_gpu
+
+    # rank 0 owns the host table: it builds the DAG and broadcasts the flattened nodes (NCCL); every rank
+    # uploads its replica from the received device buffer.
     t0 = time.time()
-    tree = ort.HOctree(LOG2CAP, DEPTH, device=local_rank, node_capacity=1 << 21)
-    harness.build_terrain(tree)
-    n_up, _ = tree.sync()
-    ctx = tree.ctx
+    ctx = ort.TraceContext(DEPTH, device=local_rank, node_capacity=1 << 21)
+    tree = None
+    update = None
+    if rank == 0:
+        tree = ort.HOctree(LOG2CAP, DEPTH, device=None)
+        harness.build_terrain(tree)
+        update = tree.take_delta()
+    n_up, _ = multi_gpu.broadcast_update(update, multi_gpu.context_applier(ctx), device=torch.device("cuda", local_rank))
+    ctx.sync()
     if args.variant is not None:
         ctx.set_option("variant", args.variant)
     for kv in args.opt:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
-    log(f"[rank {rank}] DAG built + uploaded in {time.time() - t0:.1f}s: {n_up} nodes ({n_up * 32 / 2**20:.1f} MiB)")
+    log(f"[rank {rank}] DAG built + broadcast + uploaded in {time.time() - t0:.1f}s: {n_up} nodes ({n_up * 32 / 2**20:.1f} MiB)")
 
     poses = [harness.POSES[p] for p in POSE_NAMES]
     cams = [(np.array(p[0], np.float32),) + ort.camera_coeffs(p[1], p[2]) for p in poses]
-    tiles, rows = rank_tiles(rank, world)
+    y0, rows, _frame_rows = multi_gpu.strip_rows(rank, world, H, TILE_ROWS)
     n_local = rows * W
-    y0 = rank * TILE_ROWS
     frames_per_step = len(cams) * world
     rays_per_step_total = frames_per_step * W * H          # all ranks together
     rays_per_step_local = frames_per_step * n_local
@@ -247,13 +250,32 @@ def run_product(args):
     e2e_s = time.perf_counter() - e0
     e2e_check = int((out[0] != 0).sum())
 
+    # strips -> rank 0 over NCCL (what a harness that wants the assembled frame pays on top of `value`)
+    gather = None
+    if world > 1:
+        def gather_step():
+            with torch.cuda.stream(stream):
+                for _rep in range(world):
+                    for cam in cams:
+                        frame(cam)
+                        for buf in (dv, dt, df):
+                            multi_gpu.gather_strips(buf, world, H, W, TILE_ROWS, dst=0)
+        gather_step()
+        barrier()
+        g0 = time.perf_counter()
+        g_steps = max(1, min(args.steps, 5))
+        for _ in range(g_steps):
+            gather_step()
+        barrier()
+        gather = (time.perf_counter() - g0) / g_steps
+
     clocks = sampler.stop()
 
     # max over ranks
     if world > 1:
-        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, gather], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms, warm_ms, e2e_s, wall = (float(x) for x in tt.tolist())
+        kernel_ms, warm_ms, e2e_s, wall, gather = (float(x) for x in tt.tolist())
         cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
@@ -299,6 +321,9 @@ def run_product(args):
             "clocks": clocks,
             "wall_s_timed_region": round(wall, 3),
         }
+        if gather is not None:
+            result["with_gather"] = {"value": round(rays_per_step_total / gather / 1e6, 2), "unit": "Mrays/s",
+                                     "note": "trace + NCCL gather of every frame's strips (voxel, t, face) to rank 0, wall clock, max over ranks"}
         if world == 1 and not args.no_cpu:
             result["cpu_baseline"] = cpu_baseline(tree, sample_tiles=4)
         print(json.dumps(result), flush=True)

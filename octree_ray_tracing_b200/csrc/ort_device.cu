@@ -14,6 +14,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -454,12 +455,23 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 
 	uint32_t max_id = c->n_nodes;
 	const bool dev_src = n && is_device_ptr(ids);
-	if (n && !dev_src)
+	if (n)
+	{
+		// ids are validated on the host either way (deltas are small: a few thousand entries)
+		std::vector<uint32_t> tmp;
+		const uint32_t* hid = ids;
+		if (dev_src)
+		{
+			tmp.resize(n);
+			ORT_CUDA(c, cudaMemcpy(tmp.data(), ids, n * 4, cudaMemcpyDeviceToHost));
+			hid = tmp.data();
+		}
 		for (size_t i = 0; i < n; ++i)
 		{
-			if (ids[i] == 0) return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: id 0 at entry %zu", i);
-			if (ids[i] > max_id) max_id = ids[i];
+			if (hid[i] == 0) return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: id 0 at entry %zu", i);
+			if (hid[i] > max_id) max_id = hid[i];
 		}
+	}
 	if (max_id > c->cap_nodes || root > c->cap_nodes)
 		return ort_fail(c, ORT_ERR_CAPACITY, "ort_upload_delta: id %u exceeds the mirror capacity %u", max_id, c->cap_nodes);
 
