@@ -155,42 +155,70 @@ def run_product(args):
     rays_per_step_total = frames_per_step * W * H          # all ranks together
     rays_per_step_local = frames_per_step * n_local
 
-    stream = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    dv = torch.empty(n_local, dtype=torch.int32, device="cuda")
-    df = torch.empty(n_local, dtype=torch.uint8, device="cuda")
-    dt = torch.empty(n_local, dtype=torch.float32, device="cuda")
+    own = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
+    NS = 3                                                   # frames in flight
+    streams = [torch.cuda.Stream(device=local_rank) for _ in range(NS)]
+    outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
+             torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(NS)]
+    dv, df, dt = outs[0]
     dn = torch.empty(n_local, dtype=torch.int16, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     torch.cuda.synchronize()
 
-    def frame(cam, npush=None):
-        ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, world, dv, df, dt, npush)
+    def frame(cam, out=outs[0], npush=None):
+        ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, world, out[0], out[1], out[2], npush)
 
     # algorithmic bytes: PUSH counts from an (untimed) counting pass -- identical to the oracle's counts (tests)
     pushes = 0
     hits = 0
-    with torch.cuda.stream(stream):
+    with torch.cuda.stream(own):
         for cam in cams:
-            frame(cam, dn)
-            stream.synchronize()
+            frame(cam, outs[0], dn)
+            own.synchronize()
             pushes += int((dn.to(torch.int64) & 0xFFFF).sum().item())
             hits += int((dv != 0).sum().item())
     pushes_per_step_local = pushes * world
     bytes_per_step_local = 32 * pushes_per_step_local + 9 * rays_per_step_local
+    step_cams = [cam for _rep in range(world) for cam in cams]
 
-    def timed_loop(steps, do_flush):
+    def timed_steps(steps, do_flush):
+        """One timed interval per STEP: L2 flushed before it (outside the interval), then the step's frames are
+        queued round-robin on NS streams so that the latency tail of one launch overlaps the next launch."""
         evs = []
-        with torch.cuda.stream(stream):
+        s0 = streams[0]
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s0):
+                if do_flush:
+                    flush.zero_()
+                a.record(s0)
+            for st in streams[1:]:
+                st.wait_event(a)
+            for k, cam in enumerate(step_cams):
+                ctx.set_stream(streams[k % NS])
+                frame(cam, outs[k % NS])
+            for st in streams[1:]:
+                e = torch.cuda.Event()
+                e.record(st)
+                s0.wait_event(e)
+            b.record(s0)
+            evs.append((a, b))
+        ctx.set_stream(None)
+        return evs
+
+    def serial_launches(steps, do_flush):
+        """Reference measurement: one stream, one timed interval per LAUNCH (no overlap between launches)."""
+        evs = []
+        with torch.cuda.stream(own):
             for _ in range(steps):
-                for _rep in range(world):
-                    for cam in cams:
-                        if do_flush:
-                            flush.zero_()
-                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                        a.record(stream)
-                        frame(cam)
-                        b.record(stream)
-                        evs.append((a, b))
+                for cam in step_cams:
+                    if do_flush:
+                        flush.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(own)
+                    frame(cam)
+                    b.record(own)
+                    evs.append((a, b))
         return evs
 
     def barrier():
@@ -202,29 +230,38 @@ def run_product(args):
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
 
-    sampler.active = True          # warm-up, timed loop, warm-L2 loop and e2e are all load
-    timed_loop(args.warmup, True)
+    sampler.active = True          # warm-up, timed loops and e2e are all load
+    timed_steps(args.warmup, True)
     barrier()
     launches0 = ctx.launch_count
     wall0 = time.perf_counter()
-    evs = timed_loop(args.steps, True)
+    evs = timed_steps(args.steps, True)
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count - launches0
     kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
 
+    # per-launch view of the same work: serialised launches, each timed alone
+    serial_launches(1, True)
+    barrier()
+    evs_s = serial_launches(args.steps, True)
+    barrier()
+    serial_per_launch = [a.elapsed_time(b) for a, b in evs_s]
+    serial_ms = sum(serial_per_launch)
+
     if args.quick:
         sampler.stop()
         ms = kernel_ms / args.steps
         print(json.dumps({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
+                          "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
-                          "per_frame_ms": [round(a.elapsed_time(b), 4) for a, b in evs[-3 * world:]]}), flush=True)
+                          "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]]}), flush=True)
         return None
 
     # same loop without the flush (steady state of a real frame loop: DAG stays L2-resident)
-    timed_loop(1, False)
+    timed_steps(1, False)
     barrier()
-    evs_w = timed_loop(args.steps, False)
+    evs_w = timed_steps(args.steps, False)
     barrier()
     warm_ms = sum(a.elapsed_time(b) for a, b in evs_w)
 
@@ -254,12 +291,11 @@ def run_product(args):
     gather = None
     if world > 1:
         def gather_step():
-            with torch.cuda.stream(stream):
-                for _rep in range(world):
-                    for cam in cams:
-                        frame(cam)
-                        for buf in (dv, dt, df):
-                            multi_gpu.gather_strips(buf, world, H, W, TILE_ROWS, dst=0)
+            with torch.cuda.stream(own):
+                for cam in step_cams:
+                    frame(cam)
+                    for buf in (dv, dt, df):
+                        multi_gpu.gather_strips(buf, world, H, W, TILE_ROWS, dst=0)
         gather_step()
         barrier()
         g0 = time.perf_counter()
@@ -288,7 +324,7 @@ def run_product(args):
         ms_per_step = kernel_ms / args.steps
         value = rays_per_step_total / (ms_per_step * 1e-3) / 1e6
         n_launch_local = args.steps * frames_per_step
-        avg_launch_s = kernel_ms * 1e-3 / n_launch_local
+        avg_launch_s = kernel_ms * 1e-3 / n_launch_local      # effective: launches of a step overlap
         achieved = (bytes_per_step_local / frames_per_step) / avg_launch_s / 1e9
         e2e_val = rays_per_step_total * e2e_steps / e2e_s / 1e6
         result = {
@@ -299,14 +335,18 @@ def run_product(args):
             "config": {
                 "workload": WORKLOAD, "frames_per_step": frames_per_step, "rays_per_step": rays_per_step_total,
                 "partition": f"cyclic {TILE_ROWS}-row tile strips over {world} GPU(s), DAG replicated",
-                "l2": "flushed before every frame (256 MiB memset outside the timed events)",
+                "l2": "flushed before every step (256 MiB memset outside the timed interval)",
+                "in_flight": f"{NS} streams: the frames of a step are queued round-robin so launch tails overlap",
                 "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
                 "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3),
                 "hit_fraction": round(hits / (len(cams) * n_local), 4),
-                "timing": "sum of CUDA-event intervals around each frame launch on the launching stream, max over ranks",
+                "timing": "sum of CUDA-event intervals around each step (start after the flush, end after all streams joined), max over ranks",
             },
+            "serial": {"value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s",
+                       "note": "same frames on ONE stream, one event interval per launch, L2 flushed before every launch",
+                       "per_launch_ms": [round(x, 4) for x in serial_per_launch[-len(step_cams):]]},
             "warm_l2": {"value": round(rays_per_step_total / (warm_ms / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s",
-                        "note": "same loop without the L2 flush (DAG stays L2-resident between frames)"},
+                        "note": "same loop without the L2 flush (DAG stays L2-resident between steps)"},
             "e2e": {"value": round(e2e_val, 2), "unit": "Mrays/s", "h2d_bytes_per_step": frames_per_step * 52,
                     "d2h_bytes_per_step": frames_per_step * n_local * 9, "steps": e2e_steps,
                     "api": "ort_trace_frame (host buffers, pinned; chunked D2H overlapped with the kernel)", "hits_last_frame": e2e_check},

@@ -105,6 +105,10 @@ int ort_trace_rays_async(ort_ctx* ctx, const float* d_o3, int o_stride, const fl
 
 int   ort_sync(ort_ctx* ctx);
 void* ort_stream(ort_ctx* ctx);                 /* the cudaStream_t all work of ctx is queued on */
+/* Queue subsequent work of ctx on the caller's cudaStream_t (NULL: back to the context's own stream).  Lets a
+ * harness keep several frames in flight (one stream each) so that the tail of one launch -- a handful of grazing
+ * rays with hundreds of PUSHes -- overlaps the bulk of the next.  The caller orders uploads against traces. */
+int   ort_set_stream(ort_ctx* ctx, void* stream);
 int   ort_device(const ort_ctx* ctx);
 uint32_t ort_node_count(const ort_ctx* ctx);    /* highest compact id in use on the device */
 uint32_t ort_root(const ort_ctx* ctx);

@@ -36,6 +36,7 @@ _SIGS = {
     "ort_trace_rays_async": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "ort_sync": (C.c_int, [_vp]),
     "ort_stream": (_vp, [_vp]),
+    "ort_set_stream": (C.c_int, [_vp, _vp]),
     "ort_device": (C.c_int, [_vp]),
     "ort_node_count": (C.c_uint32, [_vp]),
     "ort_root": (C.c_uint32, [_vp]),

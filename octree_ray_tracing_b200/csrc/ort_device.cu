@@ -26,7 +26,8 @@ struct ort_ctx
 {
 	int device = 0;
 	int depth = 0;
-	cudaStream_t stream = nullptr;      // all kernels + uploads
+	cudaStream_t stream = nullptr;      // all kernels + uploads (own stream, or the caller's after ort_set_stream)
+	cudaStream_t own_stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // D2H of finished chunks, overlapped with the next chunk's kernel
 	cudaEvent_t  ev_chunk[2] = { nullptr, nullptr };
 	cudaEvent_t  ev_copied[2] = { nullptr, nullptr };
@@ -356,7 +357,8 @@ int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
 	c->depth = depth;
 	c->sm_count = prop.multiProcessorCount;
 
-	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+	c->stream = c->own_stream;
 	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 	for (int i = 0; i < 2; ++i)
 	{
@@ -399,7 +401,7 @@ int ort_destroy(ort_ctx* c)
 		if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
 		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
 	}
-	if (c->stream) cudaStreamDestroy(c->stream);
+	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
 	delete c;
 	return ORT_OK;
@@ -757,6 +759,13 @@ int ort_sync(ort_ctx* c)
 }
 
 void*    ort_stream(ort_ctx* c) { return c ? c->stream : nullptr; }
+
+int ort_set_stream(ort_ctx* c, void* stream)
+{
+	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_set_stream: null context");
+	c->stream = stream ? static_cast<cudaStream_t>(stream) : c->own_stream;
+	return ORT_OK;
+}
 int      ort_device(const ort_ctx* c) { return c ? c->device : -1; }
 uint32_t ort_node_count(const ort_ctx* c) { return c ? c->n_nodes : 0; }
 uint32_t ort_root(const ort_ctx* c) { return c ? c->root : 0; }

@@ -115,6 +115,12 @@ class TraceContext:
     def sync(self):
         self._ck(self.L.ort_sync(self.h))
 
+    def set_stream(self, stream):
+        """Queue subsequent work on a caller stream (a cudaStream_t as int, a torch.cuda.Stream, or None)."""
+        if stream is not None and hasattr(stream, "cuda_stream"):
+            stream = stream.cuda_stream
+        self._ck(self.L.ort_set_stream(self.h, _vp(stream) if stream else None))
+
     # ---- host-buffer calls -------------------------------------------------------------------
     def trace_rays(self, o, d, want_npush=False):
         d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
