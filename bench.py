@@ -54,6 +54,16 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the frame kernel, from the last committed
+    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_summary.py --traffic)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -306,6 +316,10 @@ def run_product(args):
         gather = (time.perf_counter() - g0) / g_steps
 
     clocks = sampler.stop()
+    # memory-side ceilings measured on this GPU: random 32-B sector gathers over a buffer of the DAG's size (L2-resident)
+    # and over 4 GiB (HBM-resident)
+    gather_l2 = ctx.measure_gather_peak(int(n_up) * 32) if rank == 0 else 0.0
+    gather_hbm = ctx.measure_gather_peak(4 << 30) if rank == 0 else 0.0
 
     # max over ranks
     if world > 1:
@@ -353,10 +367,15 @@ def run_product(args):
             "gpu_launches": launches_all,
             "roofline": {
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": None, "peak_source": peak_src, "kernel": "ort::trace_frame_kernel",
+                "traffic": traffic_per_launch(), "peak_source": peak_src, "kernel": "ort::trace_frame_kernel<1,false>",
                 "algorithmic_bytes_per_launch": int(bytes_per_step_local / frames_per_step),
                 "avg_launch_ms": round(avg_launch_s * 1e3, 4),
-                "note": "32 B per child-slot load (PUSH) + 9 B output per ray; DAG is L2-resident so HBM is not the binding limit (latency/divergence bound)",
+                "sector_gather_peak": {"l2_resident_gbs": round(gather_l2, 1), "hbm_resident_gbs": round(gather_hbm, 1),
+                                       "frac_of_l2_resident": round(achieved / gather_l2, 4) if gather_l2 else None,
+                                       "how": "ort_measure_gather_peak: independent random 4-B loads, one 32-B sector each, buffer = DAG size / 4 GiB"},
+                "note": "algorithmic bytes = 32 B per child-slot load (PUSH) + 9 B output per ray (SURVEY 8d). The 44 MiB DAG is cache resident "
+                        "(ncu: L1 hit 93 %, DRAM traffic ~1 % of the algorithmic bytes), so frac > 1 against the HBM copy peak is expected; "
+                        "the kernel is bound by instruction issue (ncu: issue slots 83 % busy), see DESIGN.md section 4",
             },
             "clocks": clocks,
             "wall_s_timed_region": round(wall, 3),

@@ -119,6 +119,11 @@ uint64_t ort_launch_count(const ort_ctx* ctx);
  * "smem_levels", "block"}. */
 int ort_set_option(ort_ctx* ctx, const char* key, int value);
 
+/* Diagnostic for roofline reports: throughput of random 32-byte-sector gathers (independent 4-byte loads, 8 in
+ * flight per thread, full occupancy) over a `bytes`-sized buffer on ctx's GPU, in GB/s of sectors moved.  With
+ * bytes = the DAG's size (L2-resident) this is the memory-side ceiling of the traversal. */
+int ort_measure_gather_peak(ort_ctx* ctx, size_t bytes, double* gb_per_s);
+
 /* pinned host memory for callers that want zero staging */
 int ort_host_alloc(void** out, size_t bytes);
 int ort_host_free(void* p);

@@ -195,6 +195,30 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth,
 }
 
 
+// Diagnostic: random 32-byte-sector gather over an L2-resident buffer -- the memory-side ceiling of a
+// traversal whose nodes live in L2 (one 4-byte child read moves one sector).  Independent loads, 8 in
+// flight per thread, addresses from a counter hash so that L1 cannot help.
+__global__ void __launch_bounds__(256)
+gather_peak_kernel(const uint32_t* __restrict__ buf, uint32_t n_sectors, uint32_t iters, uint32_t* __restrict__ sink)
+{
+	uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+	uint32_t acc = 0;
+	for (uint32_t i = 0; i < iters; ++i)
+	{
+		uint32_t v[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			x = x * 1664525u + 1013904223u;
+			const uint32_t s = __umulhi(x ^ (x >> 15), n_sectors);            // uniform in [0, n_sectors)
+			v[k] = __ldg(buf + (static_cast<size_t>(s) << 3) + (x & 7u));
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k) acc ^= v[k];
+	}
+	if (acc == 0x9E3779B9u) *sink = acc;                                      // keep the loads alive
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent warps with lane refill ("warp-level ray compaction").
 //
@@ -780,6 +804,39 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	else if (!std::strcmp(key, "low_water")) c->opt_low_water = value;
 	else if (!std::strcmp(key, "rays_variant")) c->opt_rays_variant = value;
 	else return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: unknown key '%s'", key);
+	return ORT_OK;
+}
+
+int ort_measure_gather_peak(ort_ctx* c, size_t bytes, double* gb_per_s)
+{
+	if (!c || !gb_per_s || bytes < (1u << 20))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_measure_gather_peak: need a context, an output and >= 1 MiB");
+	DeviceGuard g(c->device);
+	uint32_t* buf = nullptr;
+	ORT_CUDA(c, cudaMalloc(&buf, bytes + 4));
+	ORT_CUDA(c, cudaMemsetAsync(buf, 0x5A, bytes + 4, c->stream));
+	const uint32_t n_sectors = static_cast<uint32_t>(bytes / 32);
+	const uint32_t blocks = static_cast<uint32_t>(c->sm_count) * 8u, iters = 256;
+	cudaEvent_t a, b;
+	ORT_CUDA(c, cudaEventCreate(&a));
+	ORT_CUDA(c, cudaEventCreate(&b));
+	float best = 1e30f;
+	for (int rep = 0; rep < 6; ++rep)                                         // rep 0 warms L2
+	{
+		ORT_CUDA(c, cudaEventRecord(a, c->stream));
+		ort::gather_peak_kernel<<<blocks, 256, 0, c->stream>>>(buf, n_sectors, iters, buf + bytes / 4);
+		++c->launches;
+		ORT_CUDA(c, cudaEventRecord(b, c->stream));
+		ORT_CUDA(c, cudaEventSynchronize(b));
+		float ms = 0;
+		ORT_CUDA(c, cudaEventElapsedTime(&ms, a, b));
+		if (rep && ms < best) best = ms;
+	}
+	cudaEventDestroy(a);
+	cudaEventDestroy(b);
+	cudaFree(buf);
+	const double loads = static_cast<double>(blocks) * 256.0 * iters * 8.0;
+	*gb_per_s = loads * 32.0 / (best * 1e-3) / 1e9;
 	return ORT_OK;
 }
 

@@ -115,6 +115,12 @@ class TraceContext:
     def sync(self):
         self._ck(self.L.ort_sync(self.h))
 
+    def measure_gather_peak(self, nbytes: int) -> float:
+        """GB/s of random 32-B sector gathers over an nbytes buffer (roofline denominator for L2-resident DAGs)."""
+        out = C.c_double(0)
+        self._ck(self.L.ort_measure_gather_peak(self.h, nbytes, C.byref(out)))
+        return out.value
+
     def set_stream(self, stream):
         """Queue subsequent work on a caller stream (a cudaStream_t as int, a torch.cuda.Stream, or None)."""
         if stream is not None and hasattr(stream, "cuda_stream"):

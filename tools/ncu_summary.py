@@ -44,7 +44,28 @@ KEYS = [
 ]
 
 
+def traffic(rep, out_json):
+    """profiles/traffic.json: DRAM bytes per launch (read + write, mean over the captured launches)."""
+    import json
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = []
+    for r in data:
+        b = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(k)
+            b += float(r[i]) * scale[units[i]]
+        tot.append(b)
+    json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "per_launch": [int(x) for x in tot], "source": rep,
+               "kernels": [r[hdr.index("Kernel Name")].split("(")[0] for r in data]}, open(out_json, "w"), indent=1)
+
+
 def main():
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        traffic(sys.argv[1], sys.argv[3])
+        return
     rep = sys.argv[1]
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
