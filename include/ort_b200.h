@@ -25,6 +25,7 @@ extern "C" {
 
 typedef struct ort_ctx  ort_ctx;   /* device side: node mirror + streams of ONE GPU                */
 typedef struct ort_tree ort_tree;  /* host side:   the reference's node_hashtable, re-implemented  */
+typedef struct ort_octree ort_octree; /* host side: och::octree's node pool, re-implemented          */
 
 enum
 {
@@ -74,6 +75,12 @@ int ort_upload_full(ort_ctx* ctx, const uint32_t* nodes8, size_t n_nodes, uint32
 /* Replaces: the writes at och_h_octree.h:155 between two frames.  Scatters n nodes to compact
  * ids ids[i] (1-based) and installs the new root. */
 int ort_upload_delta(ort_ctx* ctx, const uint32_t* ids, const uint32_t* nodes8, size_t n, uint32_t root);
+
+/* Replaces: the tracer's view of och::octree::_table (och_octree.h:32, och_octree.cpp:217).  nodes8 = the pool's
+ * first n_nodes rows; row 0 is the root, child values are raw row numbers, 0 = empty.  Switches the context to the
+ * pool layout: the walk starts at row 0 and a MISS reports hit_time 0.0F (och_octree.cpp:302) instead of INFINITY.
+ * ort_upload_delta afterwards addresses rows as id = row + 1 (its root argument is ignored in this layout). */
+int ort_upload_pool(ort_ctx* ctx, const uint32_t* nodes8, size_t n_nodes);
 
 /* Replaces: N calls of sse_trace(ox,oy,oz,dx,dy,dz, direction&, uint32_t&, float&) const
  * (och_h_octree.h:292-447).  o3: origins, 3 floats each, o_stride = 3, or ONE shared origin with
@@ -180,6 +187,28 @@ void     ort_tree_sync_stats(const ort_tree* tree, uint64_t* nodes_uploaded, int
  * pointers (owned by the tree) to ids[n], nodes8[n*8] and the new compact root; is_full = 1 means
  * the buffers hold a full flatten instead.  The delta is consumed (marked as applied). */
 size_t   ort_tree_take_delta(ort_tree* tree, const uint32_t** ids, const uint32_t** nodes8, uint32_t* root, int* is_full);
+
+/* ================================================================================================
+ * Host node pool -- och::octree (och_octree.h:10-69, och_octree.cpp:14-165)
+ * ============================================================================================== */
+
+int      ort_octree_create(ort_octree** out, int depth, uint32_t table_capacity);              /* och_octree.cpp:14 */
+void     ort_octree_destroy(ort_octree* tree);
+void     ort_octree_set(ort_octree* tree, int16_t x, int16_t y, int16_t z, uint32_t vx);       /* :74-91  */
+void     ort_octree_unset(ort_octree* tree, int16_t x, int16_t y, int16_t z);                  /* :93-139 */
+uint32_t ort_octree_at(const ort_octree* tree, int16_t x, int16_t y, int16_t z);               /* :141-160 */
+int      ort_octree_get_node_cnt(const ort_octree* tree);                                      /* :162-165 */
+/* n x (x, y, z, v, kind) int32 applied in order; kind 0 = set, 1 = unset */
+void     ort_octree_apply(ort_octree* tree, const int32_t* ops, size_t n);
+/* 1 once alloc() ran out of pool rows (the reference prints "Too many allocations" and exits, :50-54) */
+int      ort_octree_failed(const ort_octree* tree);
+int      ort_octree_depth(const ort_octree* tree);
+uint32_t ort_octree_table_capacity(const ort_octree* tree);
+const uint32_t* ort_octree_nodes(const ort_octree* tree);                                      /* _table, cap * 8 */
+int      ort_octree_attach(ort_octree* tree, ort_ctx* ctx);
+/* mirror the pool into the attached context: whole used prefix the first time, then only the rows edits touched */
+int      ort_octree_sync(ort_octree* tree);
+void     ort_octree_sync_stats(const ort_octree* tree, uint64_t* nodes_uploaded, int* was_full);
 
 /* ================================================================================================
  * Headless harness fixtures (replaces initialize_h_octree and friends,

@@ -30,6 +30,7 @@ _SIGS = {
     "ort_set_rcp_table": (C.c_int, [_vp, _vp, C.c_int]),
     "ort_upload_full": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32]),
     "ort_upload_delta": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32]),
+    "ort_upload_pool": (C.c_int, [_vp, _vp, C.c_size_t]),
     "ort_trace_rays": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "ort_trace_frame": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ort_trace_frame_async": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
@@ -71,6 +72,20 @@ _SIGS = {
     "ort_tree_sync": (C.c_int, [_vp]),
     "ort_tree_sync_stats": (None, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "ort_tree_take_delta": (C.c_size_t, [_vp, C.POINTER(_u32p), C.POINTER(_u32p), _u32p, C.POINTER(C.c_int)]),
+    "ort_octree_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_uint32]),
+    "ort_octree_destroy": (None, [_vp]),
+    "ort_octree_set": (None, [_vp, C.c_int16, C.c_int16, C.c_int16, C.c_uint32]),
+    "ort_octree_unset": (None, [_vp, C.c_int16, C.c_int16, C.c_int16]),
+    "ort_octree_at": (C.c_uint32, [_vp, C.c_int16, C.c_int16, C.c_int16]),
+    "ort_octree_get_node_cnt": (C.c_int, [_vp]),
+    "ort_octree_apply": (None, [_vp, _vp, C.c_size_t]),
+    "ort_octree_failed": (C.c_int, [_vp]),
+    "ort_octree_depth": (C.c_int, [_vp]),
+    "ort_octree_table_capacity": (C.c_uint32, [_vp]),
+    "ort_octree_nodes": (_u32p, [_vp]),
+    "ort_octree_attach": (C.c_int, [_vp, _vp]),
+    "ort_octree_sync": (C.c_int, [_vp]),
+    "ort_octree_sync_stats": (None, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "ort_fixture_heightmap": (None, [C.c_int, _vp, C.c_int]),
     "ort_fixture_build_terrain": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
 }

@@ -36,6 +36,9 @@ struct ort_ctx
 	uint32_t  cap_nodes = 0;
 	uint32_t  n_nodes = 0;              // highest compact id in use
 	uint32_t  root = 0;
+	uint32_t  index_base = 1;           // 1: ids are row+1 (h_octree layout); 0: raw rows, root = row 0 (och::octree pool)
+	bool      has_root = false;
+	float     miss_t = __builtin_inff();// hit_time of a MISS: INFINITY (och_h_octree.h:429) or 0.0F (och_octree.cpp:302)
 
 	uint32_t* d_rcp = nullptr;
 	int       rcp_log2n = 0;
@@ -144,7 +147,7 @@ __global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restri
 // explicit rays: thread i traces ray i
 template<int VARIANT, bool COUNT>
 __global__ void __launch_bounds__(256)
-trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt,
+trace_rays_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt,
                   const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, size_t n,
                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
@@ -154,7 +157,7 @@ trace_rays_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, 
 	const float* d = d3 + i * 3;
 	const float ox = __ldg(o), oy = __ldg(o + 1), oz = __ldg(o + 2);
 	const Ray r = ray_setup(rt, ox, oy, oz, __ldg(d), __ldg(d + 1), __ldg(d + 2));
-	const Hit h = traverse_variant<VARIANT, COUNT>(nodes, root, depth, ox, oy, oz, r);
+	const Hit h = traverse_variant<VARIANT, COUNT>(nodes_m1, root, depth, miss_t, ox, oy, oz, r);
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
@@ -171,7 +174,7 @@ struct FrameRows
 // a 256-thread block a 16 x 16 pixel tile
 template<int VARIANT, bool COUNT>
 __global__ void __launch_bounds__(256)
-trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt, Camera cam, FrameRows fr,
+trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
                    uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -185,7 +188,7 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth,
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
 	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	const Hit h = traverse_variant<VARIANT, COUNT>(nodes, root, depth, cam.ox, cam.oy, cam.oz, ray);
+	const Hit h = traverse_variant<VARIANT, COUNT>(nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
@@ -236,14 +239,13 @@ constexpr unsigned kBatch = 128;    // ray indices a warp draws per atomicAdd
 
 template<bool COUNT, bool FRAME>
 __global__ void __launch_bounds__(256)
-trace_persistent_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int depth, RcpTable rt,
+trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt,
                         const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, Camera cam, FrameRows fr,
                         unsigned long long n, unsigned long long* __restrict__ counter, int low_water,
                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	const uint32_t* const nodes_m1 = nodes - 8;
 	const unsigned tiles_x = FRAME ? (fr.W + 7) / 8 : 0;
 
 	uint32_t stack[kMaxDepth];
@@ -310,11 +312,11 @@ trace_persistent_kernel(const uint32_t* __restrict__ nodes, uint32_t root, int d
 					const Ray ray = ray_setup(rt, ox, oy, oz, dx, dy, dz);
 					if (fast_path_ok(ox, oy, oz, ray))
 					{
-						w.start(root, ray);
+						w.start(root, miss_t, ray);
 						active = true;
 					}
 					else
-						store(out, traverse(nodes, root, depth, ray, stack));       // out-of-domain ray: the generic walk, right away
+						store(out, traverse(nodes_m1, root, depth, miss_t, ray, stack));       // out-of-domain ray: the generic walk, right away
 				}
 			}
 			next += avail;
@@ -470,6 +472,22 @@ int ort_upload_full(ort_ctx* c, const uint32_t* nodes8, size_t n, uint32_t root)
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));   // the source may be reused by the caller right away
 	c->n_nodes = static_cast<uint32_t>(n);
 	c->root = root;
+	c->index_base = 1;
+	c->has_root = root != 0;
+	c->miss_t = __builtin_inff();
+	return ORT_OK;
+}
+
+int ort_upload_pool(ort_ctx* c, const uint32_t* nodes8, size_t n)
+{
+	if (!c || !nodes8 || n == 0 || n > ort::kIdMask)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_pool: bad arguments (n=%zu)", n);
+	const int rc = ort_upload_full(c, nodes8, n, 1);      // same copy; then switch the addressing to raw rows
+	if (rc != ORT_OK) return rc;
+	c->root = 0;
+	c->index_base = 0;
+	c->has_root = true;
+	c->miss_t = 0.0F;                                     // och_octree.cpp:302
 	return ORT_OK;
 }
 
@@ -525,7 +543,11 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 			ORT_CUDA(c, cudaStreamSynchronize(c->stream));   // pageable sources may be reused by the caller
 	}
 	c->n_nodes = max_id;
-	c->root = root;
+	if (c->index_base == 1)
+	{
+		c->root = root;
+		c->has_root = root != 0;
+	}
 	return ORT_OK;
 }
 
@@ -561,9 +583,10 @@ int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float*
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_rays: bad arguments");
 	if (!n) return ORT_OK;
 	DeviceGuard g(c->device);
-	if (c->root == 0)
+	if (!c->has_root)
 		return launch_miss(c, n, voxel, face, t, npush);
 	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
+	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
 	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
 	if (c->opt_rays_variant == 2 && c->opt_variant != 0)
 	{
@@ -573,14 +596,14 @@ int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float*
 		const ort::Camera cam0{};
 		const ort::FrameRows fr0{};
 		if (npush)
-			ort::trace_persistent_kernel<true, false><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+			ort::trace_persistent_kernel<true, false><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
 		else
-			ort::trace_persistent_kernel<false, false><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+			ort::trace_persistent_kernel<false, false><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-#define ORT_LAUNCH_RAYS(V, C) ort::trace_rays_kernel<V, C><<<blocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, o3, o_stride, d3, n, voxel, face, t, npush)
+#define ORT_LAUNCH_RAYS(V, C) ort::trace_rays_kernel<V, C><<<blocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, n, voxel, face, t, npush)
 	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_RAYS(0, true); else ORT_LAUNCH_RAYS(0, false); }
 	else { if (npush) ORT_LAUNCH_RAYS(1, true); else ORT_LAUNCH_RAYS(1, false); }
 #undef ORT_LAUNCH_RAYS
@@ -598,9 +621,10 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	if (!rows) return ORT_OK;
 	DeviceGuard g(c->device);
 	const size_t n = static_cast<size_t>(rows) * W;
-	if (c->root == 0)
+	if (!c->has_root)
 		return launch_miss(c, n, voxel, face, t, npush);
 	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
+	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
@@ -611,14 +635,14 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		const unsigned long long np = tiles * 32ull, need = (np + 255) / 256;
 		const unsigned pblocks = static_cast<unsigned>(need < static_cast<unsigned long long>(c->max_blocks_frame) ? need : c->max_blocks_frame);
 		if (npush)
-			ort::trace_persistent_kernel<true, true><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+			ort::trace_persistent_kernel<true, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
 		else
-			ort::trace_persistent_kernel<false, true><<<pblocks, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+			ort::trace_persistent_kernel<false, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, 0, c->stream>>>(c->d_nodes, c->root, c->depth, rt, cam, fr, voxel, face, t, npush)
+#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
 	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); }
 	else { if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); }
 #undef ORT_LAUNCH_FRAME

@@ -94,9 +94,10 @@ struct Hit
 	uint32_t npush;
 };
 
-// nodes: compact array, id i (1-based) at nodes[8*(i-1) .. 8*(i-1)+7]; root != 0.
+// nodes_m1: node id i lives at nodes_m1[8*i .. 8*i+7] (h_octree layout: nodes - 8, ids 1-based; och::octree pool:
+// the pool itself, raw rows, root = 0).  miss_t = hit_time reported by a MISS.
 // Baseline variant: one thread walks one ray from start to end, parent stack in local memory.
-__device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint32_t root, int depth, Ray r, uint32_t* stack)
+__device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, Ray r, uint32_t* stack)
 {
 	uint32_t node = root;
 	uint32_t dim = 1u << 22;                                                   // :326
@@ -112,7 +113,7 @@ __device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint
 	{
 		// PUSH (:342-376)
 		++h.npush;
-		const uint32_t child = __ldg(nodes + (static_cast<size_t>(node - 1) << 3) + ((idx ^ r.inv) & 7u));
+		const uint32_t child = __ldg(nodes_m1 + (static_cast<size_t>(node) << 3) + ((idx ^ r.inv) & 7u));
 
 		if (child)
 		{
@@ -162,7 +163,7 @@ __device__ __forceinline__ Hit traverse(const uint32_t* __restrict__ nodes, uint
 			{
 				h.voxel = 0;
 				h.face = 6;
-				h.t = __uint_as_float(0x7F800000u);
+				h.t = miss_t;
 				return h;
 			}
 			node = stack[level - 1];                                           // :434
@@ -208,11 +209,13 @@ struct FastWalker
 	int      level;
 	float    px, py, pz, dimf, tmin;
 	float    cx, cy, cz, bx, by, bz;
+	float    miss_t;
 	Hit      hit;
 
-	__device__ __forceinline__ void start(uint32_t root, const Ray& r)
+	__device__ __forceinline__ void start(uint32_t root, float miss_time, const Ray& r)
 	{
 		node = root;
+		miss_t = miss_time;
 		level = 1;
 		idx = r.idx;
 		inv = r.inv;
@@ -233,10 +236,10 @@ struct FastWalker
 	{
 		hit.voxel = 0;
 		hit.face = 6;
-		hit.t = __uint_as_float(0x7F800000u);
+		hit.t = miss_t;
 	}
 
-	// nodes_m1 = nodes - 8 (ids are 1-based); stack = this ray's parent stack (kMaxDepth entries, caller-owned so
+	// nodes_m1: see traverse(); stack = this ray's parent stack (kMaxDepth entries, caller-owned so
 	// that it stays a plain local array)
 	__device__ __forceinline__ bool iterate(const uint32_t* __restrict__ nodes_m1, int depth, uint32_t* stack)
 	{
@@ -337,11 +340,10 @@ struct FastWalker
 };
 
 template<bool COUNT>
-__device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes, uint32_t root, int depth, const Ray& r, uint32_t* stack)
+__device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, const Ray& r, uint32_t* stack)
 {
 	FastWalker<COUNT> w;
-	w.start(root, r);
-	const uint32_t* const nodes_m1 = nodes - 8;
+	w.start(root, miss_t, r);
 	while (!w.iterate(nodes_m1, depth, stack)) {}
 	return w.hit;
 }
@@ -355,14 +357,14 @@ __device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const
 }
 
 template<int VARIANT, bool COUNT>
-__device__ __forceinline__ Hit traverse_variant(const uint32_t* __restrict__ nodes, uint32_t root, int depth, float ox, float oy, float oz, const Ray& r)
+__device__ __forceinline__ Hit traverse_variant(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, float ox, float oy, float oz, const Ray& r)
 {
 	uint32_t stack[kMaxDepth];       // parent stack, local memory (dynamically indexed)
 	if (VARIANT == 0)
-		return traverse(nodes, root, depth, r, stack);
+		return traverse(nodes_m1, root, depth, miss_t, r, stack);
 	if (fast_path_ok(ox, oy, oz, r))
-		return traverse_fast<COUNT>(nodes, root, depth, r, stack);
-	return traverse(nodes, root, depth, r, stack);
+		return traverse_fast<COUNT>(nodes_m1, root, depth, miss_t, r, stack);
+	return traverse(nodes_m1, root, depth, miss_t, r, stack);
 }
 
 // Camera ray of pixel (x, y) -- tree_camera::update_position (test_och_h_octree.cpp:119-137) with

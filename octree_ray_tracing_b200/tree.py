@@ -302,3 +302,81 @@ class HOctree:
         self.sync()
         rot, fov = camera_coeffs(yaw, pitch)
         return self.ctx.trace_frame(pos, rot, fov, W, H, **kw)
+
+
+class Octree:
+    """och::octree(depth, table_capacity) (och_octree.h:10-69): plain pointer octree over a node pool, GPU tracer.
+    Members as in the reference: set, unset, at, get_node_cnt, sse_trace; plus the batched forms."""
+
+    def __init__(self, depth: int, table_capacity: int, device: int | None = 0):
+        self.L = lib()
+        h = _vp()
+        check(self.L.ort_octree_create(C.byref(h), depth, table_capacity))
+        self.h = h
+        self.depth = depth
+        self.dim = 1 << depth
+        self.table_capacity = table_capacity
+        self.ctx = None
+        if device is not None:
+            self.attach(TraceContext(depth, device, max(64, min(table_capacity, 1 << 16))))
+
+    def attach(self, ctx: TraceContext):
+        self.ctx = ctx
+        check(self.L.ort_octree_attach(self.h, ctx.h))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ort_octree_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def _ck_pool(self):
+        if self.L.ort_octree_failed(self.h):
+            raise OrtError(4, "Too many allocations (the reference prints this and exits, och_octree.cpp:50-54)")
+
+    def set(self, x: int, y: int, z: int, vx: int):
+        self.L.ort_octree_set(self.h, x, y, z, vx)
+        self._ck_pool()
+
+    def unset(self, x: int, y: int, z: int):
+        self.L.ort_octree_unset(self.h, x, y, z)
+
+    def at(self, x: int, y: int, z: int) -> int:
+        return self.L.ort_octree_at(self.h, x, y, z)
+
+    def get_node_cnt(self) -> int:
+        return self.L.ort_octree_get_node_cnt(self.h)
+
+    def apply(self, ops):
+        """ops: n x (x, y, z, v, kind), kind 0 = set, 1 = unset, applied in order."""
+        a = np.ascontiguousarray(ops, np.int32).reshape(-1, 5)
+        self.L.ort_octree_apply(self.h, _p(a), a.shape[0])
+        self._ck_pool()
+
+    def nodes(self):
+        return np.ctypeslib.as_array(self.L.ort_octree_nodes(self.h), shape=(self.table_capacity, 8))
+
+    def sync(self):
+        if self.ctx is None:
+            raise OrtError(6, "no device context attached: tracing needs a GPU (there is no CPU path)")
+        check(self.L.ort_octree_sync(self.h), self.ctx.h)
+        n = C.c_uint64(0)
+        full = C.c_int(0)
+        self.L.ort_octree_sync_stats(self.h, C.byref(n), C.byref(full))
+        return n.value, bool(full.value)
+
+    def sse_trace(self, o, d):
+        """One ray -> (Direction, hit_voxel, hit_time) as och_octree.cpp:167; a MISS reports hit_time 0.0."""
+        vox, face, t = self.trace_rays(np.asarray(o, np.float32).reshape(3), np.asarray(d, np.float32).reshape(1, 3))
+        return Direction(int(face[0])), int(vox[0]), float(t[0])
+
+    def trace_rays(self, o, d, **kw):
+        self.sync()
+        return self.ctx.trace_rays(o, d, **kw)
+
+    def trace_frame(self, pos, yaw, pitch, W, H, **kw):
+        self.sync()
+        rot, fov = camera_coeffs(yaw, pitch)
+        return self.ctx.trace_frame(pos, rot, fov, W, H, **kw)

@@ -273,18 +273,39 @@ void oc_clear(oc_tree* t)                                                  /* :2
  * trace -- och_h_octree.h:292-447
  * ========================================================================================== */
 
+/* The traversal of och_h_octree.h:292-447 and och_octree.cpp:167-320 -- the two differ only in how a node id
+ * maps to a table row (h_octree: id-1, octree: id), where the walk starts (root_idx vs pool row 0) and what a MISS
+ * reports as hit_time (INFINITY, och_h_octree.h:429, vs 0.0F, och_octree.cpp:302). */
+static void trace_core(const uint32_t* nodes, uint32_t root, uint32_t index_base, float miss_t, int depth,
+                       const float o[3], const float d[3],
+                       const uint32_t* rcp_tab, int log2n,
+                       uint32_t* vox, uint8_t* face, float* t_out, oc_counters* cnt);
+
 void oc_trace(const uint32_t* nodes, uint32_t root, int depth,
               const float o[3], const float d[3],
               const uint32_t* rcp_tab, int log2n,
               uint32_t* vox, uint8_t* face, float* t_out, oc_counters* cnt)
 {
-	uint64_t n_push = 0, n_step = 0, n_pop = 0;
-
 	if (!root)                                                             /* callers' guard, test_och_h_octree.cpp:443,:535 */
 	{
 		*vox = 0; *face = 6; *t_out = INFINITY;
 		return;
 	}
+	trace_core(nodes, root, 1, INFINITY, depth, o, d, rcp_tab, log2n, vox, face, t_out, cnt);
+}
+
+void oc_octree_trace(const uint32_t* pool, int depth, const float o[3], const float d[3],
+                     const uint32_t* rcp_tab, int log2n, uint32_t* vox, uint8_t* face, float* t_out, oc_counters* cnt)
+{
+	trace_core(pool, 0, 0, 0.0F, depth, o, d, rcp_tab, log2n, vox, face, t_out, cnt);   /* och_octree.cpp:207, :217, :302 */
+}
+
+static void trace_core(const uint32_t* nodes, uint32_t root, uint32_t index_base, float miss_t, int depth,
+                       const float o[3], const float d[3],
+                       const uint32_t* rcp_tab, int log2n,
+                       uint32_t* vox, uint8_t* face, float* t_out, oc_counters* cnt)
+{
+	uint64_t n_push = 0, n_step = 0, n_pop = 0;
 
 	float    coef[3], bias[3];
 	uint32_t pos[3];
@@ -314,7 +335,7 @@ void oc_trace(const uint32_t* nodes, uint32_t root, int depth,
 	{
 		/* PUSH :342-376 */
 		++n_push;
-		const uint32_t child = nodes[8 * (size_t)(node - 1) + ((idx ^ inv) & 7u)];   /* :344 */
+		const uint32_t child = nodes[8 * (size_t)(node - index_base) + ((idx ^ inv) & 7u)];   /* :344 / och_octree.cpp:217 */
 
 		if (child)
 		{
@@ -369,7 +390,7 @@ void oc_trace(const uint32_t* nodes, uint32_t root, int depth,
 			++n_pop;
 			if (--level == 0)                                              /* :423-432 MISS */
 			{
-				*vox = 0; *face = 6; *t_out = INFINITY;
+				*vox = 0; *face = 6; *t_out = miss_t;
 				goto done;
 			}
 
@@ -392,7 +413,7 @@ done:
 
 typedef struct trace_job
 {
-	const uint32_t* nodes; uint32_t root; int depth;
+	const uint32_t* nodes; uint32_t root; int depth; int pool_mode;
 	const float* o3; int o_stride; const float* d3; size_t n;
 	const uint32_t* rcp_tab; int log2n;
 	uint32_t* vox; uint8_t* face; float* t; uint16_t* npush16;
@@ -406,8 +427,12 @@ static void trace_range(trace_job* j, size_t b, size_t e, oc_counters* acc)
 	for (size_t i = b; i < e; ++i)
 	{
 		oc_counters c = { 0, 0, 0 };
-		oc_trace(j->nodes, j->root, j->depth, j->o3 + i * (size_t)j->o_stride, j->d3 + 3 * i, j->rcp_tab, j->log2n,
-		         j->vox + i, j->face + i, j->t + i, &c);
+		if (j->pool_mode)
+			oc_octree_trace(j->nodes, j->depth, j->o3 + i * (size_t)j->o_stride, j->d3 + 3 * i, j->rcp_tab, j->log2n,
+			                j->vox + i, j->face + i, j->t + i, &c);
+		else
+			oc_trace(j->nodes, j->root, j->depth, j->o3 + i * (size_t)j->o_stride, j->d3 + 3 * i, j->rcp_tab, j->log2n,
+			         j->vox + i, j->face + i, j->t + i, &c);
 		if (j->npush16)
 			j->npush16[i] = (uint16_t)(c.push > 65535u ? 65535u : c.push);
 		acc->push += c.push; acc->step += c.step; acc->pop += c.pop;
@@ -433,7 +458,31 @@ static void* trace_worker(void* arg)
 	return NULL;
 }
 
+static void trace_rays_mode(int pool_mode, const uint32_t* nodes, uint32_t root, int depth,
+                   const float* o3, int o_stride, const float* d3, size_t n,
+                   const uint32_t* rcp_tab, int log2n,
+                   uint32_t* vox, uint8_t* face, float* t,
+                   uint16_t* npush16, oc_counters* total, int nthreads);
+
 void oc_trace_rays(const uint32_t* nodes, uint32_t root, int depth,
+                   const float* o3, int o_stride, const float* d3, size_t n,
+                   const uint32_t* rcp_tab, int log2n,
+                   uint32_t* vox, uint8_t* face, float* t,
+                   uint16_t* npush16, oc_counters* total, int nthreads)
+{
+	trace_rays_mode(0, nodes, root, depth, o3, o_stride, d3, n, rcp_tab, log2n, vox, face, t, npush16, total, nthreads);
+}
+
+void oc_octree_trace_rays(const uint32_t* pool, int depth,
+                   const float* o3, int o_stride, const float* d3, size_t n,
+                   const uint32_t* rcp_tab, int log2n,
+                   uint32_t* vox, uint8_t* face, float* t,
+                   uint16_t* npush16, oc_counters* total, int nthreads)
+{
+	trace_rays_mode(1, pool, 0, depth, o3, o_stride, d3, n, rcp_tab, log2n, vox, face, t, npush16, total, nthreads);
+}
+
+static void trace_rays_mode(int pool_mode, const uint32_t* nodes, uint32_t root, int depth,
                    const float* o3, int o_stride, const float* d3, size_t n,
                    const uint32_t* rcp_tab, int log2n,
                    uint32_t* vox, uint8_t* face, float* t,
@@ -441,7 +490,7 @@ void oc_trace_rays(const uint32_t* nodes, uint32_t root, int depth,
 {
 	trace_job j;
 	memset(&j, 0, sizeof j);
-	j.nodes = nodes; j.root = root; j.depth = depth;
+	j.nodes = nodes; j.root = root; j.depth = depth; j.pool_mode = pool_mode;
 	j.o3 = o3; j.o_stride = o_stride; j.d3 = d3; j.n = n;
 	j.rcp_tab = rcp_tab; j.log2n = log2n;
 	j.vox = vox; j.face = face; j.t = t; j.npush16 = npush16;
@@ -461,6 +510,131 @@ void oc_trace_rays(const uint32_t* nodes, uint32_t root, int depth,
 	if (total)
 		*total = j.total;
 	pthread_mutex_destroy(&j.lock);
+}
+
+/* ============================================================================================
+ * och::octree -- the plain pointer octree (och_octree.h:10-69, och_octree.cpp:14-165)
+ * ========================================================================================== */
+
+oc_octree* oc_octree_create(int depth, uint32_t table_capacity)            /* och_octree.cpp:14, :21-35 */
+{
+	oc_octree* t = (oc_octree*)calloc(1, sizeof(oc_octree));
+	t->depth = depth;
+	t->cap = table_capacity;
+	t->nodes = (uint32_t*)aligned_alloc(64, (size_t)table_capacity * 32);
+	memset(t->nodes, 0, (size_t)table_capacity * 32);
+	for (uint32_t i = 1; i != table_capacity; ++i) t->nodes[8 * (size_t)i] = i + 1;   /* free list through children[0] */
+	t->nodes[8 * (size_t)(table_capacity - 1)] = 0;
+	t->head = 1;                                                           /* och_octree.h:27-28 */
+	t->node_cnt = 1;
+	return t;
+}
+
+void oc_octree_destroy(oc_octree* t)
+{
+	if (!t) return;
+	free(t->nodes);
+	free(t);
+}
+
+static uint32_t octree_alloc(oc_octree* t)                                 /* och_octree.cpp:46-63 */
+{
+	++t->node_cnt;
+	if (!t->head)
+	{
+		t->failed = 1;                                                     /* reference: printf + exit(0) */
+		return 0;
+	}
+	const uint32_t old = t->head;
+	t->head = t->nodes[8 * (size_t)old];
+	memset(t->nodes + 8 * (size_t)old, 0, 32);
+	return old;
+}
+
+static void octree_dealloc(oc_octree* t, uint32_t idx)                     /* och_octree.cpp:65-72 */
+{
+	--t->node_cnt;
+	t->nodes[8 * (size_t)idx] = t->head;
+	t->head = idx;
+}
+
+static int octree_empty(const oc_octree* t, uint32_t idx)
+{
+	const uint32_t* n = t->nodes + 8 * (size_t)idx;
+	return !(n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7]);
+}
+
+void oc_octree_set(oc_octree* t, int16_t x, int16_t y, int16_t z, uint32_t vx)   /* och_octree.cpp:74-91 (no range check) */
+{
+	const uint64_t index = oc_z_encode_16((uint16_t)x, (uint16_t)y, (uint16_t)z);
+	uint32_t curr = 0;
+	for (int i = t->depth - 1; i != 0; --i)
+	{
+		uint32_t* slot = t->nodes + 8 * (size_t)curr + ((index >> (3 * i)) & 7);
+		if (!*slot)
+		{
+			const uint32_t a = octree_alloc(t);
+			if (t->failed) return;
+			*slot = a;
+		}
+		curr = *slot;
+	}
+	t->nodes[8 * (size_t)curr + (index & 7)] = vx;
+}
+
+void oc_octree_unset(oc_octree* t, int16_t x, int16_t y, int16_t z)       /* och_octree.cpp:93-139 */
+{
+	const uint64_t index = oc_z_encode_16((uint16_t)x, (uint16_t)y, (uint16_t)z);
+	uint32_t curr = 0;
+	int sptr = 0;
+	uint32_t stack[16];
+
+	for (int i = t->depth - 1; i != 0; --i)
+	{
+		const uint32_t child = t->nodes[8 * (size_t)curr + ((index >> (3 * i)) & 7)];
+		if (!child)
+			return;
+		stack[sptr++] = curr;
+		curr = child;
+	}
+
+	t->nodes[8 * (size_t)curr + (index & 7)] = 0;
+	if (!octree_empty(t, curr))
+		return;
+	octree_dealloc(t, curr);
+
+	for (int i = 1; i != t->depth; ++i)                                    /* (this can free row 0, the root: reference behaviour) */
+	{
+		--sptr;
+		t->nodes[8 * (size_t)stack[sptr] + ((index >> (3 * i)) & 7)] = 0;
+		if (!octree_empty(t, stack[sptr]))
+			return;
+		octree_dealloc(t, stack[sptr]);
+	}
+}
+
+uint32_t oc_octree_at(const oc_octree* t, int16_t x, int16_t y, int16_t z) /* och_octree.cpp:141-160 */
+{
+	const uint64_t index = oc_z_encode_16((uint16_t)x, (uint16_t)y, (uint16_t)z);
+	uint32_t curr = 0;
+	for (int i = t->depth - 1; i > 0; --i)
+	{
+		const uint32_t c = t->nodes[8 * (size_t)curr + ((index >> (3 * i)) & 7)];
+		if (!c)
+			return 0;
+		curr = c;
+	}
+	return t->nodes[8 * (size_t)curr + (index & 7)];
+}
+
+void oc_octree_apply(oc_octree* t, const int32_t* ops, size_t n)
+{
+	for (size_t i = 0; i < n; ++i)
+	{
+		const int32_t* o = ops + 5 * i;
+		if (o[4] == 0) oc_octree_set(t, (int16_t)o[0], (int16_t)o[1], (int16_t)o[2], (uint32_t)o[3]);
+		else oc_octree_unset(t, (int16_t)o[0], (int16_t)o[1], (int16_t)o[2]);
+	}
 }
 
 /* ============================================================================================

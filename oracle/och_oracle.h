@@ -89,6 +89,34 @@ void oc_trace_rays(const uint32_t* nodes, uint32_t root, int depth,
                    uint32_t* vox, uint8_t* face, float* t,
                    uint16_t* npush16, oc_counters* total, int nthreads);
 
+/* ---- och::octree: plain pointer octree over a node pool (och_octree.h:10-69, och_octree.cpp:14-320) -------- */
+
+typedef struct oc_octree
+{
+	int       depth;
+	uint32_t  cap;
+	uint32_t* nodes;      /* cap * 8; row 0 is the root, child values are raw row numbers, 0 = empty */
+	uint32_t  head;       /* free list head (och_octree.h:27) */
+	int       node_cnt;   /* och_octree.h:28 */
+	int       failed;     /* set instead of printf + exit(0) on pool exhaustion (och_octree.cpp:50-54) */
+} oc_octree;
+
+oc_octree* oc_octree_create(int depth, uint32_t table_capacity);
+void       oc_octree_destroy(oc_octree* t);
+void       oc_octree_set(oc_octree* t, int16_t x, int16_t y, int16_t z, uint32_t vx);   /* och_octree.cpp:74-91 */
+void       oc_octree_unset(oc_octree* t, int16_t x, int16_t y, int16_t z);              /* :93-139 */
+uint32_t   oc_octree_at(const oc_octree* t, int16_t x, int16_t y, int16_t z);           /* :141-160 */
+/* ops: n x (x, y, z, v, kind) int32, kind 0 = set, 1 = unset */
+void       oc_octree_apply(oc_octree* t, const int32_t* ops, size_t n);
+/* och_octree.cpp:167-320: same walk as oc_trace from pool row 0 with raw child ids; MISS reports t = 0.0F */
+void oc_octree_trace(const uint32_t* pool, int depth, const float o[3], const float d[3],
+                     const uint32_t* rcp_tab, int log2n, uint32_t* vox, uint8_t* face, float* t, oc_counters* cnt);
+void oc_octree_trace_rays(const uint32_t* pool, int depth,
+                   const float* o3, int o_stride, const float* d3, size_t n,
+                   const uint32_t* rcp_tab, int log2n,
+                   uint32_t* vox, uint8_t* face, float* t,
+                   uint16_t* npush16, oc_counters* total, int nthreads);
+
 /* ---- camera rays (test_och_h_octree.cpp:87-138) ------------------------------------------- */
 
 /* rot[9] = t_x_fx, t_x_fy, t_x_fz, t_y_fx, ... t_z_fz (:107-115); fov_factor = 1/tanf(1.25/2) (:97) */

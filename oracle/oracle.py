@@ -51,6 +51,11 @@ class _OcTree(C.Structure):
     ]
 
 
+class _OcOctree(C.Structure):
+    _fields_ = [("depth", C.c_int), ("cap", C.c_uint32), ("nodes", C.POINTER(C.c_uint32)), ("head", C.c_uint32),
+                ("node_cnt", C.c_int), ("failed", C.c_int)]
+
+
 _lib = None
 
 
@@ -89,6 +94,16 @@ def lib():
         L.oc_simplex3_many.argtypes = [C.c_float, _vp, C.c_size_t, _vp]
         L.oc_heightmap.argtypes = [C.c_int, _vp]
         L.oc_initialize_terrain.argtypes = [C.POINTER(_OcTree), _vp, _vp, C.c_int]
+        L.oc_octree_create.restype = C.POINTER(_OcOctree)
+        L.oc_octree_create.argtypes = [C.c_int, C.c_uint32]
+        L.oc_octree_destroy.argtypes = [C.POINTER(_OcOctree)]
+        L.oc_octree_set.argtypes = [C.POINTER(_OcOctree), C.c_int16, C.c_int16, C.c_int16, C.c_uint32]
+        L.oc_octree_unset.argtypes = [C.POINTER(_OcOctree), C.c_int16, C.c_int16, C.c_int16]
+        L.oc_octree_at.restype = C.c_uint32
+        L.oc_octree_at.argtypes = [C.POINTER(_OcOctree), C.c_int16, C.c_int16, C.c_int16]
+        L.oc_octree_apply.argtypes = [C.POINTER(_OcOctree), _vp, C.c_size_t]
+        L.oc_octree_trace_rays.argtypes = [_vp, C.c_int, _vp, C.c_int, _vp, C.c_size_t, _vp, C.c_int,
+                                           _vp, _vp, _vp, _vp, C.POINTER(Counters), C.c_int]
         _lib = L
     return _lib
 
@@ -178,6 +193,70 @@ class OracleTree:
 
     def trace(self, o, d, **kw):
         return trace_rays(self.nodes(), self.root, self.depth, o, d, **kw)
+
+
+def _trace_args(o, d):
+    d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+    o = np.ascontiguousarray(o, np.float32)
+    n = d.shape[0]
+    stride = 0 if o.size == 3 else 3
+    assert stride == 0 or o.size == 3 * n
+    return o, d, n, stride, np.zeros(n, np.uint32), np.zeros(n, np.uint8), np.zeros(n, np.float32)
+
+
+class OracleOctree:
+    """Restated och::octree (och_octree.h:10-69, och_octree.cpp:14-320)."""
+
+    def __init__(self, depth: int, table_capacity: int):
+        self.L = lib()
+        self.h = self.L.oc_octree_create(depth, table_capacity)
+        self.depth, self.cap = depth, table_capacity
+
+    def __del__(self):
+        try:
+            self.L.oc_octree_destroy(self.h)
+        except Exception:
+            pass
+
+    def set(self, x, y, z, v):
+        self.L.oc_octree_set(self.h, x, y, z, v)
+
+    def unset(self, x, y, z):
+        self.L.oc_octree_unset(self.h, x, y, z)
+
+    def at(self, x, y, z):
+        return self.L.oc_octree_at(self.h, x, y, z)
+
+    def apply(self, ops):
+        a = np.ascontiguousarray(ops, np.int32).reshape(-1, 5)
+        self.L.oc_octree_apply(self.h, _ptr(a), a.shape[0])
+
+    @property
+    def node_cnt(self):
+        return self.h.contents.node_cnt
+
+    @property
+    def failed(self):
+        return bool(self.h.contents.failed)
+
+    def nodes(self):
+        return np.ctypeslib.as_array(self.h.contents.nodes, shape=(self.cap, 8))
+
+    def trace(self, o, d, rcp_tab=None, nthreads=1):
+        return octree_trace_rays(self.nodes(), self.depth, o, d, rcp_tab, nthreads)
+
+
+def octree_trace_rays(pool, depth, o, d, rcp_tab=None, nthreads=1):
+    pool = np.ascontiguousarray(pool, np.uint32)
+    o, d, n, stride, vox, face, t = _trace_args(o, d)
+    log2n = 0
+    if rcp_tab is not None:
+        rcp_tab = np.ascontiguousarray(rcp_tab, np.uint32)
+        log2n = int(rcp_tab.size).bit_length() - 1
+    tot = Counters()
+    lib().oc_octree_trace_rays(_ptr(pool), depth, _ptr(o), stride, _ptr(d), n, _ptr(rcp_tab), log2n,
+                               _ptr(vox), _ptr(face), _ptr(t), None, C.byref(tot), nthreads)
+    return vox, face, t
 
 
 def heightmap(depth: int) -> np.ndarray:
@@ -299,6 +378,18 @@ def ref():
         R.ochref_opensimplex2.argtypes = [C.c_int64, _vp, C.c_size_t, _vp]
         R.ochref_heightmap.argtypes = [C.c_int, _vp]
         R.ochref_initialize_terrain.argtypes = [_vp, _vp, _vp, C.c_int]
+        R.ochref_octree_create.restype = _vp
+        R.ochref_octree_create.argtypes = [C.c_int, C.c_uint32]
+        R.ochref_octree_set.argtypes = [_vp, C.c_int16, C.c_int16, C.c_int16, C.c_uint32]
+        R.ochref_octree_unset.argtypes = [_vp, C.c_int16, C.c_int16, C.c_int16]
+        R.ochref_octree_at.restype = C.c_uint32
+        R.ochref_octree_at.argtypes = [_vp, C.c_int16, C.c_int16, C.c_int16]
+        R.ochref_octree_node_cnt.restype = C.c_int
+        R.ochref_octree_node_cnt.argtypes = [_vp]
+        R.ochref_octree_nodes.restype = _vp
+        R.ochref_octree_nodes.argtypes = [_vp]
+        R.ochref_octree_apply.argtypes = [_vp, _vp, C.c_size_t]
+        R.ochref_octree_trace_batch.argtypes = [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp]
         R.ochref_node_hash.restype = C.c_uint32
         R.ochref_node_hash.argtypes = [_vp]
         _ref = R
@@ -389,6 +480,41 @@ class RefTree:
         t = np.zeros(n, np.float32)
         rc = self.R.ochref_trace_batch(self.h, _ptr(o), stride, _ptr(d), n, _ptr(vox), _ptr(face), _ptr(t), nthreads)
         assert rc == 0
+        return vox, face, t
+
+
+class RefOctree:
+    """The reference's own och::octree (och_octree.cpp compiled with the one hoisted declaration, see Makefile)."""
+
+    def __init__(self, depth: int, table_capacity: int):
+        self.R = ref()
+        self.h = _vp(self.R.ochref_octree_create(depth, table_capacity))
+        self.depth, self.cap = depth, table_capacity
+
+    def set(self, x, y, z, v):
+        self.R.ochref_octree_set(self.h, x, y, z, v)
+
+    def unset(self, x, y, z):
+        self.R.ochref_octree_unset(self.h, x, y, z)
+
+    def at(self, x, y, z):
+        return self.R.ochref_octree_at(self.h, x, y, z)
+
+    def apply(self, ops):
+        a = np.ascontiguousarray(ops, np.int32).reshape(-1, 5)
+        self.R.ochref_octree_apply(self.h, _ptr(a), a.shape[0])
+
+    @property
+    def node_cnt(self):
+        return self.R.ochref_octree_node_cnt(self.h)
+
+    def nodes(self):
+        p = self.R.ochref_octree_nodes(self.h)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(self.cap, 8))
+
+    def trace(self, o, d):
+        o, d, n, stride, vox, face, t = _trace_args(o, d)
+        self.R.ochref_octree_trace_batch(self.h, _ptr(o), stride, _ptr(d), n, _ptr(vox), _ptr(face), _ptr(t))
         return vox, face, t
 
 

@@ -27,6 +27,7 @@
 #define private public
 #include "och_h_octree.h"
 #undef private
+#include "och_octree.h"
 #include "och_noise.h"
 #include "opensimplex.h"
 
@@ -278,6 +279,40 @@ void ochref_initialize_terrain(void* hnd, const uint16_t* heights, const uint8_t
 					if (!(val >= -0.5F))
 						t->set(x, y, z, 0);
 				}
+	}
+}
+
+// ---- och::octree (och_octree.h, och_octree.cpp): the plain pointer octree with the same traversal ----------
+
+void* ochref_octree_create(int depth, uint32_t table_capacity) { return new och::octree(static_cast<uint16_t>(depth), table_capacity); }
+void  ochref_octree_set(void* h, int16_t x, int16_t y, int16_t z, uint32_t v) { static_cast<och::octree*>(h)->set(x, y, z, v); }
+void  ochref_octree_unset(void* h, int16_t x, int16_t y, int16_t z) { static_cast<och::octree*>(h)->unset(x, y, z); }
+uint32_t ochref_octree_at(void* h, int16_t x, int16_t y, int16_t z) { return static_cast<och::octree*>(h)->at(x, y, z); }
+int   ochref_octree_node_cnt(void* h) { return static_cast<och::octree*>(h)->get_node_cnt(); }
+uint32_t* ochref_octree_nodes(void* h) { return reinterpret_cast<uint32_t*>(static_cast<och::octree*>(h)->_table); }
+
+// ops: n x (x, y, z, v, kind) int32 with kind 0 = set, 1 = unset
+void ochref_octree_apply(void* h, const int32_t* ops, size_t n)
+{
+	och::octree* t = static_cast<och::octree*>(h);
+	for (size_t i = 0; i < n; ++i)
+	{
+		const int32_t* o = ops + 5 * i;
+		if (o[4] == 0) t->set(static_cast<int16_t>(o[0]), static_cast<int16_t>(o[1]), static_cast<int16_t>(o[2]), static_cast<uint32_t>(o[3]));
+		else t->unset(static_cast<int16_t>(o[0]), static_cast<int16_t>(o[1]), static_cast<int16_t>(o[2]));
+	}
+}
+
+void ochref_octree_trace_batch(void* h, const float* o3, int o_stride, const float* d3, size_t n, uint32_t* vox, uint8_t* face, float* t)
+{
+	const och::octree* tr = static_cast<const och::octree*>(h);
+	for (size_t i = 0; i < n; ++i)
+	{
+		const float* o = o3 + i * o_stride;
+		const float* d = d3 + i * 3;
+		och::direction dir;
+		tr->sse_trace(o[0], o[1], o[2], d[0], d[1], d[2], dir, vox[i], t[i]);
+		face[i] = static_cast<uint8_t>(dir);
 	}
 }
 
