@@ -198,6 +198,55 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 }
 
 
+// Experiment kernel for the "upper levels in shared memory" question: 1024-thread blocks (a 32 x 32 pixel tile,
+// warps still 8 x 4) copy the first n_staged nodes -- the top levels, a contiguous prefix of the level-ordered
+// array -- into shared memory and serve PUSHes on those nodes from there.  Only valid in the h_octree layout.
+// Kept selectable (variant 3) so that the decision can be re-measured; see DESIGN.md section 4 for the numbers.
+template<bool COUNT>
+__global__ void __launch_bounds__(1024)
+trace_frame_staged_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
+                          uint32_t n_staged,
+                          uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	extern __shared__ uint4 s_raw[];
+	uint32_t* s_nodes = reinterpret_cast<uint32_t*>(s_raw);
+	{
+		const uint4* src = reinterpret_cast<const uint4*>(nodes_m1 + 8);            // id 1
+		for (uint32_t i = threadIdx.x; i < 2u * n_staged; i += blockDim.x) s_raw[i] = __ldg(src + i);
+	}
+	__syncthreads();
+	const uint32_t* s_nodes_m1 = s_nodes - 8;
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
+	const int r = blockIdx.y * 32 + (warp >> 2) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	uint32_t stack[kMaxDepth];
+	Hit h;
+	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
+	{
+		FastWalker<COUNT> w;
+		w.start(root, miss_t, ray);
+		while (!w.iterate_staged(nodes_m1, depth, stack, s_nodes_m1, n_staged)) {}
+		h = w.hit;
+	}
+	else
+		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
+
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
 // Diagnostic: random 32-byte-sector gather over an L2-resident buffer -- the memory-side ceiling of a
 // traversal whose nodes live in L2 (one 4-byte child read moves one sector).  Independent loads, 8 in
 // flight per thread, addresses from a counter hash so that L1 cannot help.
@@ -638,6 +687,29 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 			ort::trace_persistent_kernel<true, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
 		else
 			ort::trace_persistent_kernel<false, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
+	if (c->opt_variant == 3 && c->index_base == 1)
+	{
+		// upper levels staged in shared memory: opt_smem_levels = number of node ids to stage (the harness passes
+		// the first id of level k+1 from ort_tree_flatten's level offsets, minus one)
+		uint32_t n_staged = c->opt_smem_levels > 0 ? static_cast<uint32_t>(c->opt_smem_levels) : 0u;
+		if (n_staged > c->n_nodes) n_staged = c->n_nodes;
+		if (n_staged > 6144u) n_staged = 6144u;                         // 192 KB of the 227 KB a block may have
+		const size_t smem = static_cast<size_t>(n_staged) * 32;
+		const dim3 g2((W + 31) / 32, (rows + 31) / 32);
+		if (npush)
+		{
+			ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			ort::trace_frame_staged_kernel<true><<<g2, 1024, smem, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_staged, voxel, face, t, npush);
+		}
+		else
+		{
+			ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+			ort::trace_frame_staged_kernel<false><<<g2, 1024, smem, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_staged, voxel, face, t, npush);
+		}
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;

@@ -243,8 +243,21 @@ struct FastWalker
 	// that it stays a plain local array)
 	__device__ __forceinline__ bool iterate(const uint32_t* __restrict__ nodes_m1, int depth, uint32_t* stack)
 	{
+		return iterate_staged(nodes_m1, depth, stack, nullptr, 0u);
+	}
+
+	// s_nodes_m1 / n_staged: the first n_staged node ids (the DAG's upper levels: a contiguous prefix of the
+	// level-ordered array) are also held in shared memory, laid out like nodes_m1.  n_staged = 0: global only.
+	__device__ __forceinline__ bool iterate_staged(const uint32_t* __restrict__ nodes_m1, int depth, uint32_t* stack,
+	                                               const uint32_t* s_nodes_m1, uint32_t n_staged)
+	{
 		if (COUNT) ++hit.npush;
-		const uint32_t child = __ldg(nodes_m1 + (node * 8u + (idx ^ inv)));      // id < 2^29: the word index fits 32 bits
+		const uint32_t word = node * 8u + (idx ^ inv);                             // id < 2^29: the word index fits 32 bits
+		uint32_t child;
+		if (n_staged != 0u && node <= n_staged)
+			child = s_nodes_m1[word];
+		else
+			child = __ldg(nodes_m1 + word);
 
 		if (child)
 		{

@@ -244,14 +244,16 @@ def test_depth12_4k_properties(ort, oc, ncpu):
 
 
 def test_kernel_variants_agree(ort, golden):
-    """Baseline walk (variant 0), fast walk (1) and persistent lane-refill (2) are the same function."""
+    """Baseline walk (variant 0), fast walk (1), persistent lane-refill (2) and the shared-memory staging
+    experiment (3) are the same function."""
     g = golden("d8_tunnels")
     ctx = ort.TraceContext(8)
     ctx.upload_full(g["nodes8"], int(g["root"]))
     W, H = 333, 217                                    # not multiples of the 8x4 tile
     pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
     ref = None
-    for variant in (0, 1, 2):
+    ctx.set_option("smem_levels", 215)                  # variant 3 stages the first 215 nodes (levels 1-4 of this DAG)
+    for variant in (0, 1, 2, 3):
         ctx.set_option("variant", variant)
         got = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
         part = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=64, tile_rows=8, tile_step=3)
