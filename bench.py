@@ -315,6 +315,20 @@ def run_product(args):
         barrier()
         gather = (time.perf_counter() - g0) / g_steps
 
+    # shaded frames (the pixels update_image draws): 4 B per ray cross PCIe instead of 9
+    cols, _ = harness.parse_voxels(harness.DEMO_VOXELS)
+    ctx.set_palette(cols)
+    hrgba = torch.empty(n_local, dtype=torch.int32).pin_memory()
+    for cam in cams:
+        ctx.trace_frame_rgba(cam[0], cam[1], cam[2], W, H, y0=y0, rows=rows, tile_rows=TILE_ROWS, tile_step=world, out=hrgba)
+    barrier()
+    r0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        for cam in step_cams:
+            ctx.trace_frame_rgba(cam[0], cam[1], cam[2], W, H, y0=y0, rows=rows, tile_rows=TILE_ROWS, tile_step=world, out=hrgba)
+    barrier()
+    rgba_s = time.perf_counter() - r0
+
     clocks = sampler.stop()
     # memory-side ceilings measured on this GPU: random 32-B sector gathers over a buffer of the DAG's size (L2-resident)
     # and over 4 GiB (HBM-resident)
@@ -323,9 +337,9 @@ def run_product(args):
 
     # max over ranks
     if world > 1:
-        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, gather], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, gather, rgba_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms, warm_ms, e2e_s, wall, gather = (float(x) for x in tt.tolist())
+        kernel_ms, warm_ms, e2e_s, wall, gather, rgba_s = (float(x) for x in tt.tolist())
         cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
@@ -364,6 +378,9 @@ def run_product(args):
             "e2e": {"value": round(e2e_val, 2), "unit": "Mrays/s", "h2d_bytes_per_step": frames_per_step * 52,
                     "d2h_bytes_per_step": frames_per_step * n_local * 9, "steps": e2e_steps,
                     "api": "ort_trace_frame (host buffers, pinned; chunked D2H overlapped with the kernel)", "hits_last_frame": e2e_check},
+            "e2e_rgba": {"value": round(rays_per_step_total * e2e_steps / rgba_s / 1e6, 2), "unit": "Mrays/s",
+                         "d2h_bytes_per_step": frames_per_step * n_local * 4,
+                         "api": "ort_trace_frame_rgba: trace_pixel's colour lookup fused into the kernel, one uint32 pixel per ray to pinned host memory"},
             "gpu_launches": launches_all,
             "roofline": {
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),

@@ -98,6 +98,13 @@ namespace och
 			if (ort_tree_table_full(tree)) throw std::runtime_error("h_octree: table too full");
 		}
 
+		// extension: the T/Z box edit in one pass (same result as the set() loop, see ort_tree_fill_box)
+		void fill_box(int x0, int y0, int z0, int x1, int y1, int z1, uint32_t v)
+		{
+			ort_tree_fill_box(tree, x0, y0, z0, x1, y1, z1, v);
+			if (ort_tree_table_full(tree)) throw std::runtime_error("h_octree: table too full");
+		}
+
 		uint32_t at(int x, int y, int z) { return ort_tree_at(tree, x, y, z); }
 
 		void set_root(uint32_t idx) { ort_tree_set_root(tree, idx); }

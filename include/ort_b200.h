@@ -110,6 +110,20 @@ int ort_trace_frame_async(ort_ctx* ctx, const float pos[3], const float rot[9], 
 int ort_trace_rays_async(ort_ctx* ctx, const float* d_o3, int o_stride, const float* d_d3, size_t n,
                          uint32_t* d_voxel, uint8_t* d_face, float* d_t, uint16_t* d_npush);
 
+/* Replaces: och::voxel_data::get_colours() as trace_pixel uses it (test_och_h_octree.cpp:84) plus the sky / inside
+ * colours (:76-77).  rgba6 = 6 colours per voxel type in face order x+,y+,z+,x-,y-,z-, packed like olc::Pixel::n
+ * (r | g<<8 | b<<16 | a<<24); voxel type v uses rgba6[6*(v-1) .. 6*(v-1)+5]. */
+int ort_set_palette(ort_ctx* ctx, const uint32_t* rgba6, uint32_t n_voxels, uint32_t exit_rgba, uint32_t inside_rgba);
+/* Parse the reference's voxels.txt format (och_voxel.h:8-27, och_voxel.cpp:195-305): "Name:" followed by six RRGGBB
+ * colours, repeated.  Writes up to max_voxels * 6 packed colours (alpha 0xFF) and names (16 bytes each, may be
+ * NULL); returns the number of voxel types found, or -1 with ort_last_error set on a malformed file. */
+int ort_parse_voxels(const char* text, size_t len, uint32_t* rgba6, char* names16, int max_voxels);
+/* Replaces: update_image (test_och_h_octree.cpp:437-457) including the colour lookup of trace_pixel (:64-85): one
+ * uint32 pixel per ray, same row addressing as ort_trace_frame.  rgba may be a host pointer (chunked, overlapped
+ * D2H, returns when the pixels are there) or a device pointer (enqueue only on ort_stream). */
+int ort_trace_frame_rgba(ort_ctx* ctx, const float pos[3], const float rot[9], float fov_factor,
+                         int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* rgba);
+
 int   ort_sync(ort_ctx* ctx);
 void* ort_stream(ort_ctx* ctx);                 /* the cudaStream_t all work of ctx is queued on */
 /* Queue subsequent work of ctx on the caller's cudaStream_t (NULL: back to the context's own stream).  Lets a
@@ -154,6 +168,10 @@ void     ort_tree_set_many(ort_tree* tree, const uint32_t* xyzv, size_t n);
 /* the T / Z edit (test_och_h_octree.cpp:408-413, :427-432): set() over the box
  * [cx-ext/2, cx+(ext+1)/2) x ... in the reference's z, y, x loop order, uint16 wrap-around included */
 void     ort_tree_set_box(ort_tree* tree, uint16_t cx, uint16_t cy, uint16_t cz, int ext, uint32_t v);
+/* Bulk form of the same edit: every voxel of [x0,x1) x [y0,y1) x [z0,z1) (clipped to the cube) becomes v in ONE
+ * pass over the cells the box cuts.  Voxel content, live nodes, fillcnt, nodecnt, refcounts and traced images equal
+ * those of the set() loop; only the slot numbers handed to NEW nodes may differ (insertion order).  ~100x faster. */
+void     ort_tree_fill_box(ort_tree* tree, int x0, int y0, int z0, int x1, int y1, int z1, uint32_t v);
 uint32_t ort_tree_at(const ort_tree* tree, int x, int y, int z);                           /* :239-258 */
 void     ort_tree_set_root(ort_tree* tree, uint32_t idx);                                  /* :260-263 */
 uint32_t ort_tree_get_root(const ort_tree* tree);                                          /* :265-268 */

@@ -35,6 +35,9 @@ _SIGS = {
     "ort_trace_frame": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ort_trace_frame_async": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ort_trace_rays_async": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
+    "ort_set_palette": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "ort_parse_voxels": (C.c_int, [C.c_char_p, C.c_size_t, _vp, _vp, C.c_int]),
+    "ort_trace_frame_rgba": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "ort_sync": (C.c_int, [_vp]),
     "ort_stream": (_vp, [_vp]),
     "ort_set_stream": (C.c_int, [_vp, _vp]),
@@ -54,6 +57,7 @@ _SIGS = {
     "ort_tree_set": (None, [_vp, C.c_uint16, C.c_uint16, C.c_uint16, C.c_uint32]),
     "ort_tree_set_many": (None, [_vp, _vp, C.c_size_t]),
     "ort_tree_set_box": (None, [_vp, C.c_uint16, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32]),
+    "ort_tree_fill_box": (None, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]),
     "ort_tree_at": (C.c_uint32, [_vp, C.c_int, C.c_int, C.c_int]),
     "ort_tree_set_root": (None, [_vp, C.c_uint32]),
     "ort_tree_get_root": (C.c_uint32, [_vp]),

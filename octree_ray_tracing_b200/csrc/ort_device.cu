@@ -40,6 +40,11 @@ struct ort_ctx
 	bool      has_root = false;
 	float     miss_t = __builtin_inff();// hit_time of a MISS: INFINITY (och_h_octree.h:429) or 0.0F (och_octree.cpp:302)
 
+	uint32_t* d_palette = nullptr;      // 6 colours per voxel type (olc::Pixel::n packing), shading epilogue
+	uint32_t  n_palette = 0;
+	uint32_t  exit_rgba = 0xFFFEBF00u;  // olc::Pixel{0x00,0xBF,0xFE} (test_och_h_octree.cpp:76)
+	uint32_t  inside_rgba = 0xFF07193Fu;// olc::Pixel{0x3F,0x19,0x07} (:77)
+
 	uint32_t* d_rcp = nullptr;
 	int       rcp_log2n = 0;
 
@@ -144,6 +149,12 @@ __global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restri
 	}
 }
 
+__global__ void fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t v, size_t n)
+{
+	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+	if (i < n) dst[i] = v;
+}
+
 // explicit rays: thread i traces ray i
 template<int VARIANT, bool COUNT>
 __global__ void __launch_bounds__(256)
@@ -197,6 +208,41 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
+
+// Shading epilogue (tree_camera::trace_pixel, test_och_h_octree.cpp:76-84) fused into the frame kernel: the hit is
+// turned into the pixel the demo would Draw() -- colours[6 * (voxel - 1) + face], the sky colour on exit, the
+// "inside" colour when the origin sits in a solid voxel -- and only that uint32 leaves the SM (4 B per pixel
+// instead of 9).  Voxel types beyond the palette (the reference reads past its array there) shade as 0.
+struct Palette
+{
+	const uint32_t* colours;
+	uint32_t n_voxels;
+	uint32_t exit_rgba, inside_rgba;
+};
+
+__global__ void __launch_bounds__(256)
+trace_frame_rgba_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
+                        Palette pal, uint32_t* __restrict__ rgba)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	const Hit h = traverse_variant<1, false>(nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray);
+
+	uint32_t px;
+	if (h.face == 6u) px = pal.exit_rgba;
+	else if (h.face == 7u) px = pal.inside_rgba;
+	else px = (h.voxel - 1u < pal.n_voxels) ? __ldg(pal.colours + 6u * (h.voxel - 1u) + h.face) : 0u;
+	rgba[static_cast<size_t>(r) * fr.W + x] = px;
+}
 
 // Experiment kernel for the "upper levels in shared memory" question: 1024-thread blocks (a 32 x 32 pixel tile,
 // warps still 8 x 4) copy the first n_staged nodes -- the top levels, a contiguous prefix of the level-ordered
@@ -468,6 +514,7 @@ int ort_destroy(ort_ctx* c)
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	cudaFree(c->d_nodes);
 	cudaFree(c->d_rcp);
+	cudaFree(c->d_palette);
 	cudaFree(c->d_counter);
 	cudaFree(c->d_stage);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -860,6 +907,100 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
 		ORT_CUDA(c, cudaMemcpyAsync(t + first, dt, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
 		ORT_CUDA(c, cudaMemcpyAsync(face + first, df, n, cudaMemcpyDeviceToHost, c->copy_stream));
 		if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush + first, dn, n * 2, cudaMemcpyDeviceToHost, c->copy_stream));
+		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+		used[slot] = true;
+		slot ^= 1;
+	}
+	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	return ORT_OK;
+}
+
+int ort_set_palette(ort_ctx* c, const uint32_t* rgba6, uint32_t n_voxels, uint32_t exit_rgba, uint32_t inside_rgba)
+{
+	if (!c || (n_voxels && !rgba6))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_set_palette: bad arguments");
+	DeviceGuard g(c->device);
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	cudaFree(c->d_palette);
+	c->d_palette = nullptr;
+	c->n_palette = 0;
+	if (n_voxels)
+	{
+		ORT_CUDA(c, cudaMalloc(&c->d_palette, static_cast<size_t>(n_voxels) * 24));
+		ORT_CUDA(c, cudaMemcpy(c->d_palette, rgba6, static_cast<size_t>(n_voxels) * 24, cudaMemcpyDefault));
+		c->n_palette = n_voxels;
+	}
+	c->exit_rgba = exit_rgba;
+	c->inside_rgba = inside_rgba;
+	return ORT_OK;
+}
+
+static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
+                             int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* d_rgba)
+{
+	const ort::Palette pal{ c->d_palette, c->n_palette, c->exit_rgba, c->inside_rgba };
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
+	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
+	if (!c->has_root)
+	{
+		// empty tree: every pixel is sky (update_image's first branch, test_och_h_octree.cpp:443-446)
+		const size_t n = static_cast<size_t>(rows) * W;
+		ort::fill_u32_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(d_rgba, c->exit_rgba, n);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
+	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
+	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
+	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
+	ort::trace_frame_rgba_kernel<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, pal, d_rgba);
+	++c->launches;
+	ORT_CUDA(c, cudaGetLastError());
+	return ORT_OK;
+}
+
+int ort_trace_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
+                         int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* rgba)
+{
+	if (!c || !pos || !rot || !rgba || W <= 0 || H <= 0 || rows < 0 || tile_rows <= 0 || tile_step <= 0 || y0 < 0)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame_rgba: bad arguments");
+	if (!rows) return ORT_OK;
+	DeviceGuard g(c->device);
+	if (is_device_ptr(rgba))
+		return launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, rgba);   // enqueue only
+
+	// host output: same geometric chunk pipeline as ort_trace_frame, one array
+	int gcd_ = 16, b_ = tile_rows;
+	while (b_) { const int r_ = gcd_ % b_; gcd_ = b_; b_ = r_; }
+	const int q = 16 / gcd_ * tile_rows;
+	static const int kParts[] = { 1, 2, 5, 8 };
+	int bounds[5] = { 0, 0, 0, 0, rows };
+	for (int k = 0, acc = 0; k < 3; ++k)
+	{
+		acc += kParts[k];
+		int r = static_cast<int>(static_cast<long long>(rows) * acc / 16) / q * q;
+		bounds[k + 1] = r < bounds[k] ? bounds[k] : r;
+	}
+	int max_rows = 0;
+	for (int k = 0; k < 4; ++k) max_rows = bounds[k + 1] - bounds[k] > max_rows ? bounds[k + 1] - bounds[k] : max_rows;
+	const size_t slot_bytes = align_up(static_cast<size_t>(max_rows) * W * 4, 256);
+	int rc = ensure_dstage(c, 2 * slot_bytes);
+	if (rc != ORT_OK) return rc;
+	char* base = static_cast<char*>(c->d_stage);
+	int slot = 0;
+	bool used[2] = { false, false };
+	for (int k = 0; k < 4; ++k)
+	{
+		const int r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
+		if (nr <= 0) continue;
+		uint32_t* d = reinterpret_cast<uint32_t*>(base + slot * slot_bytes);
+		if (used[slot]) ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+		rc = launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0 + (r0 / tile_rows) * tile_rows * tile_step, nr, tile_rows, tile_step, d);
+		if (rc != ORT_OK) return rc;
+		ORT_CUDA(c, cudaEventRecord(c->ev_chunk[slot], c->stream));
+		ORT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[slot], 0));
+		ORT_CUDA(c, cudaMemcpyAsync(rgba + static_cast<size_t>(r0) * W, d, static_cast<size_t>(nr) * W * 4, cudaMemcpyDeviceToHost, c->copy_stream));
 		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
 		used[slot] = true;
 		slot ^= 1;

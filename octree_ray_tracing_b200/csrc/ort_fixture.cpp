@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <cctype>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -238,6 +239,54 @@ static void assign_instance_counts(ort_tree* t)
 }
 
 extern "C" {
+
+int ort_parse_voxels(const char* text, size_t len, uint32_t* rgba6, char* names16, int max_voxels)
+{
+	// och_voxel.cpp:195-305: skip white space, read the name up to ':', then six colours of three hex byte pairs
+	if (!text || !rgba6 || max_voxels <= 0)
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: bad arguments"), -1;
+	size_t i = 0;
+	int n = 0;
+	auto skip_space = [&] { while (i < len && std::isspace(static_cast<unsigned char>(text[i]))) ++i; };
+	auto hexval = [](int c) { return c <= '9' ? c - '0' : (c | 0x20) - 'a' + 10; };
+	for (;;)
+	{
+		skip_space();
+		if (i >= len) break;
+		if (n == max_voxels) break;
+		char name[16] = { 0 };
+		int k = 0;
+		while (i < len && text[i] != ':')
+		{
+			if (k == 15)
+				return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: voxel-names may not exceed 15 characters (voxel %d)", n + 1), -1;
+			name[k++] = text[i++];
+		}
+		if (i >= len)
+			return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: input ended unexpectedly in the name of voxel %d", n + 1), -1;
+		if (k == 0)
+			return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: voxel-names must contain at least one character"), -1;
+		++i;   // ':'
+		for (int dir = 0; dir < 6; ++dir)
+		{
+			skip_space();
+			uint32_t px = 0xFF000000u;
+			for (int byte = 0; byte < 3; ++byte)
+			{
+				if (i + 1 >= len + 0 && i >= len)
+					return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: input ended unexpectedly (%s, colour %d)", name, dir + 1), -1;
+				if (i + 1 >= len || !std::isxdigit(static_cast<unsigned char>(text[i])) || !std::isxdigit(static_cast<unsigned char>(text[i + 1])))
+					return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: non-hex character in colour-value (%s at colour no. %d)", name, dir + 1), -1;
+				px |= static_cast<uint32_t>((hexval(text[i]) << 4) | hexval(text[i + 1])) << (8 * byte);
+				i += 2;
+			}
+			rgba6[6 * n + dir] = px;
+		}
+		if (names16) std::memcpy(names16 + 16 * n, name, 16);
+		++n;
+	}
+	return n;
+}
 
 void ort_fixture_heightmap(int depth, uint16_t* heights, int nthreads)
 {

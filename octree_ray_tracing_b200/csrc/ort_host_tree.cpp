@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
+#include <vector>
 
 namespace {
 
@@ -222,6 +224,148 @@ void ort_tree::set(uint16_t x, uint16_t y, uint16_t z, uint32_t v)
 	}
 
 	root = child;                                                // :236
+}
+
+// ------------------------------------------------------------------------------------------------
+// bulk box edit: the T/Z edit as one operation
+// ------------------------------------------------------------------------------------------------
+//
+// The reference applies a 40^3 edit as 64 000 set() calls, each a root-to-leaf copy-on-write (~0.5 M table inserts
+// and as many gravestones, 27-43 ms here, 96-137 ms in the reference).  Because the table is content-addressed, the
+// RESULT of that loop is a function of the final voxel content only: the canonical DAG plus, per node, its number
+// of instances in the expanded tree (what the refcounts count).  fill_box computes that result directly: it
+// recurses only into cells the box cuts, swaps cells the box covers for a memoised uniform subtree (or empty), and
+// moves instance counts level by level.  Live nodes, fillcnt, nodecnt, refcounts and traced images equal the
+// loop's; slot numbers of NEW nodes may differ (different insertion order, fewer gravestones on the probe paths).
+
+struct ort_tree::BoxEdit
+{
+	int lo[3], hi[3];
+	uint32_t v;
+	uint32_t uniform[17];     // memo: subtree of cell size 2^k holding only v
+};
+
+// refcount[slot] += delta with the reference's bookkeeping (gravestone at zero, saturation sticky)
+void ort_tree::count_one(uint32_t slot, int64_t delta)
+{
+	uint32_t& rc = refcounts[slot];
+	nodecnt += static_cast<uint32_t>(delta);
+	if (rc == UINT32_MAX)
+		return;
+	const int64_t nv = static_cast<int64_t>(rc) + delta;
+	if (nv >= static_cast<int64_t>(UINT32_MAX)) { rc = UINT32_MAX; return; }
+	rc = nv > 0 ? static_cast<uint32_t>(nv) : 0u;
+	if (rc == 0)
+	{
+		--fillcnt;
+		tags[slot] = 0xFF;
+		mark_dirty(slot);
+	}
+}
+
+// one subtree instance rooted at `id` (cell size 2^k) appears (delta > 0) or disappears (delta < 0): every node of
+// its DAG gains/loses as many instances as there are paths to it; aggregated per level so shared nodes are visited once
+void ort_tree::add_instances(uint32_t id, int k, int64_t delta)
+{
+	if (!id) return;
+	std::vector<std::pair<uint32_t, int64_t>> cur{ { id - 1, delta } }, next;
+	for (; k >= 1; --k)
+	{
+		next.clear();
+		for (const auto& [slot, d] : cur)
+		{
+			if (k > 1)
+			{
+				const uint32_t* n = nodes + 8 * static_cast<size_t>(slot);
+				for (int c = 0; c < 8; ++c)
+					if (n[c]) next.emplace_back(n[c] - 1, d);
+			}
+			count_one(slot, d);
+		}
+		if (k > 1)
+		{
+			std::sort(next.begin(), next.end());
+			size_t w = 0;
+			for (size_t i = 0; i < next.size(); ++i)
+			{
+				if (w && next[w - 1].first == next[i].first) next[w - 1].second += next[i].second;
+				else next[w++] = next[i];
+			}
+			next.resize(w);
+			cur.swap(next);
+		}
+	}
+}
+
+// returns the node that replaces `node` (0 = empty) for the cell [x, x+2^k)^3; instance counts of everything below
+// are already moved when it returns, the caller accounts for the returned node itself
+uint32_t ort_tree::fill_rec(BoxEdit& e, uint32_t node, int k, int x, int y, int z)
+{
+	const int s = 1 << k;
+	if (x >= e.hi[0] || y >= e.hi[1] || z >= e.hi[2] || x + s <= e.lo[0] || y + s <= e.lo[1] || z + s <= e.lo[2])
+		return node;                                              // untouched
+	if (x >= e.lo[0] && y >= e.lo[1] && z >= e.lo[2] && x + s <= e.hi[0] && y + s <= e.hi[1] && z + s <= e.hi[2])
+	{
+		uint32_t u = 0;                                           // covered: uniform subtree (or nothing)
+		if (e.v)
+		{
+			for (int j = 1; j <= k; ++j)
+				if (!e.uniform[j])
+				{
+					uint32_t n[8];
+					for (int c = 0; c < 8; ++c) n[c] = j == 1 ? e.v : e.uniform[j - 1];
+					e.uniform[j] = intern_node(n);
+					if (!e.uniform[j]) return node;               // table full: give up (flag is set)
+				}
+			u = e.uniform[k];
+		}
+		if (u == node) return node;
+		add_instances(u, k, +1);
+		add_instances(node, k, -1);
+		return u;
+	}
+
+	uint32_t n[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+	if (node) std::memcpy(n, nodes + 8 * static_cast<size_t>(node - 1), 32);
+	bool changed = false;
+	const int h = s >> 1;
+	for (int c = 0; c < 8; ++c)
+	{
+		const int cx = x + (c & 1 ? h : 0), cy = y + (c & 2 ? h : 0), cz = z + (c & 4 ? h : 0);
+		uint32_t nc;
+		if (k == 1)
+			nc = (cx >= e.lo[0] && cx < e.hi[0] && cy >= e.lo[1] && cy < e.hi[1] && cz >= e.lo[2] && cz < e.hi[2]) ? e.v : n[c];
+		else
+			nc = fill_rec(e, n[c], k - 1, cx, cy, cz);
+		changed |= nc != n[c];
+		n[c] = nc;
+	}
+	if (!changed)
+		return node;
+	uint32_t out = 0;
+	if (n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7])
+	{
+		out = intern_node(n);
+		if (!out) return node;
+		count_one(out - 1, +1);                                   // the new node first, so that out == node can never die in between
+	}
+	if (node) count_one(node - 1, -1);
+	return out;
+}
+
+void ort_tree::fill_box(const int lo[3], const int hi[3], uint32_t v)
+{
+	BoxEdit e;
+	const int dim = 1 << depth;
+	for (int a = 0; a < 3; ++a)
+	{
+		e.lo[a] = lo[a] < 0 ? 0 : lo[a];
+		e.hi[a] = hi[a] > dim ? dim : hi[a];
+		if (e.lo[a] >= e.hi[a]) return;
+	}
+	e.v = v;
+	std::memset(e.uniform, 0, sizeof e.uniform);
+	root = fill_rec(e, root, depth, 0, 0, 0);
 }
 
 uint32_t ort_tree::at(int x, int y, int z) const
@@ -514,6 +658,12 @@ void ort_tree_set_box(ort_tree* t, uint16_t cx, uint16_t cy, uint16_t cz, int ex
 		for (int y = -ext / 2; y < (ext + 1) / 2; ++y)
 			for (int x = -ext / 2; x < (ext + 1) / 2; ++x)
 				t->set(static_cast<uint16_t>(cx + x), static_cast<uint16_t>(cy + y), static_cast<uint16_t>(cz + z), v);
+}
+
+void ort_tree_fill_box(ort_tree* t, int x0, int y0, int z0, int x1, int y1, int z1, uint32_t v)
+{
+	const int lo[3] = { x0, y0, z0 }, hi[3] = { x1, y1, z1 };
+	t->fill_box(lo, hi, v);
 }
 
 uint32_t ort_tree_at(const ort_tree* t, int x, int y, int z) { return t->at(x, y, z); }

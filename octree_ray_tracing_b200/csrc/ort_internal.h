@@ -57,6 +57,9 @@ struct ort_tree
 	uint32_t intern_node(const uint32_t* n);
 	void     remove_node(uint32_t idx);
 	void     set(uint16_t x, uint16_t y, uint16_t z, uint32_t v);
+	// bulk edit: every voxel of [lo, hi) (clipped to the cube) becomes v; same content, counts and canonical DAG
+	// as the equivalent set() loop, without visiting the voxels one by one
+	void     fill_box(const int lo[3], const int hi[3], uint32_t v);
 	uint32_t at(int x, int y, int z) const;
 	void     clear();
 
@@ -68,6 +71,10 @@ struct ort_tree
 	void   clear_dirty();
 
 private:
+	struct BoxEdit;
+	uint32_t fill_rec(BoxEdit& e, uint32_t node, int k, int x, int y, int z);
+	void     add_instances(uint32_t id, int k, int64_t delta);
+	void     count_one(uint32_t slot, int64_t delta);
 	void     mark_dirty(uint32_t slot);
 	uint32_t probe(const uint32_t* n, uint8_t& tag, bool& found) const;
 	void     reset_ids();

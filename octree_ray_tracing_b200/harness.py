@@ -50,3 +50,26 @@ def random_rays(n: int, seed: int = 20261018):
     d = rs.normal(size=(n, 3))
     d /= np.linalg.norm(d, axis=1, keepdims=True)
     return o, d.astype(np.float32)
+
+
+# The demo's voxel types and face colours (the reference ships them as voxels.txt:1-30; face order x+ y+ z+ x- y- z-,
+# RRGGBB).  Voxel type ids are 1-based in this order (Stone = 1 ... Dirt = 4), as the terrain builder uses them.
+DEMO_VOXELS = """
+Stone:      44445D 4E4E5B 4E6155 2B352F 33333A 232328
+Grass:      5D2917 3D260F 4F2E14 603718 6D2E0D 3F8527
+Dark Grass: 5D2917 3D260F 4F2E14 603718 6D2E0D 317D1A
+Dirt:       5D2917 3D260F 4F2E14 603718 6D2E0D 56220F
+"""
+
+
+def parse_voxels(text: str, max_voxels: int = 256):
+    """(colours uint32[n,6] packed like olc::Pixel::n, names) from the reference's voxels.txt format."""
+    import ctypes as C
+    raw = text.encode()
+    cols = np.zeros((max_voxels, 6), np.uint32)
+    names = C.create_string_buffer(16 * max_voxels)
+    n = lib().ort_parse_voxels(raw, len(raw), _p(cols), names, max_voxels)
+    if n < 0:
+        msg = lib().ort_last_error(None)
+        raise ValueError(msg.decode() if msg else "malformed voxel file")
+    return cols[:n].copy(), [names.raw[16 * i:16 * i + 16].split(b"\0")[0].decode() for i in range(n)]

@@ -158,6 +158,22 @@ class TraceContext:
                                         _p(vox), _p(face), _p(t), _p(npush)))
         return (vox, face, t, npush) if want_npush else (vox, face, t)
 
+    # ---- shaded frames (trace_pixel's colour lookup fused into the kernel) -------------------------
+    def set_palette(self, rgba6, exit_rgba=0xFFFEBF00, inside_rgba=0xFF07193F):
+        a = np.ascontiguousarray(rgba6, np.uint32).reshape(-1, 6)
+        self._ck(self.L.ort_set_palette(self.h, _p(a), a.shape[0], exit_rgba, inside_rgba))
+
+    def trace_frame_rgba(self, pos, rot, fov_factor, W, H, y0=0, rows=None, tile_rows=1, tile_step=1, out=None):
+        """One uint32 pixel per ray (olc::Pixel::n packing).  out: host array / pinned tensor (synchronous) or a
+        CUDA tensor (enqueue only)."""
+        rows = H - y0 if rows is None else rows
+        pos = np.ascontiguousarray(pos, np.float32)
+        rot = np.ascontiguousarray(rot, np.float32)
+        if out is None:
+            out = np.empty(rows * W, np.uint32)
+        self._ck(self.L.ort_trace_frame_rgba(self.h, _p(pos), _p(rot), fov_factor, W, H, y0, rows, tile_rows, tile_step, _p(out)))
+        return out
+
     # ---- device-buffer, enqueue-only calls (pointers or torch CUDA tensors) ---------------------
     def trace_frame_async(self, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, d_vox, d_face, d_t, d_npush=None):
         pos = np.ascontiguousarray(pos, np.float32)
@@ -224,6 +240,12 @@ class HOctree:
     def set_box(self, cx: int, cy: int, cz: int, ext: int, v: int):
         """The T / Z edit: an ext^3 block of set() calls centred on (cx,cy,cz) (test_och_h_octree.cpp:408-413)."""
         self.L.ort_tree_set_box(self.h, cx & 0xFFFF, cy & 0xFFFF, cz & 0xFFFF, ext, v)
+        if self.L.ort_tree_table_full(self.h):
+            raise OrtError(4, "node table too full")
+
+    def fill_box(self, lo, hi, v: int):
+        """Bulk edit: voxels of [lo, hi) become v (same result as the set() loop, one pass; see ort_tree_fill_box)."""
+        self.L.ort_tree_fill_box(self.h, int(lo[0]), int(lo[1]), int(lo[2]), int(hi[0]), int(hi[1]), int(hi[2]), v)
         if self.L.ort_tree_table_full(self.h):
             raise OrtError(4, "node table too full")
 

@@ -186,3 +186,66 @@ def test_flatten_is_level_ordered(ort, oc):
         assert ch.min() >= lo[level] and ch.max() < lo[level + 1]
     leaf = nodes8[lo[7] - 1:]
     assert leaf.max() <= 4                           # voxel payloads, untranslated
+
+
+def test_fill_box_equals_the_set_loop(ort, oc):
+    """Bulk box edit: same voxels, live-node count, instance counts and traced image as the
+    reference's 64 000-set() loop -- on terrain, on an empty tree, clipped at the cube border, place and remove."""
+    depth, log2cap = 7, 18
+    h, g = oc.heightmap(depth), oc.grass_bits(depth)
+    A = oc.OracleTree(log2cap, depth)
+    A.initialize_terrain(h, g, True)
+    T = ort.HOctree(log2cap, depth, device=None)
+    ort.harness.build_terrain(T, h, g, tunnels=True)
+    E, F = oc.OracleTree(log2cap, depth), ort.HOctree(log2cap, depth, device=None)     # start empty
+    rs = np.random.RandomState(21)
+    rot, fov = oc.camera_coeffs(0.5, -0.7)
+    d = oc.gen_rays(rot, fov, 128, 72)
+    o = np.array([1.5, 1.5, 1.6], np.float32)
+    boxes = [((-5, 60, 20), (9, 75, 40), 1), ((100, 100, 30), (140, 140, 70), 2), ((0, 0, 0), (128, 128, 3), 0), ((64, 64, 0), (65, 65, 128), 7)]
+    boxes += [(tuple(c - e // 2), tuple(c + (e + 1) // 2), int(v)) for c, e, v in
+              ((rs.randint(0, 128, 3), int(rs.randint(1, 41)), rs.randint(0, 4)) for _ in range(14))]
+    for lo, hi, v in boxes:
+        ops = np.array([(x, y, z, v) for z in range(max(lo[2], 0), min(hi[2], 128)) for y in range(max(lo[1], 0), min(hi[1], 128))
+                        for x in range(max(lo[0], 0), min(hi[0], 128))], np.uint32).reshape(-1, 4)
+        for a, t in ((A, T), (E, F)):
+            a.set_many(ops)
+            t.fill_box(lo, hi, v)
+            assert (a.fillcnt, a.nodecnt) == (t.get_fillcnt(), t.get_nodecnt()), (lo, hi, v)
+            assert np.array_equal(np.sort(a.refcounts()[live_mask(a.cashes())]), np.sort(t.refcounts()[live_mask(t.cashes())]))
+        n8, r8, _ = T.flatten()
+        assert_same_hits(oc.trace_rays(n8, r8, depth, o, d), A.trace(o, d), f"box {lo} {hi} {v}")
+    for q in rs.randint(0, 128, (5000, 3)):
+        assert A.at(*q) == T.at(*q) and E.at(*q) == F.at(*q)
+    # single-voxel edits after bulk edits stay consistent (counts were exact)
+    ops = np.concatenate([rs.randint(0, 128, (3000, 3)), rs.randint(0, 3, (3000, 1))], 1).astype(np.uint32)
+    A.set_many(ops)
+    T.set_many(ops)
+    assert (A.fillcnt, A.nodecnt) == (T.get_fillcnt(), T.get_nodecnt())
+
+
+def test_fill_box_delta_stream(ort, oc):
+    """fill_box + take_delta drive a mirror exactly like set()-based edits do."""
+    depth, log2cap = 6, 16
+    h, g = oc.heightmap(depth), oc.grass_bits(depth)
+    A = oc.OracleTree(log2cap, depth)
+    A.initialize_terrain(h, g, False)
+    T = ort.HOctree(log2cap, depth, device=None)
+    ort.harness.build_terrain(T, h, g)
+    ids, nodes8, root, full = T.take_delta()
+    mirror = nodes8.copy()
+    rs = np.random.RandomState(3)
+    rot, fov = oc.camera_coeffs(0.3, -0.9)
+    d = oc.gen_rays(rot, fov, 96, 54)
+    o = np.array([1.5, 1.5, 1.8], np.float32)
+    for step in range(20):
+        c = rs.randint(4, 60, 3)
+        e = int(rs.randint(2, 14))
+        v = int(rs.randint(0, 3))
+        lo, hi = c - e // 2, c + (e + 1) // 2
+        T.fill_box(lo, hi, v)
+        A.set_many(np.array([(x, y, z, v) for z in range(max(lo[2], 0), min(hi[2], 64)) for y in range(max(lo[1], 0), min(hi[1], 64))
+                             for x in range(max(lo[0], 0), min(hi[0], 64))], np.uint32).reshape(-1, 4))
+        ids, nodes8, root, full = T.take_delta()
+        mirror = nodes8.copy() if full else apply_delta(mirror, ids, nodes8)
+        assert_same_hits(oc.trace_rays(mirror, root, depth, o, d), A.trace(o, d), f"step {step}")
