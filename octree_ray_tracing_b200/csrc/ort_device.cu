@@ -59,6 +59,7 @@ struct ort_ctx
 	int opt_variant = 1;                // 0 = baseline traverse(), 1 = traverse_fast() with fall-back
 	int opt_smem_levels = -1;
 	int opt_block = 256;
+	int opt_tile_shape = 0;
 	int opt_low_water = 20;             // persistent kernels refill when <= this many lanes are busy
 	int opt_rays_variant = 2;           // explicit rays: 2 = persistent refill
 	int sm_count = 0;
@@ -179,6 +180,7 @@ struct FrameRows
 {
 	int W, H;
 	int y0, rows, tile_rows, tile_step;
+	int tile_shape;     // warp tile: 0 = 8x4, 1 = 16x2, 2 = 4x8 (trace_frame_kernel only)
 };
 
 // camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
@@ -189,8 +191,11 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
                    uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	// warp tile inside the 16 x 16 block tile: 8x4 (default), or 16x2 / 4x8 for A/B measurements (fr.tile_shape)
+	int x, r;
+	if (fr.tile_shape == 1)      { x = blockIdx.x * 16 + (lane & 15);                   r = blockIdx.y * 16 + warp * 2 + (lane >> 4); }
+	else if (fr.tile_shape == 2) { x = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);   r = blockIdx.y * 16 + (warp >> 2) * 8 + (lane >> 2); }
+	else                         { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3); }
 	if (x >= fr.W || r >= fr.rows) return;
 	int y = fr.y0 + r;                                                 // contiguous strip
 	if (fr.tile_step != 1)                                             // cyclic tile strips (uniform branch)
@@ -242,6 +247,68 @@ trace_frame_rgba_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 	else if (h.face == 7u) px = pal.inside_rgba;
 	else px = (h.voxel - 1u < pal.n_voxels) ? __ldg(pal.colours + 6u * (h.voxel - 1u) + h.face) : 0u;
 	rgba[static_cast<size_t>(r) * fr.W + x] = px;
+}
+
+// Experiment kernel for the SIMT-efficiency question (variant 4): "deferred phases".  In the default kernel every
+// round of the loop runs the descend block for the lanes whose child exists AND the advance block for the lanes
+// whose child is empty -- each with about two thirds of the warp.  Here a phase that fewer than `threshold` lanes
+// want is postponed (those lanes keep their loaded child and wait) as long as the other phase has enough takers, in
+// the hope that the stragglers' phase fills up.  Costs two ballots per round.
+template<bool COUNT>
+__global__ void __launch_bounds__(256)
+trace_frame_deferred_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
+                            int threshold,
+                            uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	const bool valid = x < fr.W && r < fr.rows;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	uint32_t stack[kMaxDepth];
+	FastWalker<COUNT> w;
+	w.start(root, miss_t, ray);
+	int st = 0;                       // 0 load next child, 1 wants descend (child held), 2 wants advance, 3 finished
+	uint32_t child = 0;
+	if (!valid)
+		st = 3;
+	else if (!fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
+	{
+		w.hit = traverse(nodes_m1, root, depth, miss_t, ray, stack);
+		st = 3;
+	}
+
+	for (;;)
+	{
+		if (st == 0)
+		{
+			child = w.load_child(nodes_m1);
+			st = child ? 1 : 2;
+		}
+		const unsigned md = __ballot_sync(0xFFFFFFFFu, st == 1), ma = __ballot_sync(0xFFFFFFFFu, st == 2);
+		if ((md | ma) == 0u)
+			break;
+		const int nd = __popc(md), na = __popc(ma);
+		const bool run_d = nd >= threshold || na < threshold;
+		const bool run_a = na >= threshold || nd < threshold;
+		if (run_d && st == 1) st = w.descend(child, depth, stack) ? 3 : 0;
+		if (run_a && st == 2) st = w.advance(stack) ? 3 : 0;
+	}
+
+	if (valid)
+	{
+		const size_t i = static_cast<size_t>(r) * fr.W + x;
+		voxel[i] = w.hit.voxel;
+		face[i] = static_cast<uint8_t>(w.hit.face);
+		t[i] = w.hit.t;
+		if (COUNT) npush[i] = static_cast<uint16_t>(min(w.hit.npush, 65535u));
+	}
 }
 
 // Experiment kernel for the "upper levels in shared memory" question: 1024-thread blocks (a 32 x 32 pixel tile,
@@ -722,7 +789,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
 	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
-	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
 	if (c->opt_variant == 2)
 	{
@@ -734,6 +801,17 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 			ort::trace_persistent_kernel<true, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
 		else
 			ort::trace_persistent_kernel<false, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
+	if (c->opt_variant == 4)
+	{
+		const int thr = c->opt_low_water > 0 ? c->opt_low_water : 1;
+		if (npush)
+			ort::trace_frame_deferred_kernel<true><<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, thr, voxel, face, t, npush);
+		else
+			ort::trace_frame_deferred_kernel<false><<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, thr, voxel, face, t, npush);
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
@@ -940,7 +1018,7 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
                              int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* d_rgba)
 {
 	const ort::Palette pal{ c->d_palette, c->n_palette, c->exit_rgba, c->inside_rgba };
-	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step };
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0 };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
 	if (!c->has_root)
 	{
@@ -1039,6 +1117,7 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	else if (!std::strcmp(key, "smem_levels")) c->opt_smem_levels = value;
 	else if (!std::strcmp(key, "block")) c->opt_block = value;
 	else if (!std::strcmp(key, "low_water")) c->opt_low_water = value;
+	else if (!std::strcmp(key, "tile_shape")) c->opt_tile_shape = value;
 	else if (!std::strcmp(key, "rays_variant")) c->opt_rays_variant = value;
 	else return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: unknown key '%s'", key);
 	return ORT_OK;

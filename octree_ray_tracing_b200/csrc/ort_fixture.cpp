@@ -143,10 +143,38 @@ struct Builder
 	std::vector<std::vector<uint16_t>> hmin, hmax;    // [k] = min/max over 2^k x 2^k column blocks
 	uint32_t stone[17];                               // memoised all-stone subtree per cell size 2^k
 	bool failed = false;
+	std::vector<uint64_t> carved;                     // tunnels: one bit per voxel with z <= zmax, filled in parallel
+	int zmax = -1;
+
+	static inline bool carve_test(int x, int y, int z)   // splatter_noise(-0.5F, .., 1/16) on the global simplex_n(0.5F) (:755-763, :770)
+	{
+		return !(simplex3(0.5F, static_cast<float>(x) * (1.0F / 16.0F), static_cast<float>(y) * (1.0F / 16.0F), static_cast<float>(z) * (1.0F / 16.0F)) >= -0.5F);
+	}
+
+	// the dim^3 noise loop of remove() (:735-743) restricted to z <= max height (voxels above are empty anyway),
+	// spread over the host cores
+	void precompute_carved(int nthreads)
+	{
+		zmax = hmax[depth][0];
+		const size_t words_per_slab = (static_cast<size_t>(dim) * dim + 63) / 64;
+		carved.assign(words_per_slab * (zmax + 1), 0);
+		parallel_rows(zmax + 1, nthreads, [&](int z) {
+			uint64_t* slab = carved.data() + words_per_slab * z;
+			for (int y = 0; y < dim; ++y)
+				for (int x = 0; x < dim; ++x)
+					if (z <= h[static_cast<size_t>(y) * dim + x] && carve_test(x, y, z))
+					{
+						const size_t b = static_cast<size_t>(y) * dim + x;
+						slab[b >> 6] |= 1ull << (b & 63);
+					}
+		});
+	}
 
 	inline bool is_carved(int x, int y, int z) const
 	{
-		return !(simplex3(0.5F, static_cast<float>(x) * (1.0F / 16.0F), static_cast<float>(y) * (1.0F / 16.0F), static_cast<float>(z) * (1.0F / 16.0F)) >= -0.5F);
+		const size_t words_per_slab = (static_cast<size_t>(dim) * dim + 63) / 64;
+		const size_t b = static_cast<size_t>(y) * dim + x;
+		return (carved[words_per_slab * z + (b >> 6)] >> (b & 63)) & 1u;
 	}
 
 	inline uint32_t voxel(int x, int y, int z) const
@@ -306,7 +334,6 @@ int ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uin
 {
 	if (!tree || !heights || !grass)
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_fixture_build_terrain: bad arguments");
-	(void)nthreads;
 
 	Builder b;
 	b.tree = tree;
@@ -338,6 +365,8 @@ int ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uin
 			}
 	}
 
+	if (b.tunnels)
+		b.precompute_carved(nthreads > 0 ? nthreads : 1);
 	tree->root = b.build(0, 0, 0, b.depth);
 	if (b.failed || tree->table_full)
 		return ort_fail(nullptr, ORT_ERR_TABLE_FULL, "ort_fixture_build_terrain: node table too full (raise log2_table_capacity)");

@@ -251,38 +251,49 @@ struct FastWalker
 	__device__ __forceinline__ bool iterate_staged(const uint32_t* __restrict__ nodes_m1, int depth, uint32_t* stack,
 	                                               const uint32_t* s_nodes_m1, uint32_t n_staged)
 	{
+		const uint32_t child = load_child(nodes_m1, s_nodes_m1, n_staged);
+		return child ? descend(child, depth, stack) : advance(stack);
+	}
+
+	// PUSH's load (och_h_octree.h:344)
+	__device__ __forceinline__ uint32_t load_child(const uint32_t* __restrict__ nodes_m1, const uint32_t* s_nodes_m1 = nullptr, uint32_t n_staged = 0u)
+	{
 		if (COUNT) ++hit.npush;
 		const uint32_t word = node * 8u + (idx ^ inv);                             // id < 2^29: the word index fits 32 bits
-		uint32_t child;
 		if (n_staged != 0u && node <= n_staged)
-			child = s_nodes_m1[word];
-		else
-			child = __ldg(nodes_m1 + word);
+			return s_nodes_m1[word];
+		return __ldg(nodes_m1 + word);
+	}
 
-		if (child)
+	// PUSH with a non-empty child: HIT at the last level (returns true), else go down one level
+	__device__ __forceinline__ bool descend(uint32_t child, int depth, uint32_t* stack)
+	{
+		if (level == depth)
 		{
-			if (level == depth)
-			{
-				hit.voxel = child;
-				hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
-				hit.t = tmin;
-				return true;
-			}
-			stack[level - 1] = node | (idx << 29);
-			++level;
-			node = child;
-			dimf *= 0.5f;
-			const float mx = px + dimf, my = py + dimf, mz = pz + dimf;          // exact
-			const float tx = __fmaf_rn(mx, cx, bx);
-			const float ty = __fmaf_rn(my, cy, by);
-			const float tz = __fmaf_rn(mz, cz, bz);
-			idx = 0;
-			if (tx >= tmin) { px = mx; idx += 1u; }
-			if (ty >= tmin) { py = my; idx += 2u; }
-			if (tz >= tmin) { pz = mz; idx += 4u; }
-			return false;
+			hit.voxel = child;
+			hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
+			hit.t = tmin;
+			return true;
 		}
+		stack[level - 1] = node + (idx << 29);
+		++level;
+		node = child;
+		dimf *= 0.5f;
+		const float mx = px + dimf, my = py + dimf, mz = pz + dimf;          // exact
+		const float tx = __fmaf_rn(mx, cx, bx);
+		const float ty = __fmaf_rn(my, cy, by);
+		const float tz = __fmaf_rn(mz, cz, bz);
+		idx = 0;
+		if (tx >= tmin) { px = mx; idx += 1u; }
+		if (ty >= tmin) { py = my; idx += 2u; }
+		if (tz >= tmin) { pz = mz; idx += 4u; }
+		return false;
+	}
 
+	// PUSH with an empty child: STEP to the sibling across the nearest exit plane, POPping as far as needed;
+	// returns true on MISS
+	__device__ __forceinline__ bool advance(uint32_t* stack)
+	{
 		// the child slot is empty: leave this cell through its nearest exit plane
 		bool ax, ay;
 		for (;;)
