@@ -240,6 +240,15 @@ void ort_fixture_heightmap(int depth, uint16_t* heights, int nthreads);
  * with memoisation, so depth 12-14 take seconds.  The DAG is canonical, so it equals the
  * reference's up to slot numbering.  Returns ORT_OK or ORT_ERR_TABLE_FULL. */
 int  ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uint8_t* grass, int tunnels, int nthreads);
+/* Same, with the tunnel bitmap supplied by the caller (NULL: computed on the host threads).  carved: one bit per
+ * voxel for z <= max(heights): bit (y*dim + x) of slab z, slabs of (dim*dim + 63)/64 uint64 words; set = removed by
+ * remove(tree, splatter_noise(-0.5F, .., 1/16)) (test_och_h_octree.cpp:735-743, :755-763, :786). */
+int  ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const uint8_t* grass, int tunnels, int nthreads, const uint64_t* carved);
+/* The fixture's noise evaluations on the GPU, bit-identical to the host versions: the heightmap
+ * (get_terrain_heigth over the map, :561-566) and the tunnel bitmap in the layout above (depth 5..15; the dim^3 loop
+ * of :735-743 restricted to z <= zmax).  Outputs may be host or device pointers. */
+int  ort_fixture_heightmap_gpu(ort_ctx* ctx, int depth, uint16_t* heights);
+int  ort_fixture_carve_gpu(ort_ctx* ctx, int depth, const uint16_t* heights, int zmax, uint64_t* carved);
 
 #ifdef __cplusplus
 }

@@ -7,6 +7,7 @@
 #include "ort_internal.h"
 #include "ort_rcp_table.h"
 #include "ort_trace.cuh"
+#include "ort_noise.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -29,8 +30,15 @@ struct ort_ctx
 	cudaStream_t stream = nullptr;      // all kernels + uploads (own stream, or the caller's after ort_set_stream)
 	cudaStream_t own_stream = nullptr;
 	cudaStream_t copy_stream = nullptr; // D2H of finished chunks, overlapped with the next chunk's kernel
-	cudaEvent_t  ev_chunk[2] = { nullptr, nullptr };
-	cudaEvent_t  ev_copied[2] = { nullptr, nullptr };
+	cudaStream_t h2d_stream = nullptr;  // H2D of the next chunk's rays (host-buffer ort_trace_rays)
+	cudaEvent_t  ev_chunk[2] = { nullptr, nullptr };    // kernel of the chunk in slot i done
+	cudaEvent_t  ev_copied[2] = { nullptr, nullptr };   // slot i's results have reached the host
+	cudaEvent_t  ev_in[2] = { nullptr, nullptr };       // slot i's rays have reached the device
+	cudaStream_t aux_stream[3] = { nullptr, nullptr, nullptr };   // chunk kernels of host-buffer frames (their launch tails overlap)
+	cudaEvent_t  ev_fork = nullptr, ev_aux[3] = { nullptr, nullptr, nullptr };
+	cudaEvent_t  ev_part[8] = {};                         // kernel of chunk k of the current frame done
+	bool slot_used[2] = { false, false };
+	int  next_slot = 0;
 
 	uint32_t* d_nodes = nullptr;        // cap_nodes * 8
 	uint32_t  cap_nodes = 0;
@@ -60,6 +68,10 @@ struct ort_ctx
 	int opt_smem_levels = -1;
 	int opt_block = 256;
 	int opt_tile_shape = 0;
+	int opt_zero_copy = 0;              // pinned host outputs: 1 = the kernel stores straight into mapped host memory
+	int opt_frame_chunks = 0;           // host-buffer frames: launches per frame (0 = automatic)
+	int opt_defer_sync = 0;             // host-buffer calls return once enqueued; ort_sync() completes them
+	int opt_rays_chunk = 1 << 20;       // rays per pipeline stage of host-buffer ort_trace_rays
 	int opt_low_water = 20;             // persistent kernels refill when <= this many lanes are busy
 	int opt_rays_variant = 2;           // explicit rays: 2 = persistent refill
 	int sm_count = 0;
@@ -102,12 +114,39 @@ bool is_device_ptr(const void* p)
 	return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// device alias of a pinned (page-locked, mapped) host allocation, nullptr for anything else
+void* mapped_host_alias(const void* p)
+{
+	if (!p) return nullptr;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int ensure_dstage(ort_ctx* c, size_t bytes)
 {
 	if (bytes <= c->d_stage_bytes) return ORT_OK;
-	if (c->d_stage) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); cudaFree(c->d_stage); c->d_stage = nullptr; c->d_stage_bytes = 0; }
+	if (c->d_stage)
+	{
+		cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->h2d_stream);
+		cudaFree(c->d_stage); c->d_stage = nullptr; c->d_stage_bytes = 0;
+	}
+	c->slot_used[0] = c->slot_used[1] = false;
 	ORT_CUDA(c, cudaMalloc(&c->d_stage, bytes));
 	c->d_stage_bytes = bytes;
+	return ORT_OK;
+}
+
+// the two pipeline slots of the device staging buffer: halves of the current capacity, so that a slot of an
+// earlier (possibly still draining, see opt_defer_sync) call and a slot of this call never overlap
+inline char* stage_slot(ort_ctx* c, int slot) { return static_cast<char*>(c->d_stage) + slot * (c->d_stage_bytes / 2 / 256 * 256); }
+
+// end of a host-buffer call: wait for the results unless the caller asked to collect them with ort_sync()
+int finish_host_call(ort_ctx* c)
+{
+	if (c->opt_defer_sync) return ORT_OK;
+	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
 	return ORT_OK;
 }
 
@@ -249,6 +288,65 @@ trace_frame_rgba_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 	rgba[static_cast<size_t>(r) * fr.W + x] = px;
 }
 
+// Variants 5 / 6: TightWalker (leaner bookkeeping per round, see ort_trace.cuh).  WW = false keeps the
+// "if-if" round of the default kernel (one child load, then descend OR advance); WW = true is the "while-while"
+// shape: every lane first advances over empty child slots until it holds a non-empty child (or leaves the tree),
+// then the whole warp descends together.
+template<bool COUNT, bool WW>
+__global__ void __launch_bounds__(256)
+trace_frame_tight_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
+                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	uint32_t stack[kMaxDepth];
+	Hit h;
+	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
+	{
+		TightWalker<COUNT> w;
+		w.start(root, miss_t, ray);
+		if (WW)
+		{
+			for (;;)
+			{
+				uint32_t child;
+				bool done = false;
+				while ((child = w.load_child(nodes_m1)) == 0u)
+					if (w.advance(stack)) { done = true; break; }
+				if (done || w.descend(child, depth, stack))
+					break;
+			}
+		}
+		else
+		{
+			for (;;)
+			{
+				const uint32_t child = w.load_child(nodes_m1);
+				if (child ? w.descend(child, depth, stack) : w.advance(stack))
+					break;
+			}
+		}
+		h = w.hit;
+	}
+	else
+		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
+
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
 // Experiment kernel for the SIMT-efficiency question (variant 4): "deferred phases".  In the default kernel every
 // round of the loop runs the descend block for the lanes whose child exists AND the advance block for the lanes
 // whose child is empty -- each with about two thirds of the warp.  Here a phase that fewer than `threshold` lanes
@@ -358,6 +456,27 @@ trace_frame_staged_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, 
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
+// Fixture kernels: the noise evaluations of the demo's terrain set-up, one thread per column / voxel.
+// get_terrain_heigth over the whole map (test_och_h_octree.cpp:561-566, :587-592)
+__global__ void __launch_bounds__(256)
+fixture_heightmap_kernel(uint16_t* __restrict__ heights, int dim)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x < dim) heights[static_cast<size_t>(y) * dim + x] = ort_noise::terrain_height(x, y, dim);
+}
+
+// remove(tree, splatter_noise(-0.5F, .., 1/16))'s dim^3 test (:735-743, :755-763) for the voxels at or below the
+// surface: bit (y * dim + x) of slab z = "carved".  A warp covers 32 consecutive x and writes one 32-bit word.
+__global__ void __launch_bounds__(256)
+fixture_carve_kernel(const uint16_t* __restrict__ heights, int dim, uint32_t* __restrict__ bits, size_t words32_per_slab)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+	const bool carved = x < dim && z <= static_cast<int>(heights[static_cast<size_t>(y) * dim + x]) && ort_noise::carve_test(x, y, z);
+	const unsigned w = __ballot_sync(0xFFFFFFFFu, carved);
+	if ((threadIdx.x & 31u) == 0u && x < dim)
+		bits[static_cast<size_t>(z) * words32_per_slab + ((static_cast<size_t>(y) * dim + x) >> 5)] = w;
 }
 
 // Diagnostic: random 32-byte-sector gather over an L2-resident buffer -- the memory-side ceiling of a
@@ -548,8 +667,18 @@ int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
 	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
 	c->stream = c->own_stream;
 	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+	ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+	for (int i = 0; i < 3; ++i)
+	{
+		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
+	}
+	for (int i = 0; i < 8; ++i)
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_part[i], cudaEventDisableTiming));
 	for (int i = 0; i < 2; ++i)
 	{
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
 		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
 		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
 	}
@@ -579,6 +708,7 @@ int ort_destroy(ort_ctx* c)
 	DeviceGuard g(c->device);
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+	if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
 	cudaFree(c->d_nodes);
 	cudaFree(c->d_rcp);
 	cudaFree(c->d_palette);
@@ -588,10 +718,19 @@ int ort_destroy(ort_ctx* c)
 	for (int i = 0; i < 2; ++i)
 	{
 		if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
+		if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
 		if (c->ev_copied[i]) cudaEventDestroy(c->ev_copied[i]);
 	}
 	if (c->own_stream) cudaStreamDestroy(c->own_stream);
 	if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+	if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+	for (int i = 0; i < 3; ++i)
+	{
+		if (c->aux_stream[i]) { cudaStreamSynchronize(c->aux_stream[i]); cudaStreamDestroy(c->aux_stream[i]); }
+		if (c->ev_aux[i]) cudaEventDestroy(c->ev_aux[i]);
+	}
+	if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+	for (int i = 0; i < 8; ++i) if (c->ev_part[i]) cudaEventDestroy(c->ev_part[i]);
 	delete c;
 	return ORT_OK;
 }
@@ -805,6 +944,16 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
+	if (c->opt_variant == 5 || c->opt_variant == 6)
+	{
+		const bool ww = c->opt_variant == 6;
+		auto k = npush ? (ww ? ort::trace_frame_tight_kernel<true, true> : ort::trace_frame_tight_kernel<true, false>)
+		               : (ww ? ort::trace_frame_tight_kernel<false, true> : ort::trace_frame_tight_kernel<false, false>);
+		k<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
 	if (c->opt_variant == 4)
 	{
 		const int thr = c->opt_low_water > 0 ? c->opt_low_water : 1;
@@ -862,6 +1011,99 @@ struct StageLayout
 	}
 };
 
+static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
+                             int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* d_rgba);
+
+// Host outputs of a frame call (rgba != nullptr: shaded pixels, else voxel / face / t [/ npush]).
+//   * The rows are cut into kChunks chunks (borders on multiples of 16 rows and of tile_rows); a small first chunk gets
+//     the copy engine going early.  Each chunk is its own launch, on the auxiliary streams in turn, so the latency
+//     tail of one launch (a few grazing rays with hundreds of PUSHes) overlaps the bulk of the next instead of
+//     adding up; chunk k's results travel to the host on copy_stream as soon as its kernel is done.
+//   * Staging holds the whole frame, twice: with opt_defer_sync the next call's kernels run while this call's
+//     results are still crossing PCIe (9 B per ray at ~57 GB/s is slower than the trace).
+//   * ctx->stream is joined to the chunk kernels, so whatever the caller enqueues next (a delta upload) stays ordered.
+static int frame_to_host(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
+                         int W, int H, int y0, int rows, int tile_rows, int tile_step,
+                         uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, uint32_t* rgba)
+{
+	// chunk borders: a short first chunk, then growing ones (triangular weights).  Synchronous calls default to 8
+	// chunks; with opt_defer_sync the copy of one frame hides behind the next frame's kernels anyway, so 2 do.
+	constexpr int kMaxChunks = 8;
+	int kChunks = c->opt_frame_chunks > 0 ? c->opt_frame_chunks : (c->opt_defer_sync ? 2 : 8);
+	if (kChunks > kMaxChunks) kChunks = kMaxChunks;
+	int gcd_ = 16, b_ = tile_rows;
+	while (b_) { const int r_ = gcd_ % b_; gcd_ = b_; b_ = r_; }
+	const int q = 16 / gcd_ * tile_rows;                              // lcm(16, tile_rows)
+	int bounds[kMaxChunks + 1] = { 0 };
+	bounds[kChunks] = rows;
+	const int wsum = kChunks * (kChunks + 1) / 2;
+	for (int k = 0, acc = 0; k < kChunks - 1; ++k)
+	{
+		acc += k + 1;
+		const int r = static_cast<int>(static_cast<long long>(rows) * acc / wsum) / q * q;
+		bounds[k + 1] = r < bounds[k] ? bounds[k] : r;
+	}
+
+	const size_t n_all = static_cast<size_t>(rows) * W;
+	const StageLayout L(n_all);
+	const size_t slot_bytes = rgba ? align_up(n_all * 4, 256) : L.total;
+	int rc = ensure_dstage(c, 2 * slot_bytes);
+	if (rc != ORT_OK) return rc;
+	const int slot = c->next_slot;
+	c->next_slot ^= 1;
+	char* sb = stage_slot(c, slot);
+
+	cudaStream_t user = c->stream;
+	ORT_CUDA(c, cudaEventRecord(c->ev_fork, user));
+	for (int i = 0; i < 3; ++i)
+	{
+		ORT_CUDA(c, cudaStreamWaitEvent(c->aux_stream[i], c->ev_fork, 0));
+		if (c->slot_used[slot])
+			ORT_CUDA(c, cudaStreamWaitEvent(c->aux_stream[i], c->ev_copied[slot], 0));   // the slot's previous frame has left
+	}
+	const int n_streams = c->opt_variant == 2 ? 1 : 3;               // the persistent kernels share one work counter per context
+	int launched = 0;
+	for (int k = 0; k < kChunks; ++k)
+	{
+		const int r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
+		if (nr <= 0) continue;
+		const size_t n = static_cast<size_t>(nr) * W, first = static_cast<size_t>(r0) * W;
+		// rows r0.. of this call: same mapping with the chunk's first frame row as origin (r0 is a multiple of tile_rows)
+		const int cy0 = y0 + (r0 / tile_rows) * tile_rows * tile_step;
+		cudaStream_t ks = c->aux_stream[launched % n_streams];
+		++launched;
+		c->stream = ks;
+		if (rgba)
+			rc = launch_frame_rgba(c, pos, rot, fov_factor, W, H, cy0, nr, tile_rows, tile_step, reinterpret_cast<uint32_t*>(sb) + first);
+		else
+			rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, cy0, nr, tile_rows, tile_step,
+			                           reinterpret_cast<uint32_t*>(sb + L.off_v) + first, reinterpret_cast<uint8_t*>(sb + L.off_f) + first,
+			                           reinterpret_cast<float*>(sb + L.off_t) + first, npush ? reinterpret_cast<uint16_t*>(sb + L.off_np) + first : nullptr);
+		c->stream = user;
+		if (rc != ORT_OK) return rc;
+		ORT_CUDA(c, cudaEventRecord(c->ev_part[k], ks));
+		ORT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_part[k], 0));
+		if (rgba)
+			ORT_CUDA(c, cudaMemcpyAsync(rgba + first, reinterpret_cast<uint32_t*>(sb) + first, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+		else
+		{
+			ORT_CUDA(c, cudaMemcpyAsync(voxel + first, reinterpret_cast<uint32_t*>(sb + L.off_v) + first, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+			ORT_CUDA(c, cudaMemcpyAsync(t + first, reinterpret_cast<float*>(sb + L.off_t) + first, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+			ORT_CUDA(c, cudaMemcpyAsync(face + first, reinterpret_cast<uint8_t*>(sb + L.off_f) + first, n, cudaMemcpyDeviceToHost, c->copy_stream));
+			if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush + first, reinterpret_cast<uint16_t*>(sb + L.off_np) + first, n * 2, cudaMemcpyDeviceToHost, c->copy_stream));
+		}
+	}
+	ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+	ORT_CUDA(c, cudaEventRecord(c->ev_chunk[slot], c->copy_stream));      // (slot protocol of ort_trace_rays: "kernel done" is implied)
+	c->slot_used[slot] = true;
+	for (int i = 0; i < 3 && i < launched; ++i)
+	{
+		ORT_CUDA(c, cudaEventRecord(c->ev_aux[i], c->aux_stream[i]));
+		ORT_CUDA(c, cudaStreamWaitEvent(user, c->ev_aux[i], 0));
+	}
+	return finish_host_call(c);
+}
+
 int ort_trace_rays(ort_ctx* c, const float* o3, int o_stride, const float* d3, size_t n,
                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
 {
@@ -880,39 +1122,61 @@ int ort_trace_rays(ort_ctx* c, const float* o3, int o_stride, const float* d3, s
 		return ORT_OK;
 	}
 
-	// host buffers: stage in -> kernel -> stage out
-	const StageLayout L(n);
-	const size_t off_d = L.total, off_o = align_up(off_d + n * 12, 256);
-	const size_t o_bytes = o_stride ? n * 12 : 12;
-	int rc = ensure_dstage(c, off_o + align_up(o_bytes, 256));
+	// Host buffers: the rays are cut into chunks of opt_rays_chunk; chunk k+1's rays go H2D (h2d_stream) while
+	// chunk k is traced (stream) and chunk k-1's results go D2H (copy_stream) -- PCIe is full duplex, so the call
+	// costs about max(24 B/ray up, 9 B/ray down, kernel) instead of their sum.  Two staging slots.
+	const size_t chunk = static_cast<size_t>(c->opt_rays_chunk > 4096 ? c->opt_rays_chunk : 4096);
+	const size_t cn = n < chunk ? n : chunk;
+	const StageLayout L(cn);
+	const size_t off_d = L.total, off_o = align_up(off_d + cn * 12, 256);
+	const size_t slot_bytes = align_up(off_o + (o_stride ? cn * 12 : 12), 256);
+	int rc = ensure_dstage(c, 2 * slot_bytes);
 	if (rc != ORT_OK) return rc;
-	char* base = static_cast<char*>(c->d_stage);
 
-	const float* dd = d3;
-	const float* dorg = o3;
-	if (!in_dev)
+	for (size_t first = 0; first < n; first += cn)
 	{
-		ORT_CUDA(c, cudaMemcpyAsync(base + off_d, d3, n * 12, cudaMemcpyHostToDevice, c->stream));
-		ORT_CUDA(c, cudaMemcpyAsync(base + off_o, o3, o_bytes, cudaMemcpyHostToDevice, c->stream));
-		dd = reinterpret_cast<const float*>(base + off_d);
-		dorg = reinterpret_cast<const float*>(base + off_o);
-	}
-	uint32_t* dv = out_dev ? voxel : reinterpret_cast<uint32_t*>(base + L.off_v);
-	float*    dt = out_dev ? t : reinterpret_cast<float*>(base + L.off_t);
-	uint8_t*  df = out_dev ? face : reinterpret_cast<uint8_t*>(base + L.off_f);
-	uint16_t* dn = !npush ? nullptr : (out_dev ? npush : reinterpret_cast<uint16_t*>(base + L.off_np));
+		const size_t m = n - first < cn ? n - first : cn;
+		const int slot = c->next_slot;
+		c->next_slot ^= 1;
+		char* base = stage_slot(c, slot);
+		const float* dd = d3 + first * 3;
+		const float* dorg = o_stride ? o3 + first * 3 : o3;
+		if (!in_dev)
+		{
+			if (c->slot_used[slot])
+			{
+				ORT_CUDA(c, cudaStreamWaitEvent(c->h2d_stream, c->ev_chunk[slot], 0));    // the slot's previous kernel has read its rays
+				ORT_CUDA(c, cudaStreamWaitEvent(c->h2d_stream, c->ev_copied[slot], 0));   // (and its results have left)
+			}
+			ORT_CUDA(c, cudaMemcpyAsync(base + off_d, dd, m * 12, cudaMemcpyHostToDevice, c->h2d_stream));
+			ORT_CUDA(c, cudaMemcpyAsync(base + off_o, dorg, o_stride ? m * 12 : 12, cudaMemcpyHostToDevice, c->h2d_stream));
+			ORT_CUDA(c, cudaEventRecord(c->ev_in[slot], c->h2d_stream));
+			ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_in[slot], 0));
+			dd = reinterpret_cast<const float*>(base + off_d);
+			dorg = reinterpret_cast<const float*>(base + off_o);
+		}
+		if (!out_dev && c->slot_used[slot])
+			ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
+		uint32_t* dv = out_dev ? voxel + first : reinterpret_cast<uint32_t*>(base + L.off_v);
+		float*    dt = out_dev ? t + first : reinterpret_cast<float*>(base + L.off_t);
+		uint8_t*  df = out_dev ? face + first : reinterpret_cast<uint8_t*>(base + L.off_f);
+		uint16_t* dn = !npush ? nullptr : (out_dev ? npush + first : reinterpret_cast<uint16_t*>(base + L.off_np));
 
-	rc = ort_trace_rays_async(c, dorg, o_stride, dd, n, dv, df, dt, dn);
-	if (rc != ORT_OK) return rc;
-	if (!out_dev)
-	{
-		ORT_CUDA(c, cudaMemcpyAsync(voxel, dv, n * 4, cudaMemcpyDeviceToHost, c->stream));
-		ORT_CUDA(c, cudaMemcpyAsync(t, dt, n * 4, cudaMemcpyDeviceToHost, c->stream));
-		ORT_CUDA(c, cudaMemcpyAsync(face, df, n, cudaMemcpyDeviceToHost, c->stream));
-		if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush, dn, n * 2, cudaMemcpyDeviceToHost, c->stream));
+		rc = ort_trace_rays_async(c, dorg, o_stride, dd, m, dv, df, dt, dn);
+		if (rc != ORT_OK) return rc;
+		ORT_CUDA(c, cudaEventRecord(c->ev_chunk[slot], c->stream));
+		if (!out_dev)
+		{
+			ORT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[slot], 0));
+			ORT_CUDA(c, cudaMemcpyAsync(voxel + first, dv, m * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+			ORT_CUDA(c, cudaMemcpyAsync(t + first, dt, m * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+			ORT_CUDA(c, cudaMemcpyAsync(face + first, df, m, cudaMemcpyDeviceToHost, c->copy_stream));
+			if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush + first, dn, m * 2, cudaMemcpyDeviceToHost, c->copy_stream));
+		}
+		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
+		c->slot_used[slot] = true;
 	}
-	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
-	return ORT_OK;
+	return finish_host_call(c);
 }
 
 int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
@@ -933,65 +1197,23 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
 		return ORT_OK;
 	}
 
-	// Host outputs.  The rows are cut into chunks (multiples of 16 rows and of tile_rows); chunk k's results
-	// travel to the host on copy_stream while chunk k+1 is traced on stream (two staging slots).  PCIe, not
-	// the kernel, is the slow side (9 B per ray at ~57 GB/s vs > 10 Grays/s), so the schedule is geometric:
-	// a small first chunk gets the copy engine going early, later chunks grow (each kernel still finishes
-	// before the previous chunk's copy does) and the number of DMA pieces stays small.
-	int gcd_ = 16, b_ = tile_rows;
-	while (b_) { const int r_ = gcd_ % b_; gcd_ = b_; b_ = r_; }
-	const int q = 16 / gcd_ * tile_rows;                              // lcm(16, tile_rows): chunk borders fall on tile and block borders
-	static const int kParts[] = { 1, 2, 5, 8 };                    // sixteenths of the rows
-	int bounds[5] = { 0, 0, 0, 0, rows };
+	if (c->opt_zero_copy)
 	{
-		int acc = 0;
-		for (int k = 0; k < 3; ++k)
+		// pinned outputs: the kernel's stores go over PCIe as they are produced -- no staging, no copy engine
+		uint32_t* zv = static_cast<uint32_t*>(mapped_host_alias(voxel));
+		uint8_t*  zf = static_cast<uint8_t*>(mapped_host_alias(face));
+		float*    zt = static_cast<float*>(mapped_host_alias(t));
+		uint16_t* zn = npush ? static_cast<uint16_t*>(mapped_host_alias(npush)) : nullptr;
+		if (zv && zf && zt && (!npush || zn))
 		{
-			acc += kParts[k];
-			int r = static_cast<int>(static_cast<long long>(rows) * acc / 16);
-			r = r / q * q;
-			bounds[k + 1] = r < bounds[k] ? bounds[k] : r;
+			int rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, zv, zf, zt, zn);
+			if (rc != ORT_OK) return rc;
+			ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+			return ORT_OK;
 		}
 	}
-	int max_rows = 0;
-	for (int k = 0; k < 4; ++k) max_rows = bounds[k + 1] - bounds[k] > max_rows ? bounds[k + 1] - bounds[k] : max_rows;
-	const StageLayout L(static_cast<size_t>(max_rows) * W);
-	int rc = ensure_dstage(c, 2 * L.total);
-	if (rc != ORT_OK) return rc;
-	char* base = static_cast<char*>(c->d_stage);
 
-	int slot = 0;
-	bool used[2] = { false, false };
-	for (int k = 0; k < 4; ++k)
-	{
-		const int r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
-		if (nr <= 0) continue;
-		const size_t n = static_cast<size_t>(nr) * W, first = static_cast<size_t>(r0) * W;
-		char* s = base + slot * L.total;
-		uint32_t* dv = reinterpret_cast<uint32_t*>(s + L.off_v);
-		float*    dt = reinterpret_cast<float*>(s + L.off_t);
-		uint8_t*  df = reinterpret_cast<uint8_t*>(s + L.off_f);
-		uint16_t* dn = npush ? reinterpret_cast<uint16_t*>(s + L.off_np) : nullptr;
-
-		if (used[slot])
-			ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));   // slot's previous results have left
-		// rows r0.. of this call: same mapping with the chunk's first frame row as origin (r0 is a multiple of tile_rows)
-		const int cy0 = y0 + (r0 / tile_rows) * tile_rows * tile_step;
-		rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, cy0, nr, tile_rows, tile_step, dv, df, dt, dn);
-		if (rc != ORT_OK) return rc;
-		ORT_CUDA(c, cudaEventRecord(c->ev_chunk[slot], c->stream));
-		ORT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[slot], 0));
-		ORT_CUDA(c, cudaMemcpyAsync(voxel + first, dv, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-		ORT_CUDA(c, cudaMemcpyAsync(t + first, dt, n * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-		ORT_CUDA(c, cudaMemcpyAsync(face + first, df, n, cudaMemcpyDeviceToHost, c->copy_stream));
-		if (npush) ORT_CUDA(c, cudaMemcpyAsync(npush + first, dn, n * 2, cudaMemcpyDeviceToHost, c->copy_stream));
-		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
-		used[slot] = true;
-		slot ^= 1;
-	}
-	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
-	return ORT_OK;
+	return frame_to_host(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, voxel, face, t, npush, nullptr);
 }
 
 int ort_set_palette(ort_ctx* c, const uint32_t* rgba6, uint32_t n_voxels, uint32_t exit_rgba, uint32_t inside_rgba)
@@ -1048,43 +1270,83 @@ int ort_trace_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], flo
 	if (is_device_ptr(rgba))
 		return launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, rgba);   // enqueue only
 
-	// host output: same geometric chunk pipeline as ort_trace_frame, one array
-	int gcd_ = 16, b_ = tile_rows;
-	while (b_) { const int r_ = gcd_ % b_; gcd_ = b_; b_ = r_; }
-	const int q = 16 / gcd_ * tile_rows;
-	static const int kParts[] = { 1, 2, 5, 8 };
-	int bounds[5] = { 0, 0, 0, 0, rows };
-	for (int k = 0, acc = 0; k < 3; ++k)
+	if (c->opt_zero_copy)
+		if (uint32_t* z = static_cast<uint32_t*>(mapped_host_alias(rgba)))
+		{
+			int rc = launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, z);
+			if (rc != ORT_OK) return rc;
+			ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+			return ORT_OK;
+		}
+
+	return frame_to_host(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, nullptr, nullptr, nullptr, nullptr, rgba);
+}
+
+int ort_fixture_heightmap_gpu(ort_ctx* c, int depth, uint16_t* heights)
+{
+	if (!c || !heights || depth < 1 || depth > 15)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_fixture_heightmap_gpu: bad arguments");
+	DeviceGuard g(c->device);
+	const int dim = 1 << depth;
+	const size_t bytes = static_cast<size_t>(dim) * dim * 2;
+	const bool dev_out = is_device_ptr(heights);
+	uint16_t* d = heights;
+	if (!dev_out)
 	{
-		acc += kParts[k];
-		int r = static_cast<int>(static_cast<long long>(rows) * acc / 16) / q * q;
-		bounds[k + 1] = r < bounds[k] ? bounds[k] : r;
-	}
-	int max_rows = 0;
-	for (int k = 0; k < 4; ++k) max_rows = bounds[k + 1] - bounds[k] > max_rows ? bounds[k + 1] - bounds[k] : max_rows;
-	const size_t slot_bytes = align_up(static_cast<size_t>(max_rows) * W * 4, 256);
-	int rc = ensure_dstage(c, 2 * slot_bytes);
-	if (rc != ORT_OK) return rc;
-	char* base = static_cast<char*>(c->d_stage);
-	int slot = 0;
-	bool used[2] = { false, false };
-	for (int k = 0; k < 4; ++k)
-	{
-		const int r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
-		if (nr <= 0) continue;
-		uint32_t* d = reinterpret_cast<uint32_t*>(base + slot * slot_bytes);
-		if (used[slot]) ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[slot], 0));
-		rc = launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0 + (r0 / tile_rows) * tile_rows * tile_step, nr, tile_rows, tile_step, d);
+		int rc = ensure_dstage(c, bytes);
 		if (rc != ORT_OK) return rc;
-		ORT_CUDA(c, cudaEventRecord(c->ev_chunk[slot], c->stream));
-		ORT_CUDA(c, cudaStreamWaitEvent(c->copy_stream, c->ev_chunk[slot], 0));
-		ORT_CUDA(c, cudaMemcpyAsync(rgba + static_cast<size_t>(r0) * W, d, static_cast<size_t>(nr) * W * 4, cudaMemcpyDeviceToHost, c->copy_stream));
-		ORT_CUDA(c, cudaEventRecord(c->ev_copied[slot], c->copy_stream));
-		used[slot] = true;
-		slot ^= 1;
+		ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));      // the staging buffer may still be draining (opt_defer_sync)
+		d = static_cast<uint16_t*>(c->d_stage);
 	}
-	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+	const dim3 grid((dim + 255) / 256, dim);
+	ort::fixture_heightmap_kernel<<<grid, 256, 0, c->stream>>>(d, dim);
+	++c->launches;
+	ORT_CUDA(c, cudaGetLastError());
+	if (!dev_out)
+		ORT_CUDA(c, cudaMemcpyAsync(heights, d, bytes, cudaMemcpyDeviceToHost, c->stream));
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	return ORT_OK;
+}
+
+int ort_fixture_carve_gpu(ort_ctx* c, int depth, const uint16_t* heights, int zmax, uint64_t* carved)
+{
+	if (!c || !heights || !carved || depth < 5 || depth > 15 || zmax < 0 || zmax >= (1 << depth))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_fixture_carve_gpu: bad arguments (depth must be 5..15)");
+	DeviceGuard g(c->device);
+	const int dim = 1 << depth;
+	const size_t words64_per_slab = (static_cast<size_t>(dim) * dim + 63) / 64;
+	const size_t h_bytes = static_cast<size_t>(dim) * dim * 2;
+	const size_t out_bytes = words64_per_slab * 8 * (static_cast<size_t>(zmax) + 1);
+	const bool dev_h = is_device_ptr(heights), dev_out = is_device_ptr(carved);
+
+	uint16_t* d_h = nullptr;
+	uint32_t* d_bits = nullptr;
+	if (!dev_h)
+	{
+		ORT_CUDA(c, cudaMalloc(&d_h, h_bytes));
+		ORT_CUDA(c, cudaMemcpyAsync(d_h, heights, h_bytes, cudaMemcpyHostToDevice, c->stream));
+	}
+	if (!dev_out)
+	{
+		const cudaError_t e = cudaMalloc(&d_bits, out_bytes);
+		if (e != cudaSuccess) { cudaFree(d_h); return ort_fail(c, ORT_ERR_CUDA, "ort_fixture_carve_gpu: %zu bytes for the carve bitmap: %s", out_bytes, cudaGetErrorString(e)); }
+	}
+	uint32_t* bits = dev_out ? reinterpret_cast<uint32_t*>(carved) : d_bits;
+	// z goes into gridDim.z (<= 65535) in slices
+	for (int z0 = 0; z0 <= zmax; z0 += 32768)
+	{
+		const int nz = zmax + 1 - z0 < 32768 ? zmax + 1 - z0 : 32768;
+		const dim3 grid((dim + 255) / 256, dim, nz);
+		ort::fixture_carve_kernel<<<grid, 256, 0, c->stream>>>(dev_h ? heights : d_h, dim, bits + static_cast<size_t>(z0) * words64_per_slab * 2, words64_per_slab * 2);
+		++c->launches;
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e == cudaSuccess && !dev_out) e = cudaMemcpyAsync(carved, d_bits, out_bytes, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(d_h);
+	cudaFree(d_bits);
+	if (e != cudaSuccess)
+		return ort_fail(c, ORT_ERR_CUDA, "ort_fixture_carve_gpu: %s", cudaGetErrorString(e));
 	return ORT_OK;
 }
 
@@ -1092,6 +1354,7 @@ int ort_sync(ort_ctx* c)
 {
 	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_sync: null context");
 	DeviceGuard g(c->device);
+	ORT_CUDA(c, cudaStreamSynchronize(c->h2d_stream));
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
 	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	return ORT_OK;
@@ -1118,6 +1381,10 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	else if (!std::strcmp(key, "block")) c->opt_block = value;
 	else if (!std::strcmp(key, "low_water")) c->opt_low_water = value;
 	else if (!std::strcmp(key, "tile_shape")) c->opt_tile_shape = value;
+	else if (!std::strcmp(key, "zero_copy")) c->opt_zero_copy = value;
+	else if (!std::strcmp(key, "defer_sync")) c->opt_defer_sync = value;
+	else if (!std::strcmp(key, "frame_chunks")) c->opt_frame_chunks = value;
+	else if (!std::strcmp(key, "rays_chunk")) c->opt_rays_chunk = value;
 	else if (!std::strcmp(key, "rays_variant")) c->opt_rays_variant = value;
 	else return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: unknown key '%s'", key);
 	return ORT_OK;

@@ -16,6 +16,7 @@
 // are then computed top-down as instance counts, which is what the reference's per-instance
 // register_node calls add up to (saturating at 2^32-1 instead of wrapping for depth >= 13).
 #include "ort_internal.h"
+#include "ort_noise.h"
 
 #include <algorithm>
 #include <atomic>
@@ -26,99 +27,6 @@
 #include <thread>
 
 namespace {
-
-// ---- och::simplex_n (och_noise.h:18-367): Gustavson simplex noise in float, int truncation ----
-
-const uint8_t kPerm[256] = {
-	151, 160, 137, 91, 90, 15, 131, 13, 201, 95, 96, 53, 194, 233, 7, 225, 140, 36, 103, 30, 69, 142, 8, 99, 37, 240, 21, 10, 23, 190, 6, 148,
-	247, 120, 234, 75, 0, 26, 197, 62, 94, 252, 219, 203, 117, 35, 11, 32, 57, 177, 33, 88, 237, 149, 56, 87, 174, 20, 125, 136, 171, 168, 68, 175,
-	74, 165, 71, 134, 139, 48, 27, 166, 77, 146, 158, 231, 83, 111, 229, 122, 60, 211, 133, 230, 220, 105, 92, 41, 55, 46, 245, 40, 244, 102, 143, 54,
-	65, 25, 63, 161, 1, 216, 80, 73, 209, 76, 132, 187, 208, 89, 18, 169, 200, 196, 135, 130, 116, 188, 159, 86, 164, 100, 109, 198, 173, 186, 3, 64,
-	52, 217, 226, 250, 124, 123, 5, 202, 38, 147, 118, 126, 255, 82, 85, 212, 207, 206, 59, 227, 47, 16, 58, 17, 182, 189, 28, 42, 223, 183, 170, 213,
-	119, 248, 152, 2, 44, 154, 163, 70, 221, 153, 101, 155, 167, 43, 172, 9, 129, 22, 39, 253, 19, 98, 108, 110, 79, 113, 224, 232, 178, 185, 112, 104,
-	218, 246, 97, 228, 251, 34, 242, 193, 238, 210, 144, 12, 191, 179, 162, 241, 81, 51, 145, 235, 249, 14, 239, 107, 49, 192, 214, 31, 181, 199, 106, 157,
-	184, 84, 204, 176, 115, 121, 50, 45, 127, 4, 150, 254, 138, 236, 205, 93, 222, 114, 67, 29, 24, 72, 243, 141, 128, 195, 78, 66, 215, 61, 156, 180
-};
-
-struct G3 { float x, y, z; };
-const G3 kGrad[12] = {
-	{ 1, 1, 0 }, { -1, 1, 0 }, { 1, -1, 0 }, { -1, -1, 0 }, { 1, 0, 1 }, { -1, 0, 1 },
-	{ 1, 0, -1 }, { -1, 0, -1 }, { 0, 1, 1 }, { 0, -1, 1 }, { 0, 1, -1 }, { 0, -1, -1 }
-};
-
-inline int P(int i) { return kPerm[i & 255]; }
-
-inline float falloff2(float x, float y, int g)
-{
-	float t = 0.5F - x * x - y * y;
-	if (t < 0) return 0.0F;
-	t *= t;
-	return t * t * (kGrad[g].x * x + kGrad[g].y * y);
-}
-
-float simplex2(float freq, float x, float y)                     // och_noise.h:73-179
-{
-	x *= freq;
-	y *= freq;
-	const float F2 = 0.5F * (0.73205078F);
-	const float G2 = (3.0F - 1.73205078F) / 6.0F;
-	const float s = (x + y) * F2;
-	const int i = static_cast<int>(x + s), j = static_cast<int>(y + s);
-	const float t = static_cast<float>(i + j) * G2;
-	const float x0 = x - (static_cast<float>(i) - t), y0 = y - (static_cast<float>(j) - t);
-	const int di = x0 > y0 ? 1 : 0, dj = 1 - di;
-	const float x1 = x0 - static_cast<float>(di) + G2, y1 = y0 - static_cast<float>(dj) + G2;
-	const float x2 = x0 - 1.0F + 2.0F * G2, y2 = y0 - 1.0F + 2.0F * G2;
-	const int ii = i & 255, jj = j & 255;
-	const float n0 = falloff2(x0, y0, P(ii + P(jj)) % 12);
-	const float n1 = falloff2(x1, y1, P(ii + di + P(jj + dj)) % 12);
-	const float n2 = falloff2(x2, y2, P(ii + 1 + P(jj + 1)) % 12);
-	return 70.0F * (n0 + n1 + n2);
-}
-
-inline float falloff3(float x, float y, float z, int g)
-{
-	float t = 0.6F - x * x - y * y - z * z;
-	if (t < 0) return 0.0F;
-	t *= t;
-	return t * t * (kGrad[g].x * x + kGrad[g].y * y + kGrad[g].z * z);
-}
-
-float simplex3(float freq, float x, float y, float z)            // och_noise.h:181-366
-{
-	x *= freq; y *= freq; z *= freq;
-	const float F3 = 1.0F / 3.0F, G3c = 1.0F / 6.0F;
-	const float s = (x + y + z) * F3;
-	const int i = static_cast<int>(x + s), j = static_cast<int>(y + s), k = static_cast<int>(z + s);
-	const float t = static_cast<float>(i + j + k) * G3c;
-	const float x0 = x - (static_cast<float>(i) - t), y0 = y - (static_cast<float>(j) - t), z0 = z - (static_cast<float>(k) - t);
-
-	// rank the three offsets; the second corner steps along the largest, the third along the two largest,
-	// with the reference's tie rules (:224-281)
-	int a1, b1, c1, a2, b2, c2;
-	if (x0 >= y0)
-	{
-		if (y0 >= z0)      { a1 = 1; b1 = 0; c1 = 0; a2 = 1; b2 = 1; c2 = 0; }
-		else if (x0 >= z0) { a1 = 1; b1 = 0; c1 = 0; a2 = 1; b2 = 0; c2 = 1; }
-		else               { a1 = 0; b1 = 0; c1 = 1; a2 = 1; b2 = 0; c2 = 1; }
-	}
-	else
-	{
-		if (y0 < z0)       { a1 = 0; b1 = 0; c1 = 1; a2 = 0; b2 = 1; c2 = 1; }
-		else if (x0 < z0)  { a1 = 0; b1 = 1; c1 = 0; a2 = 0; b2 = 1; c2 = 1; }
-		else               { a1 = 0; b1 = 1; c1 = 0; a2 = 1; b2 = 1; c2 = 0; }
-	}
-
-	const float x1 = x0 - static_cast<float>(a1) + G3c, y1 = y0 - static_cast<float>(b1) + G3c, z1 = z0 - static_cast<float>(c1) + G3c;
-	const float x2 = x0 - static_cast<float>(a2) + G3c * 2.0F, y2 = y0 - static_cast<float>(b2) + G3c * 2.0F, z2 = z0 - static_cast<float>(c2) + G3c * 2.0F;
-	const float x3 = x0 - 1.0F + G3c * 3.0F, y3 = y0 - 1.0F + G3c * 3.0F, z3 = z0 - 1.0F + G3c * 3.0F;
-	const int ii = i & 255, jj = j & 255, kk = k & 255;
-	const float n0 = falloff3(x0, y0, z0, P(ii + P(jj + P(kk))) % 12);
-	const float n1 = falloff3(x1, y1, z1, P(ii + a1 + P(jj + b1 + P(kk + c1))) % 12);
-	const float n2 = falloff3(x2, y2, z2, P(ii + a2 + P(jj + b2 + P(kk + c2))) % 12);
-	const float n3 = falloff3(x3, y3, z3, P(ii + 1 + P(jj + 1 + P(kk + 1))) % 12);
-	return 32.0F * (n0 + n1 + n2 + n3);
-}
 
 template<class F>
 void parallel_rows(int rows, int nthreads, F f)
@@ -143,31 +51,71 @@ struct Builder
 	std::vector<std::vector<uint16_t>> hmin, hmax;    // [k] = min/max over 2^k x 2^k column blocks
 	uint32_t stone[17];                               // memoised all-stone subtree per cell size 2^k
 	bool failed = false;
-	std::vector<uint64_t> carved;                     // tunnels: one bit per voxel with z <= zmax, filled in parallel
+	std::vector<uint64_t> carved_own;                 // tunnels: one bit per voxel with z <= zmax (bit y*dim+x of slab z)
+	const uint64_t* carved = nullptr;                 // = carved_own.data(), or the caller's bitmap (ort_fixture_carve_gpu)
+	std::vector<std::vector<uint8_t>> any;            // [k >= 3]: cell of size 2^k holds at least one carved voxel
 	int zmax = -1;
-
-	static inline bool carve_test(int x, int y, int z)   // splatter_noise(-0.5F, .., 1/16) on the global simplex_n(0.5F) (:755-763, :770)
-	{
-		return !(simplex3(0.5F, static_cast<float>(x) * (1.0F / 16.0F), static_cast<float>(y) * (1.0F / 16.0F), static_cast<float>(z) * (1.0F / 16.0F)) >= -0.5F);
-	}
 
 	// the dim^3 noise loop of remove() (:735-743) restricted to z <= max height (voxels above are empty anyway),
 	// spread over the host cores
 	void precompute_carved(int nthreads)
 	{
-		zmax = hmax[depth][0];
 		const size_t words_per_slab = (static_cast<size_t>(dim) * dim + 63) / 64;
-		carved.assign(words_per_slab * (zmax + 1), 0);
+		carved_own.assign(words_per_slab * (zmax + 1), 0);
 		parallel_rows(zmax + 1, nthreads, [&](int z) {
-			uint64_t* slab = carved.data() + words_per_slab * z;
+			uint64_t* slab = carved_own.data() + words_per_slab * z;
 			for (int y = 0; y < dim; ++y)
 				for (int x = 0; x < dim; ++x)
-					if (z <= h[static_cast<size_t>(y) * dim + x] && carve_test(x, y, z))
+					if (z <= h[static_cast<size_t>(y) * dim + x] && ort_noise::carve_test(x, y, z))
 					{
 						const size_t b = static_cast<size_t>(y) * dim + x;
 						slab[b >> 6] |= 1ull << (b & 63);
 					}
 		});
+		carved = carved_own.data();
+	}
+
+	// "any carved voxel in the cell" per 8^3 cell from the bitmap, OR-reduced up the levels: cells without carving
+	// are built like the tunnel-free terrain (memoised stone, empty above the surface)
+	void build_any_pyramid(int nthreads)
+	{
+		any.assign(depth + 1, {});
+		if (depth < 3) return;
+		const size_t words_per_slab = (static_cast<size_t>(dim) * dim + 63) / 64;
+		const uint8_t* bytes = reinterpret_cast<const uint8_t*>(carved);
+		const int w = dim >> 3, nz = (zmax >> 3) + 1;
+		any[3].assign(static_cast<size_t>(w) * w * nz, 0);
+		parallel_rows(nz, nthreads, [&](int cz) {
+			uint8_t* out = any[3].data() + static_cast<size_t>(cz) * w * w;
+			for (int z = cz * 8; z < cz * 8 + 8 && z <= zmax; ++z)
+			{
+				const uint8_t* slab = bytes + words_per_slab * 8 * z;          // byte (y*dim + x) / 8: 8 voxels along x
+				for (int y = 0; y < dim; ++y)
+				{
+					const uint8_t* row = slab + (static_cast<size_t>(y) * dim >> 3);
+					uint8_t* orow = out + static_cast<size_t>(y >> 3) * w;
+					for (int cx = 0; cx < w; ++cx) orow[cx] |= row[cx];
+				}
+			}
+		});
+		for (int k = 4; k <= depth; ++k)
+		{
+			const int wk = dim >> k, wp = wk * 2, nzk = (zmax >> k) + 1, nzp = (zmax >> (k - 1)) + 1;
+			any[k].assign(static_cast<size_t>(wk) * wk * nzk, 0);
+			const auto& lo = any[k - 1];
+			for (int cz = 0; cz < nzp; ++cz)
+				for (int cy = 0; cy < wp; ++cy)
+					for (int cx = 0; cx < wp; ++cx)
+						if (lo[(static_cast<size_t>(cz) * wp + cy) * wp + cx])
+							any[k][(static_cast<size_t>(cz >> 1) * wk + (cy >> 1)) * wk + (cx >> 1)] = 1;
+		}
+	}
+
+	inline bool cell_carved(int x, int y, int z, int k) const     // may the cell [.., +2^k)^3 (z <= zmax) contain a carved voxel?
+	{
+		if (k < 3) return true;
+		const int wk = dim >> k;
+		return any[k][(static_cast<size_t>(z >> k) * wk + (y >> k)) * wk + (x >> k)] != 0;
 	}
 
 	inline bool is_carved(int x, int y, int z) const
@@ -212,7 +160,7 @@ struct Builder
 		const size_t bi = static_cast<size_t>(y >> k) * (dim >> k) + (x >> k);
 		if (z > hmax[k][bi])
 			return 0;                                  // entirely above the terrain
-		if (!tunnels && z + s - 1 < static_cast<int>(hmin[k][bi]) - 2)
+		if (z + s - 1 < static_cast<int>(hmin[k][bi]) - 2 && !(tunnels && cell_carved(x, y, z, k)))
 			return stone_node(k);                      // entirely plain stone
 
 		uint32_t n[8];
@@ -322,15 +270,17 @@ void ort_fixture_heightmap(int depth, uint16_t* heights, int nthreads)
 	parallel_rows(dim, nthreads, [&](int y) {
 		for (int x = 0; x < dim; ++x)
 		{
-			// get_terrain_heigth (test_och_h_octree.cpp:561-566) with noise = simplex_n(0.5F) (:35)
-			const float px = static_cast<float>(x * 4) / static_cast<float>(dim);
-			const float py = static_cast<float>(y * 4) / static_cast<float>(dim);
-			heights[static_cast<size_t>(y) * dim + x] = static_cast<uint16_t>(static_cast<int>(simplex2(0.5F, px, py) * static_cast<float>(dim) / 16 + static_cast<float>(dim / 4)));
+			heights[static_cast<size_t>(y) * dim + x] = ort_noise::terrain_height(x, y, dim);
 		}
 	});
 }
 
 int ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uint8_t* grass, int tunnels, int nthreads)
+{
+	return ort_fixture_build_terrain_ex(tree, heights, grass, tunnels, nthreads, nullptr);
+}
+
+int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const uint8_t* grass, int tunnels, int nthreads, const uint64_t* carved)
 {
 	if (!tree || !heights || !grass)
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_fixture_build_terrain: bad arguments");
@@ -366,7 +316,12 @@ int ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uin
 	}
 
 	if (b.tunnels)
-		b.precompute_carved(nthreads > 0 ? nthreads : 1);
+	{
+		b.zmax = b.hmax[b.depth][0];
+		if (carved) b.carved = carved;
+		else b.precompute_carved(nthreads > 0 ? nthreads : 1);
+		b.build_any_pyramid(nthreads > 0 ? nthreads : 1);
+	}
 	tree->root = b.build(0, 0, 0, b.depth);
 	if (b.failed || tree->table_full)
 		return ort_fail(nullptr, ORT_ERR_TABLE_FULL, "ort_fixture_build_terrain: node table too full (raise log2_table_capacity)");

@@ -363,6 +363,149 @@ struct FastWalker
 	}
 };
 
+// ------------------------------------------------------------------------------------------------
+// Tight variant.  Same decisions and the same FMAs as FastWalker; what changes is bookkeeping that the SASS of
+// FastWalker's loop showed to be avoidable (profiles/r1_v4_ncu_full.md: the loop is issue-bound, so every
+// instruction of the round counts):
+//   * the node is carried as its word index (id * 8): the child-slot address is one LOP3 (node8 | (idx ^ inv))
+//     plus the 64-bit scale-add, and a parent-stack entry is node8 | idx (the low three bits are free), so POP
+//     restores node and idx with two masks and ids are no longer squeezed below 2^29 by the stack format
+//     (the 32-bit word index still caps ids at 2^29);
+//   * the step to the sibling is three predicated FADDs instead of an if / else-if ladder;
+//   * the child index after a descend is assembled from the three compares without a branch.
+// ------------------------------------------------------------------------------------------------
+template<bool COUNT>
+struct TightWalker
+{
+	uint32_t node8, idx, inv, mti;
+	int      level;
+	float    px, py, pz, dimf, tmin;
+	float    cx, cy, cz, bx, by, bz;
+	float    miss_t;
+	Hit      hit;
+
+	__device__ __forceinline__ void start(uint32_t root, float miss_time, const Ray& r)
+	{
+		node8 = root << 3;
+		miss_t = miss_time;
+		level = 1;
+		idx = r.idx;
+		inv = r.inv;
+		px = __uint_as_float(r.px); py = __uint_as_float(r.py); pz = __uint_as_float(r.pz);
+		dimf = 0.5f;
+		tmin = 0.0f;
+		mti = 8;
+		hit.npush = 0;
+		cx = r.cx; cy = r.cy; cz = r.cz; bx = r.bx; by = r.by; bz = r.bz;
+		const float ninf = __uint_as_float(0xFF800000u);      // degenerate axes: see FastWalker
+		if (cx == ninf) { cx = 0.0f; bx = ninf; }
+		if (cy == ninf) { cy = 0.0f; by = ninf; }
+		if (cz == ninf) { cz = 0.0f; bz = ninf; }
+	}
+
+	__device__ __forceinline__ void miss()
+	{
+		hit.voxel = 0;
+		hit.face = 6;
+		hit.t = miss_t;
+	}
+
+	// PUSH's load (och_h_octree.h:344)
+	__device__ __forceinline__ uint32_t load_child(const uint32_t* __restrict__ nodes_m1)
+	{
+		if (COUNT) ++hit.npush;
+		return __ldg(nodes_m1 + (node8 | (idx ^ inv)));
+	}
+
+	// PUSH with a non-empty child: HIT at the last level (returns true), else go down one level
+	__device__ __forceinline__ bool descend(uint32_t child, int depth, uint32_t* stack)
+	{
+		if (level == depth)
+		{
+			hit.voxel = child;
+			hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
+			hit.t = tmin;
+			return true;
+		}
+		stack[level - 1] = node8 | idx;
+		++level;
+		node8 = child << 3;
+		dimf *= 0.5f;
+		const float mx = px + dimf, my = py + dimf, mz = pz + dimf;          // exact
+		const bool ux = __fmaf_rn(mx, cx, bx) >= tmin;
+		const bool uy = __fmaf_rn(my, cy, by) >= tmin;
+		const bool uz = __fmaf_rn(mz, cz, bz) >= tmin;
+		px = ux ? mx : px;
+		py = uy ? my : py;
+		pz = uz ? mz : pz;
+		idx = static_cast<uint32_t>(ux) | (static_cast<uint32_t>(uy) << 1) | (static_cast<uint32_t>(uz) << 2);
+		return false;
+	}
+
+	// PUSH with an empty child: STEP to the sibling across the nearest exit plane, POPping as far as needed;
+	// returns true on MISS
+	__device__ __forceinline__ bool advance(const uint32_t* stack)
+	{
+		bool ax, ay;
+		for (;;)
+		{
+			const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
+			const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
+			const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
+			const uint32_t tyz = min(ty, tz);
+			ax = tx <= tyz;                                                     // unsigned argmin, ties -> x, y, z (:388-406)
+			ay = !ax && ty <= tz;
+			tmin = __uint_as_float(min(tx, tyz));
+			mti = ax ? 1u : (ay ? 2u : 4u);
+
+			if (idx & mti)
+				break;                                                          // a sibling lies that way
+
+			if (((tx | ty | tz) & 0x80000000u) == 0u)
+			{
+				// multi-level POP (proof in FastWalker::advance)
+				const uint32_t pa = __float_as_uint(ax ? px : (ay ? py : pz));
+				level -= __ffs(static_cast<int>(pa >> (24 - level)));
+				if (level == 0)
+				{
+					miss();
+					return true;
+				}
+				const uint32_t keep = 0xFFFFFFFFu << (23 - level);
+				px = __uint_as_float(__float_as_uint(px) & keep);
+				py = __uint_as_float(__float_as_uint(py) & keep);
+				pz = __uint_as_float(__float_as_uint(pz) & keep);
+				dimf = __uint_as_float(static_cast<uint32_t>(127 - level) << 23);
+				const uint32_t e = stack[level - 1];
+				node8 = e & ~7u;
+				idx = e & 7u;                                                   // bit a* is set there
+				break;
+			}
+
+			if (--level == 0)
+			{
+				miss();
+				return true;
+			}
+			if (idx & 1u) px -= dimf;                                           // back to the parent's corner
+			if (idx & 2u) py -= dimf;
+			if (idx & 4u) pz -= dimf;
+			dimf += dimf;
+			const uint32_t e = stack[level - 1];
+			node8 = e & ~7u;
+			idx = e & 7u;
+		}
+
+		// step to the sibling across the exit plane (exact: the bit is set)
+		const bool az = !(ax | ay);
+		if (ax) px -= dimf;
+		if (ay) py -= dimf;
+		if (az) pz -= dimf;
+		idx ^= mti;
+		return false;
+	}
+};
+
 template<bool COUNT>
 __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, const Ray& r, uint32_t* stack)
 {

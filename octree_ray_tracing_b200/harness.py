@@ -31,11 +31,41 @@ def grass_bits(depth: int, seed: int = 1) -> np.ndarray:
     return np.random.RandomState(seed).randint(0, 2, size=(dim, dim)).astype(np.uint8)
 
 
-def build_terrain(tree: HOctree, heights=None, grass=None, tunnels: bool = False, nthreads: int | None = None):
-    """initialize_h_octree's voxel content (:767-787) through the memoising builder."""
-    heights = heightmap(tree.depth, nthreads) if heights is None else np.ascontiguousarray(heights, np.uint16)
+def heightmap_gpu(ctx, depth: int) -> np.ndarray:
+    """The same map from the CUDA kernel (bit-identical)."""
+    dim = 1 << depth
+    h = np.zeros((dim, dim), np.uint16)
+    check(lib().ort_fixture_heightmap_gpu(ctx.h, depth, _p(h)))
+    return h
+
+
+def carve_bitmap_gpu(ctx, depth: int, heights: np.ndarray) -> np.ndarray:
+    """Tunnel bitmap of remove(tree, splatter_noise(-0.5, .., 1/16)) (:735-743, :786) for z <= max height, from the CUDA
+    kernel: uint64 words, bit (y*dim + x) of slab z."""
+    dim = 1 << depth
+    zmax = int(heights.max())
+    words = (dim * dim + 63) // 64
+    bits = np.zeros((zmax + 1, words), np.uint64)
+    check(lib().ort_fixture_carve_gpu(ctx.h, depth, _p(np.ascontiguousarray(heights, np.uint16)), zmax, _p(bits)))
+    return bits
+
+
+def build_terrain(tree: HOctree, heights=None, grass=None, tunnels: bool = False, nthreads: int | None = None, gpu: bool | None = None):
+    """initialize_h_octree's voxel content (:767-787) through the memoising builder.  gpu: evaluate the noise (heightmap,
+    tunnel bitmap) with the CUDA fixture kernels of the tree's context; default: whenever the tree has a context and the
+    depth allows (>= 5).  The host threads do it otherwise -- same bits either way."""
+    ctx = getattr(tree, "ctx", None)
+    if gpu is None:
+        gpu = ctx is not None and tree.depth >= 5
+    if gpu and ctx is None:
+        raise ValueError("build_terrain(gpu=True) needs a tree with a device context")
+    if heights is None:
+        heights = heightmap_gpu(ctx, tree.depth) if gpu else heightmap(tree.depth, nthreads)
+    else:
+        heights = np.ascontiguousarray(heights, np.uint16)
     grass = grass_bits(tree.depth) if grass is None else np.ascontiguousarray(grass, np.uint8)
-    check(lib().ort_fixture_build_terrain(tree.h, _p(heights), _p(grass), int(tunnels), nthreads or os.cpu_count() or 1))
+    carved = carve_bitmap_gpu(ctx, tree.depth, heights) if (gpu and tunnels) else None
+    check(lib().ort_fixture_build_terrain_ex(tree.h, _p(heights), _p(grass), int(tunnels), nthreads or os.cpu_count() or 1, _p(carved)))
     return heights, grass
 
 

@@ -253,7 +253,7 @@ def test_kernel_variants_agree(ort, golden):
     pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
     ref = None
     ctx.set_option("smem_levels", 215)                  # variant 3 stages the first 215 nodes (levels 1-4 of this DAG)
-    for variant in (0, 1, 2, 3, 4):
+    for variant in (0, 1, 2, 3, 4, 5, 6):
         ctx.set_option("variant", variant)
         got = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
         part = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=64, tile_rows=8, tile_step=3)
@@ -274,3 +274,24 @@ def test_kernel_variants_agree(ort, golden):
         for o in outs:
             assert_same_hits(o, (g[f"{k}_vox"], g[f"{k}_face"], g[f"{k}_t"]), k)
             assert np.array_equal(o[3], outs[0][3])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth,log2cap", [(6, 16), (8, 19), (10, 22)])
+def test_gpu_fixture_kernels_match_host_and_oracle(ort, oc, depth, log2cap):
+    """the fixture's noise on the GPU -- heightmap and tunnel bitmap -- is bit-identical to the host
+    builder's (and the heightmap to the oracle's), so both routes intern the same nodes in the same order."""
+    ctx_tree = ort.HOctree(log2cap, depth, device=0)
+    h_gpu = ort.harness.heightmap_gpu(ctx_tree.ctx, depth)
+    h_host = ort.harness.heightmap(depth, 4)
+    assert np.array_equal(h_gpu, h_host)
+    if depth <= 8:
+        assert np.array_equal(h_gpu, oc.heightmap(depth))
+    g = ort.harness.grass_bits(depth)
+    ort.harness.build_terrain(ctx_tree, h_gpu, g, tunnels=True, gpu=True)
+    host_tree = ort.HOctree(log2cap, depth, device=None)
+    ort.harness.build_terrain(host_tree, h_host, g, tunnels=True, gpu=False)
+    assert (ctx_tree.get_fillcnt(), ctx_tree.get_nodecnt(), ctx_tree.get_root()) == (host_tree.get_fillcnt(), host_tree.get_nodecnt(), host_tree.get_root())
+    assert np.array_equal(ctx_tree.cashes(), host_tree.cashes())
+    assert np.array_equal(ctx_tree.nodes(), host_tree.nodes())
+    assert np.array_equal(ctx_tree.refcounts(), host_tree.refcounts())
