@@ -64,6 +64,33 @@ def traffic_per_launch():
         return None
 
 
+def issue_roofline(ctx, clocks, ms_per_step, world):
+    """The bound that actually binds: warp instructions issued per second against the chip's issue peak
+    (SMs x 4 schedulers x SM clock), instructions per step from the committed ncu capture."""
+    inst = warp_instructions_per_step()
+    mhz = (clocks or {}).get("sm_mhz")
+    if not inst or not mhz:
+        return None
+    import torch
+    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    peak = sms * 4 * mhz * 1e6
+    achieved = inst / (ms_per_step * 1e-3)          # each rank issues one GPU's share: 3 full frames' worth per step
+    return {"achieved": round(achieved / 1e9, 1), "peak": round(peak / 1e9, 1), "unit": "G warp-instr/s", "frac": round(achieved / peak, 4),
+            "warp_instructions_per_step_per_gpu": inst, "sms": sms,
+            "source": "smsp__inst_executed.sum of the three frame launches in profiles/traffic.json (ncu --set full)"}
+
+
+def warp_instructions_per_step():
+    """smsp__inst_executed.sum of the step's frame launches (poses A, B, C) from the same ncu capture -- a property of
+    the kernel build and the scene, not of the run."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        v = json.load(open(p))["warp_instructions_per_launch"]
+        return int(sum(v)) if len(v) == len(POSE_NAMES) else None
+    except Exception:
+        return None
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
 
@@ -422,6 +449,7 @@ def run_product(args):
                 "note": "algorithmic bytes = 32 B per child-slot load (PUSH) + 9 B output per ray (SURVEY 8d). The 44 MiB DAG is cache resident "
                         "(ncu: L1 hit 93 %, DRAM traffic ~1 % of the algorithmic bytes), so frac > 1 against the HBM copy peak is expected; "
                         "the kernel is bound by instruction issue (ncu: issue slots 83 % busy), see DESIGN.md section 4",
+                "issue": issue_roofline(ctx, clocks, ms_per_step, world),
             },
             "clocks": clocks,
             "wall_s_timed_region": round(wall, 3),

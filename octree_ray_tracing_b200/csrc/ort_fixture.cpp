@@ -20,6 +20,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <cctype>
 #include <cmath>
 #include <cstdlib>
@@ -49,8 +51,6 @@ struct Builder
 	const uint8_t* grass;
 	bool tunnels;
 	std::vector<std::vector<uint16_t>> hmin, hmax;    // [k] = min/max over 2^k x 2^k column blocks
-	uint32_t stone[17];                               // memoised all-stone subtree per cell size 2^k
-	bool failed = false;
 	std::vector<uint64_t> carved_own;                 // tunnels: one bit per voxel with z <= zmax (bit y*dim+x of slab z)
 	const uint64_t* carved = nullptr;                 // = carved_own.data(), or the caller's bitmap (ort_fixture_carve_gpu)
 	std::vector<std::vector<uint8_t>> any;            // [k >= 3]: cell of size 2^k holds at least one carved voxel
@@ -136,13 +136,70 @@ struct Builder
 		if (tunnels && is_carved(x, y, z)) return 0;
 		return v;
 	}
+};
 
-	uint32_t intern(const uint32_t* n)
+// Where built nodes go.  TreeSink: straight into the host table.  LocalDag: a private, content-addressed sub-DAG
+// with local ids (children of k == 1 nodes are voxel payloads, of k > 1 nodes local ids), merged into the table later.
+struct TreeSink
+{
+	ort_tree* tree;
+	bool failed = false;
+	uint32_t intern(const uint32_t* n, int)
 	{
 		const uint32_t id = tree->intern_node(n);
 		if (!id) failed = true;
 		return id;
 	}
+};
+
+struct LocalDag
+{
+	std::vector<uint32_t> words;       // 8 per node, in creation order (children before parents)
+	std::vector<uint8_t>  leaf;        // 1: children are voxel payloads
+	std::vector<uint32_t> slots;       // open addressing -> local id (1-based), 0 = empty
+	uint32_t mask = 0;
+	bool failed = false;
+
+	static inline uint32_t hash(const uint32_t* n, uint32_t is_leaf)
+	{
+		uint64_t h = 0x9E3779B97F4A7C15ull + is_leaf;
+		for (int i = 0; i < 8; ++i) { h ^= n[i]; h *= 0xFF51AFD7ED558CCDull; h ^= h >> 29; }
+		return static_cast<uint32_t>(h ^ (h >> 32));
+	}
+
+	void grow()
+	{
+		const uint32_t cap = slots.empty() ? 1024u : static_cast<uint32_t>(slots.size()) * 2u;
+		slots.assign(cap, 0);
+		mask = cap - 1;
+		for (uint32_t id = 1; id <= leaf.size(); ++id)
+		{
+			uint32_t p = hash(words.data() + 8 * static_cast<size_t>(id - 1), leaf[id - 1]) & mask;
+			while (slots[p]) p = (p + 1) & mask;
+			slots[p] = id;
+		}
+	}
+
+	uint32_t intern(const uint32_t* n, int k)
+	{
+		if (leaf.size() * 2 >= slots.size()) grow();
+		const uint32_t is_leaf = k == 1;
+		uint32_t p = hash(n, is_leaf) & mask;
+		for (uint32_t id; (id = slots[p]) != 0; p = (p + 1) & mask)
+			if (leaf[id - 1] == is_leaf && !std::memcmp(words.data() + 8 * static_cast<size_t>(id - 1), n, 32))
+				return id;
+		words.insert(words.end(), n, n + 8);
+		leaf.push_back(static_cast<uint8_t>(is_leaf));
+		return slots[p] = static_cast<uint32_t>(leaf.size());
+	}
+};
+
+template<class Sink>
+struct Walker
+{
+	const Builder& b;
+	Sink& sink;
+	uint32_t stone[17] = {};                            // memoised all-stone subtree per cell size 2^k
 
 	uint32_t stone_node(int k)                         // k = log2(cell size) >= 1
 	{
@@ -150,22 +207,22 @@ struct Builder
 		uint32_t n[8];
 		const uint32_t c = k == 1 ? 1u : stone_node(k - 1);
 		for (int i = 0; i < 8; ++i) n[i] = c;
-		return stone[k] = intern(n);
+		return stone[k] = sink.intern(n, k);
 	}
 
 	uint32_t build(int x, int y, int z, int k)         // cell [x,x+2^k) x [y,..) x [z,..); returns node id or 0
 	{
-		if (failed) return 0;
+		if (sink.failed) return 0;
 		const int s = 1 << k;
-		const size_t bi = static_cast<size_t>(y >> k) * (dim >> k) + (x >> k);
-		if (z > hmax[k][bi])
+		const size_t bi = static_cast<size_t>(y >> k) * (b.dim >> k) + (x >> k);
+		if (z > b.hmax[k][bi])
 			return 0;                                  // entirely above the terrain
-		if (z + s - 1 < static_cast<int>(hmin[k][bi]) - 2 && !(tunnels && cell_carved(x, y, z, k)))
+		if (z + s - 1 < static_cast<int>(b.hmin[k][bi]) - 2 && !(b.tunnels && b.cell_carved(x, y, z, k)))
 			return stone_node(k);                      // entirely plain stone
 
 		uint32_t n[8];
 		if (k == 1)
-			for (int c = 0; c < 8; ++c) n[c] = voxel(x + (c & 1), y + ((c >> 1) & 1), z + (c >> 2));
+			for (int c = 0; c < 8; ++c) n[c] = b.voxel(x + (c & 1), y + ((c >> 1) & 1), z + (c >> 2));
 		else
 		{
 			const int hs = s >> 1;
@@ -173,9 +230,74 @@ struct Builder
 		}
 		if (!(n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7]))
 			return 0;                                  // (only reachable with tunnels: a fully carved cell)
-		return intern(n);
+		return sink.intern(n, k);
 	}
 };
+
+// The volume is cut into 8^3 subcells; the host threads build each subcell's sub-DAG privately (no shared state but
+// the read-only maps), then the sub-DAGs are interned into the table one after the other in subcell order -- children
+// before parents, local ids translated on the way -- and the three top levels are assembled from the subcell roots.
+// Same canonical DAG as the sequential walk; slot numbering depends only on the subcell order, not on thread timing.
+uint32_t build_parallel(const Builder& b, ort_tree* tree, int nthreads, bool& failed)
+{
+	const int ks = b.depth - 3, side = 8, cell = 1 << ks;
+	std::vector<LocalDag> dags(static_cast<size_t>(side) * side * side);
+	std::vector<uint32_t> local_root(dags.size(), 0);
+	parallel_rows(static_cast<int>(dags.size()), nthreads, [&](int i) {
+		const int cx = i & 7, cy = (i >> 3) & 7, cz = i >> 6;
+		Walker<LocalDag> w{ b, dags[i] };
+		local_root[i] = w.build(cx * cell, cy * cell, cz * cell, ks);
+	});
+
+	if (std::getenv("ORT_FIXTURE_TIMING"))
+	{
+		size_t tot = 0;
+		for (const auto& d : dags) tot += d.leaf.size();
+		std::fprintf(stderr, "[ort fixture] %zu local nodes in %zu sub-DAGs\n", tot, dags.size());
+	}
+	TreeSink sink{ tree };
+	std::vector<uint32_t> sub_root(dags.size(), 0), gmap;
+	for (size_t i = 0; i < dags.size() && !sink.failed; ++i)
+	{
+		LocalDag& d = dags[i];
+		gmap.assign(d.leaf.size(), 0);
+		for (size_t j = 0; j < d.leaf.size() && !sink.failed; ++j)
+		{
+			uint32_t n[8];
+			std::memcpy(n, d.words.data() + 8 * j, 32);
+			if (!d.leaf[j])
+				for (int c = 0; c < 8; ++c) if (n[c]) n[c] = gmap[n[c] - 1];
+			gmap[j] = sink.intern(n, 0);
+		}
+		if (local_root[i]) sub_root[i] = gmap[local_root[i] - 1];
+		std::vector<uint32_t>().swap(d.words);
+		std::vector<uint32_t>().swap(d.slots);
+	}
+	// top three levels
+	uint32_t lvl[3][64 * 8];
+	auto at = [&](int level_side, const uint32_t* src, int x, int y, int z) { return src[(static_cast<size_t>(z) * level_side + y) * level_side + x]; };
+	const uint32_t* src = sub_root.data();
+	int src_side = 8;
+	uint32_t root = 0;
+	for (int pass = 0; pass < 3 && !sink.failed; ++pass)
+	{
+		const int dst_side = src_side / 2;
+		uint32_t* dst = lvl[pass];
+		for (int z = 0; z < dst_side; ++z)
+			for (int y = 0; y < dst_side; ++y)
+				for (int x = 0; x < dst_side; ++x)
+				{
+					uint32_t n[8];
+					for (int c = 0; c < 8; ++c) n[c] = at(src_side, src, 2 * x + (c & 1), 2 * y + ((c >> 1) & 1), 2 * z + (c >> 2));
+					dst[(static_cast<size_t>(z) * dst_side + y) * dst_side + x] = (n[0] | n[1] | n[2] | n[3] | n[4] | n[5] | n[6] | n[7]) ? sink.intern(n, 0) : 0u;
+				}
+		src = dst;
+		src_side = dst_side;
+		root = dst[0];
+	}
+	failed = sink.failed;
+	return root;
+}
 
 }  // namespace
 
@@ -285,6 +407,14 @@ int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const 
 	if (!tree || !heights || !grass)
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_fixture_build_terrain: bad arguments");
 
+	const bool timing = std::getenv("ORT_FIXTURE_TIMING") != nullptr;
+	auto t_prev = std::chrono::steady_clock::now();
+	auto lap = [&](const char* what) {
+		if (!timing) return;
+		const auto now = std::chrono::steady_clock::now();
+		std::fprintf(stderr, "[ort fixture] %-22s %.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+		t_prev = now;
+	};
 	Builder b;
 	b.tree = tree;
 	b.depth = tree->depth;
@@ -292,7 +422,6 @@ int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const 
 	b.h = heights;
 	b.grass = grass;
 	b.tunnels = tunnels != 0;
-	std::memset(b.stone, 0, sizeof b.stone);
 
 	// min / max pyramids over column blocks
 	b.hmin.resize(b.depth + 1);
@@ -315,6 +444,7 @@ int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const 
 			}
 	}
 
+	lap("min/max pyramids");
 	if (b.tunnels)
 	{
 		b.zmax = b.hmax[b.depth][0];
@@ -322,10 +452,22 @@ int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const 
 		else b.precompute_carved(nthreads > 0 ? nthreads : 1);
 		b.build_any_pyramid(nthreads > 0 ? nthreads : 1);
 	}
-	tree->root = b.build(0, 0, 0, b.depth);
-	if (b.failed || tree->table_full)
+	lap("tunnel bitmap");
+	bool failed = false;
+	if (b.depth >= 7 && nthreads > 1)
+		tree->root = build_parallel(b, tree, nthreads, failed);
+	else
+	{
+		TreeSink sink{ tree };
+		Walker<TreeSink> w{ b, sink };
+		tree->root = w.build(0, 0, 0, b.depth);
+		failed = sink.failed;
+	}
+	if (failed || tree->table_full)
 		return ort_fail(nullptr, ORT_ERR_TABLE_FULL, "ort_fixture_build_terrain: node table too full (raise log2_table_capacity)");
+	lap("build");
 	assign_instance_counts(tree);
+	lap("instance counts");
 	tree->invalidate_mirror();
 	return ORT_OK;
 }

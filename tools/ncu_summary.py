@@ -58,7 +58,9 @@ def traffic(rep, out_json):
             i = hdr.index(k)
             b += float(r[i]) * scale[units[i]]
         tot.append(b)
-    json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "per_launch": [int(x) for x in tot], "source": rep,
+    inst = [int(float(r[hdr.index("smsp__inst_executed.sum")])) for r in data] if "smsp__inst_executed.sum" in hdr else []
+    json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "per_launch": [int(x) for x in tot],
+               "warp_instructions_per_launch": inst, "source": rep,
                "kernels": [r[hdr.index("Kernel Name")].split("(")[0] for r in data]}, open(out_json, "w"), indent=1)
 
 
