@@ -85,9 +85,11 @@ int ort_upload_pool(ort_ctx* ctx, const uint32_t* nodes8, size_t n_nodes);
 /* Replaces: N calls of sse_trace(ox,oy,oz,dx,dy,dz, direction&, uint32_t&, float&) const
  * (och_h_octree.h:292-447).  o3: origins, 3 floats each, o_stride = 3, or ONE shared origin with
  * o_stride = 0.  d3: n directions.  Outputs per ray: voxel = hit_voxel, face = hit_direction,
- * t = hit_time.  All pointers may be host (pageable or pinned) or device pointers; host buffers
- * are staged through pinned memory and overlapped with the kernel.  npush (optional, may be
- * NULL) receives each ray's number of child-slot loads (PUSH evaluations), saturated to 65535. */
+ * t = hit_time.  All pointers may be host (pageable or pinned) or device pointers.  Host buffers
+ * run as a three-stage pipeline over chunks of "rays_chunk" rays (ort_set_option): chunk k+1's
+ * rays go up while chunk k is traced and chunk k-1's results come down (pin the buffers -- e.g.
+ * ort_host_alloc -- for the copies to overlap).  npush (optional, may be NULL) receives each
+ * ray's number of child-slot loads (PUSH evaluations), saturated to 65535. */
 int ort_trace_rays(ort_ctx* ctx, const float* o3, int o_stride, const float* d3, size_t n,
                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush);
 
@@ -97,7 +99,12 @@ int ort_trace_rays(ort_ctx* ctx, const float* o3, int o_stride, const float* d3,
  * Rows: local row r (0 <= r < rows) is frame row  y0 + (r / tile_rows) * tile_rows * tile_step
  * + r % tile_rows  -- tile_step = 1 gives the contiguous strip [y0, y0+rows); tile_step = N with
  * y0 = rank * tile_rows gives rank's share of a cyclic strip partition over N GPUs.
- * Outputs are rows * W entries in local row order, pixel index = x + r * W.  npush as above. */
+ * Outputs are rows * W entries in local row order, pixel index = x + r * W.  npush as above.
+ * Host outputs: the rows are traced in a few chunks whose kernels overlap on internal streams and
+ * whose results are copied to the host as each chunk finishes; the call returns when everything
+ * has arrived -- unless option "defer_sync" is set, in which case it returns once the work is
+ * queued and ort_sync() completes it (a frame loop then traces frame k+1 while frame k's results
+ * are still crossing PCIe; use one set of host buffers per frame in flight). */
 int ort_trace_frame(ort_ctx* ctx, const float pos[3], const float rot[9], float fov_factor,
                     int W, int H, int y0, int rows, int tile_rows, int tile_step,
                     uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush);
@@ -135,9 +142,13 @@ uint32_t ort_node_count(const ort_ctx* ctx);    /* highest compact id in use on 
 uint32_t ort_root(const ort_ctx* ctx);
 /* number of kernels of this library launched on ctx since creation (bench.py's gpu_launches) */
 uint64_t ort_launch_count(const ort_ctx* ctx);
-/* Kernel selection knobs (tuning / profiling): key in {"variant" (frames: 0 baseline, 1 fast, 2 persistent
- * lane-refill), "rays_variant" (explicit rays: 1 one thread per ray, 2 persistent lane-refill), "low_water",
- * "smem_levels", "block"}. */
+/* Options.  Behaviour: "defer_sync" (host-buffer trace calls return once queued; ort_sync() collects),
+ * "frame_chunks" (launches per host-buffer frame, 0 = automatic: 8, or 2 with defer_sync), "rays_chunk" (rays per
+ * pipeline stage of host-buffer ort_trace_rays, default 2^20), "zero_copy" (kernels store straight into pinned host
+ * outputs; measured slower than the copy engine, off by default).  Kernel selection for A/B measurements: "variant"
+ * (frames: 0 baseline walk, 1 fast walk = default, 2 persistent lane-refill, 3 upper levels staged in shared memory,
+ * 4 deferred phases, 5 tight bookkeeping, 6 while-while), "rays_variant" (explicit rays: 1 one thread per ray,
+ * 2 persistent lane-refill = default), "low_water", "smem_levels", "tile_shape", "block". */
 int ort_set_option(ort_ctx* ctx, const char* key, int value);
 
 /* Diagnostic for roofline reports: throughput of random 32-byte-sector gathers (independent 4-byte loads, 8 in
@@ -172,6 +183,11 @@ void     ort_tree_set_box(ort_tree* tree, uint16_t cx, uint16_t cy, uint16_t cz,
  * pass over the cells the box cuts.  Voxel content, live nodes, fillcnt, nodecnt, refcounts and traced images equal
  * those of the set() loop; only the slot numbers handed to NEW nodes may differ (insertion order).  ~100x faster. */
 void     ort_tree_fill_box(ort_tree* tree, int x0, int y0, int z0, int x1, int y1, int z1, uint32_t v);
+/* Table dump / load: the occupied slots (children, tag, reference count) plus root and counters, so that a scene
+ * built once (depth 14: seconds to minutes) restarts instantly and keeps accepting edits.  The loading tree must
+ * have the dump's log2_table_capacity and depth.  (No counterpart in the reference) */
+int      ort_tree_save(const ort_tree* tree, const char* path);
+int      ort_tree_load(ort_tree* tree, const char* path);
 uint32_t ort_tree_at(const ort_tree* tree, int x, int y, int z);                           /* :239-258 */
 void     ort_tree_set_root(ort_tree* tree, uint32_t idx);                                  /* :260-263 */
 uint32_t ort_tree_get_root(const ort_tree* tree);                                          /* :265-268 */

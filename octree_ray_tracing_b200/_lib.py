@@ -58,6 +58,8 @@ _SIGS = {
     "ort_tree_set_many": (None, [_vp, _vp, C.c_size_t]),
     "ort_tree_set_box": (None, [_vp, C.c_uint16, C.c_uint16, C.c_uint16, C.c_int, C.c_uint32]),
     "ort_tree_fill_box": (None, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32]),
+    "ort_tree_save": (C.c_int, [_vp, C.c_char_p]),
+    "ort_tree_load": (C.c_int, [_vp, C.c_char_p]),
     "ort_tree_at": (C.c_uint32, [_vp, C.c_int, C.c_int, C.c_int]),
     "ort_tree_set_root": (None, [_vp, C.c_uint32]),
     "ort_tree_get_root": (C.c_uint32, [_vp]),

@@ -10,6 +10,8 @@
 // slot-for-slot against the oracle).
 #include "ort_internal.h"
 
+#include <cstdio>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -679,6 +681,106 @@ int      ort_tree_log2_capacity(const ort_tree* t) { return t->log2cap; }
 const uint32_t* ort_tree_nodes(const ort_tree* t) { return t->nodes; }
 const uint8_t*  ort_tree_cashes(const ort_tree* t) { return t->tags; }
 const uint32_t* ort_tree_refcounts(const ort_tree* t) { return t->refcounts; }
+
+// Table dump / load.  File = header + one record per occupied slot (live or gravestone), in slot
+// order: slot u32, refcount u32, tag u8, 3 pad bytes, 8 children.  Loading restores the exact table -- slots, tags,
+// reference counts, root and counters -- so edits continue as if the tree had been built in this process.
+namespace {
+struct DumpHeader
+{
+	char     magic[8];          // "ORTTREE1"
+	int32_t  log2cap, depth;
+	uint32_t root, fillcnt, nodecnt, max_refcnt;
+	uint64_t records;
+};
+struct DumpRecord
+{
+	uint32_t slot, refcount;
+	uint8_t  tag, pad[3];
+	uint32_t children[8];
+};
+}  // namespace
+
+int ort_tree_save(const ort_tree* t, const char* path)
+{
+	if (!t || !path) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_save: bad arguments");
+	FILE* f = std::fopen(path, "wb");
+	if (!f) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_save: cannot open '%s' for writing", path);
+	DumpHeader h{};
+	std::memcpy(h.magic, "ORTTREE1", 8);
+	h.log2cap = t->log2cap; h.depth = t->depth;
+	h.root = t->root; h.fillcnt = t->fillcnt; h.nodecnt = t->nodecnt; h.max_refcnt = t->max_refcnt;
+	for (uint32_t s = 0; s < t->cap; ++s) h.records += t->tags[s] != 0;
+	bool ok = std::fwrite(&h, sizeof h, 1, f) == 1;
+	std::vector<DumpRecord> buf;
+	buf.reserve(1 << 16);
+	for (uint32_t s = 0; s < t->cap && ok; ++s)
+	{
+		if (t->tags[s])
+		{
+			DumpRecord r{};
+			r.slot = s; r.refcount = t->refcounts[s]; r.tag = t->tags[s];
+			std::memcpy(r.children, t->nodes + 8 * static_cast<size_t>(s), 32);
+			buf.push_back(r);
+		}
+		if (buf.size() == (1u << 16) || (s + 1 == t->cap && !buf.empty()))
+		{
+			ok = std::fwrite(buf.data(), sizeof(DumpRecord), buf.size(), f) == buf.size();
+			buf.clear();
+		}
+	}
+	ok = (std::fclose(f) == 0) && ok;
+	return ok ? ORT_OK : ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_save: write to '%s' failed", path);
+}
+
+int ort_tree_load(ort_tree* t, const char* path)
+{
+	if (!t || !path) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: bad arguments");
+	FILE* f = std::fopen(path, "rb");
+	if (!f) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: cannot open '%s'", path);
+	DumpHeader h{};
+	if (std::fread(&h, sizeof h, 1, f) != 1 || std::memcmp(h.magic, "ORTTREE1", 8) != 0)
+	{
+		std::fclose(f);
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: '%s' is not a table dump", path);
+	}
+	if (h.log2cap != t->log2cap || h.depth != t->depth)
+	{
+		std::fclose(f);
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: dump is h_octree<%d,%d>, tree is h_octree<%d,%d>", h.log2cap, h.depth, t->log2cap, t->depth);
+	}
+	std::memset(t->tags, 0, t->cap);
+	std::vector<DumpRecord> buf(1 << 16);
+	uint64_t left = h.records;
+	bool ok = true;
+	while (left && ok)
+	{
+		const size_t n = left < buf.size() ? static_cast<size_t>(left) : buf.size();
+		ok = std::fread(buf.data(), sizeof(DumpRecord), n, f) == n;
+		for (size_t i = 0; i < n && ok; ++i)
+		{
+			const DumpRecord& r = buf[i];
+			if (r.slot >= t->cap || r.tag == 0) { ok = false; break; }
+			t->tags[r.slot] = r.tag;
+			t->refcounts[r.slot] = r.refcount;
+			std::memcpy(t->nodes + 8 * static_cast<size_t>(r.slot), r.children, 32);
+		}
+		left -= n;
+	}
+	std::fclose(f);
+	if (!ok)
+	{
+		std::memset(t->tags, 0, t->cap);
+		t->root = 0; t->fillcnt = 0; t->nodecnt = 0;
+		t->invalidate_mirror();
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: '%s' is truncated or corrupt", path);
+	}
+	t->root = h.root; t->fillcnt = h.fillcnt; t->nodecnt = h.nodecnt; t->max_refcnt = h.max_refcnt;
+	t->table_full = false;
+	t->clear_dirty();
+	t->invalidate_mirror();
+	return ORT_OK;
+}
 
 size_t ort_tree_flatten(ort_tree* t, const uint32_t** nodes8, uint32_t* root, uint32_t* level_offsets)
 {

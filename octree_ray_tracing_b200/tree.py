@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import enum
+import os
 
 import numpy as np
 
@@ -248,6 +249,14 @@ class HOctree:
         self.L.ort_tree_fill_box(self.h, int(lo[0]), int(lo[1]), int(lo[2]), int(hi[0]), int(hi[1]), int(hi[2]), v)
         if self.L.ort_tree_table_full(self.h):
             raise OrtError(4, "node table too full")
+
+    def save(self, path: str):
+        """Dump the table (occupied slots, tags, reference counts, root, counters) to a file."""
+        check(self.L.ort_tree_save(self.h, os.fsencode(path)))
+
+    def load(self, path: str):
+        """Restore a dump made by save(); the device mirror is re-uploaded at the next sync."""
+        check(self.L.ort_tree_load(self.h, os.fsencode(path)))
 
     def at(self, x: int, y: int, z: int) -> int:
         return self.L.ort_tree_at(self.h, x, y, z)

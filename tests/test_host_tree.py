@@ -249,3 +249,35 @@ def test_fill_box_delta_stream(ort, oc):
         ids, nodes8, root, full = T.take_delta()
         mirror = nodes8.copy() if full else apply_delta(mirror, ids, nodes8)
         assert_same_hits(oc.trace_rays(mirror, root, depth, o, d), A.trace(o, d), f"step {step}")
+
+
+def test_table_dump_and_load_round_trip(ort, oc, tmp_path):
+    """save()/load(): the restored table is the saved one slot for slot and keeps taking edits like the original."""
+    depth, log2cap = 7, 17
+    A = ort.HOctree(log2cap, depth, device=None)
+    ort.harness.build_terrain(A, tunnels=True, gpu=False)
+    rs = np.random.RandomState(5)
+    ops = np.concatenate([rs.randint(0, 1 << depth, (2000, 3)), rs.randint(0, 3, (2000, 1))], 1).astype(np.uint32)
+    A.set_many(ops)                                     # leaves gravestones behind
+    path = str(tmp_path / "table.ort")
+    A.save(path)
+    B = ort.HOctree(log2cap, depth, device=None)
+    B.load(path)
+    for get in ("get_root", "get_fillcnt", "get_nodecnt"):
+        assert getattr(A, get)() == getattr(B, get)()
+    assert np.array_equal(A.cashes(), B.cashes())
+    live = A.cashes() != 0
+    assert np.array_equal(A.nodes()[live], B.nodes()[live]) and np.array_equal(A.refcounts()[live], B.refcounts()[live])
+    more = np.concatenate([rs.randint(0, 1 << depth, (2000, 3)), rs.randint(0, 3, (2000, 1))], 1).astype(np.uint32)
+    A.set_many(more)
+    B.set_many(more)
+    assert np.array_equal(A.cashes(), B.cashes()) and A.get_root() == B.get_root() and A.get_fillcnt() == B.get_fillcnt()
+    assert np.array_equal(A.flatten()[0], B.flatten()[0])
+    # wrong shape and garbage are refused
+    C = ort.HOctree(log2cap + 1, depth, device=None)
+    with pytest.raises(Exception):
+        C.load(path)
+    bad = tmp_path / "bad.ort"
+    bad.write_bytes(b"not a table")
+    with pytest.raises(Exception):
+        B.load(str(bad))
