@@ -160,6 +160,10 @@ def run_product(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (use --impl reference for the CPU trace)")
     torch.cuda.set_device(local_rank)
+    numa_bound = False
+    if world > 1 and not args.no_numa:
+        from octree_ray_tracing_b200 import multi_gpu as _mg
+        numa_bound = _mg.bind_to_gpu_numa(physical_gpu_index(local_rank))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -193,7 +197,7 @@ def run_product(args):
     rays_per_step_local = frames_per_step * n_local
 
     own = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    NS = 3                                                   # frames in flight
+    NS = args.streams or (3 if world == 1 else min(8, 3 * world))   # frames in flight: small strips need more of them to hide launch tails
     streams = [torch.cuda.Stream(device=local_rank) for _ in range(NS)]
     outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
              torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(NS)]
@@ -414,6 +418,7 @@ def run_product(args):
             "config": {
                 "workload": WORKLOAD, "frames_per_step": frames_per_step, "rays_per_step": rays_per_step_total,
                 "partition": f"cyclic {TILE_ROWS}-row tile strips over {world} GPU(s), DAG replicated",
+                "host_placement": "rank pinned to its GPU's NUMA node (NVML ideal CPUs)" if numa_bound else "default",
                 "l2": "flushed before every step (256 MiB memset outside the timed interval)",
                 "in_flight": f"{NS} streams: the frames of a step are queued round-robin so launch tails overlap",
                 "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
@@ -558,6 +563,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--streams", type=int, default=0, help="frames in flight in the device-resident loop (0 = 3 on one GPU, up to 8 on several)")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--quick", action="store_true", help="profiling aid: only the device-resident timed loop (no warm-L2 loop, no e2e, no CPU leg)")
     ap.add_argument("--variant", type=int, default=None, help="kernel variant (ort_set_option 'variant')")
     ap.add_argument("--opt", action="append", default=[], help="key=value passed to ort_set_option")

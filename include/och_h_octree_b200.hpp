@@ -9,7 +9,7 @@
 //
 // Differences by design: tracing runs on a B200 (no CPU path: construction throws std::runtime_error if no
 // sm_100 device is usable); an empty tree traces to direction::exit instead of dereferencing nodes[-1];
-// the table-full condition throws instead of exit(0).  Added: trace_rays / trace_frame (batched) and sync().
+// the table-full condition throws instead of exit(0).  Added: trace_rays / trace_frame / trace_frame_rgba (batched), fill_box, sync(), save / load.
 #pragma once
 
 #include <cstdint>
@@ -148,6 +148,31 @@ namespace och
 			sync();
 			check(ort_trace_frame(ctx, p, rot, fov, W, H, 0, H, 1, 1, voxel, face, t, nullptr), "ort_trace_frame");
 		}
+
+		// the pixels update_image would Draw() (test_och_h_octree.cpp:64-85, :437-457): colours = voxels.get_colours()
+		// (6 olc::Pixel::n values per voxel type), one uint32 per pixel
+		void set_palette(const uint32_t* colours6, uint32_t n_voxels, uint32_t exit_rgba = 0xFFFEBF00u, uint32_t inside_rgba = 0xFF07193Fu)
+		{
+			check(ort_set_palette(ctx, colours6, n_voxels, exit_rgba, inside_rgba), "ort_set_palette");
+		}
+
+		void trace_frame_rgba(float3 pos, float yaw, float pitch, int W, int H, uint32_t* rgba) const
+		{
+			float rot[9], fov;
+			ort_camera_coeffs(yaw, pitch, rot, &fov);
+			const float p[3] = { pos.x, pos.y, pos.z };
+			sync();
+			check(ort_trace_frame_rgba(ctx, p, rot, fov, W, H, 0, H, 1, 1, rgba), "ort_trace_frame_rgba");
+		}
+
+		// frame loops: with deferred completion the trace_frame* calls above return once their work is queued and
+		// wait_frames() collects the results -- frame k+1 is traced while frame k's pixels cross PCIe
+		void defer_completion(bool on) { check(ort_set_option(ctx, "defer_sync", on ? 1 : 0), "ort_set_option"); }
+		void wait_frames() const { check(ort_sync(ctx), "ort_sync"); }
+
+		// table dump / load (see ort_tree_save)
+		void save(const char* path) const { check(ort_tree_save(tree, path), "ort_tree_save"); }
+		void load(const char* path) { check(ort_tree_load(tree, path), "ort_tree_load"); }
 
 		ort_ctx* context() const { return ctx; }
 		ort_tree* handle() const { return tree; }

@@ -295,3 +295,54 @@ def test_gpu_fixture_kernels_match_host_and_oracle(ort, oc, depth, log2cap):
     assert np.array_equal(ctx_tree.cashes(), host_tree.cashes())
     assert np.array_equal(ctx_tree.nodes(), host_tree.nodes())
     assert np.array_equal(ctx_tree.refcounts(), host_tree.refcounts())
+
+
+@pytest.mark.gpu
+def test_host_buffer_pipelines_keep_results(ort, golden):
+    """The host-buffer paths are pipelines (chunk kernels on several streams, staged D2H, optional deferred completion,
+    chunked H2D/trace/D2H for explicit rays): every chunking / completion mode returns the same bits."""
+    g = golden("d8_tunnels")
+    ctx = ort.TraceContext(8)
+    ctx.upload_full(g["nodes8"], int(g["root"]))
+    W, H = 419, 301
+    poses = [(g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"]))]
+    rot2, fov2 = ort.camera_coeffs(0.3, -0.9)
+    poses.append((np.array([1.3, 1.6, 1.7], np.float32), rot2, fov2))
+    cols, _ = ort.harness.parse_voxels(ort.harness.DEMO_VOXELS)
+    ctx.set_palette(cols)
+    ref = [ctx.trace_frame(p, r, f, W, H, want_npush=True) for p, r, f in poses]
+    ref_rgba = [ctx.trace_frame_rgba(p, r, f, W, H).copy() for p, r, f in poses]
+    for chunks in (1, 2, 5, 8):
+        ctx.set_option("frame_chunks", chunks)
+        for (p, r, f), want, want_rgba in zip(poses, ref, ref_rgba):
+            got = ctx.trace_frame(p, r, f, W, H, want_npush=True)
+            assert_same_hits(got, want, f"{chunks} chunks")
+            assert np.array_equal(got[3], want[3])
+            assert np.array_equal(ctx.trace_frame_rgba(p, r, f, W, H), want_rgba)
+    # deferred completion: queue everything, collect once; cyclic tile strips as well
+    ctx.set_option("frame_chunks", 0)
+    ctx.set_option("defer_sync", 1)
+    outs = [(np.zeros(W * H, np.uint32), np.zeros(W * H, np.uint8), np.zeros(W * H, np.float32), None) for _ in range(6)]
+    rgbas = [np.zeros(W * H, np.uint32) for _ in range(6)]
+    for k in range(6):
+        p, r, f = poses[k % 2]
+        ctx.trace_frame(p, r, f, W, H, out=outs[k])
+        ctx.trace_frame_rgba(p, r, f, W, H, out=rgbas[k])
+    ctx.sync()
+    ctx.set_option("defer_sync", 0)
+    for k in range(6):
+        assert_same_hits(outs[k], ref[k % 2], f"deferred frame {k}")
+        assert np.array_equal(rgbas[k], ref_rgba[k % 2])
+    # explicit rays through many small pipeline stages, mixed with a frame call in between
+    o, d = g["rand_o"], g["rand_d"]
+    want = (g["rand_vox"], g["rand_face"], g["rand_t"])
+    for chunk in (4096, 5000, 1 << 20):
+        ctx.set_option("rays_chunk", chunk)
+        assert_same_hits(ctx.trace_rays(o, d), want, f"rays_chunk {chunk}")
+        assert_same_hits(ctx.trace_frame(*poses[0], W, H), ref[0], "frame after rays")
+    shared = np.array([1.5, 1.5, 1.9], np.float32)
+    dd = np.ascontiguousarray(d[:20000])
+    a = ctx.trace_rays(shared, dd)
+    ctx.set_option("rays_chunk", 4096)
+    b = ctx.trace_rays(shared, dd)
+    assert_same_hits(a, b, "shared origin, chunked")

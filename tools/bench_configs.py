@@ -109,27 +109,38 @@ def config5(args):
             ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, tr, world, dv, df, dt, dn)
             stream.synchronize()
             pushes += int((dn.to(torch.int64) & 0xFFFF).sum().item())
-        for name, gather in (("trace", False), ("trace+gather", True)):
-            for rep in range(2 + args.steps):
-                if rep == 2:
-                    torch.cuda.synchronize()
-                    if world > 1:
-                        dist.barrier()
-                    torch.cuda.synchronize()
-                    a = time.perf_counter()
-                for cam in cams:
-                    ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, tr, world, dv, df, dt)
-                    if gather:
-                        for buf in (dv, dt, df):
+    # frames in flight on NS streams (own output buffers each) so that launch tails overlap, as in bench.py
+    NS = args.streams
+    streams = [torch.cuda.Stream(device=local) for _ in range(NS)]
+    outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
+             torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(NS)]
+    torch.cuda.synchronize()
+    for name, gather in (("trace", False), ("trace+gather", True)):
+        for rep in range(2 + args.steps):
+            if rep == 2:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+                torch.cuda.synchronize()
+                a = time.perf_counter()
+            for k, cam in enumerate(cams):
+                st = streams[k % NS]
+                o = outs[k % NS]
+                ctx.set_stream(st)
+                ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, tr, world, o[0], o[1], o[2])
+                if gather:
+                    with torch.cuda.stream(st):
+                        for buf in (o[0], o[2], o[1]):
                             multi_gpu.gather_strips(buf, world, H, W, tr, dst=0)
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-            sec = (time.perf_counter() - a) / args.steps
-            tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
-            if world > 1:
-                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            out[name] = float(tt.item())
+        ctx.set_stream(None)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        sec = (time.perf_counter() - a) / args.steps
+        tt = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        out[name] = float(tt.item())
     pt = torch.tensor([float(pushes), float(n_local * len(cams))], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(pt)
@@ -153,6 +164,7 @@ if __name__ == "__main__":
     ap.add_argument("--depth", type=int, default=None)
     ap.add_argument("--frames", type=int, default=100)
     ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--streams", type=int, default=3, help="config 5: frames in flight")
     ap.add_argument("--bulk", action="store_true", help="config 4: use the bulk box edit instead of the 64000-set() loop")
     args = ap.parse_args()
     if args.depth is None:
