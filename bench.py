@@ -293,10 +293,10 @@ def run_product(args):
     if args.quick:
         sampler.stop()
         ms = kernel_ms / args.steps
-        print(json.dumps({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
+        emit({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
-                          "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]]}), flush=True)
+                          "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]]})
         return None
 
     # same loop without the flush (steady state of a real frame loop: DAG stays L2-resident)
@@ -464,7 +464,7 @@ def run_product(args):
                                      "note": "trace + NCCL gather of every frame's strips (voxel, t, face) to rank 0, wall clock, max over ranks"}
         if world == 1 and not args.no_cpu:
             result["cpu_baseline"] = cpu_baseline(tree, sample_tiles=4)
-        print(json.dumps(result), flush=True)
+        emit(result)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -544,7 +544,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = n * args.steps / dt / 1e6
     sample = f"every {sample_tiles}th 8-row tile of the 3 poses' 4K frames ({n} rays per step), {cores} threads"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -553,10 +553,31 @@ def run_reference(args):
         "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner when
+    NCCL_DEBUG is set in the environment), so the real stdout is kept aside for the result line and file descriptor 1
+    is pointed at stderr for everybody else."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
