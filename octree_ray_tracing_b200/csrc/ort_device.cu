@@ -234,7 +234,7 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 	int x, r;
 	if (fr.tile_shape == 1)      { x = blockIdx.x * 16 + (lane & 15);                   r = blockIdx.y * 16 + warp * 2 + (lane >> 4); }
 	else if (fr.tile_shape == 2) { x = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);   r = blockIdx.y * 16 + (warp >> 2) * 8 + (lane >> 2); }
-	else                         { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3); }
+	else                         { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * static_cast<int>(blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3); }   // block tile: 16 x (blockDim.x / 16)
 	if (x >= fr.W || r >= fr.rows) return;
 	int y = fr.y0 + r;                                                 // contiguous strip
 	if (fr.tile_step != 1)                                             // cyclic tile strips (uniform branch)
@@ -988,7 +988,10 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
+	// block = 16 x 16 pixels by default; 16 x 8 / 16 x 4 (option "block" = 128 / 64) for measurements of block-retirement granularity
+	const int fblock = (c->opt_tile_shape == 0 && (c->opt_block == 128 || c->opt_block == 64)) ? c->opt_block : 256;
+	const dim3 fgrid((W + 15) / 16, (rows + fblock / 16 - 1) / (fblock / 16));
+#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<fgrid, fblock, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
 	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); }
 	else { if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); }
 #undef ORT_LAUNCH_FRAME
