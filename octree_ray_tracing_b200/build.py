@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libort_b200.so")
 SOURCES = ["ort_device.cu", "ort_host_tree.cpp", "ort_host_octree.cpp", "ort_fixture.cpp"]
-HEADERS = ["ort_internal.h", "ort_trace.cuh", "ort_rcp_table.h", os.path.join("..", "..", "include", "ort_b200.h")]
+HEADERS = ["ort_internal.h", "ort_trace.cuh", "ort_kernels.cuh", "ort_noise.h", "ort_rcp_table.h", os.path.join("..", "..", "include", "ort_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
