@@ -494,6 +494,25 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
+	if (c->opt_variant == 7)
+	{
+		const unsigned long long base_biased = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(nodes_m1)) - 4ull * ort::kMagicBits;
+		if (npush) ort::trace_frame_pipe_kernel<true><<<grid, 256, 0, c->stream>>>(nodes_m1, base_biased, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush);
+		else       ort::trace_frame_pipe_kernel<false><<<grid, 256, 0, c->stream>>>(nodes_m1, base_biased, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
+	if (c->opt_variant >= 8 && c->opt_variant <= 11 && !npush)
+	{
+		// probes: 8 = +6 FMA-pipe, 9 = +6 ALU-pipe, 10 = +12 FMA-pipe, 11 = +0 (the same loop shape without extra work)
+		auto k = c->opt_variant == 8 ? ort::trace_frame_probe_kernel<6, 0> : c->opt_variant == 9 ? ort::trace_frame_probe_kernel<0, 6>
+		       : c->opt_variant == 10 ? ort::trace_frame_probe_kernel<12, 0> : ort::trace_frame_probe_kernel<0, 0>;
+		k<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
 	if (c->opt_variant == 4)
 	{
 		const int thr = c->opt_low_water > 0 ? c->opt_low_water : 1;

@@ -68,6 +68,7 @@ ort_tree::ort_tree(int log2cap_, int depth_)
 	dirty_bits = static_cast<uint64_t*>(std::calloc((cap + 63) / 64, 8));
 	id_interior = static_cast<uint32_t*>(std::calloc(cap, 4));
 	id_leaf = static_cast<uint32_t*>(std::calloc(cap, 4));
+	id_level = static_cast<uint8_t*>(std::calloc(cap, 1));
 }
 
 ort_tree::~ort_tree()
@@ -78,6 +79,7 @@ ort_tree::~ort_tree()
 	std::free(dirty_bits);
 	std::free(id_interior);
 	std::free(id_leaf);
+	std::free(id_level);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -409,8 +411,28 @@ void ort_tree::reset_ids()
 		id_leaf[s & 0x7FFFFFFFu] = 0;
 	}
 	id_owner.clear();
+	id_extra.clear();
 	free_ids.clear();
 	next_id = 1;
+}
+
+// Storage of the compact id of (slot, level); assign = the caller is about to hand out an id (claims id_interior for
+// this level if it is still unclaimed)
+uint32_t& ort_tree::id_ref(uint32_t slot, int level, bool assign)
+{
+	if (level == depth)
+		return id_leaf[slot];
+	if (id_interior[slot] == 0u)
+	{
+		if (assign) id_level[slot] = static_cast<uint8_t>(level);
+		if (assign || id_extra.empty()) return id_interior[slot];
+		// lookup only: an id for this level may still sit among the extras (the primary was freed, the extra was not)
+		auto it = id_extra.find((static_cast<uint64_t>(slot) << 8) | static_cast<uint64_t>(level));
+		return it != id_extra.end() ? it->second : id_interior[slot];
+	}
+	if (id_level[slot] == level)
+		return id_interior[slot];
+	return id_extra[(static_cast<uint64_t>(slot) << 8) | static_cast<uint64_t>(level)];
 }
 
 void ort_tree::clear_dirty()
@@ -436,22 +458,21 @@ size_t ort_tree::flatten(uint32_t* level_offsets)
 		return 0;
 
 	std::vector<uint32_t> cur, next;
-	auto give_id = [&](uint32_t slot, bool leaf) {
-		uint32_t& id = (leaf ? id_leaf : id_interior)[slot];
+	auto give_id = [&](uint32_t slot, int level) {
+		uint32_t& id = id_ref(slot, level, true);
 		id = next_id++;
-		id_owner.push_back(slot | (leaf ? 0x80000000u : 0u));
+		id_owner.push_back(slot | (level == depth ? 0x80000000u : 0u));
 		return id;
 	};
 
 	cur.push_back(root - 1);
-	give_id(root - 1, depth == 1);
+	give_id(root - 1, 1);
 	flat_root = 1;
 
 	for (int level = 1; level <= depth; ++level)
 	{
 		if (level_offsets) level_offsets[level - 1] = static_cast<uint32_t>(flat.size() / 8 + 1);
 		const bool leaf = level == depth;
-		const bool child_leaf = level + 1 == depth;
 		next.clear();
 		flat.resize(flat.size() + cur.size() * 8);
 		uint32_t* out = flat.data() + flat.size() - cur.size() * 8;
@@ -467,10 +488,10 @@ size_t ort_tree::flatten(uint32_t* level_offsets)
 					uint32_t id = 0;
 					if (n[c])
 					{
-						id = (child_leaf ? id_leaf : id_interior)[n[c] - 1];
+						id = id_ref(n[c] - 1, level + 1, false);
 						if (!id)
 						{
-							id = give_id(n[c] - 1, child_leaf);
+							id = give_id(n[c] - 1, level + 1);
 							next.push_back(n[c] - 1);
 						}
 					}
@@ -488,14 +509,13 @@ size_t ort_tree::flatten(uint32_t* level_offsets)
 uint32_t ort_tree::delta_visit(uint32_t slot, int level)
 {
 	const bool leaf = level == depth;
-	uint32_t* ids = leaf ? id_leaf : id_interior;
-	if (ids[slot])
-		return ids[slot];
+	if (const uint32_t have = id_ref(slot, level, false))
+		return have;
 
 	uint32_t id;
 	if (!free_ids.empty()) { id = free_ids.back(); free_ids.pop_back(); }
 	else id = next_id++;
-	ids[slot] = id;
+	id_ref(slot, level, true) = id;
 	id_owner.push_back(slot | (leaf ? 0x80000000u : 0u));
 
 	const size_t at = delta_nodes.size();
@@ -532,6 +552,18 @@ bool ort_tree::build_delta()
 		if (id_interior[s]) { free_ids.push_back(id_interior[s]); id_interior[s] = 0; }
 		if (id_leaf[s]) { free_ids.push_back(id_leaf[s]); id_leaf[s] = 0; }
 	}
+	if (!id_extra.empty())
+		for (auto it = id_extra.begin(); it != id_extra.end();)
+		{
+			const uint32_t s = static_cast<uint32_t>(it->first >> 8);
+			if (dirty_bits[s >> 6] & (1ull << (s & 63)))
+			{
+				if (it->second) free_ids.push_back(it->second);
+				it = id_extra.erase(it);
+			}
+			else
+				++it;
+		}
 	const size_t n_dirty = dirty.size();
 	clear_dirty();
 
@@ -630,7 +662,7 @@ int ort_tree_create(ort_tree** out, int log2cap, int depth)
 	if (!out || log2cap < 4 || log2cap > 30 || depth < 1 || depth > 16)
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_create: log2_table_capacity in 4..30 and depth in 1..16 required");
 	ort_tree* t = new (std::nothrow) ort_tree(log2cap, depth);
-	if (!t || !t->tags || !t->refcounts || !t->nodes || !t->dirty_bits || !t->id_interior || !t->id_leaf)
+	if (!t || !t->tags || !t->refcounts || !t->nodes || !t->dirty_bits || !t->id_interior || !t->id_leaf || !t->id_level)
 	{
 		delete t;
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_create: out of host memory");

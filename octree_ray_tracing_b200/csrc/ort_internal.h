@@ -5,6 +5,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <unordered_map>
 #include <vector>
 
 // Records `msg` as the calling thread's last error (and on ctx when given) and returns `code`.
@@ -34,8 +35,14 @@ struct ort_tree
 	uint32_t synced_root_slot = 0;
 	uint64_t* dirty_bits = nullptr;      // one bit per slot: written or killed since the last sync
 	std::vector<uint32_t> dirty;
-	uint32_t* id_interior = nullptr;     // slot -> compact id when used above the last level (0 = none)
-	uint32_t* id_leaf = nullptr;         // slot -> compact id when used at level `depth`
+	// slot -> compact id.  A node's children mean different things at different levels (ids above the last level,
+	// voxel payloads at it) and the table is content-addressed across levels, so the id belongs to (slot, level):
+	// id_leaf for level `depth`, id_interior for the first level above it at which the slot was met (recorded in
+	// id_level), id_extra[(slot << 8) | level] for the rare slot that also serves at another level.
+	uint32_t* id_interior = nullptr;
+	uint32_t* id_leaf = nullptr;
+	uint8_t*  id_level = nullptr;
+	std::unordered_map<uint64_t, uint32_t> id_extra;
 	std::vector<uint32_t> id_owner;      // slots that own ids (bit 31 = leaf role), for cheap resets
 	std::vector<uint32_t> free_ids;
 	uint32_t next_id = 1;
@@ -79,4 +86,5 @@ private:
 	uint32_t probe(const uint32_t* n, uint8_t& tag, bool& found) const;
 	void     reset_ids();
 	uint32_t delta_visit(uint32_t slot, int level);
+	uint32_t& id_ref(uint32_t slot, int level, bool assign);
 };

@@ -194,6 +194,103 @@ trace_frame_tight_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, i
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
+// Variant 7: PipeWalker (ALU-lean bookkeeping, see ort_trace.cuh).
+template<bool COUNT>
+__global__ void __launch_bounds__(256)
+trace_frame_pipe_kernel(const uint32_t* __restrict__ nodes_m1, unsigned long long base_biased, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
+                        uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	Hit h;
+	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
+	{
+		uint32_t stack_n[kMaxDepth];
+		float stack_f[kMaxDepth];
+		PipeWalker<COUNT> w;
+		w.start(root, miss_t, ray);
+		for (;;)
+		{
+			const uint32_t child = w.load_child(base_biased);
+			if (child ? w.descend(child, depth, stack_n, stack_f) : w.advance(stack_n, stack_f))
+				break;
+		}
+		h = w.hit;
+	}
+	else
+	{
+		uint32_t stack[kMaxDepth];
+		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
+	}
+
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
+// Probe kernels (variants 8 / 9): the default walk plus PROBE_FMA dependent-free FMA-pipe instructions or PROBE_ALU
+// ALU-pipe instructions per round, on dummy accumulators that are folded into the result only if they take an
+// impossible value.  They answer "which resource binds the loop?": extra work on a unit that has slack is free.
+template<int PROBE_FMA, int PROBE_ALU>
+__global__ void __launch_bounds__(256)
+trace_frame_probe_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
+                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t)
+{
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+	uint32_t stack[kMaxDepth];
+	Hit h;
+	float facc[3] = { dx, dy, dz };
+	uint32_t iacc[3] = { ray.px, ray.py, ray.pz };
+	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
+	{
+		FastWalker<false> w;
+		w.start(root, miss_t, ray);
+		for (;;)
+		{
+			const uint32_t child = w.load_child(nodes_m1);
+#pragma unroll
+			for (int k = 0; k < PROBE_FMA; ++k)
+				asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(facc[k % 3]) : "f"(w.cx), "f"(w.bx));
+#pragma unroll
+			for (int k = 0; k < PROBE_ALU; ++k)
+				asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(iacc[k % 3]) : "r"(w.idx), "r"(w.inv));
+			if (child ? w.descend(child, depth, stack) : w.advance(stack))
+				break;
+		}
+		h = w.hit;
+	}
+	else
+		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
+	if (facc[0] + facc[1] + facc[2] == 1.2345e-30f || (iacc[0] ^ iacc[1] ^ iacc[2]) == 0xDEADBEEFu)
+		h.voxel ^= 0x80000000u;                                                  // never true; keeps the probes alive
+
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+}
+
 // Experiment kernel for the SIMT-efficiency question (variant 4): "deferred phases".  In the default kernel every
 // round of the loop runs the descend block for the lanes whose child exists AND the advance block for the lanes
 // whose child is empty -- each with about two thirds of the warp.  Here a phase that fewer than `threshold` lanes

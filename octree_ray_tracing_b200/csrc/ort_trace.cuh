@@ -506,6 +506,175 @@ struct TightWalker
 	}
 };
 
+// ------------------------------------------------------------------------------------------------
+// ALU-lean variant ("PipeWalker").  Probe kernels (ort_kernels.cuh, variants 8-11) showed how the loop is bound:
+// six extra FMA-pipe instructions per round cost +7.9 %, six extra ALU-pipe instructions +16.7 % -- an ALU-pipe
+// instruction (LOP3, SEL, FSEL, ISETP, FSETP, VIMNMX, SHF ...: one warp instruction per two cycles) costs twice an
+// FMA-pipe one.  Same decisions and the same t values as FastWalker; the bookkeeping moves off the ALU pipe:
+//   * child pick after a descend: `set.ge.f32` yields 1.0f / 0.0f, the position takes the half step by an exact
+//     FMA (p + u * size) and the child-slot index is accumulated in float, already XORed with inv_signs:
+//     idx' = inv + sum_a w_a u_a with w_a = +-2^a, kept as F = 2^23 + idx' (every partial sum is a small integer at
+//     ulp 1, so the FMAs are exact).  bits(F) = 0x4B000000 | idx' goes straight into the 64-bit address IMAD; the
+//     constant is folded into the base pointer.  No FSETP / FSEL / SEL / LOP3 for the pick;
+//   * a sibling step is three predicated FADD pairs (position, F);
+//   * the parent stack holds node id and F in two local arrays -- POP restores both with loads, no unpacking;
+//   * multi-level POP: the position bits below the current level are zero and the current level's bit on the exit
+//     axis is clear (that is why we pop), so the ancestor to resume at is simply the LOWEST set bit b of the exit
+//     axis' position word (the exponent's lowest bit is the sentinel for "through the root"):  b = pa & -pa,
+//     positions &= -b, cell size = as_float(0x3F800000 | b) - 1, level = 23 - flo(b).
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kMagicBits = 0x4B000000u;     // bits of 8388608.0f = 2^23
+
+__device__ __forceinline__ float set_ge(float a, float b)    // 1.0f if a >= b (ordered) else 0.0f -- one instruction
+{
+	float r;
+	asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+	return r;
+}
+
+template<bool COUNT>
+struct PipeWalker
+{
+	uint32_t node, inv, mti;
+	int      level;
+	float    F;                      // 2^23 + ((child index) ^ inv)
+	float    px, py, pz, dimf, tmin;
+	float    cx, cy, cz, bx, by, bz;
+	float    wx, wy, wz, c0;         // idx' = inv + wx*ux + wy*uy + wz*uz;  c0 = 2^23 + inv
+	float    miss_t;
+	Hit      hit;
+
+	__device__ __forceinline__ void start(uint32_t root, float miss_time, const Ray& r)
+	{
+		node = root;
+		miss_t = miss_time;
+		level = 1;
+		inv = r.inv;
+		px = __uint_as_float(r.px); py = __uint_as_float(r.py); pz = __uint_as_float(r.pz);
+		dimf = 0.5f;
+		tmin = 0.0f;
+		mti = 8;
+		hit.npush = 0;
+		cx = r.cx; cy = r.cy; cz = r.cz; bx = r.bx; by = r.by; bz = r.bz;
+		const float ninf = __uint_as_float(0xFF800000u);      // degenerate axes: see FastWalker
+		if (cx == ninf) { cx = 0.0f; bx = ninf; }
+		if (cy == ninf) { cy = 0.0f; by = ninf; }
+		if (cz == ninf) { cz = 0.0f; bz = ninf; }
+		wx = (inv & 1u) ? -1.0f : 1.0f;
+		wy = (inv & 2u) ? -2.0f : 2.0f;
+		wz = (inv & 4u) ? -4.0f : 4.0f;
+		c0 = __uint_as_float(kMagicBits | inv);
+		F = __uint_as_float(kMagicBits | (r.idx ^ inv));
+	}
+
+	__device__ __forceinline__ void miss()
+	{
+		hit.voxel = 0;
+		hit.face = 6;
+		hit.t = miss_t;
+	}
+
+	// PUSH's load (och_h_octree.h:344).  base_biased = address of nodes_m1 minus 4 * kMagicBits (computed on the host),
+	// so that bits(F) = kMagicBits | idx' can be used as the word offset as it is: two 64-bit IMADs, no logic op
+	__device__ __forceinline__ uint32_t load_child(unsigned long long base_biased)
+	{
+		if (COUNT) ++hit.npush;
+		const unsigned long long a = base_biased + static_cast<unsigned long long>(node) * 32ull + static_cast<unsigned long long>(__float_as_uint(F)) * 4ull;
+		return __ldg(reinterpret_cast<const uint32_t*>(a));
+	}
+
+	// PUSH with a non-empty child: HIT at the last level (returns true), else go down one level
+	__device__ __forceinline__ bool descend(uint32_t child, int depth, uint32_t* stack_n, float* stack_f)
+	{
+		if (level == depth)
+		{
+			hit.voxel = child;
+			hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
+			hit.t = tmin;
+			return true;
+		}
+		stack_n[level - 1] = node;
+		stack_f[level - 1] = F;
+		++level;
+		node = child;
+		dimf *= 0.5f;
+		const float ux = set_ge(__fmaf_rn(px + dimf, cx, bx), tmin);            // px + dimf is exact
+		const float uy = set_ge(__fmaf_rn(py + dimf, cy, by), tmin);
+		const float uz = set_ge(__fmaf_rn(pz + dimf, cz, bz), tmin);
+		px = __fmaf_rn(ux, dimf, px);                                              // exact: + size or + 0
+		py = __fmaf_rn(uy, dimf, py);
+		pz = __fmaf_rn(uz, dimf, pz);
+		F = __fmaf_rn(uz, wz, __fmaf_rn(uy, wy, __fmaf_rn(ux, wx, c0)));           // exact small integers at ulp 1
+		return false;
+	}
+
+	// PUSH with an empty child: STEP to the sibling across the nearest exit plane, POPping as far as needed;
+	// returns true on MISS
+	__device__ __forceinline__ bool advance(const uint32_t* stack_n, const float* stack_f)
+	{
+		bool ax, ay;
+		for (;;)
+		{
+			const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
+			const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
+			const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
+			const uint32_t tyz = min(ty, tz);
+			ax = tx <= tyz;                                                     // unsigned argmin, ties -> x, y, z (:388-406)
+			ay = !ax && ty <= tz;
+			tmin = __uint_as_float(min(tx, tyz));
+			mti = 4u;
+			if (ay) mti = 2u;
+			if (ax) mti = 1u;
+
+			if (((__float_as_uint(F) ^ inv) & mti) != 0u)
+				break;                                                          // a sibling lies that way
+
+			if (((tx | ty | tz) & 0x80000000u) == 0u)
+			{
+				// multi-level POP (proof of the shortcut in FastWalker::advance; the bit trick is explained above)
+				uint32_t pa = __float_as_uint(pz);
+				if (ay) pa = __float_as_uint(py);
+				if (ax) pa = __float_as_uint(px);
+				const uint32_t b = pa & (0u - pa);
+				if (b == 0x00800000u)
+				{
+					miss();                                                         // popped through the root
+					return true;
+				}
+				const uint32_t keep = 0u - b;
+				px = __uint_as_float(__float_as_uint(px) & keep);
+				py = __uint_as_float(__float_as_uint(py) & keep);
+				pz = __uint_as_float(__float_as_uint(pz) & keep);
+				dimf = __uint_as_float(0x3F800000u | b) - 1.0f;                 // b * 2^-23, exact
+				level = __clz(static_cast<int>(b)) - 8;                         // 23 - flo(b)
+				node = stack_n[level - 1];
+				F = stack_f[level - 1];                                         // bit a* (un-XORed) is set there
+				break;
+			}
+
+			// a negative or -inf t is in play: the reference's sequence verbatim, one level at a time
+			if (--level == 0)
+			{
+				miss();
+				return true;
+			}
+			const uint32_t u = __float_as_uint(F) ^ inv;
+			if (u & 1u) px -= dimf;                                             // back to the parent's corner
+			if (u & 2u) py -= dimf;
+			if (u & 4u) pz -= dimf;
+			dimf += dimf;
+			node = stack_n[level - 1];
+			F = stack_f[level - 1];
+		}
+
+		// step to the sibling across the exit plane (exact: the bit is set)
+		if (ax) { px -= dimf; F -= wx; }
+		else if (ay) { py -= dimf; F -= wy; }
+		else { pz -= dimf; F -= wz; }
+		return false;
+	}
+};
+
 template<bool COUNT>
 __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, const Ray& r, uint32_t* stack)
 {

@@ -253,7 +253,7 @@ def test_kernel_variants_agree(ort, golden):
     pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
     ref = None
     ctx.set_option("smem_levels", 215)                  # variant 3 stages the first 215 nodes (levels 1-4 of this DAG)
-    for variant in (0, 1, 2, 3, 4, 5, 6):
+    for variant in (0, 1, 2, 3, 4, 5, 6, 7):
         ctx.set_option("variant", variant)
         got = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
         part = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=64, tile_rows=8, tile_step=3)
@@ -346,3 +346,34 @@ def test_host_buffer_pipelines_keep_results(ort, golden):
     ctx.set_option("rays_chunk", 4096)
     b = ctx.trace_rays(shared, dd)
     assert_same_hits(a, b, "shared origin, chunked")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("depth,log2cap", [(1, 8), (2, 8), (16, 18)])
+def test_extreme_depths_trace_vs_oracle(ort, oc, depth, log2cap):
+    """Depth 1 (one node) and depth 16 (65536^3, a 16-entry parent stack, voxel-size 2^-16 steps): GPU trace of random,
+    axis-parallel and corner-grazing rays equals the oracle on the same table."""
+    rs = np.random.RandomState(100 + depth)
+    dim = 1 << depth
+    A, T = oc.OracleTree(log2cap, depth), ort.HOctree(log2cap, depth)
+    n = 6 if depth <= 2 else 4000
+    pts = rs.randint(0, dim, (n, 3))
+    if depth == 16:                                           # a dense blob so that rays actually hit something
+        pts[: n // 2] = 32768 + rs.randint(-40, 40, (n // 2, 3))
+    pts[:2] = [[0, 0, 0], [dim - 1, dim - 1, dim - 1]]
+    ops = np.concatenate([pts, rs.randint(1, 5, (n, 1))], 1).astype(np.uint32)
+    A.set_many(ops)
+    T.set_many(ops)
+    m = 30000
+    o = rs.uniform(1.001, 1.999, (m, 3)).astype(np.float32)
+    target = (1.0 + (pts[rs.randint(0, n, m)] + rs.uniform(0, 1, (m, 3))) / dim).astype(np.float32)
+    d = target - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    d[:300, 1:] = 0.0                                        # axis-parallel
+    d[300:600, 2] = 0.0
+    o[600:900] = np.float32(1.5)                             # origins on cell planes
+    got = T.trace_rays(o, d, want_npush=True)
+    want = A.trace(o, d)
+    assert_same_hits(got, want, f"depth {depth}")
+    assert (got[0] != 0).sum() > m // 10

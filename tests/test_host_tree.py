@@ -281,3 +281,67 @@ def test_table_dump_and_load_round_trip(ort, oc, tmp_path):
     bad.write_bytes(b"not a table")
     with pytest.raises(Exception):
         B.load(str(bad))
+
+
+@pytest.mark.parametrize("depth,log2cap", [(1, 8), (2, 8), (16, 18)])
+def test_extreme_depths_match_oracle(ort, oc, depth, log2cap):
+    """Smallest and largest tree the interface allows (uint16 coordinates: depth 16 = 65536^3): same table as the
+    restatement of the reference after random sets and removals, corners included."""
+    rs = np.random.RandomState(depth)
+    dim = 1 << depth
+    a, p = oc.OracleTree(log2cap, depth), ort.HOctree(log2cap, depth, device=None)
+    n = 24 if depth <= 2 else 2500
+    pts = rs.randint(0, dim, (n, 3))
+    pts[:4] = [[0, 0, 0], [dim - 1, dim - 1, dim - 1], [0, dim - 1, 0], [dim - 1, 0, dim - 1]]
+    ops = np.concatenate([pts, rs.randint(1, 5, (n, 1))], 1).astype(np.uint32)
+    rem = ops[rs.permutation(n)[: n // 3]].copy()
+    rem[:, 3] = 0
+    for batch in (ops, rem, ops[: n // 2]):
+        a.set_many(batch)
+        p.set_many(batch)
+        assert (a.root, a.fillcnt, a.nodecnt) == (p.get_root(), p.get_fillcnt(), p.get_nodecnt())
+        assert np.array_equal(a.cashes(), p.cashes())
+        lm = live_mask(a.cashes())
+        assert np.array_equal(a.nodes()[lm], p.nodes()[lm]) and np.array_equal(a.refcounts()[lm], p.refcounts()[lm])
+    assert [a.at(*q) for q in pts[:200]] == [p.at(*q) for q in pts[:200]]
+    nodes8, root, lo = p.flatten()
+    # (a slot that serves both above and at the last level gets two compact ids, so >= rather than ==)
+    assert p.get_fillcnt() <= nodes8.shape[0] <= p.get_fillcnt() + 8 and len(lo) == depth + 1
+
+
+def test_slots_shared_across_levels_flatten_and_delta(ort, oc):
+    """The table is content-addressed across levels: with small payloads a last-level node such as (2,0,0,..) has the
+    same bytes as an interior node pointing at slot 1, and chains of single-child nodes can meet the same slot at
+    different heights.  Compact ids therefore belong to (slot, level); both the fresh flatten and the delta stream must
+    keep every interpretation apart.  (Found by the depth-16 case: isolated voxels = long single-child chains.)"""
+    depth, log2cap = 16, 18
+    rs = np.random.RandomState(116)
+    dim = 1 << depth
+    A, T = oc.OracleTree(log2cap, depth), ort.HOctree(log2cap, depth, device=None)
+    n = 4000
+    pts = rs.randint(0, dim, (n, 3))
+    pts[: n // 2] = 32768 + rs.randint(-40, 40, (n // 2, 3))
+    ops = np.concatenate([pts, rs.randint(1, 5, (n, 1))], 1).astype(np.uint32)
+    m = 20000
+    o = rs.uniform(1.001, 1.999, (m, 3)).astype(np.float32)
+    target = (1.0 + (pts[rs.randint(0, n, m)] + rs.uniform(0, 1, (m, 3))) / dim).astype(np.float32)
+    d = target - o
+    d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+
+    A.set_many(ops[:1000])
+    T.set_many(ops[:1000])
+    ids, nodes8, root, full = T.take_delta()
+    assert full
+    mirror = nodes8.copy()
+    assert_same_hits(oc.trace_rays(mirror, root, depth, o, d), A.trace(o, d), "first flatten")
+    for k in range(1000, n, 500):                      # grow through deltas, with some removals
+        batch = ops[k:k + 500].copy()
+        batch[::7, 3] = 0
+        A.set_many(batch)
+        T.set_many(batch)
+        ids, nodes8, root, full = T.take_delta()
+        mirror = nodes8.copy() if full else apply_delta(mirror, ids, nodes8)
+        assert_same_hits(oc.trace_rays(mirror, root, depth, o, d), A.trace(o, d), f"delta after {k}")
+    fresh, root2, _ = T.flatten()
+    assert fresh.shape[0] > T.get_fillcnt()             # some slot really has more than one role in this scene
+    assert_same_hits(oc.trace_rays(fresh, root2, depth, o, d), A.trace(o, d), "fresh flatten")
