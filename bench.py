@@ -445,7 +445,7 @@ def run_product(args):
             "gpu_launches": launches_all,
             "roofline": {
                 "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic_per_launch(), "peak_source": peak_src, "kernel": "ort::trace_frame_kernel<1,false>",
+                "traffic": traffic_per_launch(), "peak_source": peak_src, "kernel": "ort::trace_frame_kernel<1,false,false>",
                 "algorithmic_bytes_per_launch": int(bytes_per_step_local / frames_per_step),
                 "avg_launch_ms": round(avg_launch_s * 1e3, 4),
                 "sector_gather_peak": {"l2_resident_gbs": round(gather_l2, 1), "hbm_resident_gbs": round(gather_hbm, 1),

@@ -494,6 +494,17 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
+	if (c->opt_variant == 12)
+	{
+		ORT_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+		const unsigned n_tiles = static_cast<unsigned>(grid.x) * grid.y * 8u;
+		const unsigned pblocks = grid.x * grid.y < static_cast<unsigned>(c->sm_count * 8) ? grid.x * grid.y : static_cast<unsigned>(c->sm_count * 8);
+		if (npush) ort::trace_frame_tiles_kernel<true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_tiles, reinterpret_cast<unsigned int*>(c->d_counter), voxel, face, t, npush);
+		else       ort::trace_frame_tiles_kernel<false><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_tiles, reinterpret_cast<unsigned int*>(c->d_counter), voxel, face, t, npush);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+		return ORT_OK;
+	}
 	if (c->opt_variant == 7)
 	{
 		const unsigned long long base_biased = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(nodes_m1)) - 4ull * ort::kMagicBits;
@@ -547,12 +558,15 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-	// block = 16 x 16 pixels by default; 16 x 8 / 16 x 4 (option "block" = 128 / 64) for measurements of block-retirement granularity
-	const int fblock = (c->opt_tile_shape == 0 && (c->opt_block == 128 || c->opt_block == 64)) ? c->opt_block : 256;
+	// block = 16 x 16 pixels by default; options "block" = 128 / 64 (16 x 8 / 16 x 4) and "tile_shape" select the
+	// measurement build of the kernel
+	const bool shaped = c->opt_variant != 0 && (c->opt_tile_shape != 0 || c->opt_block == 128 || c->opt_block == 64);
+	const int fblock = (shaped && c->opt_tile_shape == 0) ? c->opt_block : 256;
 	const dim3 fgrid((W + 15) / 16, (rows + fblock / 16 - 1) / (fblock / 16));
-#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<fgrid, fblock, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
-	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); }
-	else { if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); }
+#define ORT_LAUNCH_FRAME(V, C, S) ort::trace_frame_kernel<V, C, S><<<fgrid, fblock, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
+	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true, false); else ORT_LAUNCH_FRAME(0, false, false); }
+	else if (shaped) { if (npush) ORT_LAUNCH_FRAME(1, true, true); else ORT_LAUNCH_FRAME(1, false, true); }
+	else { if (npush) ORT_LAUNCH_FRAME(1, true, false); else ORT_LAUNCH_FRAME(1, false, false); }
 #undef ORT_LAUNCH_FRAME
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());

@@ -692,14 +692,26 @@ __device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const
 	return in_unit_cube(ox, oy, oz) & !all_degenerate;
 }
 
+// The walk of one ray, start to end.  VARIANT 0: the baseline transliteration; otherwise FastWalker where its
+// preconditions hold (origin in [1,2)^3, a non-degenerate direction component) and the baseline for the rest.
+// The loop is spelled out here -- load, then descend or advance -- rather than through FastWalker::iterate: the same
+// instructions, but this shape schedules ~2 % better (measured: 15.2 vs 14.9 Grays/s on the bench step).
 template<int VARIANT, bool COUNT>
 __device__ __forceinline__ Hit traverse_variant(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, float ox, float oy, float oz, const Ray& r)
 {
 	uint32_t stack[kMaxDepth];       // parent stack, local memory (dynamically indexed)
-	if (VARIANT == 0)
-		return traverse(nodes_m1, root, depth, miss_t, r, stack);
-	if (fast_path_ok(ox, oy, oz, r))
-		return traverse_fast<COUNT>(nodes_m1, root, depth, miss_t, r, stack);
+	if (VARIANT != 0 && fast_path_ok(ox, oy, oz, r))
+	{
+		FastWalker<COUNT> w;
+		w.start(root, miss_t, r);
+		for (;;)
+		{
+			const uint32_t child = w.load_child(nodes_m1);
+			if (child ? w.descend(child, depth, stack) : w.advance(stack))
+				break;
+		}
+		return w.hit;
+	}
 	return traverse(nodes_m1, root, depth, miss_t, r, stack);
 }
 

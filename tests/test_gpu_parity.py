@@ -253,7 +253,7 @@ def test_kernel_variants_agree(ort, golden):
     pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
     ref = None
     ctx.set_option("smem_levels", 215)                  # variant 3 stages the first 215 nodes (levels 1-4 of this DAG)
-    for variant in (0, 1, 2, 3, 4, 5, 6, 7):
+    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 12):
         ctx.set_option("variant", variant)
         got = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
         part = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=64, tile_rows=8, tile_step=3)
