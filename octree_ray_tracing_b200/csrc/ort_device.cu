@@ -637,7 +637,7 @@ static int frame_to_host(ort_ctx* c, const float pos[3], const float rot[9], flo
 		if (c->slot_used[slot])
 			ORT_CUDA(c, cudaStreamWaitEvent(c->aux_stream[i], c->ev_copied[slot], 0));   // the slot's previous frame has left
 	}
-	const int n_streams = c->opt_variant == 2 ? 1 : 3;               // the persistent kernels share one work counter per context
+	const int n_streams = (c->opt_variant == 2 || c->opt_variant == 12) ? 1 : 3;               // the persistent kernels share one work counter per context
 	int launched = 0;
 	for (int k = 0; k < kChunks; ++k)
 	{
