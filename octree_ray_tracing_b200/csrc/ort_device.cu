@@ -371,6 +371,9 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 			const size_t off = align_up(n * 4, 16);
 			int rc = ensure_dstage(c, off + n * 32);
 			if (rc != ORT_OK) return rc;
+			// the staging buffer may still hold results of deferred host-buffer calls that are on their way out
+			for (int i = 0; i < 2; ++i)
+				if (c->slot_used[i]) ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_copied[i], 0));
 			char* base = static_cast<char*>(c->d_stage);
 			ORT_CUDA(c, cudaMemcpyAsync(base, ids, n * 4, cudaMemcpyHostToDevice, c->stream));
 			ORT_CUDA(c, cudaMemcpyAsync(base + off, nodes8, n * 32, cudaMemcpyHostToDevice, c->stream));

@@ -377,3 +377,44 @@ def test_extreme_depths_trace_vs_oracle(ort, oc, depth, log2cap):
     want = A.trace(o, d)
     assert_same_hits(got, want, f"depth {depth}")
     assert (got[0] != 0).sum() > m // 10
+
+
+@pytest.mark.gpu
+def test_edits_between_deferred_frames(ort, oc, golden):
+    """A frame loop with deferred completion and edits in between: frame k is still crossing PCIe when the delta of
+    edit k+1 is staged and frame k+1 is queued.  Every frame must show exactly the tree as it was when it was queued."""
+    depth, log2cap = 8, 19
+    h, g = oc.heightmap(depth), oc.grass_bits(depth)
+    A = oc.OracleTree(log2cap, depth)
+    A.initialize_terrain(h, g, False)
+    T = ort.HOctree(log2cap, depth)
+    ort.harness.build_terrain(T, h, g, gpu=False)
+    T.sync()
+    tab = builtin_table()
+    W, H = 640, 360
+    pos = np.array([1.5, 1.5, 1.62], np.float32)
+    rot, fov = ort.camera_coeffs(0.4, -1.0)
+    d = oc.gen_rays(rot, fov, W, H)
+    rs = np.random.RandomState(77)
+    frames, wants = [], []
+    T.ctx.set_option("defer_sync", 1)
+    for k in range(6):
+        c = rs.randint(60, 190, 3)
+        c[2] = int(h[c[1], c[0]])
+        v = k % 2
+        T.fill_box(c - 12, c + 12, v)
+        box = np.array([(x, y, z, v) for z in range(c[2] - 12, c[2] + 12) for y in range(c[1] - 12, c[1] + 12) for x in range(c[0] - 12, c[0] + 12)
+                        if 0 <= z < 256], np.uint32)
+        A.set_many(box)
+        n_up, full = T.sync()                                        # delta upload while earlier frames drain
+        assert n_up > 0 and not full
+        out = (np.zeros(W * H, np.uint32), np.zeros(W * H, np.uint8), np.zeros(W * H, np.float32), None)
+        T.ctx.trace_frame(pos, rot, fov, W, H, out=out)              # returns once queued
+        frames.append(out)
+        wants.append(A.trace(pos, d, rcp_tab=tab, nthreads=4))       # the straight table that saw the same edits
+        assert (A.fillcnt, A.nodecnt) == (T.get_fillcnt(), T.get_nodecnt())
+    T.ctx.sync()
+    T.ctx.set_option("defer_sync", 0)
+    for k in range(6):
+        assert_same_hits(frames[k], wants[k], f"deferred frame {k}")
+    assert any(not np.array_equal(frames[k][0], frames[k + 1][0]) for k in range(5))     # the edits are visible
