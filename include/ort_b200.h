@@ -65,6 +65,11 @@ int ort_destroy(ort_ctx* ctx);
  * exponents, zeros, infinities follow the rule documented at oc_rcp_table_bits.
  * The built-in default is the 2048-entry table of Intel's RCPPS (csrc/ort_rcp_table.h). */
 int ort_set_rcp_table(ort_ctx* ctx, const uint32_t* tab, int log2n);
+/* Derive that table from the CPU this process runs on (x86 RCPSS), for hosts whose reciprocal differs from the
+ * built-in Intel table: fills tab[1 << log2n] and returns how many probe inputs the table model gets wrong (0 = the
+ * GPU trace will equal this host's CPU trace bit for bit after ort_set_rcp_table(ctx, tab, log2n)); -1 if the build
+ * has no RCPSS.  log2n = 11 suffices on Intel; try larger values until the return value is 0 elsewhere. */
+long ort_host_rcp_table(uint32_t* tab, int log2n);
 
 /* Replaces: the tracer's view of table->nodes[] / root_idx (och_h_octree.h:82, :95, :344).
  * nodes8 = n_nodes * 8 uint32 in COMPACT numbering: node id i (1-based) is row i-1; interior

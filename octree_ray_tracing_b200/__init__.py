@@ -7,5 +7,5 @@ reference's own C++ interface (``HOctree`` mirrors ``och::h_octree``), used by t
 headless harness and ``bench.py``.
 """
 from ._lib import OrtError, lib, LIB_PATH  # noqa: F401
-from .tree import HOctree, Octree, TraceContext, Direction, camera_coeffs  # noqa: F401
+from .tree import HOctree, Octree, TraceContext, Direction, camera_coeffs, host_rcp_table  # noqa: F401
 from . import harness  # noqa: F401

@@ -28,6 +28,7 @@ _SIGS = {
     "ort_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, C.c_uint32]),
     "ort_destroy": (C.c_int, [_vp]),
     "ort_set_rcp_table": (C.c_int, [_vp, _vp, C.c_int]),
+    "ort_host_rcp_table": (C.c_long, [_vp, C.c_int]),
     "ort_upload_full": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32]),
     "ort_upload_delta": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32]),
     "ort_upload_pool": (C.c_int, [_vp, _vp, C.c_size_t]),

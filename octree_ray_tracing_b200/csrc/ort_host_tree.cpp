@@ -714,6 +714,56 @@ const uint32_t* ort_tree_nodes(const ort_tree* t) { return t->nodes; }
 const uint8_t*  ort_tree_cashes(const ort_tree* t) { return t->tags; }
 const uint32_t* ort_tree_refcounts(const ort_tree* t) { return t->refcounts; }
 
+// The host CPU's RCPSS as a table (the reference's reciprocal, och_h_octree.h:316, is whatever the CPU it runs on
+// implements): entry k = RCPSS(1.0 + k * 2^-log2n) for 1.0 <= x < 2.0.  Returns the number of probe inputs (all
+// mantissas of [1,2) plus a sample of other exponents) on which the table model -- top log2n mantissa bits decide,
+// exponent handled arithmetically, see ort::rcp_model -- disagrees with the instruction: 0 means the GPU will match
+// this host bit for bit once the table is passed to ort_set_rcp_table.  -1 on non-x86 builds.
+#if defined(__SSE__) || defined(_M_X64) || defined(__x86_64__)
+#include <xmmintrin.h>
+static inline uint32_t host_rcp_bits(uint32_t x)
+{
+	float f, r;
+	std::memcpy(&f, &x, 4);
+	r = _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(f)));
+	uint32_t b;
+	std::memcpy(&b, &r, 4);
+	return b;
+}
+static inline uint32_t model_rcp_bits(const uint32_t* tab, int log2n, uint32_t x)      // the host twin of ort::rcp_model
+{
+	const uint32_t sign = x & 0x80000000u, e = (x >> 23) & 0xFFu, m = x & 0x7FFFFFu;
+	if (e == 255u) return m ? (x | 0x00400000u) : sign;
+	if (e == 0u) return sign | 0x7F800000u;
+	const uint32_t r = tab[m >> (23 - log2n)];
+	const int re = static_cast<int>(r >> 23) - (static_cast<int>(e) - 127);
+	if (re <= 0) return sign;
+	return sign | (static_cast<uint32_t>(re) << 23) | (r & 0x7FFFFFu);
+}
+long ort_host_rcp_table(uint32_t* tab, int log2n)
+{
+	if (!tab || log2n < 1 || log2n > 23) return -1;
+	const int sh = 23 - log2n;
+	for (uint32_t k = 0; k < (1u << log2n); ++k) tab[k] = host_rcp_bits(0x3F800000u | (k << sh));
+	long bad = 0;
+	for (uint32_t m = 0; m < (1u << 23); ++m)
+	{
+		const uint32_t x = 0x3F800000u | m;
+		bad += host_rcp_bits(x) != model_rcp_bits(tab, log2n, x);
+		bad += host_rcp_bits(x | 0x80000000u) != model_rcp_bits(tab, log2n, x | 0x80000000u);
+	}
+	for (uint32_t e = 0; e < 256; ++e)
+		for (uint32_t m = 0; m < (1u << 23); m += 4099u)
+		{
+			const uint32_t x = (e << 23) | m;
+			bad += host_rcp_bits(x) != model_rcp_bits(tab, log2n, x);
+		}
+	return bad;
+}
+#else
+long ort_host_rcp_table(uint32_t*, int) { return -1; }
+#endif
+
 // Table dump / load.  File = header + one record per occupied slot (live or gravestone), in slot
 // order: slot u32, refcount u32, tag u8, 3 pad bytes, 8 children.  Loading restores the exact table -- slots, tags,
 // reference counts, root and counters -- so edits continue as if the tree had been built in this process.

@@ -45,6 +45,13 @@ def _p(a):
     raise TypeError(type(a))
 
 
+def host_rcp_table(log2n: int = 11):
+    """(table, mismatches): this host CPU's RCPSS as a table for TraceContext.set_rcp_table (see ort_host_rcp_table)."""
+    tab = np.zeros(1 << log2n, np.uint32)
+    bad = lib().ort_host_rcp_table(_p(tab), log2n)
+    return tab, int(bad)
+
+
 def camera_coeffs(yaw: float, pitch: float):
     """rot[9], fov_factor as tree_camera::update_position computes them (test_och_h_octree.cpp:95-115)."""
     rot = np.zeros(9, np.float32)

@@ -1,9 +1,11 @@
 """CPU tests of the product's host side (C++ node store, flatten/delta, fixture builder, camera)
 against the oracle.  No GPU needed: nothing here calls a trace entry point."""
+import os
+
 import numpy as np
 import pytest
 
-from conftest import assert_same_hits, same_bits
+from conftest import ROOT, assert_same_hits, same_bits
 
 
 def live_mask(tags):
@@ -345,3 +347,18 @@ def test_slots_shared_across_levels_flatten_and_delta(ort, oc):
     fresh, root2, _ = T.flatten()
     assert fresh.shape[0] > T.get_fillcnt()             # some slot really has more than one role in this scene
     assert_same_hits(oc.trace_rays(fresh, root2, depth, o, d), A.trace(o, d), "fresh flatten")
+
+
+def test_host_rcp_probe_matches_builtin_table_on_this_host(ort, oc):
+    """ort_host_rcp_table: the product's own probe of the host's RCPSS.  On the Intel hosts this project runs on it
+    reproduces the built-in table exactly and the table model has no mismatch; it also equals the oracle's probe."""
+    tab, bad = ort.host_rcp_table(11)
+    otab, obad = oc.rcp_table_from_hw(11)
+    assert np.array_equal(tab, otab)
+    if bad == 0:                                        # Intel-style 11-bit table: must be the built-in one
+        import re
+        txt = open(os.path.join(ROOT, "octree_ray_tracing_b200", "csrc", "ort_rcp_table.h")).read()
+        builtin = np.array([int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", txt)], np.uint32)
+        assert np.array_equal(tab, builtin)
+    else:                                               # another vendor: a finer table must exist
+        assert any(ort.host_rcp_table(k)[1] == 0 for k in (12, 14, 16, 20, 23))
