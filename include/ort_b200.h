@@ -150,7 +150,9 @@ uint64_t ort_launch_count(const ort_ctx* ctx);
 /* Options.  Behaviour: "defer_sync" (host-buffer trace calls return once queued; ort_sync() collects),
  * "frame_chunks" (launches per host-buffer frame, 0 = automatic: 8, or 2 with defer_sync), "rays_chunk" (rays per
  * pipeline stage of host-buffer ort_trace_rays, default 2^20), "zero_copy" (kernels store straight into pinned host
- * outputs; measured slower than the copy engine, off by default).  Kernel selection for A/B measurements: "variant"
+ * outputs; measured slower than the copy engine, off by default), "band_rotate" (which 16-row band of a frame launch
+ * is scheduled first; -1 = automatic: the first band that looks below the horizon, so the long grazing rays start
+ * early and the cheap sky rows fill the end of the launch).  Kernel selection for A/B measurements: "variant"
  * (frames: 0 baseline walk, 1 fast walk = default, 2 persistent lane-refill, 3 upper levels staged in shared memory,
  * 4 deferred phases, 5 tight bookkeeping, 6 while-while), "rays_variant" (explicit rays: 1 one thread per ray,
  * 2 persistent lane-refill = default), "low_water", "smem_levels", "tile_shape", "block". */

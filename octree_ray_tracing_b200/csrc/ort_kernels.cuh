@@ -67,6 +67,7 @@ struct FrameRows
 	int W, H;
 	int y0, rows, tile_rows, tile_step;
 	int tile_shape;     // warp tile: 0 = 8x4, 1 = 16x2, 2 = 4x8 (trace_frame_kernel only)
+	int band_rotate;    // block row b is traced by blockIdx.y = (b - band_rotate) mod gridDim.y: which 16-row band starts first
 };
 
 // camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
@@ -83,7 +84,13 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 	if (SHAPED && fr.tile_shape == 1)      { x = blockIdx.x * 16 + (lane & 15);                   r = blockIdx.y * 16 + warp * 2 + (lane >> 4); }
 	else if (SHAPED && fr.tile_shape == 2) { x = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);   r = blockIdx.y * 16 + (warp >> 2) * 8 + (lane >> 2); }
 	else if (SHAPED)                       { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * static_cast<int>(blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3); }
-	else                                   { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3); }
+	else
+	{
+		unsigned by = blockIdx.y + static_cast<unsigned>(fr.band_rotate);
+		if (by >= gridDim.y) by -= gridDim.y;
+		x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+		r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
+	}
 	if (x >= fr.W || r >= fr.rows) return;
 	int y = fr.y0 + r;                                                 // contiguous strip
 	if (fr.tile_step != 1)                                             // cyclic tile strips (uniform branch)
@@ -118,8 +125,10 @@ trace_frame_rgba_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
                         Palette pal, uint32_t* __restrict__ rgba)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned by = blockIdx.y + static_cast<unsigned>(fr.band_rotate);
+	if (by >= gridDim.y) by -= gridDim.y;
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
+	const int r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
 	int y = fr.y0 + r;
 	if (fr.tile_step != 1)
