@@ -222,7 +222,36 @@ def run_product(args):
     bytes_per_step_local = 32 * pushes_per_step_local + 9 * rays_per_step_local
     step_cams = [cam for _rep in range(world) for cam in cams]
 
+    if args.launch == "auto":
+        args.launch = "streams" if world == 1 else "batch"       # measured: 1 GPU 14.8 (streams) vs 14.6 (batch); 8 GPUs see DESIGN.md section 9
+    # one output set per frame of the step for the batched launch (ort_trace_frames_async: the whole step in one launch)
+    batch_outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
+                   torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(frames_per_step)] if args.launch == "batch" else []
+    batch_jobs = [(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, world, o[0], o[1], o[2]) for cam, o in zip(step_cams, batch_outs)]
+
+    def timed_steps_batched(steps, do_flush):
+        """One timed interval per STEP, the step's frames in one batched launch on one stream."""
+        evs = []
+        s0 = streams[0]
+        ctx.set_stream(s0)
+        for _ in range(steps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(s0):
+                if do_flush:
+                    flush.zero_()
+                a.record(s0)
+            ctx.trace_frames_async(batch_jobs)
+            b.record(s0)
+            evs.append((a, b))
+        ctx.set_stream(None)
+        return evs
+
     def timed_steps(steps, do_flush):
+        if args.launch == "batch":
+            return timed_steps_batched(steps, do_flush)
+        return timed_steps_streams(steps, do_flush)
+
+    def timed_steps_streams(steps, do_flush):
         """One timed interval per STEP: L2 flushed before it (outside the interval), then the step's frames are
         queued round-robin on NS streams so that the latency tail of one launch overlaps the next launch."""
         evs = []
@@ -420,7 +449,8 @@ def run_product(args):
                 "partition": f"cyclic {TILE_ROWS}-row tile strips over {world} GPU(s), DAG replicated",
                 "host_placement": "rank pinned to its GPU's NUMA node (NVML ideal CPUs)" if numa_bound else "default",
                 "l2": "flushed before every step (256 MiB memset outside the timed interval)",
-                "in_flight": f"{NS} streams: the frames of a step are queued round-robin so launch tails overlap",
+                "in_flight": ("one batched launch per step (ort_trace_frames_async): the frames' blocks stream through the SMs back to back"
+                              if args.launch == "batch" else f"{NS} streams: the frames of a step are queued round-robin so launch tails overlap"),
                 "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
                 "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3),
                 "hit_fraction": round(hits / (len(cams) * n_local), 4),
@@ -584,6 +614,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--launch", default="auto", choices=["auto", "batch", "streams"],
+                    help="device-resident loop: the step's frames in one batched launch (ort_trace_frames_async) or one launch per frame on several streams")
     ap.add_argument("--streams", type=int, default=0, help="frames in flight in the device-resident loop (0 = 3 on one GPU, up to 8 on several)")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--quick", action="store_true", help="profiling aid: only the device-resident timed loop (no warm-L2 loop, no e2e, no CPU leg)")

@@ -35,6 +35,7 @@ _SIGS = {
     "ort_trace_rays": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "ort_trace_frame": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
     "ort_trace_frame_async": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "ort_trace_frames_async": (C.c_int, [_vp, _vp, C.c_int]),
     "ort_trace_rays_async": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_size_t, _vp, _vp, _vp, _vp]),
     "ort_set_palette": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, C.c_uint32]),
     "ort_parse_voxels": (C.c_int, [C.c_char_p, C.c_size_t, _vp, _vp, C.c_int]),

@@ -7,6 +7,7 @@
 #include "ort_internal.h"
 #include "ort_rcp_table.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -599,6 +600,55 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 #undef ORT_LAUNCH_FRAME
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
+	return ORT_OK;
+}
+
+int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
+{
+	if (!c || n_jobs < 0 || (n_jobs && !jobs))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frames_async: bad arguments");
+	DeviceGuard g(c->device);
+	for (int i = 0; i < n_jobs; ++i)
+	{
+		const ort_frame_job& j = jobs[i];
+		if (j.W <= 0 || j.H <= 0 || j.rows < 0 || j.tile_rows <= 0 || j.tile_step <= 0 || j.y0 < 0 || (j.rows && (!j.voxel || !j.face || !j.t)))
+			return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frames_async: bad job %d", i);
+	}
+	if (!c->has_root || c->opt_variant != 1)
+	{
+		// empty tree, or a measurement variant is selected: one ordinary launch per job
+		for (int i = 0; i < n_jobs; ++i)
+		{
+			const ort_frame_job& j = jobs[i];
+			const int rc = ort_trace_frame_async(c, j.pos, j.rot, j.fov_factor, j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, j.voxel, j.face, j.t, j.npush);
+			if (rc != ORT_OK) return rc;
+		}
+		return ORT_OK;
+	}
+	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
+	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
+	for (int first = 0; first < n_jobs; first += ort::kMaxJobs)
+	{
+		ort::FrameJobBatch batch{};
+		int n = 0;
+		unsigned gx = 0, gy = 0;
+		for (int i = first; i < n_jobs && n < ort::kMaxJobs; ++i)
+		{
+			const ort_frame_job& j = jobs[i];
+			if (!j.rows) continue;
+			ort::FrameJob& d = batch.job[n++];
+			d.cam = make_camera(j.pos, j.rot, j.fov_factor, j.W, j.H);
+			const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((j.rows + 15) / 16) : horizon_band(d.cam, j.W, j.y0, j.rows, j.tile_rows, j.tile_step);
+			d.fr = ort::FrameRows{ j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, 0, rotate };
+			d.voxel = j.voxel; d.face = j.face; d.t = j.t; d.npush = j.npush;
+			gx = std::max(gx, static_cast<unsigned>((j.W + 15) / 16));
+			gy = std::max(gy, static_cast<unsigned>((j.rows + 15) / 16));
+		}
+		if (!n) continue;
+		ort::trace_frames_kernel<<<dim3(gx, gy, static_cast<unsigned>(n)), 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, batch);
+		++c->launches;
+		ORT_CUDA(c, cudaGetLastError());
+	}
 	return ORT_OK;
 }
 

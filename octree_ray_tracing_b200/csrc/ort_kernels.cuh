@@ -109,6 +109,57 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 }
 
 
+// Several frame jobs in ONE launch (blockIdx.z = job): strips of different frames, or the views of a multi-camera
+// rig.  Separate launches each end with the latency tail of their longest rays; here the blocks of all jobs stream
+// through the SMs back to back and only the last job's tail is exposed.  The jobs travel in the kernel parameters.
+constexpr int kMaxJobs = 16;
+
+struct FrameJob
+{
+	Camera cam;
+	FrameRows fr;
+	uint32_t* voxel;
+	uint8_t*  face;
+	float*    t;
+	uint16_t* npush;    // may be null
+};
+
+struct FrameJobBatch
+{
+	FrameJob job[kMaxJobs];
+};
+
+__global__ void __launch_bounds__(256)
+trace_frames_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, const __grid_constant__ FrameJobBatch batch)
+{
+	const FrameJob& jb = batch.job[blockIdx.z];
+	const FrameRows& fr = jb.fr;
+	const int bands = (fr.rows + 15) >> 4;
+	if (static_cast<int>(blockIdx.y) >= bands) return;                  // the grid is sized for the largest job
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	int by = static_cast<int>(blockIdx.y) + fr.band_rotate;
+	if (by >= bands) by -= bands;
+	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	const int r = by * 16 + (warp >> 1) * 4 + (lane >> 3);
+	if (x >= fr.W || r >= fr.rows) return;
+	int y = fr.y0 + r;
+	if (fr.tile_step != 1)
+		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+
+	float dx, dy, dz;
+	camera_ray(jb.cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup(rt, jb.cam.ox, jb.cam.oy, jb.cam.oz, dx, dy, dz);
+	Hit h;
+	if (jb.npush) h = traverse_variant<1, true>(nodes_m1, root, depth, miss_t, jb.cam.ox, jb.cam.oy, jb.cam.oz, ray);
+	else          h = traverse_variant<1, false>(nodes_m1, root, depth, miss_t, jb.cam.ox, jb.cam.oy, jb.cam.oz, ray);
+
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	jb.voxel[i] = h.voxel;
+	jb.face[i] = static_cast<uint8_t>(h.face);
+	jb.t[i] = h.t;
+	if (jb.npush) jb.npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
 // Shading epilogue (tree_camera::trace_pixel, test_och_h_octree.cpp:76-84) fused into the frame kernel: the hit is
 // turned into the pixel the demo would Draw() -- colours[6 * (voxel - 1) + face], the sky colour on exit, the
 // "inside" colour when the origin sits in a solid voxel -- and only that uint32 leaves the SM (4 B per pixel

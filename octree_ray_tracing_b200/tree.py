@@ -60,6 +60,19 @@ def camera_coeffs(yaw: float, pitch: float):
     return rot, float(np.float32(fov.value))
 
 
+class FrameJob(C.Structure):
+    """ort_frame_job (include/ort_b200.h): one frame / strip of a batched launch."""
+    _fields_ = [("pos", C.c_float * 3), ("rot", C.c_float * 9), ("fov_factor", C.c_float),
+                ("W", C.c_int), ("H", C.c_int), ("y0", C.c_int), ("rows", C.c_int), ("tile_rows", C.c_int), ("tile_step", C.c_int),
+                ("voxel", C.c_void_p), ("face", C.c_void_p), ("t", C.c_void_p), ("npush", C.c_void_p)]
+
+
+def _addr(a):
+    if a is None:
+        return None
+    return a.data_ptr() if hasattr(a, "data_ptr") else int(a)
+
+
 class TraceContext:
     """One GPU's node mirror + streams (``ort_ctx``)."""
 
@@ -188,6 +201,21 @@ class TraceContext:
         rot = np.ascontiguousarray(rot, np.float32)
         self._ck(self.L.ort_trace_frame_async(self.h, _p(pos), _p(rot), fov_factor, W, H, y0, rows, tile_rows, tile_step,
                                               _p(d_vox), _p(d_face), _p(d_t), _p(d_npush)))
+
+    def trace_frames_async(self, jobs):
+        """jobs: iterable of (pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, d_vox, d_face, d_t[, d_npush]) --
+        all of them in one launch (ort_trace_frames_async)."""
+        jobs = list(jobs)
+        arr = (FrameJob * len(jobs))()
+        for k, j in enumerate(jobs):
+            pos, rot, fov, W, H, y0, rows, tile_rows, tile_step, dv, df, dt = j[:12]
+            dn = j[12] if len(j) > 12 else None
+            arr[k].pos[:] = [float(x) for x in pos]
+            arr[k].rot[:] = [float(x) for x in rot]
+            arr[k].fov_factor = float(fov)
+            arr[k].W, arr[k].H, arr[k].y0, arr[k].rows, arr[k].tile_rows, arr[k].tile_step = W, H, y0, rows, tile_rows, tile_step
+            arr[k].voxel, arr[k].face, arr[k].t, arr[k].npush = _addr(dv), _addr(df), _addr(dt), _addr(dn)
+        self._ck(self.L.ort_trace_frames_async(self.h, C.byref(arr), len(jobs)))
 
     def trace_rays_async(self, d_o, o_stride, d_d, n, d_vox, d_face, d_t, d_npush=None):
         self._ck(self.L.ort_trace_rays_async(self.h, _p(d_o), o_stride, _p(d_d), n, _p(d_vox), _p(d_face), _p(d_t), _p(d_npush)))

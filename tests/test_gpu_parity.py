@@ -418,3 +418,42 @@ def test_edits_between_deferred_frames(ort, oc, golden):
     for k in range(6):
         assert_same_hits(frames[k], wants[k], f"deferred frame {k}")
     assert any(not np.array_equal(frames[k][0], frames[k + 1][0]) for k in range(5))     # the edits are visible
+
+
+@pytest.mark.gpu
+def test_batched_frames_equal_separate_launches(ort, golden):
+    """ort_trace_frames_async: jobs of different poses, sizes and strip layouts in one launch give what one
+    ort_trace_frame per job gives (20 jobs: more than one parameter batch)."""
+    import torch
+    g = golden("d8_tunnels")
+    ctx = ort.TraceContext(8)
+    ctx.upload_full(g["nodes8"], int(g["root"]))
+    rs = np.random.RandomState(4)
+    jobs, wants, outs = [], [], []
+    for k in range(20):
+        W, H = int(rs.randint(40, 300)), int(rs.randint(30, 200))
+        pos = rs.uniform(1.05, 1.95, 3).astype(np.float32)
+        rot, fov = ort.camera_coeffs(float(rs.uniform(-3, 3)), float(rs.uniform(-1.4, 0.6)))
+        if k % 3 == 0:
+            y0, rows, tr, ts = 8 * (k % 2), None, 8, 2
+            rows = len([y for y in range(H) if (y // 8) % 2 == (k % 2)])
+        else:
+            y0, rows, tr, ts = int(rs.randint(0, H // 2)), None, 1, 1
+            rows = int(rs.randint(1, H - y0 + 1))
+        want = ctx.trace_frame(pos, rot, fov, W, H, y0=y0, rows=rows, tile_rows=tr, tile_step=ts, want_npush=(k % 4 == 0))
+        n = rows * W
+        dv = torch.zeros(n, dtype=torch.int32, device="cuda")
+        df = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        dt = torch.zeros(n, dtype=torch.float32, device="cuda")
+        dn = torch.zeros(n, dtype=torch.int16, device="cuda") if k % 4 == 0 else None
+        jobs.append((pos, rot, fov, W, H, y0, rows, tr, ts, dv, df, dt, dn))
+        wants.append(want)
+        outs.append((dv, df, dt, dn))
+    ctx.trace_frames_async(jobs)
+    ctx.sync()
+    torch.cuda.synchronize()
+    for k, (want, (dv, df, dt, dn)) in enumerate(zip(wants, outs)):
+        got = (dv.cpu().numpy().view(np.uint32), df.cpu().numpy(), dt.cpu().numpy())
+        assert_same_hits(got, want, f"job {k}")
+        if dn is not None:
+            assert np.array_equal(dn.cpu().numpy().view(np.uint16), want[3])
