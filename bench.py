@@ -190,6 +190,21 @@ def run_product(args):
 
     poses = [harness.POSES[p] for p in POSE_NAMES]
     cams = [(np.array(p[0], np.float32),) + ort.camera_coeffs(p[1], p[2]) for p in poses]
+
+    # every rank must hold the same DAG: each traces the same small frames and the digests are compared across ranks
+    replica_check = None
+    if world > 1:
+        dig = []
+        for cam in cams:
+            v, f, t = ctx.trace_frame(cam[0], cam[1], cam[2], 480, 270)
+            dig += [int(v.astype(np.uint64).sum()), int(f.astype(np.uint64).sum()), int(t.view(np.uint32).astype(np.uint64).sum() & 0x7FFFFFFFFFFFFFFF), int((v != 0).sum())]
+        mine = torch.tensor(dig, dtype=torch.int64, device="cuda")
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi) or dig[3] < 1000:
+            raise SystemExit(f"[rank {rank}] replica check FAILED: the ranks do not trace the same DAG (digests {dig[:4]} vs min {lo[:4].tolist()} max {hi[:4].tolist()})")
+        replica_check = f"ok: {len(dig)} digests of 3 traced 480x270 frames equal on all {world} ranks"
     y0, rows, _frame_rows = multi_gpu.strip_rows(rank, world, H, TILE_ROWS)
     n_local = rows * W
     frames_per_step = len(cams) * world
@@ -322,6 +337,14 @@ def run_product(args):
     if args.quick:
         sampler.stop()
         ms = kernel_ms / args.steps
+        if world > 1:
+            tq = torch.tensor([ms, serial_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tq, op=dist.ReduceOp.MAX)
+            ms, serial_ms = float(tq[0]), float(tq[1])
+            dist.barrier()
+            dist.destroy_process_group()
+        if rank != 0:
+            return None
         emit({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
@@ -427,8 +450,10 @@ def run_product(args):
         cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
+        pushes_per_ray_all = float(cnt[2].item()) / rays_per_step_total
     else:
         launches_all = launches
+        pushes_per_ray_all = pushes_per_step_local / rays_per_step_local
 
     result = None
     if rank == 0:
@@ -447,12 +472,13 @@ def run_product(args):
             "config": {
                 "workload": WORKLOAD, "frames_per_step": frames_per_step, "rays_per_step": rays_per_step_total,
                 "partition": f"cyclic {TILE_ROWS}-row tile strips over {world} GPU(s), DAG replicated",
+                "replica_check": replica_check,
                 "host_placement": "rank pinned to its GPU's NUMA node (NVML ideal CPUs)" if numa_bound else "default",
                 "l2": "flushed before every step (256 MiB memset outside the timed interval)",
                 "in_flight": ("one batched launch per step (ort_trace_frames_async): the frames' blocks stream through the SMs back to back"
                               if args.launch == "batch" else f"{NS} streams: the frames of a step are queued round-robin so launch tails overlap"),
                 "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
-                "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3),
+                "pushes_per_ray": round(pushes_per_ray_all, 3),
                 "hit_fraction": round(hits / (len(cams) * n_local), 4),
                 "timing": "sum of CUDA-event intervals around each step (start after the flush, end after all streams joined), max over ranks",
             },

@@ -102,6 +102,10 @@ def broadcast_update(update, apply, device="cpu", src: int = 0):
         payload = torch.empty(words, dtype=torch.int32, device=device)
     if world > 1 and words:
         dist.broadcast(payload, src=src)
+    if payload.is_cuda:
+        # apply() hands raw pointers to the context, which copies on ITS stream: the payload must be complete first
+        # (the NCCL broadcast and the host-to-device copy above only order torch's current stream, not the host)
+        torch.cuda.current_stream(payload.device).synchronize()
     if is_full:
         apply(None, payload.view(-1, 8), root, True)
     else:
