@@ -238,7 +238,7 @@ def run_product(args):
     step_cams = [cam for _rep in range(world) for cam in cams]
 
     if args.launch == "auto":
-        args.launch = "streams" if world == 1 else "batch"       # measured: 1 GPU 14.8 (streams) vs 14.6 (batch); 8 GPUs see DESIGN.md section 9
+        args.launch = "streams"       # measured: 1 GPU 14.8 (streams) vs 14.6 (batch); 8 GPUs 105 vs 92 Grays/s
     # one output set per frame of the step for the batched launch (ort_trace_frames_async: the whole step in one launch)
     batch_outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
                    torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(frames_per_step)] if args.launch == "batch" else []
