@@ -212,7 +212,9 @@ def run_product(args):
     rays_per_step_local = frames_per_step * n_local
 
     own = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
-    NS = args.streams or (3 if world == 1 else min(8, 3 * world))   # frames in flight: small strips need more of them to hide launch tails
+    # frames in flight: small strips need more of them to hide launch tails, but too many concurrent launches dilute
+    # the L1 locality of each (measured: 2 GPUs 3/4/6 streams -> 28.2/28.2/26.5, 4 GPUs 4/6/8 -> 54.0/52.1/53.2, 8 GPUs 5/8/12 -> 101.8/104.5/102.3 Grays/s)
+    NS = args.streams or (3 if world == 1 else (4 if world <= 4 else 8))
     streams = [torch.cuda.Stream(device=local_rank) for _ in range(NS)]
     outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
              torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(NS)]
