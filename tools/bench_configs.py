@@ -94,6 +94,16 @@ def config5(args):
     t_build = time.time() - t0
     n_nodes, _ = multi_gpu.broadcast_update(update, multi_gpu.context_applier(ctx), device=torch.device("cuda", local))
     ctx.sync()
+    if world > 1:                                   # all replicas must trace the same picture before anything is timed
+        p0 = harness.POSES["B"]
+        rot0, fov0 = ort.camera_coeffs(p0[1], p0[2])
+        v, f, t = ctx.trace_frame(np.array(p0[0], np.float32), rot0, fov0, 480, 270)
+        mine = torch.tensor([int(v.astype(np.uint64).sum()), int(f.astype(np.uint64).sum()), int((v != 0).sum())], dtype=torch.int64, device="cuda")
+        lo, hi = mine.clone(), mine.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi) or int(mine[2]) < 1000:
+            raise SystemExit(f"[rank {rank}] replica check FAILED: ranks do not trace the same DAG")
     y0, rows, _ = multi_gpu.strip_rows(rank, world, H, tr)
     n_local = rows * W
     dv = torch.empty(n_local, dtype=torch.int32, device="cuda")
