@@ -57,7 +57,6 @@ struct ort_ctx
 
 	// staging (grown on demand)
 	void*  d_stage = nullptr;  size_t d_stage_bytes = 0;   // device side of host-pointer calls
-	void*  h_stage = nullptr;  size_t h_stage_bytes = 0;   // pinned
 
 	unsigned long long* d_counter = nullptr; // work counter of the persistent kernels
 	int max_blocks_rays = 0, max_blocks_frame = 0;
@@ -147,15 +146,6 @@ int finish_host_call(ort_ctx* c)
 	if (c->opt_defer_sync) return ORT_OK;
 	ORT_CUDA(c, cudaStreamSynchronize(c->copy_stream));
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
-	return ORT_OK;
-}
-
-int ensure_hstage(ort_ctx* c, size_t bytes)
-{
-	if (bytes <= c->h_stage_bytes) return ORT_OK;
-	if (c->h_stage) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->copy_stream); cudaFreeHost(c->h_stage); c->h_stage = nullptr; c->h_stage_bytes = 0; }
-	ORT_CUDA(c, cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocDefault));
-	c->h_stage_bytes = bytes;
 	return ORT_OK;
 }
 
@@ -256,7 +246,6 @@ int ort_destroy(ort_ctx* c)
 	cudaFree(c->d_palette);
 	cudaFree(c->d_counter);
 	cudaFree(c->d_stage);
-	if (c->h_stage) cudaFreeHost(c->h_stage);
 	for (int i = 0; i < 2; ++i)
 	{
 		if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
