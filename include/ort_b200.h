@@ -75,7 +75,9 @@ long ort_host_rcp_table(uint32_t* tab, int log2n);
  * nodes8 = n_nodes * 8 uint32 in COMPACT numbering: node id i (1-based) is row i-1; interior
  * children are compact ids, children of level-`depth` nodes are voxel payloads; 0 = empty.
  * root = compact id of the root, 0 = empty tree (every ray then misses, as the reference's
- * callers arrange: test_och_h_octree.cpp:443, :535).  Host or device pointers. */
+ * callers arrange: test_och_h_octree.cpp:443, :535).  Host or device pointers; a device source is
+ * read on the context's own stream, so whatever produced it (an NCCL broadcast, a copy on
+ * another stream) must have completed -- synchronise the producer first. */
 int ort_upload_full(ort_ctx* ctx, const uint32_t* nodes8, size_t n_nodes, uint32_t root);
 /* Replaces: the writes at och_h_octree.h:155 between two frames.  Scatters n nodes to compact
  * ids ids[i] (1-based) and installs the new root. */

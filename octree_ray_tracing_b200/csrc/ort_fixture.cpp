@@ -371,7 +371,7 @@ int ort_parse_voxels(const char* text, size_t len, uint32_t* rgba6, char* names1
 			uint32_t px = 0xFF000000u;
 			for (int byte = 0; byte < 3; ++byte)
 			{
-				if (i + 1 >= len + 0 && i >= len)
+				if (i >= len)
 					return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: input ended unexpectedly (%s, colour %d)", name, dir + 1), -1;
 				if (i + 1 >= len || !std::isxdigit(static_cast<unsigned char>(text[i])) || !std::isxdigit(static_cast<unsigned char>(text[i + 1])))
 					return ort_fail(nullptr, ORT_ERR_INVALID, "ort_parse_voxels: non-hex character in colour-value (%s at colour no. %d)", name, dir + 1), -1;
