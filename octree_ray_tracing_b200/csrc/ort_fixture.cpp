@@ -156,6 +156,7 @@ struct LocalDag
 {
 	std::vector<uint32_t> words;       // 8 per node, in creation order (children before parents)
 	std::vector<uint8_t>  leaf;        // 1: children are voxel payloads
+	std::vector<uint8_t>  lvl;         // k = log2(cell size) of the node
 	std::vector<uint32_t> slots;       // open addressing -> local id (1-based), 0 = empty
 	uint32_t mask = 0;
 	bool failed = false;
@@ -190,6 +191,7 @@ struct LocalDag
 				return id;
 		words.insert(words.end(), n, n + 8);
 		leaf.push_back(static_cast<uint8_t>(is_leaf));
+		lvl.push_back(static_cast<uint8_t>(k));
 		return slots[p] = static_cast<uint32_t>(leaf.size());
 	}
 };
@@ -249,6 +251,7 @@ uint32_t build_parallel(const Builder& b, ort_tree* tree, int nthreads, bool& fa
 		local_root[i] = w.build(cx * cell, cy * cell, cz * cell, ks);
 	});
 
+	const auto t_par = std::chrono::steady_clock::now();
 	if (std::getenv("ORT_FIXTURE_TIMING"))
 	{
 		size_t tot = 0;
@@ -256,18 +259,43 @@ uint32_t build_parallel(const Builder& b, ort_tree* tree, int nthreads, bool& fa
 		std::fprintf(stderr, "[ort fixture] %zu local nodes in %zu sub-DAGs\n", tot, dags.size());
 	}
 	TreeSink sink{ tree };
-	std::vector<uint32_t> sub_root(dags.size(), 0), gmap;
+	std::vector<uint32_t> sub_root(dags.size(), 0), gmap, order;
+	constexpr size_t kLook = 12;                       // nodes prepared (children translated, table lines prefetched) ahead of the intern
+	uint32_t prep[kLook][8];
 	for (size_t i = 0; i < dags.size() && !sink.failed; ++i)
 	{
 		LocalDag& d = dags[i];
-		gmap.assign(d.leaf.size(), 0);
-		for (size_t j = 0; j < d.leaf.size() && !sink.failed; ++j)
+		const size_t n = d.leaf.size();
+		gmap.assign(n, 0);
+		// level by level (children before parents; the nodes of one level are independent of each other)
+		size_t first_of[18] = { 0 };
+		for (size_t j = 0; j < n; ++j) ++first_of[d.lvl[j] + 1];
+		for (int k = 1; k < 18; ++k) first_of[k] += first_of[k - 1];
+		order.resize(n);
 		{
-			uint32_t n[8];
-			std::memcpy(n, d.words.data() + 8 * j, 32);
+			size_t fill[18];
+			std::memcpy(fill, first_of, sizeof fill);
+			for (size_t j = 0; j < n; ++j) order[fill[d.lvl[j]]++] = static_cast<uint32_t>(j);
+		}
+		auto prepare = [&](size_t pos) {
+			const uint32_t j = order[pos];
+			uint32_t* out = prep[pos % kLook];
+			std::memcpy(out, d.words.data() + 8 * static_cast<size_t>(j), 32);
 			if (!d.leaf[j])
-				for (int c = 0; c < 8; ++c) if (n[c]) n[c] = gmap[n[c] - 1];
-			gmap[j] = sink.intern(n, 0);
+				for (int c = 0; c < 8; ++c) if (out[c]) out[c] = gmap[out[c] - 1];
+			tree->prefetch_node(out);
+		};
+		for (int k = 1; k <= ks && !sink.failed; ++k)
+		{
+			const size_t lo = first_of[k], hi = first_of[k + 1];
+			for (size_t pos = lo; pos < hi && pos < lo + kLook; ++pos) prepare(pos);
+			for (size_t pos = lo; pos < hi && !sink.failed; ++pos)
+			{
+				uint32_t node[8];
+				std::memcpy(node, prep[pos % kLook], 32);
+				if (pos + kLook < hi) prepare(pos + kLook);
+				gmap[order[pos]] = sink.intern(node, 0);
+			}
 		}
 		if (local_root[i]) sub_root[i] = gmap[local_root[i] - 1];
 		std::vector<uint32_t>().swap(d.words);
@@ -296,6 +324,8 @@ uint32_t build_parallel(const Builder& b, ort_tree* tree, int nthreads, bool& fa
 		root = dst[0];
 	}
 	failed = sink.failed;
+	if (std::getenv("ORT_FIXTURE_TIMING"))
+		std::fprintf(stderr, "[ort fixture]   of which merge         %.3f s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t_par).count());
 	return root;
 }
 
@@ -303,10 +333,21 @@ uint32_t build_parallel(const Builder& b, ort_tree* tree, int nthreads, bool& fa
 
 // refcount(node) = number of instances of the node in the fully expanded tree = what one
 // register_node call per instance (the reference's builders) would have produced.
-static void assign_instance_counts(ort_tree* t)
+static void assign_instance_counts(ort_tree* t, int nthreads)
 {
 	if (!t->root) return;
-	std::vector<uint64_t> acc(t->cap, 0);
+	struct Acc
+	{
+		uint64_t* p; size_t bytes;
+		~Acc() { ort_zfree(p, bytes); }
+		uint64_t& operator[](size_t i) { return p[i]; }
+	} acc{ static_cast<uint64_t*>(ort_zalloc(static_cast<size_t>(t->cap) * 8)), static_cast<size_t>(t->cap) * 8 };
+	if (!acc.p) return;
+	if (t->depth >= 11)
+	{
+		void* const ptrs[] = { acc.p };
+		ort_prefault(ptrs, &acc.bytes, 1, nthreads);
+	}
 	std::vector<uint32_t> cur{ t->root - 1 }, next;
 	acc[t->root - 1] = 1;
 	uint64_t total = 0;
@@ -318,6 +359,17 @@ static void assign_instance_counts(ort_tree* t)
 		for (size_t i = 0; i < cur.size(); ++i) { cnt[i] = acc[cur[i]]; acc[cur[i]] = 0; }
 		for (size_t i = 0; i < cur.size(); ++i)
 		{
+			// software pipeline over the random slots of the level: node rows far ahead, their children's cells nearer
+			if (i + 24 < cur.size())
+			{
+				__builtin_prefetch(t->nodes + 8 * static_cast<size_t>(cur[i + 24]));
+				__builtin_prefetch(t->refcounts + cur[i + 24]);
+			}
+			if (level != t->depth && i + 8 < cur.size())
+			{
+				const uint32_t* pn = t->nodes + 8 * static_cast<size_t>(cur[i + 8]);
+				for (int c = 0; c < 8; ++c) if (pn[c]) __builtin_prefetch(&acc[pn[c] - 1]);
+			}
 			const uint32_t slot = cur[i];
 			const uint64_t sum = static_cast<uint64_t>(t->refcounts[slot]) + cnt[i];
 			t->refcounts[slot] = sum > UINT32_MAX ? UINT32_MAX : static_cast<uint32_t>(sum);
@@ -453,6 +505,8 @@ int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const 
 		b.build_any_pyramid(nthreads > 0 ? nthreads : 1);
 	}
 	lap("tunnel bitmap");
+	if (b.depth >= 11) tree->prefault(nthreads > 0 ? nthreads : 1);     // a scene of this size fills the table: zero its pages in parallel
+	lap("table page faults");
 	bool failed = false;
 	if (b.depth >= 7 && nthreads > 1)
 		tree->root = build_parallel(b, tree, nthreads, failed);
@@ -466,7 +520,7 @@ int ort_fixture_build_terrain_ex(ort_tree* tree, const uint16_t* heights, const 
 	if (failed || tree->table_full)
 		return ort_fail(nullptr, ORT_ERR_TABLE_FULL, "ort_fixture_build_terrain: node table too full (raise log2_table_capacity)");
 	lap("build");
-	assign_instance_counts(tree);
+	assign_instance_counts(tree, nthreads > 0 ? nthreads : 1);
 	lap("instance counts");
 	tree->invalidate_mirror();
 	return ORT_OK;

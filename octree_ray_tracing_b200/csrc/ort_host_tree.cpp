@@ -10,6 +10,14 @@
 // slot-for-slot against the oracle).
 #include "ort_internal.h"
 
+#include <thread>
+
+#include <atomic>
+
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
+
 #include <cstdio>
 
 #include <algorithm>
@@ -58,28 +66,101 @@ inline uint64_t morton3(uint32_t x, uint32_t y, uint32_t z)
 // construction
 // ------------------------------------------------------------------------------------------------
 
+// Zeroed storage for the table arrays.  At L = 24..27 they are 0.6..5 GB of sparsely and randomly accessed memory:
+// anonymous mappings come zero-filled for free (no memset pass) and transparent huge pages cut both the page-fault
+// count and the TLB misses of every probe.  Small tables use the heap.
+namespace { constexpr size_t kBigAlloc = size_t(8) << 20; }
+
+void* ort_zalloc(size_t bytes)
+{
+	if (bytes < kBigAlloc)
+	{
+		// 64-byte aligned so that a 32-byte node row never straddles a cache line
+		const size_t padded = (bytes + 63) / 64 * 64;
+		void* p = std::aligned_alloc(64, padded ? padded : 64);
+		if (p) std::memset(p, 0, padded ? padded : 64);
+		return p;
+	}
+#if defined(__linux__)
+	void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+	if (p == MAP_FAILED) return nullptr;
+#ifdef MADV_HUGEPAGE
+	madvise(p, bytes, MADV_HUGEPAGE);
+#endif
+	return p;
+#else
+	return std::calloc(bytes, 1);
+#endif
+}
+
+void ort_zfree(void* p, size_t bytes)
+{
+	if (!p) return;
+#if defined(__linux__)
+	if (bytes >= kBigAlloc) { munmap(p, bytes); return; }
+#endif
+	std::free(p);
+}
+
 ort_tree::ort_tree(int log2cap_, int depth_)
 	: log2cap(log2cap_), depth(depth_), cap(1u << log2cap_), idx_mask(((cap - 1u) >> 4) << 4)
 {
-	tags = static_cast<uint8_t*>(std::calloc(cap, 1));
-	refcounts = static_cast<uint32_t*>(std::calloc(cap, 4));
-	nodes = static_cast<uint32_t*>(std::aligned_alloc(64, static_cast<size_t>(cap) * 32));
-	if (nodes) std::memset(nodes, 0, static_cast<size_t>(cap) * 32);
-	dirty_bits = static_cast<uint64_t*>(std::calloc((cap + 63) / 64, 8));
-	id_interior = static_cast<uint32_t*>(std::calloc(cap, 4));
-	id_leaf = static_cast<uint32_t*>(std::calloc(cap, 4));
-	id_level = static_cast<uint8_t*>(std::calloc(cap, 1));
+	const size_t n = cap;
+	tags = static_cast<uint8_t*>(ort_zalloc(n));
+	refcounts = static_cast<uint32_t*>(ort_zalloc(n * 4));
+	nodes = static_cast<uint32_t*>(ort_zalloc(n * 32));
+	dirty_bits = static_cast<uint64_t*>(ort_zalloc((n + 63) / 64 * 8));
+	id_interior = static_cast<uint32_t*>(ort_zalloc(n * 4));
+	id_leaf = static_cast<uint32_t*>(ort_zalloc(n * 4));
+	id_level = static_cast<uint8_t*>(ort_zalloc(n));
 }
 
 ort_tree::~ort_tree()
 {
-	std::free(tags);
-	std::free(refcounts);
-	std::free(nodes);
-	std::free(dirty_bits);
-	std::free(id_interior);
-	std::free(id_leaf);
-	std::free(id_level);
+	const size_t n = cap;
+	ort_zfree(tags, n);
+	ort_zfree(refcounts, n * 4);
+	ort_zfree(nodes, n * 32);
+	ort_zfree(dirty_bits, (n + 63) / 64 * 8);
+	ort_zfree(id_interior, n * 4);
+	ort_zfree(id_leaf, n * 4);
+	ort_zfree(id_level, n);
+}
+
+// First-touch the table arrays from several threads: the kernel zeroes the (huge) pages in parallel instead of one
+// at a time inside the first insert that happens to land on them.  Worth it before bulk builds that will touch the
+// whole table anyway (3 s of page-zeroing at L = 26 otherwise); pointless for small or sparsely used tables.
+void ort_prefault(void* const* ptrs, const size_t* bytes, int n_ranges, int nthreads)
+{
+	constexpr size_t kStep = size_t(2) << 20;
+	std::vector<std::pair<volatile char*, size_t>> chunks;
+	for (int r = 0; r < n_ranges; ++r)
+		if (ptrs[r] && bytes[r] >= kBigAlloc)
+			for (size_t off = 0; off < bytes[r]; off += kStep)
+				chunks.emplace_back(static_cast<volatile char*>(ptrs[r]) + off, std::min(kStep, bytes[r] - off));
+	if (chunks.empty()) return;
+	if (nthreads < 1) nthreads = 1;
+	std::atomic<size_t> next{ 0 };
+	auto work = [&] {
+		for (size_t i; (i = next.fetch_add(1)) < chunks.size();)
+			for (size_t off = 0; off < chunks[i].second; off += 4096)
+			{
+				const char v = chunks[i].first[off];
+				chunks[i].first[off] = v;          // a write, so the page is really allocated; same value, so live data is untouched
+			}
+	};
+	std::vector<std::thread> pool;
+	for (int w = 1; w < nthreads; ++w) pool.emplace_back(work);
+	work();
+	for (auto& th : pool) th.join();
+}
+
+void ort_tree::prefault(int nthreads)
+{
+	const size_t n = cap;
+	void* const ptrs[] = { nodes, refcounts, tags, id_interior, id_leaf, id_level };
+	const size_t bytes[] = { n * 32, n * 4, n, n * 4, n * 4, n };
+	ort_prefault(ptrs, bytes, 6, nthreads);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -121,6 +202,16 @@ inline uint32_t ort_tree::probe(const uint32_t* n, uint8_t& tag, bool& found) co
 	}
 	found = false;
 	return grave != UINT32_MAX ? grave : i;
+}
+
+// Pull the cache lines a probe for `n` will touch first (tag group and the head of its node rows): lets callers
+// that know their next few nodes (the fixture merge) overlap the DRAM round trips of a table far larger than the caches.
+void ort_tree::prefetch_node(const uint32_t* n) const
+{
+	const uint32_t i = fnv1a_signed(n) & idx_mask;
+	__builtin_prefetch(tags + i);
+	__builtin_prefetch(nodes + 8 * static_cast<size_t>(i));
+	__builtin_prefetch(nodes + 8 * static_cast<size_t>(i) + 16);
 }
 
 uint32_t ort_tree::register_node(const uint32_t* n)
@@ -457,6 +548,8 @@ size_t ort_tree::flatten(uint32_t* level_offsets)
 	if (root == 0)
 		return 0;
 
+	flat.reserve((static_cast<size_t>(fillcnt) + 64) * 8);     // (a few slots serve on two levels and get two rows)
+	id_owner.reserve(static_cast<size_t>(fillcnt) + 64);
 	std::vector<uint32_t> cur, next;
 	auto give_id = [&](uint32_t slot, int level) {
 		uint32_t& id = id_ref(slot, level, true);
@@ -477,8 +570,23 @@ size_t ort_tree::flatten(uint32_t* level_offsets)
 		flat.resize(flat.size() + cur.size() * 8);
 		uint32_t* out = flat.data() + flat.size() - cur.size() * 8;
 
-		for (uint32_t slot : cur)
+		const size_t n_cur = cur.size();
+		for (size_t ci = 0; ci < n_cur; ++ci)
 		{
+			// two-stage software pipeline over the (random) slots of this level: rows far ahead, then -- once a row has
+			// arrived -- the id cells of its children
+			if (ci + 24 < n_cur) __builtin_prefetch(nodes + 8 * static_cast<size_t>(cur[ci + 24]));
+			if (!leaf && ci + 8 < n_cur)
+			{
+				const uint32_t* pn = nodes + 8 * static_cast<size_t>(cur[ci + 8]);
+				for (int c = 0; c < 8; ++c)
+					if (pn[c])
+					{
+						__builtin_prefetch((level + 1 == depth ? id_leaf : id_interior) + (pn[c] - 1));
+						if (level + 1 != depth) __builtin_prefetch(id_level + (pn[c] - 1));
+					}
+			}
+			const uint32_t slot = cur[ci];
 			const uint32_t* n = nodes + 8 * static_cast<size_t>(slot);
 			if (leaf)
 				std::memcpy(out, n, 32);

@@ -11,6 +11,12 @@
 // Records `msg` as the calling thread's last error (and on ctx when given) and returns `code`.
 int ort_fail(ort_ctx* ctx, int code, const char* fmt, ...);
 
+// Zero-filled storage for table-sized arrays (anonymous mapping + transparent huge pages above 8 MB, heap below) and
+// parallel first-touch of such ranges (the kernel then zeroes the pages on several cores).
+void* ort_zalloc(size_t bytes);
+void  ort_zfree(void* p, size_t bytes);
+void  ort_prefault(void* const* ptrs, const size_t* bytes, int n_ranges, int nthreads);
+
 // Host node store.  Field meanings follow och::h_octree (och_h_octree.h:70-99).
 struct ort_tree
 {
@@ -62,6 +68,8 @@ struct ort_tree
 	uint32_t register_node(const uint32_t* n);
 	// insert-or-find WITHOUT touching reference counts (fixture builder; counts are filled in later)
 	uint32_t intern_node(const uint32_t* n);
+	void     prefetch_node(const uint32_t* n) const;
+	void     prefault(int nthreads);
 	void     remove_node(uint32_t idx);
 	void     set(uint16_t x, uint16_t y, uint16_t z, uint32_t v);
 	// bulk edit: every voxel of [lo, hi) (clipped to the cube) becomes v; same content, counts and canonical DAG
