@@ -103,3 +103,23 @@ def parse_voxels(text: str, max_voxels: int = 256):
         msg = lib().ort_last_error(None)
         raise ValueError(msg.decode() if msg else "malformed voxel file")
     return cols[:n].copy(), [names.raw[16 * i:16 * i + 16].split(b"\0")[0].decode() for i in range(n)]
+
+
+def save_png(path: str, rgba: np.ndarray, W: int, H: int):
+    """Write a frame of ort_trace_frame_rgba pixels (olc::Pixel::n packing: r | g<<8 | b<<16 | a<<24) as an 8-bit RGBA
+    PNG -- the headless stand-in for looking at the demo window.  Standard library only (zlib)."""
+    import struct
+    import zlib
+    px = np.ascontiguousarray(rgba, np.uint32).reshape(H, W)
+    rows = np.empty((H, 1 + 4 * W), np.uint8)
+    rows[:, 0] = 0                                             # filter type 0 on every scanline
+    rows[:, 1:] = px.view(np.uint8).reshape(H, 4 * W)          # little-endian uint32 -> bytes r, g, b, a
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(tag + data) & 0xFFFFFFFF)
+
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n")
+        f.write(chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, 8, 6, 0, 0, 0)))
+        f.write(chunk(b"IDAT", zlib.compress(rows.tobytes(), 6)))
+        f.write(chunk(b"IEND", b""))

@@ -51,3 +51,27 @@ def test_rgba_frame_equals_colour_lookup_of_the_hits(ort, golden):
     assert (got == INSIDE).all()
     ctx.upload_full(np.zeros((0, 8), np.uint32), 0)
     assert (ctx.trace_frame_rgba(g["poseA_pos"], g["poseA_rot"], float(g["poseA_fov"]), 64, 36) == EXIT).all()
+
+
+def test_save_png_round_trip(ort, tmp_path):
+    """harness.save_png: a valid RGBA PNG whose decoded scanlines are the pixels that went in."""
+    import struct
+    import zlib
+    W, H = 37, 21
+    rs = np.random.RandomState(0)
+    px = rs.randint(0, 2**32, W * H, dtype=np.uint64).astype(np.uint32)
+    path = tmp_path / "f.png"
+    ort.harness.save_png(str(path), px, W, H)
+    raw = path.read_bytes()
+    assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+    pos, chunks = 8, {}
+    while pos < len(raw):
+        n, tag = struct.unpack(">I4s", raw[pos:pos + 8])
+        data = raw[pos + 8:pos + 8 + n]
+        assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(tag + data) & 0xFFFFFFFF
+        chunks[tag] = data
+        pos += 12 + n
+    assert struct.unpack(">IIBBBBB", chunks[b"IHDR"]) == (W, H, 8, 6, 0, 0, 0)
+    rows = np.frombuffer(zlib.decompress(chunks[b"IDAT"]), np.uint8).reshape(H, 1 + 4 * W)
+    assert (rows[:, 0] == 0).all()
+    assert np.array_equal(rows[:, 1:].reshape(-1).view(np.uint32), px)
