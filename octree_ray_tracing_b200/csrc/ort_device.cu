@@ -1028,6 +1028,14 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	else if (!std::strcmp(key, "tile_shape")) c->opt_tile_shape = value;
 	else if (!std::strcmp(key, "zero_copy")) c->opt_zero_copy = value;
 	else if (!std::strcmp(key, "band_rotate")) c->opt_band_rotate = value;
+	else if (!std::strcmp(key, "l1_carveout"))
+	{
+		// measurement: shared-memory carve-out (percent) of the default frame kernels; they use no shared memory, so 0
+		// asks for the largest L1
+		DeviceGuard g(c->device);
+		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+	}
 	else if (!std::strcmp(key, "defer_sync")) c->opt_defer_sync = value;
 	else if (!std::strcmp(key, "frame_chunks")) c->opt_frame_chunks = value;
 	else if (!std::strcmp(key, "rays_chunk")) c->opt_rays_chunk = value;
