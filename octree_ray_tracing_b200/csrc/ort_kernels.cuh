@@ -563,8 +563,10 @@ gather_peak_kernel(const uint32_t* __restrict__ buf, uint32_t n_sectors, uint32_
 
 constexpr unsigned kBatch = 128;    // ray indices a warp draws per atomicAdd
 
-template<bool COUNT, bool FRAME>
-__global__ void __launch_bounds__(256)
+// MINB = minimum resident blocks per SM the compiler must allow for (register budget): 1 -> 47 registers, 57 %
+// occupancy; 6 -> 40 registers (a few spilled words), 75 %; 8 -> 32 registers, 100 %.
+template<bool COUNT, bool FRAME, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt,
                         const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, Camera cam, FrameRows fr,
                         unsigned long long n, unsigned long long* __restrict__ counter, int low_water,

@@ -49,6 +49,16 @@ ctx.sync()
 pushes = float((dn.to(torch.int64) & 0xFFFF).sum().item()) / n
 ref = (dv.clone(), df.clone(), dt.clone())
 res = {"n_rays": n, "pushes_per_ray": round(pushes, 3), "hit_fraction": round(float((dv != 0).float().mean().item()), 4), "rays": {}, "frames": {}}
+for pb in (1, 8):
+    ctx.set_option("rays_variant", 2)
+    ctx.set_option("persist_blocks", pb)
+    for lw in (16, 20, 24):
+        ctx.set_option("low_water", lw)
+        ms = timeit(lambda: ctx.trace_rays_async(do, 3, dd, n, dv, df, dt))
+        ctx.sync()
+        same = bool((dv == ref[0]).all().item() and (df == ref[1]).all().item() and (dt.view(torch.int32) == ref[2].view(torch.int32)).all().item())
+        res["rays"][f"variant2_blocks{pb}_lw{lw}"] = {"ms": round(ms, 3), "Mrays/s": round(n / ms / 1e3, 1), "same_as_ref": same}
+ctx.set_option("persist_blocks", 6)
 for rv, lws in ((1, (0,)), (2, (0, 8, 16, 20, 24, 28))):
     ctx.set_option("rays_variant", rv)
     for lw in lws:
