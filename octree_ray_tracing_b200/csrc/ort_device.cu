@@ -647,7 +647,11 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 			gy = std::max(gy, static_cast<unsigned>((j.rows + 15) / 16));
 		}
 		if (!n) continue;
-		ort::trace_frames_kernel<<<dim3(gx, gy, static_cast<unsigned>(n)), 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, batch);
+		bool count = false;
+		for (int i = 0; i < n; ++i) count |= batch.job[i].npush != nullptr;
+		const dim3 bgrid(gx, gy, static_cast<unsigned>(n));
+		if (count) ort::trace_frames_kernel<true><<<bgrid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, batch);
+		else       ort::trace_frames_kernel<false><<<bgrid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, batch);
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 	}

@@ -112,7 +112,7 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 // Several frame jobs in ONE launch (blockIdx.z = job): strips of different frames, or the views of a multi-camera
 // rig.  Separate launches each end with the latency tail of their longest rays; here the blocks of all jobs stream
 // through the SMs back to back and only the last job's tail is exposed.  The jobs travel in the kernel parameters.
-constexpr int kMaxJobs = 16;
+constexpr int kMaxJobs = 32;
 
 struct FrameJob
 {
@@ -129,6 +129,7 @@ struct FrameJobBatch
 	FrameJob job[kMaxJobs];
 };
 
+template<bool COUNT>          // COUNT: some job of the batch wants per-ray PUSH counts (jobs without an npush pointer skip the store)
 __global__ void __launch_bounds__(256)
 trace_frames_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, const __grid_constant__ FrameJobBatch batch)
 {
@@ -149,15 +150,13 @@ trace_frames_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int de
 	float dx, dy, dz;
 	camera_ray(jb.cam, x, y, dx, dy, dz);
 	const Ray ray = ray_setup(rt, jb.cam.ox, jb.cam.oy, jb.cam.oz, dx, dy, dz);
-	Hit h;
-	if (jb.npush) h = traverse_variant<1, true>(nodes_m1, root, depth, miss_t, jb.cam.ox, jb.cam.oy, jb.cam.oz, ray);
-	else          h = traverse_variant<1, false>(nodes_m1, root, depth, miss_t, jb.cam.ox, jb.cam.oy, jb.cam.oz, ray);
+	const Hit h = traverse_variant<1, COUNT>(nodes_m1, root, depth, miss_t, jb.cam.ox, jb.cam.oy, jb.cam.oz, ray);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	jb.voxel[i] = h.voxel;
 	jb.face[i] = static_cast<uint8_t>(h.face);
 	jb.t[i] = h.t;
-	if (jb.npush) jb.npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+	if (COUNT && jb.npush) jb.npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
 // Shading epilogue (tree_camera::trace_pixel, test_och_h_octree.cpp:76-84) fused into the frame kernel: the hit is
