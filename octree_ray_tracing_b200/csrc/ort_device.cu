@@ -594,7 +594,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	// measurement build of the kernel
 	const bool shaped = c->opt_variant != 0 && (c->opt_tile_shape != 0 || c->opt_block == 128 || c->opt_block == 64);
 	const int fblock = (shaped && c->opt_tile_shape == 0) ? c->opt_block : 256;
-	const dim3 fgrid((W + 15) / 16, (rows + fblock / 16 - 1) / (fblock / 16));
+	const dim3 fgrid = c->opt_tile_shape == 3 && shaped ? dim3((W + 31) / 32, (rows + 7) / 8) : dim3((W + 15) / 16, (rows + fblock / 16 - 1) / (fblock / 16));
 #define ORT_LAUNCH_FRAME(V, C, S) ort::trace_frame_kernel<V, C, S><<<fgrid, fblock, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
 	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true, false); else ORT_LAUNCH_FRAME(0, false, false); }
 	else if (shaped) { if (npush) ORT_LAUNCH_FRAME(1, true, true); else ORT_LAUNCH_FRAME(1, false, true); }

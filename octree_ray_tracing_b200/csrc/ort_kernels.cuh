@@ -83,6 +83,7 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 	int x, r;
 	if (SHAPED && fr.tile_shape == 1)      { x = blockIdx.x * 16 + (lane & 15);                   r = blockIdx.y * 16 + warp * 2 + (lane >> 4); }
 	else if (SHAPED && fr.tile_shape == 2) { x = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);   r = blockIdx.y * 16 + (warp >> 2) * 8 + (lane >> 2); }
+	else if (SHAPED && fr.tile_shape == 3) { x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);   r = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3); }   // 32 x 8 block: stays inside one 8-row strip
 	else if (SHAPED)                       { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * static_cast<int>(blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3); }
 	else
 	{

@@ -14,7 +14,9 @@
 #pragma once
 
 #include <cstdint>
+#ifndef ORT_HOST_EMU          // tests/host_emu compiles this header for the host with its own stand-ins for the intrinsics
 #include <cuda_runtime.h>
+#endif
 
 namespace ort {
 
@@ -527,9 +529,13 @@ constexpr uint32_t kMagicBits = 0x4B000000u;     // bits of 8388608.0f = 2^23
 
 __device__ __forceinline__ float set_ge(float a, float b)    // 1.0f if a >= b (ordered) else 0.0f -- one instruction
 {
+#ifdef ORT_HOST_EMU
+	return a >= b ? 1.0f : 0.0f;
+#else
 	float r;
 	asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
 	return r;
+#endif
 }
 
 template<bool COUNT>
@@ -684,12 +690,16 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes_
 	return w.hit;
 }
 
-// the fast path's preconditions: origin inside [1,2)^3 and at least one non-degenerate direction component
+// the fast path's preconditions: origin inside [1,2)^3, a start position in [1,2)^3 and at least one non-degenerate
+// direction component.  The second is not implied by the first: a coordinate of exactly 1.0f on an axis travelled in the
+// positive direction is mirrored to |3 - 1| = 2.0f, whose masked bits (och_h_octree.h:320) are 0 -- a position the
+// reference then walks as raw bit patterns (denormals), which only traverse() reproduces.
 __device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const Ray& r)
 {
 	const uint32_t ninf = 0xFF800000u;
 	const bool all_degenerate = (__float_as_uint(r.cx) == ninf) & (__float_as_uint(r.cy) == ninf) & (__float_as_uint(r.cz) == ninf);
-	return in_unit_cube(ox, oy, oz) & !all_degenerate;
+	const bool pos_in_cube = (r.px & r.py & r.pz & 0x3F800000u) == 0x3F800000u;      // pos is masked to 0x3FC00000: exponent field 127
+	return in_unit_cube(ox, oy, oz) & pos_in_cube & !all_degenerate;
 }
 
 // The walk of one ray, start to end.  VARIANT 0: the baseline transliteration; otherwise FastWalker where its

@@ -59,3 +59,28 @@ def assert_same_hits(got, want, what=""):
     wtb = np.ascontiguousarray(wt, np.float32).view(np.uint32)
     bad_t = np.flatnonzero(gtb != wtb)
     assert bad_t.size == 0, f"{what}: {bad_t.size} hit-time mismatches (bitwise), first at ray {bad_t[:5]}"
+
+
+def degenerate_rays(ort, depth):
+    """280 000 rays built to hit every special case of the kernels' fast path: zero and denormal direction components
+    (coef = -inf), origins on cell planes -- including coordinates of exactly 1.0f, which mirror to 2.0f on an axis
+    travelled in the positive direction and leave [1,2) --, origins outside [1,2)^3, grazing rays."""
+    rs = np.random.RandomState(7)
+    o, d = ort.harness.random_rays(200_000, seed=11)
+    # degenerate directions
+    dz = d[:40_000].copy()
+    dz[np.arange(40_000), rs.randint(0, 3, 40_000)] = rs.choice(np.array([0.0, -0.0, 1e-42, -1e-42], np.float32), 40_000)
+    d2 = d[40_000:60_000].copy()
+    d2[:, :2] = 0.0                                              # two degenerate axes
+    # on-plane origins: coordinates snapped to multiples of 2^-k
+    op = o[:40_000].copy()
+    k = rs.randint(1, depth + 1, size=op.shape)
+    op = (np.floor((op - 1.0) * (1 << k)) / (1 << k) + 1.0).astype(np.float32)
+    # origins outside the cube (FastWalker must hand these to the baseline walk)
+    oo = (o[:20_000] + rs.choice(np.array([-1.0, 1.0, 0.0], np.float32), size=(20_000, 3))).astype(np.float32)
+    # grazing rays just above the terrain
+    og = o[:20_000].copy(); og[:, 2] = 1.0 + 5.0 / 16.0 + 1e-3
+    dg = d[:20_000].copy(); dg[:, 2] = -np.abs(dg[:, 2]) * 1e-3
+    O = np.concatenate([o, o[:40_000], o[40_000:60_000], op, oo, og])
+    D = np.concatenate([d, dz, d2, d[:40_000], d[:20_000], dg])
+    return O, D

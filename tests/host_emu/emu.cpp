@@ -1,0 +1,166 @@
+// emu.cpp -- TEST INFRASTRUCTURE: csrc/ort_trace.cuh compiled for the host (see cuda_shim.h).  Exports the per-ray walks
+// of the CUDA kernels as plain C functions over host arrays so that tests/test_host_emu.py can compare them bit for bit
+// with the oracle without a GPU, and count what they do (rounds per level).  Built on demand by
+// the test into tests/host_emu/_build/; never part of libort_b200.so.
+#include "cuda_shim.h"
+#include "../../octree_ray_tracing_b200/csrc/ort_trace.cuh"
+
+#include <cstddef>
+#include <omp.h>
+
+namespace {
+
+struct Stats
+{
+	unsigned long long rounds_by_level[ort::kMaxDepth + 2];   // child-slot loads issued with the walker at that level
+	unsigned long long rays, slow_path_rays;                  // slow path: rays outside FastWalker's preconditions
+};
+
+// walker ids follow ort_set_option("variant"): 0 baseline traverse(), 1 FastWalker, 5 TightWalker, 7 PipeWalker
+template<bool COUNT>
+ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, float miss_t, float ox, float oy, float oz, const ort::Ray& ray,
+              Stats* st)
+{
+	uint32_t stack[ort::kMaxDepth];
+	if (walker == 0 || !ort::fast_path_ok(ox, oy, oz, ray))
+	{
+		if (st) ++st->slow_path_rays;
+		ort::Hit h = ort::traverse(nodes_m1, root, depth, miss_t, ray, stack);
+		if (!COUNT) h.npush = 0;
+		return h;
+	}
+	if (walker == 1)
+	{
+		ort::FastWalker<COUNT> w;
+		w.start(root, miss_t, ray);
+		for (;;)
+		{
+			if (st) ++st->rounds_by_level[w.level];
+			const uint32_t child = w.load_child(nodes_m1);
+			if (child ? w.descend(child, depth, stack) : w.advance(stack))
+				break;
+		}
+		return w.hit;
+	}
+	if (walker == 5)
+	{
+		ort::TightWalker<COUNT> w;
+		w.start(root, miss_t, ray);
+		for (;;)
+		{
+			const uint32_t child = w.load_child(nodes_m1);
+			if (child ? w.descend(child, depth, stack) : w.advance(stack))
+				break;
+		}
+		return w.hit;
+	}
+	if (walker == 7)
+	{
+		uint32_t stack_n[ort::kMaxDepth];
+		float stack_f[ort::kMaxDepth];
+		ort::PipeWalker<COUNT> w;
+		w.start(root, miss_t, ray);
+		const unsigned long long base_biased = reinterpret_cast<unsigned long long>(nodes_m1) - 4ull * ort::kMagicBits;
+		for (;;)
+		{
+			const uint32_t child = w.load_child(base_biased);
+			if (child ? w.descend(child, depth, stack_n, stack_f) : w.advance(stack_n, stack_f))
+				break;
+		}
+		return w.hit;
+	}
+	ort::Hit bad;
+	bad.voxel = 0xFFFFFFFFu; bad.face = 0xFF; bad.t = -1.0f; bad.npush = 0;
+	return bad;
+}
+
+void merge(Stats* dst, const Stats& s)
+{
+	for (int i = 0; i < ort::kMaxDepth + 2; ++i) dst->rounds_by_level[i] += s.rounds_by_level[i];
+	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays;
+}
+
+}  // namespace
+
+extern "C" {
+
+// nodes8: the compact device array as ort_tree_flatten yields it (node id i at nodes8[8*(i-1)]).
+int emu_trace_rays(const uint32_t* nodes8, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
+                   const float* o3, int o_stride, const float* d3, size_t n, int walker,
+                   uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
+{
+	const uint32_t* nodes_m1 = nodes8 - 8;
+	const ort::RcpTable rt{rcp_tab, 23 - log2n};
+	Stats total{};
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+	{
+		Stats st{};
+#pragma omp for schedule(dynamic, 4096)
+		for (long long i = 0; i < static_cast<long long>(n); ++i)
+		{
+			const float* o = o3 + static_cast<size_t>(i) * o_stride;
+			const float* d = d3 + static_cast<size_t>(i) * 3;
+			const ort::Ray r = ort::ray_setup(rt, o[0], o[1], o[2], d[0], d[1], d[2]);
+			ort::Hit h;
+			if (root == 0) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
+			else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr)
+			               : walk<false>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr);
+			++st.rays;
+			voxel[i] = h.voxel;
+			face[i] = static_cast<uint8_t>(h.face);
+			t[i] = h.t;
+			if (npush) npush[i] = static_cast<uint16_t>(h.npush < 65535u ? h.npush : 65535u);
+		}
+#pragma omp critical
+		merge(&total, st);
+	}
+	if (stats_out) std::memcpy(stats_out, &total, sizeof(total));
+	return 0;
+}
+
+// camera rays generated like the frame kernels do (ort::camera_ray), rows [y0, y0 + rows) of a W x H frame
+int emu_trace_frame(const uint32_t* nodes8, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
+                    const float pos[3], const float rot[9], float fov, int W, int H, int y0, int rows, int walker,
+                     uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
+{
+	const uint32_t* nodes_m1 = nodes8 - 8;
+	const ort::RcpTable rt{rcp_tab, 23 - log2n};
+	ort::Camera cam;
+	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
+	for (int i = 0; i < 9; ++i) cam.r[i] = rot[i];
+	cam.fov = fov;
+	cam.aspect = static_cast<float>(W) / static_cast<float>(H);
+	cam.vfx = 2.0F / static_cast<float>(W);
+	cam.vfy = 2.0F / static_cast<float>(H);
+	Stats total{};
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+	{
+		Stats st{};
+#pragma omp for schedule(dynamic, 4)
+		for (int r = 0; r < rows; ++r)
+			for (int x = 0; x < W; ++x)
+			{
+				float dx, dy, dz;
+				ort::camera_ray(cam, x, y0 + r, dx, dy, dz);
+				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+				ort::Hit h;
+				if (root == 0) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
+				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr)
+				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr);
+				++st.rays;
+				const size_t i = static_cast<size_t>(r) * W + x;
+				voxel[i] = h.voxel;
+				face[i] = static_cast<uint8_t>(h.face);
+				t[i] = h.t;
+				if (npush) npush[i] = static_cast<uint16_t>(h.npush < 65535u ? h.npush : 65535u);
+			}
+#pragma omp critical
+		merge(&total, st);
+	}
+	if (stats_out) std::memcpy(stats_out, &total, sizeof(total));
+	return 0;
+}
+
+int emu_stats_words(void) { return static_cast<int>(sizeof(Stats) / sizeof(unsigned long long)); }
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+"""TEST INFRASTRUCTURE: ctypes wrapper of tests/host_emu/emu.cpp -- the device traversal header (csrc/ort_trace.cuh)
+compiled for the host.  Lets the CPU-only suite check the kernels' per-ray code against the oracle; it is not a product
+path (nothing under octree_ray_tracing_b200/ imports it)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "octree_ray_tracing_b200", "csrc")
+SO = os.path.join(HERE, "_build", "libort_emu.so")
+_lib = None
+
+STAT_FIELDS = ["rays", "slow_path_rays"]
+
+
+def build(force: bool = False) -> str:
+    deps = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h"), os.path.join(CSRC, "ort_trace.cuh")]
+    if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
+        return SO
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-mfma", "-mavx2", "-ffp-contract=off", "-fPIC", "-shared",
+           "-Wall", "-Wno-unused-function", deps[0], "-o", SO]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    if out.returncode:
+        raise RuntimeError("host emulation build failed:\n" + out.stderr)
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = C.CDLL(build())
+        _lib.emu_stats_words.restype = C.c_int
+    return _lib
+
+
+def default_rcp_table() -> np.ndarray:
+    """The table the product ships (csrc/ort_rcp_table.h)."""
+    txt = open(os.path.join(CSRC, "ort_rcp_table.h")).read()
+    return np.array([int(x, 16) for x in re.findall(r"0x([0-9a-f]{8})u", txt)], np.uint32)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _stats(raw):
+    nlev = len(raw) - len(STAT_FIELDS)
+    d = {"rounds_by_level": raw[:nlev].copy()}
+    d.update({k: int(v) for k, v in zip(STAT_FIELDS, raw[nlev:])})
+    return d
+
+
+def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None):
+    nodes8 = np.ascontiguousarray(nodes8, np.uint32)
+    tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
+    d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
+    n = len(d)
+    o = np.ascontiguousarray(o, np.float32)
+    o_stride = 0 if o.size == 3 else 3
+    vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
+    npush = np.empty(n, np.uint16) if want_npush else None
+    stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
+    lib().emu_trace_rays(_p(nodes8), C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
+                         _p(o), o_stride, _p(d), C.c_size_t(n), walker,
+                         _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
+    out = [vox, face, t]
+    if want_npush:
+        out.append(npush)
+    if want_stats:
+        out.append(_stats(stats))
+    return tuple(out)
+
+
+def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walker=1, rcp_tab=None, miss_t=np.inf,
+                want_npush=False, want_stats=False, nthreads=None):
+    nodes8 = np.ascontiguousarray(nodes8, np.uint32)
+    tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
+    rows = H - y0 if rows is None else rows
+    n = rows * W
+    pos = np.ascontiguousarray(pos, np.float32); rot = np.ascontiguousarray(rot, np.float32)
+    vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
+    npush = np.empty(n, np.uint16) if want_npush else None
+    stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
+    lib().emu_trace_frame(_p(nodes8), C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
+                          _p(pos), _p(rot), C.c_float(fov), W, H, y0, rows, walker,
+                           _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
+    out = [vox, face, t]
+    if want_npush:
+        out.append(npush)
+    if want_stats:
+        out.append(_stats(stats))
+    return tuple(out)

@@ -457,3 +457,40 @@ def test_batched_frames_equal_separate_launches(ort, golden):
         assert_same_hits(got, want, f"job {k}")
         if dn is not None:
             assert np.array_equal(dn.cpu().numpy().view(np.uint16), want[3])
+
+
+@pytest.mark.gpu
+def test_degenerate_rays_and_corner_cameras_vs_oracle(ort, oc, ncpu):
+    """Rays outside the fast walkers' preconditions must take the baseline walk in every kernel: zero / denormal
+    direction components, origins outside [1,2)^3, on-plane origins and -- found by tests/test_host_emu.py -- a
+    coordinate of exactly 1.0f travelled in the positive direction (mirrored to 2.0f, masked position bits 0).
+    Explicit-ray kernels (one-shot and persistent) and frame kernels (camera on the cube's corner / faces)."""
+    from conftest import degenerate_rays
+    depth = 8
+    T = ort.HOctree(19, depth)
+    ort.harness.build_terrain(T, tunnels=True)
+    nodes8, root, _ = T.flatten()
+    tab = builtin_table()
+    O, D = degenerate_rays(ort, depth)
+    assert (O == 1.0).any(axis=1).sum() > 100
+    want = oc.trace_rays(nodes8, root, depth, O, D, rcp_tab=tab, nthreads=ncpu, want_counts=True)
+    T.sync()
+    ctx = T.ctx
+    for variant, rays_variant in ((0, 1), (1, 1), (1, 2), (5, 1), (7, 1)):
+        ctx.set_option("variant", variant)
+        ctx.set_option("rays_variant", rays_variant)
+        got = ctx.trace_rays(O, D, want_npush=True)
+        assert_same_hits(got, want[:3], f"variant {variant}, rays_variant {rays_variant}")
+        assert np.array_equal(got[3], want[3]), f"variant {variant}, rays_variant {rays_variant}: PUSH counts"
+    ctx.set_option("rays_variant", 1)
+    W, H = 320, 200
+    for pos, yaw, pitch in [((1.0, 1.0, 1.0), 0.785, 0.6), ((1.0, 1.5, 1.75), 0.0, 0.0), ((1.5, 1.0, 1.5), 1.5708, -0.2), ((1.25, 1.5, 1.0), 0.3, 1.2)]:
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        d = oc.gen_rays(rot, fov, W, H)
+        wv, wf, wt, wn, _ = oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=ncpu, want_counts=True)
+        for variant in (0, 1, 2, 5, 7, 12):
+            ctx.set_option("variant", variant)
+            got = ctx.trace_frame(np.array(pos, np.float32), rot, fov, W, H, want_npush=True)
+            assert_same_hits(got, (wv, wf, wt), f"camera at {pos}, variant {variant}")
+            assert np.array_equal(got[3], wn), f"camera at {pos}, variant {variant}: PUSH counts"
+    ctx.set_option("variant", 1)

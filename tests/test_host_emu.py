@@ -1,0 +1,122 @@
+"""The device-side traversal code (csrc/ort_trace.cuh: camera rays, the RCPPS table model, the baseline walk and the
+FastWalker / TightWalker / PipeWalker bookkeeping incl. the multi-level POP) compiled for the HOST by tests/host_emu and
+held against the reference's golden outputs and the CPU oracle -- the same bar as the GPU parity tests (voxel, face and
+hit time bit-exact, per-ray PUSH counts equal), but runnable where there is no GPU.  Test infrastructure only: the
+product library has no CPU path (tests/test_capi_symbols.py checks that)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_same_hits, degenerate_rays
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+
+WALKERS = (0, 1, 5, 7)
+POSES = {"A": ((1.5, 1.5, 1.5), 0.0, 0.0), "B": ((1.5, 1.5, 1.5), 0.7, -0.6), "C": ((1.1, 1.1, 1.4), 0.785, -0.3)}
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu as m
+    m.lib()
+    return m
+
+
+@pytest.mark.parametrize("name", ["d6_tunnels", "d8_tunnels"])
+@pytest.mark.parametrize("walker", WALKERS)
+def test_device_walkers_on_the_reference_golden_vectors(emu, golden, name, walker):
+    """Expected outputs come from the unmodified reference (tests/golden/make_golden.py): frames of the three poses
+    (in-kernel camera rays), random rays and the edge-case rays (axis-parallel, on-plane origins, +-0, tiny / huge
+    components -- the ones that leave FastWalker's preconditions or take its one-level POP path)."""
+    g = golden(name)
+    depth, root = int(g["depth"]), int(g["root"])
+    W, H = int(g["W"]), int(g["H"])
+    for p in "ABC":
+        got = emu.trace_frame(g["nodes8"], root, depth, g[f"pose{p}_pos"], g[f"pose{p}_rot"], float(g[f"pose{p}_fov"]), W, H, walker=walker)
+        assert_same_hits(got, (g[f"pose{p}_vox"], g[f"pose{p}_face"], g[f"pose{p}_t"]), f"{name} frame {p}, walker {walker}")
+    for k in ("rand", "edge"):
+        got = emu.trace_rays(g["nodes8"], root, depth, g[f"{k}_o"], g[f"{k}_d"], walker=walker)
+        assert_same_hits(got, (g[f"{k}_vox"], g[f"{k}_face"], g[f"{k}_t"]), f"{name} {k} rays, walker {walker}")
+
+
+def test_device_walkers_vs_oracle_depth10_frames_and_push_counts(emu, ort, oc):
+    """BASELINE config 1 shape (depth-10 terrain, poses A/B/C) at 640x360: every walker returns the oracle's hits and
+    performs exactly the oracle's number of child-slot loads per ray -- the multi-level POP and the float position
+    bookkeeping change how a round is computed, never which rounds happen."""
+    depth = 10
+    T = ort.HOctree(22, depth, device=None)
+    ort.harness.build_terrain(T, tunnels=False)
+    nodes8, root, _ = T.flatten()
+    tab = emu.default_rcp_table()
+    ncpu = max(1, min(16, os.cpu_count() or 1))
+    W, H = 640, 360
+    for p, (pos, yaw, pitch) in POSES.items():
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        d = oc.gen_rays(rot, fov, W, H)
+        wv, wf, wt, wn, _ = oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=ncpu, want_counts=True)
+        assert (wv != 0).sum() > 1000
+        for walker in WALKERS:
+            got = emu.trace_frame(nodes8, root, depth, pos, rot, fov, W, H, walker=walker, want_npush=True, want_stats=True)
+            assert_same_hits(got, (wv, wf, wt), f"depth 10 pose {p}, walker {walker}")
+            assert np.array_equal(got[3], wn), f"per-ray PUSH counts differ from the oracle's (pose {p}, walker {walker})"
+            st = got[4]
+            assert st["rays"] == W * H
+            if walker == 1:
+                assert int(st["rounds_by_level"].sum()) == int(wn.astype(np.int64).sum())
+                assert st["slow_path_rays"] < W * H // 100      # camera rays take the fast path (bar a few axis-parallel ones)
+
+
+def test_device_walkers_vs_oracle_incoherent_and_degenerate_rays(emu, ort, oc):
+    """BASELINE config 3 shape on the depth-8 tunnel scene plus rays built to hit every special case of the fast path:
+    zero and denormal direction components (coef = -inf), origins on cell planes, origins outside [1,2)^3, grazing rays."""
+    depth = 8
+    T = ort.HOctree(19, depth, device=None)
+    ort.harness.build_terrain(T, tunnels=True)
+    nodes8, root, _ = T.flatten()
+    tab = emu.default_rcp_table()
+    O, D = degenerate_rays(ort, depth)
+    want = oc.trace_rays(nodes8, root, depth, O, D, rcp_tab=tab, nthreads=max(1, min(16, os.cpu_count() or 1)), want_counts=True)
+    assert 0.05 < (want[0] != 0).mean() < 0.9
+    for walker in WALKERS:
+        got = emu.trace_rays(nodes8, root, depth, O, D, walker=walker, want_npush=True)
+        assert_same_hits(got, want[:3], f"walker {walker}")
+        assert np.array_equal(got[3], want[3]), f"walker {walker}: PUSH counts"
+
+
+def test_device_walkers_with_the_camera_on_the_cube_boundary(emu, ort, oc):
+    """A camera coordinate of exactly 1.0f: rays travelling in the positive direction on that axis start from the mirrored
+    coordinate 2.0f, whose masked position bits are 0 (och_h_octree.h:314-320).  The reference walks that as raw bit
+    patterns; fast_path_ok must send exactly those rays to the baseline walk (the others keep the fast path)."""
+    depth = 8
+    T = ort.HOctree(19, depth, device=None)
+    ort.harness.build_terrain(T, tunnels=True)
+    nodes8, root, _ = T.flatten()
+    tab = emu.default_rcp_table()
+    W, H = 320, 200
+    for pos, yaw, pitch in [((1.0, 1.0, 1.0), 0.785, 0.6), ((1.0, 1.5, 1.75), 0.0, 0.0), ((1.5, 1.0, 1.5), 1.5708, -0.2), ((1.25, 1.5, 1.0), 0.3, 1.2)]:
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        d = oc.gen_rays(rot, fov, W, H)
+        wv, wf, wt, wn, _ = oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=4, want_counts=True)
+        for walker in WALKERS:
+            got = emu.trace_frame(nodes8, root, depth, pos, rot, fov, W, H, walker=walker, want_npush=True, want_stats=True)
+            assert_same_hits(got, (wv, wf, wt), f"camera at {pos}, walker {walker}")
+            assert np.array_equal(got[3], wn), f"camera at {pos}, walker {walker}: PUSH counts"
+            if walker:
+                assert got[4]["slow_path_rays"] > 0, "rays travelling +axis from the 1.0f coordinate must leave the fast path"
+
+
+def test_device_camera_rays_equal_the_oracle_rays(emu, oc):
+    """ort::camera_ray (every operation rounded separately, IEEE sqrt and division) against the oracle's statement of
+    tree_camera::update_position: traced through a single solid voxel so that the per-pixel direction decides t."""
+    nodes8 = np.zeros((2, 8), np.uint32)
+    nodes8[0, :] = 2                         # root: all eight children -> node 2
+    nodes8[1, :] = 7                         # last level: all voxels solid, payload 7
+    W, H = 161, 97
+    for pos, yaw, pitch in [((2.5, 1.5, 1.5), 3.14159, 0.0), ((1.2, -0.5, 1.7), 1.3, 0.2), ((1.5, 1.5, 3.0), 0.3, -1.2)]:
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        d = oc.gen_rays(rot, fov, W, H)
+        want = oc.trace_rays(nodes8, 1, 2, np.array(pos, np.float32), d, rcp_tab=emu.default_rcp_table())
+        got = emu.trace_frame(nodes8, 1, 2, pos, rot, fov, W, H, walker=1)
+        assert_same_hits(got, want, f"camera rays from {pos}")
