@@ -205,16 +205,23 @@ def run_product(args):
         if not torch.equal(lo, hi) or dig[3] < 1000:
             raise SystemExit(f"[rank {rank}] replica check FAILED: the ranks do not trace the same DAG (digests {dig[:4]} vs min {lo[:4].tolist()} max {hi[:4].tolist()})")
         replica_check = f"ok: {len(dig)} digests of 3 traced 480x270 frames equal on all {world} ranks"
-    y0, rows, _frame_rows = multi_gpu.strip_rows(rank, world, H, TILE_ROWS)
+    # partition rank / world: the process's own, or (--as-rank r/n, a one-GPU measurement aid for --quick) the share
+    # rank r of an n-GPU job would trace -- same strips, same frames per step, same number of streams
+    prank, pworld = rank, world
+    if args.as_rank:
+        if world != 1 or not args.quick:
+            raise SystemExit("bench.py: --as-rank is a single-GPU measurement aid and needs --quick")
+        prank, pworld = (int(x) for x in args.as_rank.split("/"))
+    y0, rows, _frame_rows = multi_gpu.strip_rows(prank, pworld, H, TILE_ROWS)
     n_local = rows * W
-    frames_per_step = len(cams) * world
+    frames_per_step = len(cams) * pworld
     rays_per_step_total = frames_per_step * W * H          # all ranks together
     rays_per_step_local = frames_per_step * n_local
 
     own = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     # frames in flight: small strips need more of them to hide launch tails, but too many concurrent launches dilute
     # the L1 locality of each (measured: 2 GPUs 3/4/6 streams -> 28.2/28.2/26.5, 4 GPUs 4/6/8 -> 54.0/52.1/53.2, 8 GPUs 5/8/12 -> 101.8/104.5/102.3 Grays/s)
-    NS = args.streams or (3 if world == 1 else (4 if world <= 4 else 8))
+    NS = args.streams or (3 if pworld == 1 else (4 if pworld <= 4 else 8))
     streams = [torch.cuda.Stream(device=local_rank) for _ in range(NS)]
     outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
              torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(NS)]
@@ -224,7 +231,7 @@ def run_product(args):
     torch.cuda.synchronize()
 
     def frame(cam, out=outs[0], npush=None):
-        ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, world, out[0], out[1], out[2], npush)
+        ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, pworld, out[0], out[1], out[2], npush)
 
     # algorithmic bytes: PUSH counts from an (untimed) counting pass -- identical to the oracle's counts (tests)
     pushes = 0
@@ -235,16 +242,16 @@ def run_product(args):
             own.synchronize()
             pushes += int((dn.to(torch.int64) & 0xFFFF).sum().item())
             hits += int((dv != 0).sum().item())
-    pushes_per_step_local = pushes * world
+    pushes_per_step_local = pushes * pworld
     bytes_per_step_local = 32 * pushes_per_step_local + 9 * rays_per_step_local
-    step_cams = [cam for _rep in range(world) for cam in cams]
+    step_cams = [cam for _rep in range(pworld) for cam in cams]
 
     if args.launch == "auto":
         args.launch = "streams"       # measured: 1 GPU 14.8 (streams) vs 14.6 (batch); 8 GPUs 105 vs 92 Grays/s
     # one output set per frame of the step for the batched launch (ort_trace_frames_async: the whole step in one launch)
     batch_outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
                    torch.empty(n_local, dtype=torch.float32, device="cuda")) for _ in range(frames_per_step)] if args.launch == "batch" else []
-    batch_jobs = [(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, world, o[0], o[1], o[2]) for cam, o in zip(step_cams, batch_outs)]
+    batch_jobs = [(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, pworld, o[0], o[1], o[2]) for cam, o in zip(step_cams, batch_outs)]
 
     def timed_steps_batched(steps, do_flush):
         """One timed interval per STEP, the step's frames in one batched launch on one stream."""
@@ -350,7 +357,9 @@ def run_product(args):
         emit({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
-                          "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]]})
+                          "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]],
+                          "tile_rows": TILE_ROWS, "streams": NS,
+                          "as_rank": (f"{prank}/{pworld}: value = what {pworld} GPUs would total if every rank ran like this one" if args.as_rank else None)})
         return None
 
     # same loop without the flush (steady state of a real frame loop: DAG stays L2-resident)
@@ -635,6 +644,7 @@ def emit(obj):
 
 
 def main():
+    global TILE_ROWS
     claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -647,9 +657,12 @@ def main():
     ap.add_argument("--streams", type=int, default=0, help="frames in flight in the device-resident loop (0 = 3 on one GPU, up to 8 on several)")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--quick", action="store_true", help="profiling aid: only the device-resident timed loop (no warm-L2 loop, no e2e, no CPU leg)")
+    ap.add_argument("--tile-rows", type=int, default=TILE_ROWS, help="rows per tile of the cyclic strip partition (a multiple of 8)")
+    ap.add_argument("--as-rank", default=None, metavar="R/N", help="with --quick on one GPU: trace the share rank R of an N-GPU job would")
     ap.add_argument("--variant", type=int, default=None, help="kernel variant (ort_set_option 'variant')")
     ap.add_argument("--opt", action="append", default=[], help="key=value passed to ort_set_option")
     args = ap.parse_args()
+    TILE_ROWS = args.tile_rows
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)

@@ -68,7 +68,22 @@ struct FrameRows
 	int y0, rows, tile_rows, tile_step;
 	int tile_shape;     // warp tile: 0 = 8x4, 1 = 16x2, 2 = 4x8 (trace_frame_kernel only)
 	int band_rotate;    // block row b is traced by blockIdx.y = (b - band_rotate) mod gridDim.y: which 16-row band starts first
+	int tile_shift;     // log2(tile_rows) + 1 when tile_rows is a power of two (the row mapping then needs no division), else 0
 };
+
+// strip-local row r -> frame row: contiguous strip, or tiles of tile_rows rows every tile_rows * tile_step rows
+// (uniform branches: every thread of a launch takes the same one)
+__device__ __forceinline__ int frame_row(const FrameRows& fr, int r)
+{
+	if (fr.tile_step == 1)
+		return fr.y0 + r;
+	if (fr.tile_shift)
+	{
+		const int m = (1 << (fr.tile_shift - 1)) - 1;
+		return fr.y0 + (r & ~m) * fr.tile_step + (r & m);
+	}
+	return fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+}
 
 // camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
 // a 256-thread block a 16 x 16 pixel tile.  SHAPED = true is the measurement build that also takes other warp tiles
@@ -93,9 +108,7 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 		r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
 	}
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;                                                 // contiguous strip
-	if (fr.tile_step != 1)                                             // cyclic tile strips (uniform branch)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -144,9 +157,7 @@ trace_frames_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int de
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = by * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(jb.cam, x, y, dx, dy, dz);
@@ -181,9 +192,7 @@ trace_frame_rgba_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -210,9 +219,7 @@ trace_frame_tight_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, i
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -278,9 +285,7 @@ trace_frame_tiles_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, i
 		const int x = static_cast<int>(blk % blocks_x) * 16 + static_cast<int>(sub & 1u) * 8 + static_cast<int>(lane & 7u);
 		const int r = static_cast<int>(blk / blocks_x) * 16 + static_cast<int>(sub >> 1) * 4 + static_cast<int>(lane >> 3);
 		if (x >= fr.W || r >= fr.rows) continue;
-		int y = fr.y0 + r;
-		if (fr.tile_step != 1)
-			y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+		const int y = frame_row(fr, r);
 
 		float dx, dy, dz;
 		camera_ray(cam, x, y, dx, dy, dz);
@@ -305,9 +310,7 @@ trace_frame_pipe_kernel(const uint32_t* __restrict__ nodes_m1, unsigned long lon
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -352,9 +355,7 @@ trace_frame_probe_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, i
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -407,9 +408,7 @@ trace_frame_deferred_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root
 	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
 	const bool valid = x < fr.W && r < fr.rows;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -477,9 +476,7 @@ trace_frame_staged_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, 
 	const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
 	const int r = blockIdx.y * 32 + (warp >> 2) * 4 + (lane >> 3);
 	if (x >= fr.W || r >= fr.rows) return;
-	int y = fr.y0 + r;
-	if (fr.tile_step != 1)
-		y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
@@ -620,9 +617,7 @@ trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 					const int x = static_cast<int>(tile % tiles_x) * 8 + static_cast<int>(l & 7u);
 					const int r = static_cast<int>(tile / tiles_x) * 4 + static_cast<int>(l >> 3);
 					valid = x < fr.W && r < fr.rows;
-					int y = fr.y0 + r;
-					if (fr.tile_step != 1)
-						y = fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+					const int y = frame_row(fr, r);
 					ox = cam.ox; oy = cam.oy; oz = cam.oz;
 					camera_ray(cam, x, y, dx, dy, dz);
 					out = static_cast<size_t>(r) * fr.W + x;

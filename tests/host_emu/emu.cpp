@@ -84,12 +84,13 @@ void merge(Stats* dst, const Stats& s)
 
 extern "C" {
 
-// nodes8: the compact device array as ort_tree_flatten yields it (node id i at nodes8[8*(i-1)]).
-int emu_trace_rays(const uint32_t* nodes8, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
+// nodes8: the compact device array as ort_tree_flatten yields it (node id i at nodes8[8*(i-1)], index_base 1), or the
+// och::octree pool (raw rows, root = row 0, index_base 0).  has_root = 0: empty tree, every ray is a MISS.
+int emu_trace_rays(const uint32_t* nodes8, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
                    const float* o3, int o_stride, const float* d3, size_t n, int walker,
                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
 {
-	const uint32_t* nodes_m1 = nodes8 - 8;
+	const uint32_t* nodes_m1 = nodes8 - 8 * static_cast<ptrdiff_t>(index_base);
 	const ort::RcpTable rt{rcp_tab, 23 - log2n};
 	Stats total{};
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
@@ -102,7 +103,7 @@ int emu_trace_rays(const uint32_t* nodes8, uint32_t root, int depth, float miss_
 			const float* d = d3 + static_cast<size_t>(i) * 3;
 			const ort::Ray r = ort::ray_setup(rt, o[0], o[1], o[2], d[0], d[1], d[2]);
 			ort::Hit h;
-			if (root == 0) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
+			if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
 			else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr)
 			               : walk<false>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr);
 			++st.rays;
@@ -119,11 +120,11 @@ int emu_trace_rays(const uint32_t* nodes8, uint32_t root, int depth, float miss_
 }
 
 // camera rays generated like the frame kernels do (ort::camera_ray), rows [y0, y0 + rows) of a W x H frame
-int emu_trace_frame(const uint32_t* nodes8, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
+int emu_trace_frame(const uint32_t* nodes8, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
                     const float pos[3], const float rot[9], float fov, int W, int H, int y0, int rows, int walker,
                      uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
 {
-	const uint32_t* nodes_m1 = nodes8 - 8;
+	const uint32_t* nodes_m1 = nodes8 - 8 * static_cast<ptrdiff_t>(index_base);
 	const ort::RcpTable rt{rcp_tab, 23 - log2n};
 	ort::Camera cam;
 	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
@@ -144,7 +145,7 @@ int emu_trace_frame(const uint32_t* nodes8, uint32_t root, int depth, float miss
 				ort::camera_ray(cam, x, y0 + r, dx, dy, dz);
 				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
 				ort::Hit h;
-				if (root == 0) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
+				if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
 				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr)
 				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr);
 				++st.rays;

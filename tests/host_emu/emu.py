@@ -57,7 +57,8 @@ def _stats(raw):
     return d
 
 
-def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None):
+def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None, pool=False):
+    """pool=True: nodes8 is an och::octree pool (raw rows, root = row 0; the caller passes miss_t=0.0)."""
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
     d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
@@ -67,7 +68,7 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
     vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
     npush = np.empty(n, np.uint16) if want_npush else None
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
-    lib().emu_trace_rays(_p(nodes8), C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
+    lib().emu_trace_rays(_p(nodes8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
                          _p(o), o_stride, _p(d), C.c_size_t(n), walker,
                          _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
     out = [vox, face, t]
@@ -79,7 +80,7 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
 
 
 def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walker=1, rcp_tab=None, miss_t=np.inf,
-                want_npush=False, want_stats=False, nthreads=None):
+                want_npush=False, want_stats=False, nthreads=None, pool=False):
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
     rows = H - y0 if rows is None else rows
@@ -88,7 +89,7 @@ def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walke
     vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
     npush = np.empty(n, np.uint16) if want_npush else None
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
-    lib().emu_trace_frame(_p(nodes8), C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
+    lib().emu_trace_frame(_p(nodes8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
                           _p(pos), _p(rot), C.c_float(fov), W, H, y0, rows, walker,
                            _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
     out = [vox, face, t]

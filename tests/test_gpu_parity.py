@@ -82,14 +82,20 @@ def test_strips_and_cyclic_tiles_reassemble_the_frame(ort, golden):
         assert_same_hits(part, [f[y:y + rows].ravel() for f in full], f"strip {y}+{rows}")
         y += rows
     assert y == H
-    # cyclic 8-row tiles over 4 "ranks" (H = 360 = 45 tiles: ranks get 12,11,11,11 tiles)
-    tr, N = 8, 4
-    for rank in range(N):
-        tiles = list(range(rank, H // tr, N))
-        rows = len(tiles) * tr
-        part = ctx.trace_frame(pos, rot, fov, W, H, y0=rank * tr, rows=rows, tile_rows=tr, tile_step=N)
-        want_rows = np.concatenate([np.arange(t * tr, (t + 1) * tr) for t in tiles])
-        assert_same_hits(part, [f[want_rows].ravel() for f in full], f"cyclic rank {rank}")
+    # cyclic 8-row tiles over 4 "ranks" (H = 360 = 45 tiles: ranks get 12,11,11,11 tiles); tile heights that are
+    # powers of two take the shift/mask row mapping, the others the division (ort::frame_row)
+    ctx.set_palette((np.arange(6 * 8, dtype=np.uint32).reshape(8, 6) * 0x010305) | 0xFF000000)
+    rgba_full = ctx.trace_frame_rgba(pos, rot, fov, W, H).reshape(H, W)
+    assert len(np.unique(rgba_full)) > 6
+    for tr, N in ((8, 4), (16, 3), (1, 5), (5, 3), (12, 2)):
+        for rank in range(N):
+            tiles = list(range(rank, H // tr, N))
+            rows = len(tiles) * tr
+            want_rows = np.concatenate([np.arange(t * tr, (t + 1) * tr) for t in tiles])
+            part = ctx.trace_frame(pos, rot, fov, W, H, y0=rank * tr, rows=rows, tile_rows=tr, tile_step=N)
+            assert_same_hits(part, [f[want_rows].ravel() for f in full], f"cyclic {tr}-row tiles, rank {rank} of {N}")
+            rgba = ctx.trace_frame_rgba(pos, rot, fov, W, H, y0=rank * tr, rows=rows, tile_rows=tr, tile_step=N)
+            assert np.array_equal(rgba.ravel(), rgba_full[want_rows].ravel()), f"rgba, cyclic {tr}-row tiles, rank {rank} of {N}"
 
 
 def test_empty_tree_and_tiny_inputs(ort):

@@ -107,6 +107,38 @@ def test_device_walkers_with_the_camera_on_the_cube_boundary(emu, ort, oc):
                 assert got[4]["slow_path_rays"] > 0, "rays travelling +axis from the 1.0f coordinate must leave the fast path"
 
 
+def test_device_walkers_on_the_pool_octree_layout(emu, ort, oc):
+    """och::octree (SURVEY 8f-1): the same walkers over the pool layout -- raw row indices, root = row 0, MISS reports
+    hit_time 0.0F (och_octree.cpp:302) -- against the oracle's restatement of och_octree.cpp:167-320."""
+    from golden.make_golden import edge_rays
+    rs = np.random.RandomState(8)
+    depth, cap = 7, 1 << 16
+    A, T = oc.OracleOctree(depth, cap), ort.Octree(depth, cap, device=None)
+    ops = []
+    for _ in range(40):
+        c = rs.randint(8, 120, 3)
+        e = rs.randint(2, 10)
+        v = int(rs.randint(1, 6))
+        ops += [(c[0] + x, c[1] + y, c[2] + z, v, 0) for x in range(e) for y in range(e) for z in range(e)]
+    ops = np.array(ops, np.int32)
+    A.apply(ops)
+    T.apply(ops)
+    tab = emu.default_rcp_table()
+    n = 200_000
+    o = rs.uniform(1.001, 1.999, (n, 3)).astype(np.float32)
+    d = rs.normal(size=(n, 3)).astype(np.float32)
+    eo, ed = edge_rays(rs, 300)
+    O, D = np.concatenate([o, eo]), np.concatenate([d, ed])
+    want = A.trace(O, D, rcp_tab=tab, nthreads=4)
+    assert (want[0] != 0).sum() > 1000
+    pool = np.array(T.nodes())
+    for walker in WALKERS:
+        got = emu.trace_rays(pool, 0, depth, O, D, walker=walker, miss_t=0.0, pool=True)
+        assert_same_hits(got, want, f"pool layout, walker {walker}")
+    miss = want[1] == 6
+    assert miss.any() and (want[2][miss] == 0.0).all()
+
+
 def test_device_camera_rays_equal_the_oracle_rays(emu, oc):
     """ort::camera_ray (every operation rounded separately, IEEE sqrt and division) against the oracle's statement of
     tree_camera::update_position: traced through a single solid voxel so that the per-pixel direction decides t."""
