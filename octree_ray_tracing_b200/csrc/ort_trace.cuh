@@ -690,16 +690,23 @@ __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes_
 	return w.hit;
 }
 
-// the fast path's preconditions: origin inside [1,2)^3, a start position in [1,2)^3 and at least one non-degenerate
-// direction component.  The second is not implied by the first: a coordinate of exactly 1.0f on an axis travelled in the
-// positive direction is mirrored to |3 - 1| = 2.0f, whose masked bits (och_h_octree.h:320) are 0 -- a position the
-// reference then walks as raw bit patterns (denormals), which only traverse() reproduces.
+// the fast path's preconditions: origin inside [1,2)^3, a start position in [1,2)^3, no NaN reciprocal and at least one
+// non-degenerate direction component.
+//  * The second is not implied by the first: a coordinate of exactly 1.0f on an axis travelled in the positive direction
+//    is mirrored to |3 - 1| = 2.0f, whose masked bits (och_h_octree.h:320) are 0 -- a position the reference then walks
+//    as raw bit patterns (denormals), which only traverse() reproduces.
+//  * A NaN direction component gives a NaN coef and NaN t values.  x86 keeps the operand's sign (negative here: bit
+//    patterns that sort last), the GPU's FMA returns 0x7FFFFFFF (sorts before every negative t); traverse()
+//    canonicalises NaN like x86, the fast walkers do not.
+// coef always carries the sign bit (och_h_octree.h:312), so as unsigned bits: regular < 0xFF800000 (-inf) < NaN.
 __device__ __forceinline__ bool fast_path_ok(float ox, float oy, float oz, const Ray& r)
 {
 	const uint32_t ninf = 0xFF800000u;
-	const bool all_degenerate = (__float_as_uint(r.cx) == ninf) & (__float_as_uint(r.cy) == ninf) & (__float_as_uint(r.cz) == ninf);
+	const uint32_t cx = __float_as_uint(r.cx), cy = __float_as_uint(r.cy), cz = __float_as_uint(r.cz);
+	const bool no_nan = max(cx, max(cy, cz)) <= ninf;
+	const bool some_regular = min(cx, min(cy, cz)) < ninf;                            // not all three degenerate (-inf)
 	const bool pos_in_cube = (r.px & r.py & r.pz & 0x3F800000u) == 0x3F800000u;      // pos is masked to 0x3FC00000: exponent field 127
-	return in_unit_cube(ox, oy, oz) & pos_in_cube & !all_degenerate;
+	return in_unit_cube(ox, oy, oz) & pos_in_cube & no_nan & some_regular;
 }
 
 // The walk of one ray, start to end.  VARIANT 0: the baseline transliteration; otherwise FastWalker where its

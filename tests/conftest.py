@@ -62,9 +62,9 @@ def assert_same_hits(got, want, what=""):
 
 
 def degenerate_rays(ort, depth):
-    """280 000 rays built to hit every special case of the kernels' fast path: zero and denormal direction components
+    """310 000 rays built to hit every special case of the kernels' fast path: zero and denormal direction components
     (coef = -inf), origins on cell planes -- including coordinates of exactly 1.0f, which mirror to 2.0f on an axis
-    travelled in the positive direction and leave [1,2) --, origins outside [1,2)^3, grazing rays."""
+    travelled in the positive direction and leave [1,2) --, origins outside [1,2)^3, grazing rays, NaN / inf / huge / tiny components."""
     rs = np.random.RandomState(7)
     o, d = ort.harness.random_rays(200_000, seed=11)
     # degenerate directions
@@ -81,6 +81,14 @@ def degenerate_rays(ort, depth):
     # grazing rays just above the terrain
     og = o[:20_000].copy(); og[:, 2] = 1.0 + 5.0 / 16.0 + 1e-3
     dg = d[:20_000].copy(); dg[:, 2] = -np.abs(dg[:, 2]) * 1e-3
-    O = np.concatenate([o, o[:40_000], o[40_000:60_000], op, oo, og])
-    D = np.concatenate([d, dz, d2, d[:40_000], d[:20_000], dg])
+    # NaN (both signs), +-inf, huge and near-denormal components: one or two per direction, one per origin
+    special = np.array([np.nan, 0.0, np.inf, -np.inf, 3e38, -3e38, 1e-38, -1e-38], np.float32)
+    special[1:2] = np.array([0xFFC00000], np.uint32).view(np.float32)
+    n = 10_000
+    s1 = d[60_000:70_000].copy(); s1[np.arange(n), rs.randint(0, 3, n)] = rs.choice(special, n)
+    s2 = d[70_000:80_000].copy(); k = rs.randint(0, 3, n)
+    s2[np.arange(n), k] = rs.choice(special, n); s2[np.arange(n), (k + 1) % 3] = rs.choice(special, n)
+    so = o[80_000:90_000].copy(); so[np.arange(n), rs.randint(0, 3, n)] = rs.choice(special, n)
+    O = np.concatenate([o, o[:40_000], o[40_000:60_000], op, oo, og, o[60_000:80_000], so])
+    D = np.concatenate([d, dz, d2, d[:40_000], d[:20_000], dg, s1, s2, d[80_000:90_000]])
     return O, D

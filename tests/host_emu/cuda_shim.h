@@ -23,13 +23,35 @@
 
 static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
-static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
-static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline float __fadd_rn(float a, float b) { return a + b; }
-static inline float __fsub_rn(float a, float b) { return a - b; }
-static inline float __fdiv_rn(float a, float b) { return a / b; }
-static inline float __fsqrt_rn(float a) { return std::sqrt(a); }
-template<class T> static inline T __ldg(const T* p) { return *p; }
+// NaN results: x86 propagates an operand's sign and payload, the GPU's FP32 pipes return the canonical 0x7FFFFFFF --
+// the one place where the two machines' IEEE arithmetic differs visibly (the traversal orders t values by their bit
+// patterns), so the stand-ins reproduce the device's NaN.
+static inline float emu_nan(float r) { return r != r ? __uint_as_float(0x7FFFFFFFu) : r; }
+static inline float __fmaf_rn(float a, float b, float c) { return emu_nan(std::fmaf(a, b, c)); }
+static inline float __fmul_rn(float a, float b) { return emu_nan(a * b); }
+static inline float __fadd_rn(float a, float b) { return emu_nan(a + b); }
+static inline float __fsub_rn(float a, float b) { return emu_nan(a - b); }
+static inline float __fdiv_rn(float a, float b) { return emu_nan(a / b); }
+static inline float __fsqrt_rn(float a) { return emu_nan(std::sqrt(a)); }
+// Every global load of the traversal goes through __ldg: the emulator checks each address against the two arrays a
+// kernel may read (the node array and the reciprocal table) -- the job compute-sanitizer's memcheck would do on the
+// device.  An out-of-range load is counted and yields 0 instead of faulting.
+struct EmuBounds
+{
+	const char* lo[2];
+	const char* hi[2];
+	unsigned long long violations;
+};
+inline thread_local EmuBounds g_emu_bounds = { { nullptr, nullptr }, { nullptr, nullptr }, 0 };
+template<class T> static inline T __ldg(const T* p)
+{
+	const char* a = reinterpret_cast<const char*>(p);
+	const EmuBounds& b = g_emu_bounds;
+	if ((a >= b.lo[0] && a + sizeof(T) <= b.hi[0]) || (a >= b.lo[1] && a + sizeof(T) <= b.hi[1]))
+		return *p;
+	++g_emu_bounds.violations;
+	return T{};
+}
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz(static_cast<unsigned>(x)) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }

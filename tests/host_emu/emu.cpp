@@ -14,6 +14,7 @@ struct Stats
 {
 	unsigned long long rounds_by_level[ort::kMaxDepth + 2];   // child-slot loads issued with the walker at that level
 	unsigned long long rays, slow_path_rays;                  // slow path: rays outside FastWalker's preconditions
+	unsigned long long oob_loads;                             // loads outside the node array / reciprocal table (cuda_shim.h)
 };
 
 // walker ids follow ort_set_option("variant"): 0 baseline traverse(), 1 FastWalker, 5 TightWalker, 7 PipeWalker
@@ -74,10 +75,19 @@ ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, fl
 	return bad;
 }
 
+void set_bounds(const uint32_t* nodes8, size_t n_rows, const uint32_t* rcp_tab, int log2n)
+{
+	g_emu_bounds.lo[0] = reinterpret_cast<const char*>(nodes8);
+	g_emu_bounds.hi[0] = reinterpret_cast<const char*>(nodes8 + 8 * n_rows);
+	g_emu_bounds.lo[1] = reinterpret_cast<const char*>(rcp_tab);
+	g_emu_bounds.hi[1] = reinterpret_cast<const char*>(rcp_tab + (static_cast<size_t>(1) << log2n));
+	g_emu_bounds.violations = 0;
+}
+
 void merge(Stats* dst, const Stats& s)
 {
 	for (int i = 0; i < ort::kMaxDepth + 2; ++i) dst->rounds_by_level[i] += s.rounds_by_level[i];
-	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays;
+	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays; dst->oob_loads += s.oob_loads;
 }
 
 }  // namespace
@@ -86,7 +96,7 @@ extern "C" {
 
 // nodes8: the compact device array as ort_tree_flatten yields it (node id i at nodes8[8*(i-1)], index_base 1), or the
 // och::octree pool (raw rows, root = row 0, index_base 0).  has_root = 0: empty tree, every ray is a MISS.
-int emu_trace_rays(const uint32_t* nodes8, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
+int emu_trace_rays(const uint32_t* nodes8, size_t n_rows, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
                    const float* o3, int o_stride, const float* d3, size_t n, int walker,
                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
 {
@@ -96,6 +106,7 @@ int emu_trace_rays(const uint32_t* nodes8, int index_base, int has_root, uint32_
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
 	{
 		Stats st{};
+		set_bounds(nodes8, n_rows, rcp_tab, log2n);
 #pragma omp for schedule(dynamic, 4096)
 		for (long long i = 0; i < static_cast<long long>(n); ++i)
 		{
@@ -112,15 +123,16 @@ int emu_trace_rays(const uint32_t* nodes8, int index_base, int has_root, uint32_
 			t[i] = h.t;
 			if (npush) npush[i] = static_cast<uint16_t>(h.npush < 65535u ? h.npush : 65535u);
 		}
+		st.oob_loads = g_emu_bounds.violations;
 #pragma omp critical
 		merge(&total, st);
 	}
 	if (stats_out) std::memcpy(stats_out, &total, sizeof(total));
-	return 0;
+	return total.oob_loads ? 1 : 0;                              // 1: some load left the node array / the table
 }
 
 // camera rays generated like the frame kernels do (ort::camera_ray), rows [y0, y0 + rows) of a W x H frame
-int emu_trace_frame(const uint32_t* nodes8, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
+int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
                     const float pos[3], const float rot[9], float fov, int W, int H, int y0, int rows, int walker,
                      uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
 {
@@ -137,6 +149,7 @@ int emu_trace_frame(const uint32_t* nodes8, int index_base, int has_root, uint32
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
 	{
 		Stats st{};
+		set_bounds(nodes8, n_rows, rcp_tab, log2n);
 #pragma omp for schedule(dynamic, 4)
 		for (int r = 0; r < rows; ++r)
 			for (int x = 0; x < W; ++x)
@@ -155,11 +168,12 @@ int emu_trace_frame(const uint32_t* nodes8, int index_base, int has_root, uint32
 				t[i] = h.t;
 				if (npush) npush[i] = static_cast<uint16_t>(h.npush < 65535u ? h.npush : 65535u);
 			}
+		st.oob_loads = g_emu_bounds.violations;
 #pragma omp critical
 		merge(&total, st);
 	}
 	if (stats_out) std::memcpy(stats_out, &total, sizeof(total));
-	return 0;
+	return total.oob_loads ? 1 : 0;                              // 1: some load left the node array / the table
 }
 
 int emu_stats_words(void) { return static_cast<int>(sizeof(Stats) / sizeof(unsigned long long)); }

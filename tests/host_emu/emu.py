@@ -16,7 +16,7 @@ CSRC = os.path.join(ROOT, "octree_ray_tracing_b200", "csrc")
 SO = os.path.join(HERE, "_build", "libort_emu.so")
 _lib = None
 
-STAT_FIELDS = ["rays", "slow_path_rays"]
+STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads"]
 
 
 def build(force: bool = False) -> str:
@@ -57,7 +57,7 @@ def _stats(raw):
     return d
 
 
-def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None, pool=False):
+def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False):
     """pool=True: nodes8 is an och::octree pool (raw rows, root = row 0; the caller passes miss_t=0.0)."""
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
@@ -68,9 +68,11 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
     vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
     npush = np.empty(n, np.uint16) if want_npush else None
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
-    lib().emu_trace_rays(_p(nodes8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
+    oob = lib().emu_trace_rays(_p(nodes8), C.c_size_t(nodes8.size // 8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
                          _p(o), o_stride, _p(d), C.c_size_t(n), walker,
                          _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
+    if oob and not allow_oob:
+        raise MemoryError("host emulation: the walk loaded from outside the node array / reciprocal table")
     out = [vox, face, t]
     if want_npush:
         out.append(npush)
@@ -80,7 +82,7 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
 
 
 def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walker=1, rcp_tab=None, miss_t=np.inf,
-                want_npush=False, want_stats=False, nthreads=None, pool=False):
+                want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False):
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
     rows = H - y0 if rows is None else rows
@@ -89,9 +91,11 @@ def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walke
     vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
     npush = np.empty(n, np.uint16) if want_npush else None
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
-    lib().emu_trace_frame(_p(nodes8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
+    oob = lib().emu_trace_frame(_p(nodes8), C.c_size_t(nodes8.size // 8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
                           _p(pos), _p(rot), C.c_float(fov), W, H, y0, rows, walker,
                            _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
+    if oob and not allow_oob:
+        raise MemoryError("host emulation: the walk loaded from outside the node array / reciprocal table")
     out = [vox, face, t]
     if want_npush:
         out.append(npush)

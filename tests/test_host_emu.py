@@ -1,7 +1,9 @@
 """The device-side traversal code (csrc/ort_trace.cuh: camera rays, the RCPPS table model, the baseline walk and the
 FastWalker / TightWalker / PipeWalker bookkeeping incl. the multi-level POP) compiled for the HOST by tests/host_emu and
 held against the reference's golden outputs and the CPU oracle -- the same bar as the GPU parity tests (voxel, face and
-hit time bit-exact, per-ray PUSH counts equal), but runnable where there is no GPU.  Test infrastructure only: the
+hit time bit-exact, per-ray PUSH counts equal), but runnable where there is no GPU.  Every global load of the walk is
+bounds-checked against the node array and the reciprocal table (cuda_shim.h; emu.py raises MemoryError on a stray load)
+-- the memcheck this pool's GPUs do not offer.  Test infrastructure only: the
 product library has no CPU path (tests/test_capi_symbols.py checks that)."""
 import os
 import sys

@@ -147,3 +147,25 @@ def test_live_trace_random_trees(oc):
         assert_same_hits(A.trace(o, d), B.trace(o, d), f"random d{D}")
         o, d = edge_rays(rs, 500)
         assert_same_hits(A.trace(o, d), B.trace(o, d), f"edge d{D}")
+
+
+def test_oracle_equals_the_real_reference_on_degenerate_rays(oc):
+    """The ray classes the kernels special-case (tests/conftest.py degenerate_rays: +-0 / denormal / NaN / inf direction
+    components, on-plane origins incl. exactly 1.0f, origins outside the cube, grazing rays) through the REAL
+    och::h_octree::sse_trace (oracle/_ref) and the restatement: bitwise equal.  Live where the reference is built."""
+    if not oc.have_ref():
+        pytest.skip("oracle/_ref not built (no /root/reference on this machine)")
+    import octree_ray_tracing_b200 as ort
+    from conftest import degenerate_rays
+    depth = 8
+    T = ort.HOctree(19, depth, device=None)
+    ort.harness.build_terrain(T, tunnels=True)
+    nodes8, root, _ = T.flatten()
+    R = oc.RefTree(19, depth)
+    R.import_compact(nodes8, root)
+    O, D = degenerate_rays(ort, depth)
+    assert np.isnan(D).any() and np.isinf(D).any() and (O == 1.0).any()
+    want = R.trace(O, D, nthreads=4)
+    got = oc.trace_rays(nodes8, root, depth, O, D, nthreads=4)
+    from conftest import assert_same_hits
+    assert_same_hits(got, want, "oracle vs real reference, degenerate rays")
