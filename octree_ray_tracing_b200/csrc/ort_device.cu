@@ -392,15 +392,6 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 // trace
 // ------------------------------------------------------------------------------------------------
 
-// FrameRows::tile_shift
-static int tile_shift_of(int tile_rows)
-{
-	if (tile_rows <= 0 || (tile_rows & (tile_rows - 1)) != 0) return 0;
-	int s = 0;
-	while ((1 << s) < tile_rows) ++s;
-	return s + 1;
-}
-
 static ort::Camera make_camera(const float pos[3], const float rot[9], float fov_factor, int W, int H);
 
 // Which 16-row band of the launch should be scheduled first.  A launch ends when its longest rays do, and those are
@@ -509,7 +500,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
-	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape, rotate, tile_shift_of(tile_rows) };
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape, rotate, ort::tile_shift_of(tile_rows) };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
 	if (c->opt_variant == 2)
 	{
@@ -650,7 +641,7 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 			ort::FrameJob& d = batch.job[n++];
 			d.cam = make_camera(j.pos, j.rot, j.fov_factor, j.W, j.H);
 			const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((j.rows + 15) / 16) : horizon_band(d.cam, j.W, j.y0, j.rows, j.tile_rows, j.tile_step);
-			d.fr = ort::FrameRows{ j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, 0, rotate, tile_shift_of(j.tile_rows) };
+			d.fr = ort::FrameRows{ j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, 0, rotate, ort::tile_shift_of(j.tile_rows) };
 			d.voxel = j.voxel; d.face = j.face; d.t = j.t; d.npush = j.npush;
 			gx = std::max(gx, static_cast<unsigned>((j.W + 15) / 16));
 			gy = std::max(gy, static_cast<unsigned>((j.rows + 15) / 16));
@@ -924,7 +915,7 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
 	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
-	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, rotate, tile_shift_of(tile_rows) };
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, rotate, ort::tile_shift_of(tile_rows) };
 	ort::trace_frame_rgba_kernel<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, pal, d_rgba);
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());

@@ -62,28 +62,7 @@ trace_rays_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dept
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
-struct FrameRows
-{
-	int W, H;
-	int y0, rows, tile_rows, tile_step;
-	int tile_shape;     // warp tile: 0 = 8x4, 1 = 16x2, 2 = 4x8 (trace_frame_kernel only)
-	int band_rotate;    // block row b is traced by blockIdx.y = (b - band_rotate) mod gridDim.y: which 16-row band starts first
-	int tile_shift;     // log2(tile_rows) + 1 when tile_rows is a power of two (the row mapping then needs no division), else 0
-};
-
-// strip-local row r -> frame row: contiguous strip, or tiles of tile_rows rows every tile_rows * tile_step rows
-// (uniform branches: every thread of a launch takes the same one)
-__device__ __forceinline__ int frame_row(const FrameRows& fr, int r)
-{
-	if (fr.tile_step == 1)
-		return fr.y0 + r;
-	if (fr.tile_shift)
-	{
-		const int m = (1 << (fr.tile_shift - 1)) - 1;
-		return fr.y0 + (r & ~m) * fr.tile_step + (r & m);
-	}
-	return fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
-}
+// FrameRows / frame_row (strip-local row -> frame row) live in ort_trace.cuh, next to the camera
 
 // camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
 // a 256-thread block a 16 x 16 pixel tile.  SHAPED = true is the measurement build that also takes other warp tiles

@@ -756,4 +756,37 @@ __device__ __forceinline__ void camera_ray(const Camera& c, int x, int y, float&
 	dz = __fmul_rn(-rv, rm);
 }
 
+// Rows of a frame one launch traces (ort_trace_frame: y0, rows, tile_rows, tile_step) and how the kernels map them.
+struct FrameRows
+{
+	int W, H;
+	int y0, rows, tile_rows, tile_step;
+	int tile_shape;     // warp tile: 0 = 8x4, 1 = 16x2, 2 = 4x8 (trace_frame_kernel only)
+	int band_rotate;    // block row b is traced by blockIdx.y = (b - band_rotate) mod gridDim.y: which 16-row band starts first
+	int tile_shift;     // log2(tile_rows) + 1 when tile_rows is a power of two (the row mapping then needs no division), else 0
+};
+
+// FrameRows::tile_shift for a tile height (host side)
+inline int tile_shift_of(int tile_rows)
+{
+	if (tile_rows <= 0 || (tile_rows & (tile_rows - 1)) != 0) return 0;
+	int s = 0;
+	while ((1 << s) < tile_rows) ++s;
+	return s + 1;
+}
+
+// strip-local row r -> frame row: contiguous strip, or tiles of tile_rows rows every tile_rows * tile_step rows
+// (uniform branches: every thread of a launch takes the same one)
+__device__ __forceinline__ int frame_row(const FrameRows& fr, int r)
+{
+	if (fr.tile_step == 1)
+		return fr.y0 + r;
+	if (fr.tile_shift)
+	{
+		const int m = (1 << (fr.tile_shift - 1)) - 1;
+		return fr.y0 + (r & ~m) * fr.tile_step + (r & m);
+	}
+	return fr.y0 + (r / fr.tile_rows) * fr.tile_rows * fr.tile_step + r % fr.tile_rows;
+}
+
 }  // namespace ort

@@ -131,9 +131,9 @@ int emu_trace_rays(const uint32_t* nodes8, size_t n_rows, int index_base, int ha
 	return total.oob_loads ? 1 : 0;                              // 1: some load left the node array / the table
 }
 
-// camera rays generated like the frame kernels do (ort::camera_ray), rows [y0, y0 + rows) of a W x H frame
+// camera rays generated like the frame kernels do (ort::camera_ray); rows as ort_trace_frame takes them (ort::frame_row)
 int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
-                    const float pos[3], const float rot[9], float fov, int W, int H, int y0, int rows, int walker,
+                    const float pos[3], const float rot[9], float fov, int W, int H, int y0, int rows, int tile_rows, int tile_step, int walker,
                      uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
 {
 	const uint32_t* nodes_m1 = nodes8 - 8 * static_cast<ptrdiff_t>(index_base);
@@ -145,6 +145,7 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 	cam.aspect = static_cast<float>(W) / static_cast<float>(H);
 	cam.vfx = 2.0F / static_cast<float>(W);
 	cam.vfy = 2.0F / static_cast<float>(H);
+	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, 0, ort::tile_shift_of(tile_rows) };
 	Stats total{};
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
 	{
@@ -155,7 +156,7 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 			for (int x = 0; x < W; ++x)
 			{
 				float dx, dy, dz;
-				ort::camera_ray(cam, x, y0 + r, dx, dy, dz);
+				ort::camera_ray(cam, x, ort::frame_row(fr, r), dx, dy, dz);
 				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
 				ort::Hit h;
 				if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }

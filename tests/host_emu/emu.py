@@ -81,7 +81,7 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
     return tuple(out)
 
 
-def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walker=1, rcp_tab=None, miss_t=np.inf,
+def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, tile_rows=1, tile_step=1, walker=1, rcp_tab=None, miss_t=np.inf,
                 want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False):
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
@@ -92,7 +92,7 @@ def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, walke
     npush = np.empty(n, np.uint16) if want_npush else None
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
     oob = lib().emu_trace_frame(_p(nodes8), C.c_size_t(nodes8.size // 8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
-                          _p(pos), _p(rot), C.c_float(fov), W, H, y0, rows, walker,
+                          _p(pos), _p(rot), C.c_float(fov), W, H, y0, rows, tile_rows, tile_step, walker,
                            _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
     if oob and not allow_oob:
         raise MemoryError("host emulation: the walk loaded from outside the node array / reciprocal table")

@@ -141,6 +141,27 @@ def test_device_walkers_on_the_pool_octree_layout(emu, ort, oc):
     assert miss.any() and (want[2][miss] == 0.0).all()
 
 
+def test_device_row_mapping_of_cyclic_strips(emu, golden):
+    """ort::frame_row (shift / mask for power-of-two tile heights, division otherwise) against the host-side partition
+    (multi_gpu.strip_rows): the strips of all ranks reassemble the frame, for even and ragged tile counts."""
+    from octree_ray_tracing_b200 import multi_gpu
+    g = golden("d6_tunnels")
+    depth, root = int(g["depth"]), int(g["root"])
+    W, H = 96, 118                                       # 118 rows: the last tile is partial for most tile heights
+    pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
+    full = [x.reshape(H, W) for x in emu.trace_frame(g["nodes8"], root, depth, pos, rot, fov, W, H)]
+    assert (full[0] != 0).sum() > 500
+    for tile_rows, world in ((8, 4), (8, 8), (16, 3), (1, 5), (5, 3), (12, 2), (32, 2), (7, 1)):
+        seen = np.zeros(H, np.int32)
+        for rank in range(world):
+            y0, rows, frame_rows = multi_gpu.strip_rows(rank, world, H, tile_rows)
+            seen[frame_rows] += 1
+            # the kernels trace whole tiles; rows past the frame's end are clipped by the caller (rows counts only real ones)
+            part = emu.trace_frame(g["nodes8"], root, depth, pos, rot, fov, W, H, y0=y0, rows=rows, tile_rows=tile_rows, tile_step=world)
+            assert_same_hits(part, [f[frame_rows].ravel() for f in full], f"{tile_rows}-row tiles, rank {rank} of {world}")
+        assert (seen == 1).all()
+
+
 def test_device_camera_rays_equal_the_oracle_rays(emu, oc):
     """ort::camera_ray (every operation rounded separately, IEEE sqrt and division) against the oracle's statement of
     tree_camera::update_position: traced through a single solid voxel so that the per-pixel direction decides t."""
