@@ -180,3 +180,80 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 int emu_stats_words(void) { return static_cast<int>(sizeof(Stats) / sizeof(unsigned long long)); }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// SIMT cost model of the frame kernel (a design aid, not a test): the rays of an 8 x 4 pixel tile advance in lockstep,
+// one FastWalker round per step, like the lanes of a warp.  Per warp-round the model records which of the two
+// branches of the round (descend: non-empty child / advance: empty child) have takers -- a warp pays for every
+// branch that has at least one lane in it.
+// out[0] warp-rounds, [1] with descend lanes only, [2] with advance lanes only, [3] with both,
+// [4] sum of active lanes over warp-rounds, [5] sum of descend lanes, [6] sum of advance lanes, [7] warps,
+// [8] sum over warps of the longest lane's rounds (= warp-rounds), [9] lane-rounds (sum of all lanes' rounds)
+// ------------------------------------------------------------------------------------------------
+extern "C" int emu_warp_model(const uint32_t* nodes8, size_t n_rows, uint32_t root, int depth, const uint32_t* rcp_tab, int log2n,
+                              const float pos[3], const float rot[9], float fov, int W, int H, unsigned long long* out, int nthreads)
+{
+	const uint32_t* nodes_m1 = nodes8 - 8;
+	const ort::RcpTable rt{rcp_tab, 23 - log2n};
+	ort::Camera cam;
+	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
+	for (int i = 0; i < 9; ++i) cam.r[i] = rot[i];
+	cam.fov = fov;
+	cam.aspect = static_cast<float>(W) / static_cast<float>(H);
+	cam.vfx = 2.0F / static_cast<float>(W);
+	cam.vfy = 2.0F / static_cast<float>(H);
+	const int tx = (W + 7) / 8, ty = (H + 3) / 4;
+	unsigned long long tot[10] = {};
+#pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
+	{
+		unsigned long long loc[10] = {};
+		set_bounds(nodes8, n_rows, rcp_tab, log2n);
+#pragma omp for schedule(dynamic, 64)
+		for (int tile = 0; tile < tx * ty; ++tile)
+		{
+			ort::FastWalker<false> w[32];
+			uint32_t stack[32][ort::kMaxDepth];
+			bool active[32];
+			int n_active = 0;
+			for (int l = 0; l < 32; ++l)
+			{
+				const int x = (tile % tx) * 8 + (l & 7), y = (tile / tx) * 4 + (l >> 3);
+				active[l] = false;
+				if (x >= W || y >= H) continue;
+				float dx, dy, dz;
+				ort::camera_ray(cam, x, y, dx, dy, dz);
+				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+				if (!ort::fast_path_ok(cam.ox, cam.oy, cam.oz, ray)) continue;      // slow-path rays are outside the model
+				w[l].start(root, __uint_as_float(0x7F800000u), ray);
+				active[l] = true;
+				++n_active;
+			}
+			if (!n_active) continue;
+			++loc[7];
+			while (n_active)
+			{
+				int nd = 0, na = 0;
+				for (int l = 0; l < 32; ++l)
+				{
+					if (!active[l]) continue;
+					const uint32_t child = w[l].load_child(nodes_m1);
+					bool done;
+					if (child) { ++nd; done = w[l].descend(child, depth, stack[l]); }
+					else       { ++na; done = w[l].advance(stack[l]); }
+					if (done) active[l] = false;
+				}
+				++loc[0];
+				loc[nd && !na ? 1 : (!nd && na ? 2 : 3)] += 1;
+				loc[4] += nd + na; loc[5] += nd; loc[6] += na;
+				loc[9] += nd + na;
+				n_active = 0;
+				for (int l = 0; l < 32; ++l) n_active += active[l];
+			}
+		}
+		loc[8] = loc[0];
+#pragma omp critical
+		for (int i = 0; i < 10; ++i) tot[i] += loc[i];
+	}
+	std::memcpy(out, tot, sizeof(tot));
+	return 0;
+}

@@ -102,3 +102,16 @@ def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, tile_
     if want_stats:
         out.append(_stats(stats))
     return tuple(out)
+
+
+def warp_model(nodes8, root, depth, pos, rot, fov, W, H, rcp_tab=None, nthreads=None):
+    """SIMT cost model of the frame kernel (emu.cpp: emu_warp_model): the rays of each 8x4 tile advance in lockstep, one
+    round per step.  Returns a dict of totals over the frame."""
+    nodes8 = np.ascontiguousarray(nodes8, np.uint32)
+    tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
+    pos = np.ascontiguousarray(pos, np.float32); rot = np.ascontiguousarray(rot, np.float32)
+    out = np.zeros(10, np.uint64)
+    lib().emu_warp_model(_p(nodes8), C.c_size_t(nodes8.size // 8), C.c_uint32(root), depth, _p(tab), int(np.log2(len(tab))),
+                         _p(pos), _p(rot), C.c_float(fov), W, H, _p(out), nthreads or os.cpu_count() or 1)
+    keys = ["warp_rounds", "descend_only", "advance_only", "both", "active_lanes", "descend_lanes", "advance_lanes", "warps", "_", "lane_rounds"]
+    return {k: int(v) for k, v in zip(keys, out) if k != "_"}

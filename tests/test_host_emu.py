@@ -175,3 +175,20 @@ def test_device_camera_rays_equal_the_oracle_rays(emu, oc):
         want = oc.trace_rays(nodes8, 1, 2, np.array(pos, np.float32), d, rcp_tab=emu.default_rcp_table())
         got = emu.trace_frame(nodes8, 1, 2, pos, rot, fov, W, H, walker=1)
         assert_same_hits(got, want, f"camera rays from {pos}")
+
+
+def test_simt_model_accounts_for_every_round(emu, golden):
+    """tools/simt_model.py's lockstep model (emu_warp_model): its lane-rounds are the PUSH counts of the frame, a warp runs
+    at least as many rounds as its longest lane, and the three kinds of warp-rounds partition the total."""
+    g = golden("d8_tunnels")
+    depth, root = int(g["depth"]), int(g["root"])
+    W, H = int(g["W"]), int(g["H"])
+    pos, rot, fov = g["poseB_pos"], g["poseB_rot"], float(g["poseB_fov"])
+    m = emu.warp_model(g["nodes8"], root, depth, pos, rot, fov, W, H)
+    npush = emu.trace_frame(g["nodes8"], root, depth, pos, rot, fov, W, H, walker=1, want_npush=True)[3].astype(np.int64)
+    assert m["lane_rounds"] == int(npush.sum()) == m["active_lanes"] == m["descend_lanes"] + m["advance_lanes"]
+    assert m["warp_rounds"] == m["descend_only"] + m["advance_only"] + m["both"]
+    tiles = npush.reshape(H, W)[: H // 4 * 4, : W // 8 * 8].reshape(H // 4, 4, W // 8, 8).max(axis=(1, 3))
+    if H % 4 == 0 and W % 8 == 0:
+        assert m["warp_rounds"] == int(tiles.sum())          # lockstep: a warp runs as long as its longest lane
+    assert m["warps"] == ((W + 7) // 8) * ((H + 3) // 4)
