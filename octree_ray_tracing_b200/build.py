@@ -49,8 +49,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     cmd = [nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     out = subprocess.run(cmd, capture_output=True, text=True)
     log = out.stdout + out.stderr
+    # build.log is tracked (ptxas -v: registers, spills, stack per kernel); compile times would only make it churn
+    stable = "\n".join(line for line in log.splitlines() if "Compile time" not in line)
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
+        f.write(" ".join(cmd) + "\n" + stable + "\n")
     if verbose or out.returncode:
         print(log)
     if out.returncode:
