@@ -13,7 +13,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "octree_ray_tracing_b200", "csrc")
-SO = os.path.join(HERE, "_build", "libort_emu.so")
+SANITIZE = os.environ.get("ORT_EMU_SANITIZE", "") == "1"      # tools/sanitize_host.sh: ASan + UBSan over the walkers' local arrays
+SO = os.path.join(HERE, "_build", "libort_emu_san.so" if SANITIZE else "libort_emu.so")
 _lib = None
 
 STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads"]
@@ -26,6 +27,8 @@ def build(force: bool = False) -> str:
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     cmd = ["g++", "-O2", "-std=c++17", "-fopenmp", "-mfma", "-mavx2", "-ffp-contract=off", "-fPIC", "-shared",
            "-Wall", "-Wno-unused-function", deps[0], "-o", SO]
+    if SANITIZE:
+        cmd[1:2] = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
     out = subprocess.run(cmd, capture_output=True, text=True)
     if out.returncode:
         raise RuntimeError("host emulation build failed:\n" + out.stderr)

@@ -162,6 +162,41 @@ def test_device_row_mapping_of_cyclic_strips(emu, golden):
         assert (seen == 1).all()
 
 
+@pytest.mark.parametrize("depth,log2cap", [(1, 8), (2, 8), (16, 18)])
+def test_device_walkers_at_extreme_depths(emu, ort, oc, depth, log2cap):
+    """Depth 1 (one node) and depth 16 (a 16-entry parent stack, voxel-size 2^-16 steps, the multi-level POP across 15
+    levels): the scene of the GPU test of the same name, through the emulated walkers.  tools/sanitize_host.sh runs this
+    with ASan on the walkers' local stacks."""
+    rs = np.random.RandomState(100 + depth)
+    dim = 1 << depth
+    T = ort.HOctree(log2cap, depth, device=None)
+    n = 6 if depth <= 2 else 4000
+    pts = rs.randint(0, dim, (n, 3))
+    if depth == 16:
+        pts[: n // 2] = 32768 + rs.randint(-40, 40, (n // 2, 3))
+    pts[:2] = [[0, 0, 0], [dim - 1, dim - 1, dim - 1]]
+    ops = np.concatenate([pts, rs.randint(1, 5, (n, 1))], 1).astype(np.uint32)
+    T.set_many(ops)
+    nodes8, root, _ = T.flatten()
+    m = 30000
+    o = rs.uniform(1.001, 1.999, (m, 3)).astype(np.float32)
+    target = (1.0 + (pts[rs.randint(0, n, m)] + rs.uniform(0, 1, (m, 3))) / dim).astype(np.float32)
+    d = target - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    d[:300, 1:] = 0.0
+    d[300:600, 2] = 0.0
+    o[600:900] = np.float32(1.5)
+    o[900:1200] = np.float32(1.0)                             # on the cube's own faces: the baseline walk's domain
+    tab = emu.default_rcp_table()
+    want = oc.trace_rays(nodes8, root, depth, o, d, rcp_tab=tab, nthreads=4, want_counts=True)
+    assert (want[0] != 0).sum() > m // 10
+    for walker in WALKERS:
+        got = emu.trace_rays(nodes8, root, depth, o, d, walker=walker, want_npush=True)
+        assert_same_hits(got, want, f"depth {depth}, walker {walker}")
+        assert np.array_equal(got[3], want[3]), f"depth {depth}, walker {walker}: PUSH counts"
+
+
 def test_device_camera_rays_equal_the_oracle_rays(emu, oc):
     """ort::camera_ray (every operation rounded separately, IEEE sqrt and division) against the oracle's statement of
     tree_camera::update_position: traced through a single solid voxel so that the per-pixel direction decides t."""
