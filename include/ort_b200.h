@@ -70,6 +70,11 @@ int ort_set_rcp_table(ort_ctx* ctx, const uint32_t* tab, int log2n);
  * GPU trace will equal this host's CPU trace bit for bit after ort_set_rcp_table(ctx, tab, log2n)); -1 if the build
  * has no RCPSS.  log2n = 11 suffices on Intel; try larger values until the return value is 0 elsewhere. */
 long ort_host_rcp_table(uint32_t* tab, int log2n);
+/* Does this host's RCPSS reproduce `tab` (probed on one input per entry, both signs)?  1 yes, 0 no, -1 no RCPSS in this
+ * build.  ort_create() runs this probe against the built-in table and warns once on stderr when it fails, because the
+ * GPU would then disagree with a reference running on this very host; ort_rcp_host_status() returns what it found. */
+int ort_host_rcp_matches(const uint32_t* tab, int log2n);
+int ort_rcp_host_status(const ort_ctx* ctx);
 
 /* Replaces: the tracer's view of table->nodes[] / root_idx (och_h_octree.h:82, :95, :344).
  * nodes8 = n_nodes * 8 uint32 in COMPACT numbering: node id i (1-based) is row i-1; interior
@@ -154,6 +159,39 @@ int ort_parse_voxels(const char* text, size_t len, uint32_t* rgba6, char* names1
  * D2H, returns when the pixels are there) or a device pointer (enqueue only on ort_stream). */
 int ort_trace_frame_rgba(ort_ctx* ctx, const float pos[3], const float rot[9], float fov_factor,
                          int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* rgba);
+
+/* ==============================================================================================
+ * Multi-GPU: one process per GPU, the DAG replicated, a frame cut into cyclic tile strips -- rank r
+ * traces tiles r, r + world, ... (tile_rows rows each) with ort_trace_frame(y0 = r * tile_rows, tile_step = world).
+ * The trace needs no exchange.  NCCL (loaded at run time, libnccl.so.2) carries exactly two things: the DAG / its edit
+ * deltas from the rank that owns the host table, and the finished strips to the rank that consumes the frame --
+ * the multi-GPU form of update_image's single frame (test_och_h_octree.cpp:437-457).
+ * ============================================================================================== */
+typedef struct ort_mg ort_mg;
+/* 128 bytes identifying the job: created on one rank, shipped to the others by the application (any channel). */
+int ort_mg_unique_id(void* id128);
+/* Collective: the communicator of ctx's GPU, rank of world.  world == 1 needs neither NCCL nor an id. */
+int ort_mg_create(ort_mg** out, ort_ctx* ctx, int rank, int world, const void* id128);
+int ort_mg_destroy(ort_mg* mg);
+int ort_mg_rank(const ort_mg* mg);
+int ort_mg_world(const ort_mg* mg);
+int ort_mg_nccl_version(void);                       /* 0 when NCCL cannot be loaded */
+/* rows of rank's strip of an H-row frame (the frame's last tile may be short) */
+int ort_mg_strip_rows(int rank, int world, int H, int tile_rows);
+/* Collective: ship one update -- a full flatten (is_full) or a delta (ids + rows), as ort_tree_take_delta yields it --
+ * from rank src (host pointers, read there only) to every rank's context.  Replaces the upload half of
+ * ort_tree_sync for a replicated DAG. */
+int ort_mg_broadcast_update(ort_mg* mg, const uint32_t* ids, const uint32_t* nodes8, size_t n, uint32_t root, int is_full, int src);
+/* Collective: trace this rank's strips of a W x H frame and gather the frame on rank dst, whose voxel / face / t are
+ * device buffers of W * H entries (ignored on the other ranks).  W % 4 == 0.  Enqueue only: the trace runs on
+ * ort_stream(ctx), send / receive / unpack on the communicator's own stream, strips in a ring of three slots, so the
+ * trace of the next frame overlaps the wire time of this one.  ort_mg_sync() returns when every frame queued so far
+ * is complete. */
+int ort_mg_trace_frame_gather(ort_mg* mg, const float pos[3], const float rot[9], float fov_factor, int W, int H, int tile_rows, int dst,
+                              uint32_t* voxel, uint8_t* face, float* t);
+int ort_mg_sync(ort_mg* mg);
+void* ort_mg_stream(ort_mg* mg);                     /* the cudaStream_t of the gather (for event timing) */
+double ort_mg_wire_bytes(const ort_mg* mg);          /* bytes this rank has sent + received for gathers so far */
 
 int   ort_sync(ort_ctx* ctx);
 void* ort_stream(ort_ctx* ctx);                 /* the cudaStream_t all work of ctx is queued on */

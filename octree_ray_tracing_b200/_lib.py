@@ -8,7 +8,10 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libort_b200.so")
+# ORT_B200_EXPERIMENTS=1 selects the measurement build (the same sources with -DORT_EXPERIMENTS: additionally carries the
+# kernels that were measured and not adopted, see csrc/ort_experiments.cuh); the default is the product library.
+EXPERIMENTS = os.environ.get("ORT_B200_EXPERIMENTS", "") == "1"
+LIB_PATH = os.path.join(HERE, "libort_b200_exp.so" if EXPERIMENTS else "libort_b200.so")
 
 _vp = C.c_void_p
 _u32p = C.POINTER(C.c_uint32)
@@ -29,6 +32,8 @@ _SIGS = {
     "ort_destroy": (C.c_int, [_vp]),
     "ort_set_rcp_table": (C.c_int, [_vp, _vp, C.c_int]),
     "ort_host_rcp_table": (C.c_long, [_vp, C.c_int]),
+    "ort_host_rcp_matches": (C.c_int, [_vp, C.c_int]),
+    "ort_rcp_host_status": (C.c_int, [_vp]),
     "ort_upload_full": (C.c_int, [_vp, _vp, C.c_size_t, C.c_uint32]),
     "ort_upload_delta": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32]),
     "ort_upload_pool": (C.c_int, [_vp, _vp, C.c_size_t]),
@@ -99,6 +104,18 @@ _SIGS = {
     "ort_fixture_build_terrain_ex": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "ort_fixture_heightmap_gpu": (C.c_int, [_vp, C.c_int, _vp]),
     "ort_fixture_carve_gpu": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp]),
+    "ort_mg_unique_id": (C.c_int, [_vp]),
+    "ort_mg_create": (C.c_int, [C.POINTER(_vp), _vp, C.c_int, C.c_int, _vp]),
+    "ort_mg_destroy": (C.c_int, [_vp]),
+    "ort_mg_rank": (C.c_int, [_vp]),
+    "ort_mg_world": (C.c_int, [_vp]),
+    "ort_mg_nccl_version": (C.c_int, []),
+    "ort_mg_strip_rows": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "ort_mg_broadcast_update": (C.c_int, [_vp, _vp, _vp, C.c_size_t, C.c_uint32, C.c_int, C.c_int]),
+    "ort_mg_trace_frame_gather": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "ort_mg_sync": (C.c_int, [_vp]),
+    "ort_mg_stream": (_vp, [_vp]),
+    "ort_mg_wire_bytes": (C.c_double, [_vp]),
 }
 
 _lib = None

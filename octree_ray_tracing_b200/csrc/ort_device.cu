@@ -58,11 +58,13 @@ struct ort_ctx
 	// staging (grown on demand)
 	void*  d_stage = nullptr;  size_t d_stage_bytes = 0;   // device side of host-pointer calls
 
-	unsigned long long* d_counter = nullptr; // work counter of the persistent kernels
+	unsigned long long* d_counters = nullptr; // work counters of the persistent kernels: a ring, one per launch (kCounterRing)
+	unsigned next_counter = 0;
 	int max_blocks_rays = 0, max_blocks_frame = 0;
 
 	uint64_t launches = 0;
-	int opt_variant = 1;                // 0 = baseline traverse(), 1 = traverse_fast() with fall-back
+	int opt_variant = 13;               // 0 = traverse(), 1 = round 1's FastWalker, 13 = round 2's tiers (LeanWalker first); others: ORT_EXPERIMENTS builds
+	int rcp_host_status = -1;           // 1: this host's RCPPS equals the built-in table, 0: it differs (warned once), -1: not probed
 	int opt_smem_levels = -1;
 	int opt_block = 256;
 	int opt_tile_shape = 0;
@@ -152,9 +154,58 @@ int finish_host_call(ort_ctx* c)
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+// every public entry point starts here: a successful call leaves no stale error message behind
+inline void enter(ort_ctx* c)
+{
+	g_last_error.clear();
+	if (c) c->last_error.clear();
+}
+
+constexpr unsigned kCounterRing = 64;      // persistent launches that may be in flight at once (on any streams)
+
+// the work counter of the next persistent launch (the caller zeroes it on the launch's stream)
+inline unsigned long long* next_counter(ort_ctx* c)
+{
+	return c->d_counters + (c->next_counter++ % kCounterRing);
+}
+
+// LeanWalker's slot words are node * 8 + 2^23-magic + index in 32 bits: ids stay below 0x16A00000
+inline bool lean_capable(const ort_ctx* c) { return c->n_nodes < 0x16000000u; }
+
 }  // namespace
 
 #include "ort_kernels.cuh"
+
+namespace {
+
+ort::Dag make_dag(const ort_ctx* c)
+{
+	ort::Dag g;
+	g.nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
+	g.base_biased = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(g.nodes_m1)) - 4ull * ort::kMagicBits;
+	g.root = c->root;
+	g.depth = c->depth;
+	g.leaf_dimf = std::ldexp(1.0F, -c->depth);
+	g.miss_t = c->miss_t;
+	g.plane_mask = (1u << (23 - c->depth)) - 1u;
+	g.rt = ort::RcpTable{ c->d_rcp, 23 - c->rcp_log2n };
+	return g;
+}
+
+// the walk a launch uses: the selected variant, with the lean tiers falling back to round 1's walker for DAGs beyond
+// the lean id range
+inline int walk_variant(const ort_ctx* c)
+{
+	if (c->opt_variant == 0) return 0;
+	if (c->opt_variant == 1 || !lean_capable(c)) return 1;
+	return ort::kLean;
+}
+
+}  // namespace
+
+#ifdef ORT_EXPERIMENTS
+#include "ort_experiments.cuh"
+#endif
 
 
 // ------------------------------------------------------------------------------------------------
@@ -163,7 +214,14 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 extern "C" {
 
-const char* ort_version(void) { return "ort_b200 0.1 (sm_100a)"; }
+const char* ort_version(void)
+{
+#ifdef ORT_EXPERIMENTS
+	return "ort_b200 0.2 (sm_100a, +experiments)";
+#else
+	return "ort_b200 0.2 (sm_100a)";
+#endif
+}
 
 const char* ort_last_error(const ort_ctx* ctx)
 {
@@ -173,8 +231,10 @@ const char* ort_last_error(const ort_ctx* ctx)
 
 int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
 {
+	enter(nullptr);
 	if (!out || depth < 1 || depth > ort::kMaxDepth)
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_create: depth must be 1..%d", ort::kMaxDepth);
+	*out = nullptr;
 
 	int ndev = 0;
 	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -197,43 +257,69 @@ int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
 	c->depth = depth;
 	c->sm_count = prop.multiProcessorCount;
 
-	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
-	c->stream = c->own_stream;
-	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
-	ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-	for (int i = 0; i < 3; ++i)
+	// everything below may fail half-way: ort_destroy() releases whatever exists by then
+	const int rc = [&]() -> int {
+		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+		c->stream = c->own_stream;
+		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		for (int i = 0; i < 3; ++i)
+		{
+			ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
+			ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
+		}
+		for (int i = 0; i < 8; ++i)
+			ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_part[i], cudaEventDisableTiming));
+		for (int i = 0; i < 2; ++i)
+		{
+			ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+			ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
+			ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+		}
+
+		if (node_capacity < 64) node_capacity = 64;
+		ORT_CUDA(nullptr, cudaMalloc(&c->d_nodes, static_cast<size_t>(node_capacity) * 32));
+		c->cap_nodes = node_capacity;
+
+		ORT_CUDA(nullptr, cudaMalloc(&c->d_counters, sizeof(unsigned long long) * kCounterRing));
+		{
+			const size_t smem = ort::lean_smem_bytes(depth);
+			int b = 0;
+			ORT_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ort::trace_persistent_kernel<false, false>, 256, smem));
+			c->max_blocks_rays = b * c->sm_count;
+			ORT_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ort::trace_persistent_kernel<false, true>, 256, smem));
+			c->max_blocks_frame = b * c->sm_count;
+		}
+		return ort_set_rcp_table(c, ort_rcp_table_default, ORT_RCP_TABLE_LOG2N);
+	}();
+	if (rc != ORT_OK)
 	{
-		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
-		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_aux[i], cudaEventDisableTiming));
-	}
-	for (int i = 0; i < 8; ++i)
-		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_part[i], cudaEventDisableTiming));
-	for (int i = 0; i < 2; ++i)
-	{
-		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_chunk[i], cudaEventDisableTiming));
-		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_copied[i], cudaEventDisableTiming));
+		const std::string keep = g_last_error;
+		ort_destroy(c);
+		g_last_error = keep;
+		return rc;
 	}
 
-	if (node_capacity < 64) node_capacity = 64;
-	ORT_CUDA(nullptr, cudaMalloc(&c->d_nodes, static_cast<size_t>(node_capacity) * 32));
-	c->cap_nodes = node_capacity;
-
-	ORT_CUDA(nullptr, cudaMalloc(&c->d_counter, sizeof(unsigned long long)));
+	// The built-in RCPPS table is the one Intel's instruction yields.  A reference running on another vendor's CPU
+	// computes other reciprocals, and a "drop-in" that silently disagreed with the host it runs next to would be a
+	// trap: probe this host's instruction once and say so (ort_host_rcp_table() + ort_set_rcp_table() fix it).
+	c->rcp_host_status = ort_host_rcp_matches(ort_rcp_table_default, ORT_RCP_TABLE_LOG2N);
+	if (c->rcp_host_status == 0)
 	{
-		int b = 0;
-		ORT_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ort::trace_persistent_kernel<false, false>, 256, 0));
-		c->max_blocks_rays = b * c->sm_count;
-		ORT_CUDA(nullptr, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, ort::trace_persistent_kernel<false, true>, 256, 0));
-		c->max_blocks_frame = b * c->sm_count;
+		static bool warned = false;
+		if (!warned)
+		{
+			warned = true;
+			std::fprintf(stderr, "ort_b200: warning: this host's RCPPS differs from the built-in reciprocal table; GPU results will match a reference "
+			                     "run on an Intel host, not on this one.  Call ort_host_rcp_table() and ort_set_rcp_table() to match this host.\n");
+		}
 	}
-
 	*out = c;
-	const int rc = ort_set_rcp_table(c, ort_rcp_table_default, ORT_RCP_TABLE_LOG2N);
-	if (rc != ORT_OK) { *out = nullptr; ort_destroy(c); }
-	return rc;
+	return ORT_OK;
 }
+
+int ort_rcp_host_status(const ort_ctx* c) { return c ? c->rcp_host_status : -1; }
 
 int ort_destroy(ort_ctx* c)
 {
@@ -245,7 +331,7 @@ int ort_destroy(ort_ctx* c)
 	cudaFree(c->d_nodes);
 	cudaFree(c->d_rcp);
 	cudaFree(c->d_palette);
-	cudaFree(c->d_counter);
+	cudaFree(c->d_counters);
 	cudaFree(c->d_stage);
 	for (int i = 0; i < 2; ++i)
 	{
@@ -269,6 +355,7 @@ int ort_destroy(ort_ctx* c)
 
 int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
 {
+	enter(c);
 	if (!c || !tab || log2n < 1 || log2n > 23)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_set_rcp_table: need a table of 2^1..2^23 entries");
 	DeviceGuard g(c->device);
@@ -286,15 +373,18 @@ int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
 
 int ort_upload_full(ort_ctx* c, const uint32_t* nodes8, size_t n, uint32_t root)
 {
+	enter(c);
 	if (!c || (n && !nodes8) || root > n || n > ort::kIdMask)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_full: bad arguments (n=%zu root=%u)", n, root);
 	DeviceGuard g(c->device);
-	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	// A full upload replaces (and may reallocate) the array every launch in flight reads -- on the context's streams and on
+	// any stream the caller handed over with ort_set_stream since: wait for the whole device, not for one stream.
+	ORT_CUDA(c, cudaDeviceSynchronize());
 	if (n > c->cap_nodes)
 	{
 		// grow with head-room for the deltas that will follow
 		size_t want = n + n / 4 + 4096;
-		if (want > ort::kIdMask) want = ort::kIdMask;   // compact ids are 29-bit (3 bits of each stack entry carry the child index)
+		if (want > ort::kIdMask) want = ort::kIdMask;   // compact ids are 29-bit (FastWalker: 3 bits of each stack entry carry the child index)
 		cudaFree(c->d_nodes);
 		c->d_nodes = nullptr;
 		c->cap_nodes = 0;
@@ -327,12 +417,17 @@ int ort_upload_pool(ort_ctx* c, const uint32_t* nodes8, size_t n)
 
 int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, size_t n, uint32_t root)
 {
+	enter(c);
 	if (!c || (n && (!ids || !nodes8)))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: bad arguments");
 	DeviceGuard g(c->device);
 
 	uint32_t max_id = c->n_nodes;
 	const bool dev_src = n && is_device_ptr(ids);
+	if (n && dev_src != is_device_ptr(nodes8))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: ids and nodes8 must both be host or both be device pointers");
+	if (n && (reinterpret_cast<uintptr_t>(nodes8) & 3u))
+		return ort_fail(c, ORT_ERR_INVALID, "ort_upload_delta: nodes8 must be 4-byte aligned");
 	if (n)
 	{
 		// ids are validated on the host either way (deltas are small: a few thousand entries)
@@ -373,11 +468,13 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 			d_src = reinterpret_cast<const uint32_t*>(base + off);
 		}
 		const uint32_t threads = 256, blocks = static_cast<uint32_t>((2 * n + threads - 1) / threads);
-		ort::scatter_nodes_kernel<<<blocks, threads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_nodes), d_ids, reinterpret_cast<const uint4*>(d_src), static_cast<uint32_t>(n));
+		// (the kernel reads the source rows word by word: a device-side [ids | nodes] payload puts them at any 4-byte offset)
+		ort::scatter_nodes_kernel<<<blocks, threads, 0, c->stream>>>(reinterpret_cast<uint4*>(c->d_nodes), d_ids, d_src, static_cast<uint32_t>(n));
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
-		if (!dev_src)
-			ORT_CUDA(c, cudaStreamSynchronize(c->stream));   // pageable sources may be reused by the caller
+		// host sources may be reused by the caller; device sources usually belong to a caching allocator that knows
+		// nothing about this stream -- either way the scatter has read them when the call returns
+		ORT_CUDA(c, cudaStreamSynchronize(c->stream));
 	}
 	c->n_nodes = max_id;
 	if (c->index_base == 1)
@@ -431,174 +528,122 @@ static ort::Camera make_camera(const float pos[3], const float rot[9], float fov
 static int launch_miss(ort_ctx* c, size_t n, uint32_t* v, uint8_t* f, float* t, uint16_t* np)
 {
 	if (!n) return ORT_OK;
-	ort::fill_miss_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(v, f, t, np, n);
+	// root 0: every ray is a MISS of the h_octree kind (the callers' guard, test_och_h_octree.cpp:443)
+	ort::fill_miss_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(v, f, t, np, __builtin_inff(), n);
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
 }
 
+static int bad_variant(ort_ctx* c)
+{
+#ifdef ORT_EXPERIMENTS
+	return ort_fail(c, ORT_ERR_INVALID, "variant %d is not a frame kernel of this build", c->opt_variant);
+#else
+	return ort_fail(c, ORT_ERR_INVALID, "variant %d is an experiment kernel: this library was built without ORT_EXPERIMENTS (use libort_b200_exp.so)", c->opt_variant);
+#endif
+}
+
 int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float* d3, size_t n,
                          uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
 {
+	enter(c);
 	if (!c || (n && (!o3 || !d3 || !voxel || !face || !t)) || (o_stride != 0 && o_stride != 3))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_rays: bad arguments");
 	if (!n) return ORT_OK;
 	DeviceGuard g(c->device);
 	if (!c->has_root)
 		return launch_miss(c, n, voxel, face, t, npush);
-	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
-	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
-	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
-	if (c->opt_rays_variant == 2 && c->opt_variant != 0)
+	const ort::Dag dag = make_dag(c);
+	const size_t smem = ort::lean_smem_bytes(c->depth);
+	if (c->opt_rays_variant == 2 && c->opt_variant != 0 && lean_capable(c))
 	{
-		ORT_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+		// persistent warps with lane refill; every launch draws from its own counter of the ring, zeroed on the launch's
+		// stream, so launches on different caller streams (ort_set_stream) do not interfere
+		unsigned long long* counter = next_counter(c);
+		ORT_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
 		const unsigned long long need = (n + 255) / 256;
-		const unsigned pblocks = static_cast<unsigned>(need < static_cast<unsigned long long>(c->max_blocks_rays) ? need : c->max_blocks_rays);
 		const ort::Camera cam0{};
 		const ort::FrameRows fr0{};
-		if (npush)
-			ort::trace_persistent_kernel<true, false><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
-		else if (c->opt_persist_blocks == 1)
-			ort::trace_persistent_kernel<false, false><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
-		else
-		{
-			// default: the build capped at 40 registers (6 resident blocks per SM instead of 4: 1.92 -> 1.74 ms on 16.7 M
-			// incoherent rays); 8 = the 32-register build (1.77 ms), 1 = uncapped (47 registers)
-			const int per_sm = c->opt_persist_blocks == 8 ? 8 : 6;
-			const unsigned long long cap_blocks = static_cast<unsigned long long>(c->sm_count) * per_sm;
-			const unsigned pb = static_cast<unsigned>(need < cap_blocks ? need : cap_blocks);
-			if (per_sm == 6)
-				ort::trace_persistent_kernel<false, false, 6><<<pb, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
-			else
-				ort::trace_persistent_kernel<false, false, 8><<<pb, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, cam0, fr0, n, c->d_counter, c->opt_low_water, voxel, face, t, npush);
-		}
+		// the build capped at 40 registers (6 resident blocks per SM) is the default; 8 = the 32-register build, 1 = uncapped
+		const int per_sm = npush ? 0 : (c->opt_persist_blocks == 8 ? 8 : (c->opt_persist_blocks == 1 ? 0 : 6));
+		const unsigned long long cap_blocks = per_sm ? static_cast<unsigned long long>(c->sm_count) * per_sm : static_cast<unsigned long long>(c->max_blocks_rays);
+		const unsigned pb = static_cast<unsigned>(need < cap_blocks ? need : cap_blocks);
+		if (npush)            ort::trace_persistent_kernel<true, false><<<pb, 256, smem, c->stream>>>(dag, o3, o_stride, d3, cam0, fr0, n, counter, c->opt_low_water, voxel, face, t, npush);
+		else if (per_sm == 0) ort::trace_persistent_kernel<false, false><<<pb, 256, smem, c->stream>>>(dag, o3, o_stride, d3, cam0, fr0, n, counter, c->opt_low_water, voxel, face, t, npush);
+		else if (per_sm == 6) ort::trace_persistent_kernel<false, false, 6><<<pb, 256, smem, c->stream>>>(dag, o3, o_stride, d3, cam0, fr0, n, counter, c->opt_low_water, voxel, face, t, npush);
+		else                  ort::trace_persistent_kernel<false, false, 8><<<pb, 256, smem, c->stream>>>(dag, o3, o_stride, d3, cam0, fr0, n, counter, c->opt_low_water, voxel, face, t, npush);
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-#define ORT_LAUNCH_RAYS(V, C) ort::trace_rays_kernel<V, C><<<blocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, o3, o_stride, d3, n, voxel, face, t, npush)
-	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_RAYS(0, true); else ORT_LAUNCH_RAYS(0, false); }
-	else { if (npush) ORT_LAUNCH_RAYS(1, true); else ORT_LAUNCH_RAYS(1, false); }
+	const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+#define ORT_LAUNCH_RAYS(V, C) ort::trace_rays_kernel<V, C><<<blocks, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, o3, o_stride, d3, n, voxel, face, t, npush)
+	switch (walk_variant(c))
+	{
+	case 0:  if (npush) ORT_LAUNCH_RAYS(0, true); else ORT_LAUNCH_RAYS(0, false); break;
+	case 1:  if (npush) ORT_LAUNCH_RAYS(1, true); else ORT_LAUNCH_RAYS(1, false); break;
+	default: if (npush) ORT_LAUNCH_RAYS(ort::kLean, true); else ORT_LAUNCH_RAYS(ort::kLean, false); break;
+	}
 #undef ORT_LAUNCH_RAYS
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
 }
 
+static bool frame_args_ok(const float* pos, const float* rot, int W, int H, int y0, int rows, int tile_rows, int tile_step)
+{
+	return pos && rot && W > 0 && H > 0 && rows >= 0 && tile_rows > 0 && tile_step > 0 && y0 >= 0;
+}
+
 int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
                           int W, int H, int y0, int rows, int tile_rows, int tile_step,
                           uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
 {
-	if (!c || !pos || !rot || W <= 0 || H <= 0 || rows < 0 || tile_rows <= 0 || tile_step <= 0 || y0 < 0 || (rows && (!voxel || !face || !t)))
+	enter(c);
+	if (!c || !frame_args_ok(pos, rot, W, H, y0, rows, tile_rows, tile_step) || (rows && (!voxel || !face || !t)))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: bad arguments");
 	if (!rows) return ORT_OK;
 	DeviceGuard g(c->device);
 	const size_t n = static_cast<size_t>(rows) * W;
 	if (!c->has_root)
 		return launch_miss(c, n, voxel, face, t, npush);
-	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
-	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
+	const ort::Dag dag = make_dag(c);
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape, rotate, ort::tile_shift_of(tile_rows) };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
-	if (c->opt_variant == 2)
+	const size_t smem = ort::lean_smem_bytes(c->depth);
+	if (c->opt_variant == 2 && lean_capable(c))
 	{
-		ORT_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
+		// the persistent lane-refill kernel over the pixels of the strip (in 8 x 4 tile order)
+		unsigned long long* counter = next_counter(c);
+		ORT_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
 		const unsigned long long tiles = static_cast<unsigned long long>((W + 7) / 8) * ((rows + 3) / 4);
 		const unsigned long long np = tiles * 32ull, need = (np + 255) / 256;
 		const unsigned pblocks = static_cast<unsigned>(need < static_cast<unsigned long long>(c->max_blocks_frame) ? need : c->max_blocks_frame);
-		if (npush)
-			ort::trace_persistent_kernel<true, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
-		else
-			ort::trace_persistent_kernel<false, true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, nullptr, 0, nullptr, cam, fr, np, c->d_counter, c->opt_low_water, voxel, face, t, npush);
+		if (npush) ort::trace_persistent_kernel<true, true><<<pblocks, 256, smem, c->stream>>>(dag, nullptr, 0, nullptr, cam, fr, np, counter, c->opt_low_water, voxel, face, t, npush);
+		else       ort::trace_persistent_kernel<false, true><<<pblocks, 256, smem, c->stream>>>(dag, nullptr, 0, nullptr, cam, fr, np, counter, c->opt_low_water, voxel, face, t, npush);
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-	if (c->opt_variant == 5 || c->opt_variant == 6)
+#ifdef ORT_EXPERIMENTS
 	{
-		const bool ww = c->opt_variant == 6;
-		auto k = npush ? (ww ? ort::trace_frame_tight_kernel<true, true> : ort::trace_frame_tight_kernel<true, false>)
-		               : (ww ? ort::trace_frame_tight_kernel<false, true> : ort::trace_frame_tight_kernel<false, false>);
-		k<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush);
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-		return ORT_OK;
+		const int rc = launch_frame_experiment(c, dag, cam, fr, voxel, face, t, npush);
+		if (rc == ORT_ERR_CUDA) return ort_fail(c, ORT_ERR_CUDA, "experiment variant %d: launch failed: %s", c->opt_variant, cudaGetErrorString(cudaGetLastError()));
+		if (rc == ORT_OK) return ORT_OK;
 	}
-	if (c->opt_variant == 12)
+#endif
+	if (c->opt_variant != 0 && c->opt_variant != 1 && c->opt_variant != 2 && c->opt_variant != ort::kLean)
+		return bad_variant(c);
+#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, cam, fr, voxel, face, t, npush)
+	switch (walk_variant(c))
 	{
-		ORT_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned long long), c->stream));
-		const unsigned n_tiles = static_cast<unsigned>(grid.x) * grid.y * 8u;
-		const unsigned pblocks = grid.x * grid.y < static_cast<unsigned>(c->sm_count * 8) ? grid.x * grid.y : static_cast<unsigned>(c->sm_count * 8);
-		if (npush) ort::trace_frame_tiles_kernel<true><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_tiles, reinterpret_cast<unsigned int*>(c->d_counter), voxel, face, t, npush);
-		else       ort::trace_frame_tiles_kernel<false><<<pblocks, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_tiles, reinterpret_cast<unsigned int*>(c->d_counter), voxel, face, t, npush);
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-		return ORT_OK;
+	case 0:  if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); break;
+	case 1:  if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); break;
+	default: if (npush) ORT_LAUNCH_FRAME(ort::kLean, true); else ORT_LAUNCH_FRAME(ort::kLean, false); break;
 	}
-	if (c->opt_variant == 7)
-	{
-		const unsigned long long base_biased = static_cast<unsigned long long>(reinterpret_cast<uintptr_t>(nodes_m1)) - 4ull * ort::kMagicBits;
-		if (npush) ort::trace_frame_pipe_kernel<true><<<grid, 256, 0, c->stream>>>(nodes_m1, base_biased, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush);
-		else       ort::trace_frame_pipe_kernel<false><<<grid, 256, 0, c->stream>>>(nodes_m1, base_biased, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush);
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-		return ORT_OK;
-	}
-	if (c->opt_variant >= 8 && c->opt_variant <= 11 && !npush)
-	{
-		// probes: 8 = +6 FMA-pipe, 9 = +6 ALU-pipe, 10 = +12 FMA-pipe, 11 = +0 (the same loop shape without extra work)
-		auto k = c->opt_variant == 8 ? ort::trace_frame_probe_kernel<6, 0> : c->opt_variant == 9 ? ort::trace_frame_probe_kernel<0, 6>
-		       : c->opt_variant == 10 ? ort::trace_frame_probe_kernel<12, 0> : ort::trace_frame_probe_kernel<0, 0>;
-		k<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t);
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-		return ORT_OK;
-	}
-	if (c->opt_variant == 4)
-	{
-		const int thr = c->opt_low_water > 0 ? c->opt_low_water : 1;
-		if (npush)
-			ort::trace_frame_deferred_kernel<true><<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, thr, voxel, face, t, npush);
-		else
-			ort::trace_frame_deferred_kernel<false><<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, thr, voxel, face, t, npush);
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-		return ORT_OK;
-	}
-	if (c->opt_variant == 3 && c->index_base == 1)
-	{
-		// upper levels staged in shared memory: opt_smem_levels = number of node ids to stage (the harness passes
-		// the first id of level k+1 from ort_tree_flatten's level offsets, minus one)
-		uint32_t n_staged = c->opt_smem_levels > 0 ? static_cast<uint32_t>(c->opt_smem_levels) : 0u;
-		if (n_staged > c->n_nodes) n_staged = c->n_nodes;
-		if (n_staged > 6144u) n_staged = 6144u;                         // 192 KB of the 227 KB a block may have
-		const size_t smem = static_cast<size_t>(n_staged) * 32;
-		const dim3 g2((W + 31) / 32, (rows + 31) / 32);
-		if (npush)
-		{
-			ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			ort::trace_frame_staged_kernel<true><<<g2, 1024, smem, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_staged, voxel, face, t, npush);
-		}
-		else
-		{
-			ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-			ort::trace_frame_staged_kernel<false><<<g2, 1024, smem, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, n_staged, voxel, face, t, npush);
-		}
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-		return ORT_OK;
-	}
-	// block = 16 x 16 pixels by default; options "block" = 128 / 64 (16 x 8 / 16 x 4) and "tile_shape" select the
-	// measurement build of the kernel
-	const bool shaped = c->opt_variant != 0 && (c->opt_tile_shape != 0 || c->opt_block == 128 || c->opt_block == 64);
-	const int fblock = (shaped && c->opt_tile_shape == 0) ? c->opt_block : 256;
-	const dim3 fgrid = c->opt_tile_shape == 3 && shaped ? dim3((W + 31) / 32, (rows + 7) / 8) : dim3((W + 15) / 16, (rows + fblock / 16 - 1) / (fblock / 16));
-#define ORT_LAUNCH_FRAME(V, C, S) ort::trace_frame_kernel<V, C, S><<<fgrid, fblock, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, voxel, face, t, npush)
-	if (c->opt_variant == 0) { if (npush) ORT_LAUNCH_FRAME(0, true, false); else ORT_LAUNCH_FRAME(0, false, false); }
-	else if (shaped) { if (npush) ORT_LAUNCH_FRAME(1, true, true); else ORT_LAUNCH_FRAME(1, false, true); }
-	else { if (npush) ORT_LAUNCH_FRAME(1, true, false); else ORT_LAUNCH_FRAME(1, false, false); }
 #undef ORT_LAUNCH_FRAME
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
@@ -607,34 +652,37 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 
 int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 {
+	enter(c);
 	if (!c || n_jobs < 0 || (n_jobs && !jobs))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frames_async: bad arguments");
 	DeviceGuard g(c->device);
 	for (int i = 0; i < n_jobs; ++i)
 	{
 		const ort_frame_job& j = jobs[i];
-		if (j.W <= 0 || j.H <= 0 || j.rows < 0 || j.tile_rows <= 0 || j.tile_step <= 0 || j.y0 < 0 || (j.rows && (!j.voxel || !j.face || !j.t)))
+		if (!frame_args_ok(j.pos, j.rot, j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step) || (j.rows && (!j.voxel || !j.face || !j.t)))
 			return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frames_async: bad job %d", i);
 	}
-	if (!c->has_root || c->opt_variant != 1)
+	if (!c->has_root)
 	{
-		// empty tree, or a measurement variant is selected: one ordinary launch per job
 		for (int i = 0; i < n_jobs; ++i)
 		{
-			const ort_frame_job& j = jobs[i];
-			const int rc = ort_trace_frame_async(c, j.pos, j.rot, j.fov_factor, j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, j.voxel, j.face, j.t, j.npush);
+			const int rc = launch_miss(c, static_cast<size_t>(jobs[i].rows) * jobs[i].W, jobs[i].voxel, jobs[i].face, jobs[i].t, jobs[i].npush);
 			if (rc != ORT_OK) return rc;
 		}
 		return ORT_OK;
 	}
-	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
-	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
-	for (int first = 0; first < n_jobs; first += ort::kMaxJobs)
+	if (c->opt_variant != 0 && c->opt_variant != 1 && c->opt_variant != ort::kLean)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frames_async: the batched launch exists for variants 0, 1 and 13 (selected: %d)", c->opt_variant);
+	const ort::Dag dag = make_dag(c);
+	const size_t smem = ort::lean_smem_bytes(c->depth);
+	int i = 0;
+	while (i < n_jobs)
 	{
+		// the next batch: up to kMaxJobs non-empty jobs, consumed in order
 		ort::FrameJobBatch batch{};
 		int n = 0;
 		unsigned gx = 0, gy = 0;
-		for (int i = first; i < n_jobs && n < ort::kMaxJobs; ++i)
+		for (; i < n_jobs && n < ort::kMaxJobs; ++i)
 		{
 			const ort_frame_job& j = jobs[i];
 			if (!j.rows) continue;
@@ -646,12 +694,18 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 			gx = std::max(gx, static_cast<unsigned>((j.W + 15) / 16));
 			gy = std::max(gy, static_cast<unsigned>((j.rows + 15) / 16));
 		}
-		if (!n) continue;
+		if (!n) break;
 		bool count = false;
-		for (int i = 0; i < n; ++i) count |= batch.job[i].npush != nullptr;
+		for (int k = 0; k < n; ++k) count |= batch.job[k].npush != nullptr;
 		const dim3 bgrid(gx, gy, static_cast<unsigned>(n));
-		if (count) ort::trace_frames_kernel<true><<<bgrid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, batch);
-		else       ort::trace_frames_kernel<false><<<bgrid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, batch);
+#define ORT_LAUNCH_BATCH(V, C) ort::trace_frames_kernel<V, C><<<bgrid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, batch)
+		switch (walk_variant(c))
+		{
+		case 0:  if (count) ORT_LAUNCH_BATCH(0, true); else ORT_LAUNCH_BATCH(0, false); break;
+		case 1:  if (count) ORT_LAUNCH_BATCH(1, true); else ORT_LAUNCH_BATCH(1, false); break;
+		default: if (count) ORT_LAUNCH_BATCH(ort::kLean, true); else ORT_LAUNCH_BATCH(ort::kLean, false); break;
+		}
+#undef ORT_LAUNCH_BATCH
 		++c->launches;
 		ORT_CUDA(c, cudaGetLastError());
 	}
@@ -722,7 +776,7 @@ static int frame_to_host(ort_ctx* c, const float pos[3], const float rot[9], flo
 		if (c->slot_used[slot])
 			ORT_CUDA(c, cudaStreamWaitEvent(c->aux_stream[i], c->ev_copied[slot], 0));   // the slot's previous frame has left
 	}
-	const int n_streams = (c->opt_variant == 2 || c->opt_variant == 12) ? 1 : 3;               // the persistent kernels share one work counter per context
+	const int n_streams = 3;
 	int launched = 0;
 	for (int k = 0; k < kChunks; ++k)
 	{
@@ -768,6 +822,7 @@ static int frame_to_host(ort_ctx* c, const float pos[3], const float rot[9], flo
 int ort_trace_rays(ort_ctx* c, const float* o3, int o_stride, const float* d3, size_t n,
                    uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
 {
+	enter(c);
 	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_trace_rays: null context");
 	if (!n) return ORT_OK;
 	if (!o3 || !d3 || !voxel || !face || !t || (o_stride != 0 && o_stride != 3))
@@ -844,9 +899,10 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
                     int W, int H, int y0, int rows, int tile_rows, int tile_step,
                     uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush)
 {
+	enter(c);
 	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: null context");
 	if (rows == 0) return ORT_OK;
-	if (!voxel || !face || !t || W <= 0 || rows < 0)
+	if (!voxel || !face || !t || !frame_args_ok(pos, rot, W, H, y0, rows, tile_rows, tile_step))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: bad arguments");
 	DeviceGuard g(c->device);
 
@@ -879,6 +935,7 @@ int ort_trace_frame(ort_ctx* c, const float pos[3], const float rot[9], float fo
 
 int ort_set_palette(ort_ctx* c, const uint32_t* rgba6, uint32_t n_voxels, uint32_t exit_rgba, uint32_t inside_rgba)
 {
+	enter(c);
 	if (!c || (n_voxels && !rgba6))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_set_palette: bad arguments");
 	DeviceGuard g(c->device);
@@ -911,12 +968,16 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
 		ORT_CUDA(c, cudaGetLastError());
 		return ORT_OK;
 	}
-	const ort::RcpTable rt{ c->d_rcp, 23 - c->rcp_log2n };
-	const uint32_t* nodes_m1 = c->d_nodes - 8 * static_cast<ptrdiff_t>(c->index_base);
+	const ort::Dag dag = make_dag(c);
 	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, rotate, ort::tile_shift_of(tile_rows) };
-	ort::trace_frame_rgba_kernel<<<grid, 256, 0, c->stream>>>(nodes_m1, c->root, c->depth, c->miss_t, rt, cam, fr, pal, d_rgba);
+	switch (walk_variant(c))
+	{
+	case 0:  ort::trace_frame_rgba_kernel<0><<<grid, 256, 0, c->stream>>>(dag, cam, fr, pal, d_rgba); break;
+	case 1:  ort::trace_frame_rgba_kernel<1><<<grid, 256, 0, c->stream>>>(dag, cam, fr, pal, d_rgba); break;
+	default: ort::trace_frame_rgba_kernel<ort::kLean><<<grid, 256, ort::lean_smem_bytes(c->depth), c->stream>>>(dag, cam, fr, pal, d_rgba); break;
+	}
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
@@ -925,6 +986,7 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
 int ort_trace_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor,
                          int W, int H, int y0, int rows, int tile_rows, int tile_step, uint32_t* rgba)
 {
+	enter(c);
 	if (!c || !pos || !rot || !rgba || W <= 0 || H <= 0 || rows < 0 || tile_rows <= 0 || tile_step <= 0 || y0 < 0)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame_rgba: bad arguments");
 	if (!rows) return ORT_OK;
@@ -946,6 +1008,7 @@ int ort_trace_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], flo
 
 int ort_fixture_heightmap_gpu(ort_ctx* c, int depth, uint16_t* heights)
 {
+	enter(c);
 	if (!c || !heights || depth < 1 || depth > 15)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_fixture_heightmap_gpu: bad arguments");
 	DeviceGuard g(c->device);
@@ -972,6 +1035,7 @@ int ort_fixture_heightmap_gpu(ort_ctx* c, int depth, uint16_t* heights)
 
 int ort_fixture_carve_gpu(ort_ctx* c, int depth, const uint16_t* heights, int zmax, uint64_t* carved)
 {
+	enter(c);
 	if (!c || !heights || !carved || depth < 5 || depth > 15 || zmax < 0 || zmax >= (1 << depth))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_fixture_carve_gpu: bad arguments (depth must be 5..15)");
 	DeviceGuard g(c->device);
@@ -1014,6 +1078,7 @@ int ort_fixture_carve_gpu(ort_ctx* c, int depth, const uint16_t* heights, int zm
 
 int ort_sync(ort_ctx* c)
 {
+	enter(c);
 	if (!c) return ort_fail(c, ORT_ERR_INVALID, "ort_sync: null context");
 	DeviceGuard g(c->device);
 	ORT_CUDA(c, cudaStreamSynchronize(c->h2d_stream));
@@ -1037,6 +1102,7 @@ uint64_t ort_launch_count(const ort_ctx* c) { return c ? c->launches : 0; }
 
 int ort_set_option(ort_ctx* c, const char* key, int value)
 {
+	enter(c);
 	if (!c || !key) return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: bad arguments");
 	if (!std::strcmp(key, "variant")) c->opt_variant = value;
 	else if (!std::strcmp(key, "smem_levels")) c->opt_smem_levels = value;
@@ -1051,8 +1117,8 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 		// measurement: shared-memory carve-out (percent) of the default frame kernels; they use no shared memory, so 0
 		// asks for the largest L1
 		DeviceGuard g(c->device);
-		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
-		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
+		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<ort::kLean, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
 	}
 	else if (!std::strcmp(key, "defer_sync")) c->opt_defer_sync = value;
 	else if (!std::strcmp(key, "frame_chunks")) c->opt_frame_chunks = value;
@@ -1064,6 +1130,7 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 
 int ort_measure_gather_peak(ort_ctx* c, size_t bytes, double* gb_per_s)
 {
+	enter(c);
 	if (!c || !gb_per_s || bytes < (1u << 20))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_measure_gather_peak: need a context, an output and >= 1 MiB");
 	DeviceGuard g(c->device);
@@ -1128,3 +1195,5 @@ void ort_camera_coeffs(float yaw, float pitch, float rot[9], float* fov_factor)
 }
 
 }  // extern "C"
+
+#include "ort_mg.cuh"

@@ -868,8 +868,23 @@ long ort_host_rcp_table(uint32_t* tab, int log2n)
 		}
 	return bad;
 }
+// Quick probe used by ort_create: does this CPU's RCPSS reproduce `tab` (one input per table entry, both signs)?
+// 1 yes, 0 no.
+int ort_host_rcp_matches(const uint32_t* tab, int log2n)
+{
+	if (!tab || log2n < 1 || log2n > 23) return -1;
+	const int sh = 23 - log2n;
+	for (uint32_t k = 0; k < (1u << log2n); ++k)
+	{
+		const uint32_t x = 0x3F800000u | (k << sh) | ((1u << sh) >> 1);      // the middle of the entry's mantissa range
+		if (host_rcp_bits(x) != model_rcp_bits(tab, log2n, x)) return 0;
+		if (host_rcp_bits(x | 0x80000000u) != model_rcp_bits(tab, log2n, x | 0x80000000u)) return 0;
+	}
+	return 1;
+}
 #else
 long ort_host_rcp_table(uint32_t*, int) { return -1; }
+int ort_host_rcp_matches(const uint32_t*, int) { return -1; }
 #endif
 
 // Table dump / load.  File = header + one record per occupied slot (live or gravestone), in slot

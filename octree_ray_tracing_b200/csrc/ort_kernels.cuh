@@ -1,6 +1,7 @@
-// ort_kernels.cuh -- every __global__ function of libort_b200.so (sm_100a): the trace kernels (default and the
-// selectable experiment variants), the delta scatter, the fixture noise kernels and the roofline diagnostic.
-// Included by ort_device.cu only; the per-ray traversal itself lives in ort_trace.cuh.
+// ort_kernels.cuh -- the __global__ functions of libort_b200.so (sm_100a): the trace kernels, the delta scatter, the
+// strip unpack of the multi-GPU gather, the fixture noise kernels and the roofline diagnostic.  Included by
+// ort_device.cu only; the per-ray traversal itself lives in ort_trace.cuh.  Kernels that were measured and not adopted
+// live in ort_experiments.cuh and are compiled into libort_b200_exp.so only (-DORT_EXPERIMENTS).
 #pragma once
 
 #include <cstddef>
@@ -10,28 +11,32 @@
 #include "ort_noise.h"
 #include "ort_trace.cuh"
 
-// ------------------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------------------
-
 namespace ort {
 
-// delta upload: one thread per 16-byte half node
-__global__ void scatter_nodes_kernel(uint4* __restrict__ nodes, const uint32_t* __restrict__ ids, const uint4* __restrict__ src, uint32_t n)
+// ------------------------------------------------------------------------------------------------
+// small kernels
+// ------------------------------------------------------------------------------------------------
+
+// delta upload: one thread per 16-byte half node.  The source rows need only 4-byte alignment (a broadcast payload
+// [ids | nodes] puts them at any word offset); the destination halves are 16-byte aligned.
+__global__ void scatter_nodes_kernel(uint4* __restrict__ nodes, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ src, uint32_t n)
 {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < 2u * n)
-		nodes[2u * (ids[i >> 1] - 1u) + (i & 1u)] = src[i];
+	{
+		const uint32_t* s = src + 4u * static_cast<size_t>(i);
+		nodes[2u * static_cast<size_t>(ids[i >> 1] - 1u) + (i & 1u)] = make_uint4(s[0], s[1], s[2], s[3]);
+	}
 }
 
-__global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush, size_t n)
+__global__ void fill_miss_kernel(uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush, float miss_t, size_t n)
 {
 	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (i < n)
 	{
 		voxel[i] = 0;
 		face[i] = 6;
-		t[i] = __uint_as_float(0x7F800000u);
+		t[i] = miss_t;
 		if (npush) npush[i] = 0;
 	}
 }
@@ -42,20 +47,70 @@ __global__ void fill_u32_kernel(uint32_t* __restrict__ dst, uint32_t v, size_t n
 	if (i < n) dst[i] = v;
 }
 
+// ------------------------------------------------------------------------------------------------
+// the walk of one ray
+// ------------------------------------------------------------------------------------------------
+
+// What every trace kernel needs to know about the DAG (one kernel parameter).
+struct Dag
+{
+	const uint32_t*    nodes_m1;     // node id i at nodes_m1[8 * i ..] (h_octree layout: ids 1-based; och::octree pool: raw rows)
+	unsigned long long base_biased;  // address of nodes_m1 minus 4 * kMagicBits (LeanWalker's slot words carry the 2^23 magic)
+	uint32_t           root;
+	int                depth;
+	float              leaf_dimf;    // 2^-depth: the size of a voxel = the children's size at the last level
+	float              miss_t;       // hit_time of a MISS: INFINITY (och_h_octree.h:429) or 0.0F (och_octree.cpp:302)
+	uint32_t           plane_mask;   // (1 << (23 - depth)) - 1: origin mantissa bits below the finest grid (Ray::t0or)
+	RcpTable           rt;
+};
+
+// walk selection ("variant" option): 0 = traverse(), the reference's state machine in integer ops; 1 = round 1's
+// FastWalker (+ traverse() outside its domain); kLean = round 2's tiers: LeanWalker where a negative t can never
+// occur, FastWalker for rays with a degenerate axis or an on-grid origin whose t rounds below zero, traverse()
+// outside [1,2)^3.
+constexpr int kLean = 13;
+constexpr int kLeanShift = 13;      // LeanStack column pitch: 23 - log2(256 threads * 4 bytes); lean kernels run 256-thread blocks
+
+// dynamic shared memory of a lean kernel: one column of (depth - 1) parent-stack words per thread
+inline size_t lean_smem_bytes(int depth) { return static_cast<size_t>(depth > 1 ? depth - 1 : 1) * 256 * 4; }
+
+__device__ __forceinline__ uint32_t lean_stack_base(const uint32_t* s_stack, int depth)
+{
+	// the entry of level L sits at exponent field 127 - L; the deepest level pushed is depth - 1
+	return static_cast<uint32_t>(__cvta_generic_to_shared(s_stack)) + threadIdx.x * 4u - (static_cast<uint32_t>(128 - depth) << (23 - kLeanShift));
+}
+
+template<int VARIANT, bool COUNT>
+__device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float oz, float dx, float dy, float dz, const uint32_t* s_stack)
+{
+	const Ray ray = ray_setup(g.rt, ox, oy, oz, dx, dy, dz, VARIANT == kLean ? g.plane_mask : 0u);
+	if (VARIANT == kLean && fast_path_ok(ox, oy, oz, ray) && lean_path_ok(ray))
+	{
+		LeanWalker<COUNT> w;
+		w.start(g.root, ray);
+		const LeanStack<kLeanShift> st{ lean_stack_base(s_stack, g.depth) };
+		while (!w.round(g.base_biased, g.leaf_dimf, g.miss_t, st)) {}
+		return w.hit;
+	}
+	return traverse_variant<VARIANT, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, ox, oy, oz, ray);
+}
+
+// ------------------------------------------------------------------------------------------------
+// trace kernels
+// ------------------------------------------------------------------------------------------------
+
 // explicit rays: thread i traces ray i
 template<int VARIANT, bool COUNT>
 __global__ void __launch_bounds__(256)
-trace_rays_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt,
-                  const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, size_t n,
+trace_rays_kernel(const Dag g, const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, size_t n,
                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
+	extern __shared__ uint32_t s_stack[];
 	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
 	if (i >= n) return;
 	const float* o = o3 + i * static_cast<size_t>(o_stride);
 	const float* d = d3 + i * 3;
-	const float ox = __ldg(o), oy = __ldg(o + 1), oz = __ldg(o + 2);
-	const Ray r = ray_setup(rt, ox, oy, oz, __ldg(d), __ldg(d + 1), __ldg(d + 2));
-	const Hit h = traverse_variant<VARIANT, COUNT>(nodes_m1, root, depth, miss_t, ox, oy, oz, r);
+	const Hit h = trace_ray<VARIANT, COUNT>(g, __ldg(o), __ldg(o + 1), __ldg(o + 2), __ldg(d), __ldg(d + 1), __ldg(d + 2), s_stack);
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
@@ -64,35 +119,31 @@ trace_rays_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dept
 
 // FrameRows / frame_row (strip-local row -> frame row) live in ort_trace.cuh, next to the camera
 
-// camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes),
-// a 256-thread block a 16 x 16 pixel tile.  SHAPED = true is the measurement build that also takes other warp tiles
-// (fr.tile_shape) and block heights (blockDim.x / 16 rows); the default build has the mapping fixed, which is worth
-// ~2 % (no runtime branches or special-register reads in the prologue).
-template<int VARIANT, bool COUNT, bool SHAPED>
-__global__ void __launch_bounds__(256)
-trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+// camera rays: a warp owns an 8 x 4 pixel tile (coherent rays -> shared upper-level nodes), a 256-thread block a
+// 16 x 16 pixel tile; block row b of the launch is traced by blockIdx.y = (b - band_rotate) mod (number of bands).
+__device__ __forceinline__ bool frame_pixel(const FrameRows& fr, unsigned block_y, unsigned bands, int& x, int& r)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned by = block_y + static_cast<unsigned>(fr.band_rotate);
+	if (by >= bands) by -= bands;
+	x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+	r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
+	return x < fr.W && r < fr.rows;
+}
+
+template<int VARIANT, bool COUNT>
+__global__ void __launch_bounds__(256)
+trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
+                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+{
+	extern __shared__ uint32_t s_stack[];
 	int x, r;
-	if (SHAPED && fr.tile_shape == 1)      { x = blockIdx.x * 16 + (lane & 15);                   r = blockIdx.y * 16 + warp * 2 + (lane >> 4); }
-	else if (SHAPED && fr.tile_shape == 2) { x = blockIdx.x * 16 + (warp & 3) * 4 + (lane & 3);   r = blockIdx.y * 16 + (warp >> 2) * 8 + (lane >> 2); }
-	else if (SHAPED && fr.tile_shape == 3) { x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);   r = blockIdx.y * 8 + (warp >> 2) * 4 + (lane >> 3); }   // 32 x 8 block: stays inside one 8-row strip
-	else if (SHAPED)                       { x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);   r = blockIdx.y * static_cast<int>(blockDim.x >> 4) + (warp >> 1) * 4 + (lane >> 3); }
-	else
-	{
-		unsigned by = blockIdx.y + static_cast<unsigned>(fr.band_rotate);
-		if (by >= gridDim.y) by -= gridDim.y;
-		x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-		r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
-	}
-	if (x >= fr.W || r >= fr.rows) return;
+	if (!frame_pixel(fr, blockIdx.y, gridDim.y, x, r)) return;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	const Hit h = traverse_variant<VARIANT, COUNT>(nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray);
+	const Hit h = trace_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, dx, dy, dz, s_stack);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
@@ -100,7 +151,6 @@ trace_frame_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int dep
 	t[i] = h.t;
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
-
 
 // Several frame jobs in ONE launch (blockIdx.z = job): strips of different frames, or the views of a multi-camera
 // rig.  Separate launches each end with the latency tail of their longest rays; here the blocks of all jobs stream
@@ -122,26 +172,22 @@ struct FrameJobBatch
 	FrameJob job[kMaxJobs];
 };
 
-template<bool COUNT>          // COUNT: some job of the batch wants per-ray PUSH counts (jobs without an npush pointer skip the store)
+template<int VARIANT, bool COUNT>          // COUNT: some job of the batch wants per-ray PUSH counts (jobs without an npush pointer skip the store)
 __global__ void __launch_bounds__(256)
-trace_frames_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, const __grid_constant__ FrameJobBatch batch)
+trace_frames_kernel(const Dag g, const __grid_constant__ FrameJobBatch batch)
 {
+	extern __shared__ uint32_t s_stack[];
 	const FrameJob& jb = batch.job[blockIdx.z];
 	const FrameRows& fr = jb.fr;
-	const int bands = (fr.rows + 15) >> 4;
-	if (static_cast<int>(blockIdx.y) >= bands) return;                  // the grid is sized for the largest job
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	int by = static_cast<int>(blockIdx.y) + fr.band_rotate;
-	if (by >= bands) by -= bands;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = by * 16 + (warp >> 1) * 4 + (lane >> 3);
-	if (x >= fr.W || r >= fr.rows) return;
+	const unsigned bands = static_cast<unsigned>((fr.rows + 15) >> 4);
+	if (blockIdx.y >= bands) return;                                    // the grid is sized for the largest job
+	int x, r;
+	if (!frame_pixel(fr, blockIdx.y, bands, x, r)) return;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(jb.cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, jb.cam.ox, jb.cam.oy, jb.cam.oz, dx, dy, dz);
-	const Hit h = traverse_variant<1, COUNT>(nodes_m1, root, depth, miss_t, jb.cam.ox, jb.cam.oy, jb.cam.oz, ray);
+	const Hit h = trace_ray<VARIANT, COUNT>(g, jb.cam.ox, jb.cam.oy, jb.cam.oz, dx, dy, dz, s_stack);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	jb.voxel[i] = h.voxel;
@@ -161,367 +207,24 @@ struct Palette
 	uint32_t exit_rgba, inside_rgba;
 };
 
+template<int VARIANT>
 __global__ void __launch_bounds__(256)
-trace_frame_rgba_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                        Palette pal, uint32_t* __restrict__ rgba)
+trace_frame_rgba_kernel(const Dag g, Camera cam, FrameRows fr, Palette pal, uint32_t* __restrict__ rgba)
 {
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	unsigned by = blockIdx.y + static_cast<unsigned>(fr.band_rotate);
-	if (by >= gridDim.y) by -= gridDim.y;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
-	if (x >= fr.W || r >= fr.rows) return;
+	extern __shared__ uint32_t s_stack[];
+	int x, r;
+	if (!frame_pixel(fr, blockIdx.y, gridDim.y, x, r)) return;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	const Hit h = traverse_variant<1, false>(nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray);
+	const Hit h = trace_ray<VARIANT, false>(g, cam.ox, cam.oy, cam.oz, dx, dy, dz, s_stack);
 
 	uint32_t px;
 	if (h.face == 6u) px = pal.exit_rgba;
 	else if (h.face == 7u) px = pal.inside_rgba;
 	else px = (h.voxel - 1u < pal.n_voxels) ? __ldg(pal.colours + 6u * (h.voxel - 1u) + h.face) : 0u;
 	rgba[static_cast<size_t>(r) * fr.W + x] = px;
-}
-
-// Variants 5 / 6: TightWalker (leaner bookkeeping per round, see ort_trace.cuh).  WW = false keeps the
-// "if-if" round of the default kernel (one child load, then descend OR advance); WW = true is the "while-while"
-// shape: every lane first advances over empty child slots until it holds a non-empty child (or leaves the tree),
-// then the whole warp descends together.
-template<bool COUNT, bool WW>
-__global__ void __launch_bounds__(256)
-trace_frame_tight_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
-{
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
-	if (x >= fr.W || r >= fr.rows) return;
-	const int y = frame_row(fr, r);
-
-	float dx, dy, dz;
-	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	uint32_t stack[kMaxDepth];
-	Hit h;
-	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
-	{
-		TightWalker<COUNT> w;
-		w.start(root, miss_t, ray);
-		if (WW)
-		{
-			for (;;)
-			{
-				uint32_t child;
-				bool done = false;
-				while ((child = w.load_child(nodes_m1)) == 0u)
-					if (w.advance(stack)) { done = true; break; }
-				if (done || w.descend(child, depth, stack))
-					break;
-			}
-		}
-		else
-		{
-			for (;;)
-			{
-				const uint32_t child = w.load_child(nodes_m1);
-				if (child ? w.descend(child, depth, stack) : w.advance(stack))
-					break;
-			}
-		}
-		h = w.hit;
-	}
-	else
-		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
-
-	const size_t i = static_cast<size_t>(r) * fr.W + x;
-	voxel[i] = h.voxel;
-	face[i] = static_cast<uint8_t>(h.face);
-	t[i] = h.t;
-	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
-}
-
-// Variant 12: persistent warps over tiles.  The default kernel's blocks retire when their slowest warp does, which
-// leaves warp slots empty (achieved occupancy 83 %).  Here a resident grid is launched once and every WARP draws its
-// next 8 x 4 tile from a global counter as soon as it is done, in the order the default kernel would have used
-// (8 consecutive tiles = one 16 x 16 block tile), so slots never wait for a block mate.
-template<bool COUNT>
-__global__ void __launch_bounds__(256, 8)
-trace_frame_tiles_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                         unsigned int n_tiles, unsigned int* __restrict__ counter,
-                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
-{
-	const unsigned lane = threadIdx.x & 31u;
-	const unsigned blocks_x = (fr.W + 15) / 16;
-	for (;;)
-	{
-		unsigned tile = 0;
-		if (lane == 0) tile = atomicAdd(counter, 1u);
-		tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-		if (tile >= n_tiles) return;
-		const unsigned blk = tile >> 3, sub = tile & 7u;
-		const int x = static_cast<int>(blk % blocks_x) * 16 + static_cast<int>(sub & 1u) * 8 + static_cast<int>(lane & 7u);
-		const int r = static_cast<int>(blk / blocks_x) * 16 + static_cast<int>(sub >> 1) * 4 + static_cast<int>(lane >> 3);
-		if (x >= fr.W || r >= fr.rows) continue;
-		const int y = frame_row(fr, r);
-
-		float dx, dy, dz;
-		camera_ray(cam, x, y, dx, dy, dz);
-		const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-		const Hit h = traverse_variant<1, COUNT>(nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray);
-
-		const size_t i = static_cast<size_t>(r) * fr.W + x;
-		voxel[i] = h.voxel;
-		face[i] = static_cast<uint8_t>(h.face);
-		t[i] = h.t;
-		if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
-	}
-}
-
-// Variant 7: PipeWalker (ALU-lean bookkeeping, see ort_trace.cuh).
-template<bool COUNT>
-__global__ void __launch_bounds__(256)
-trace_frame_pipe_kernel(const uint32_t* __restrict__ nodes_m1, unsigned long long base_biased, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                        uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
-{
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
-	if (x >= fr.W || r >= fr.rows) return;
-	const int y = frame_row(fr, r);
-
-	float dx, dy, dz;
-	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	Hit h;
-	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
-	{
-		uint32_t stack_n[kMaxDepth];
-		float stack_f[kMaxDepth];
-		PipeWalker<COUNT> w;
-		w.start(root, miss_t, ray);
-		for (;;)
-		{
-			const uint32_t child = w.load_child(base_biased);
-			if (child ? w.descend(child, depth, stack_n, stack_f) : w.advance(stack_n, stack_f))
-				break;
-		}
-		h = w.hit;
-	}
-	else
-	{
-		uint32_t stack[kMaxDepth];
-		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
-	}
-
-	const size_t i = static_cast<size_t>(r) * fr.W + x;
-	voxel[i] = h.voxel;
-	face[i] = static_cast<uint8_t>(h.face);
-	t[i] = h.t;
-	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
-}
-
-// Probe kernels (variants 8 / 9): the default walk plus PROBE_FMA dependent-free FMA-pipe instructions or PROBE_ALU
-// ALU-pipe instructions per round, on dummy accumulators that are folded into the result only if they take an
-// impossible value.  They answer "which resource binds the loop?": extra work on a unit that has slack is free.
-template<int PROBE_FMA, int PROBE_ALU>
-__global__ void __launch_bounds__(256)
-trace_frame_probe_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t)
-{
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
-	if (x >= fr.W || r >= fr.rows) return;
-	const int y = frame_row(fr, r);
-
-	float dx, dy, dz;
-	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	uint32_t stack[kMaxDepth];
-	Hit h;
-	float facc[3] = { dx, dy, dz };
-	uint32_t iacc[3] = { ray.px, ray.py, ray.pz };
-	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
-	{
-		FastWalker<false> w;
-		w.start(root, miss_t, ray);
-		for (;;)
-		{
-			const uint32_t child = w.load_child(nodes_m1);
-#pragma unroll
-			for (int k = 0; k < PROBE_FMA; ++k)
-				asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(facc[k % 3]) : "f"(w.cx), "f"(w.bx));
-#pragma unroll
-			for (int k = 0; k < PROBE_ALU; ++k)
-				asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(iacc[k % 3]) : "r"(w.idx), "r"(w.inv));
-			if (child ? w.descend(child, depth, stack) : w.advance(stack))
-				break;
-		}
-		h = w.hit;
-	}
-	else
-		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
-	if (facc[0] + facc[1] + facc[2] == 1.2345e-30f || (iacc[0] ^ iacc[1] ^ iacc[2]) == 0xDEADBEEFu)
-		h.voxel ^= 0x80000000u;                                                  // never true; keeps the probes alive
-
-	const size_t i = static_cast<size_t>(r) * fr.W + x;
-	voxel[i] = h.voxel;
-	face[i] = static_cast<uint8_t>(h.face);
-	t[i] = h.t;
-}
-
-// Experiment kernel for the SIMT-efficiency question (variant 4): "deferred phases".  In the default kernel every
-// round of the loop runs the descend block for the lanes whose child exists AND the advance block for the lanes
-// whose child is empty -- each with about two thirds of the warp.  Here a phase that fewer than `threshold` lanes
-// want is postponed (those lanes keep their loaded child and wait) as long as the other phase has enough takers, in
-// the hope that the stragglers' phase fills up.  Costs two ballots per round.
-template<bool COUNT>
-__global__ void __launch_bounds__(256)
-trace_frame_deferred_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                            int threshold,
-                            uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
-{
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
-	const int r = blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3);
-	const bool valid = x < fr.W && r < fr.rows;
-	const int y = frame_row(fr, r);
-
-	float dx, dy, dz;
-	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	uint32_t stack[kMaxDepth];
-	FastWalker<COUNT> w;
-	w.start(root, miss_t, ray);
-	int st = 0;                       // 0 load next child, 1 wants descend (child held), 2 wants advance, 3 finished
-	uint32_t child = 0;
-	if (!valid)
-		st = 3;
-	else if (!fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
-	{
-		w.hit = traverse(nodes_m1, root, depth, miss_t, ray, stack);
-		st = 3;
-	}
-
-	for (;;)
-	{
-		if (st == 0)
-		{
-			child = w.load_child(nodes_m1);
-			st = child ? 1 : 2;
-		}
-		const unsigned md = __ballot_sync(0xFFFFFFFFu, st == 1), ma = __ballot_sync(0xFFFFFFFFu, st == 2);
-		if ((md | ma) == 0u)
-			break;
-		const int nd = __popc(md), na = __popc(ma);
-		const bool run_d = nd >= threshold || na < threshold;
-		const bool run_a = na >= threshold || nd < threshold;
-		if (run_d && st == 1) st = w.descend(child, depth, stack) ? 3 : 0;
-		if (run_a && st == 2) st = w.advance(stack) ? 3 : 0;
-	}
-
-	if (valid)
-	{
-		const size_t i = static_cast<size_t>(r) * fr.W + x;
-		voxel[i] = w.hit.voxel;
-		face[i] = static_cast<uint8_t>(w.hit.face);
-		t[i] = w.hit.t;
-		if (COUNT) npush[i] = static_cast<uint16_t>(min(w.hit.npush, 65535u));
-	}
-}
-
-// Experiment kernel for the "upper levels in shared memory" question: 1024-thread blocks (a 32 x 32 pixel tile,
-// warps still 8 x 4) copy the first n_staged nodes -- the top levels, a contiguous prefix of the level-ordered
-// array -- into shared memory and serve PUSHes on those nodes from there.  Only valid in the h_octree layout.
-// Kept selectable (variant 3) so that the decision can be re-measured; see DESIGN.md section 4 for the numbers.
-template<bool COUNT>
-__global__ void __launch_bounds__(1024)
-trace_frame_staged_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt, Camera cam, FrameRows fr,
-                          uint32_t n_staged,
-                          uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
-{
-	extern __shared__ uint4 s_raw[];
-	uint32_t* s_nodes = reinterpret_cast<uint32_t*>(s_raw);
-	{
-		const uint4* src = reinterpret_cast<const uint4*>(nodes_m1 + 8);            // id 1
-		for (uint32_t i = threadIdx.x; i < 2u * n_staged; i += blockDim.x) s_raw[i] = __ldg(src + i);
-	}
-	__syncthreads();
-	const uint32_t* s_nodes_m1 = s_nodes - 8;
-
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int x = blockIdx.x * 32 + (warp & 3) * 8 + (lane & 7);
-	const int r = blockIdx.y * 32 + (warp >> 2) * 4 + (lane >> 3);
-	if (x >= fr.W || r >= fr.rows) return;
-	const int y = frame_row(fr, r);
-
-	float dx, dy, dz;
-	camera_ray(cam, x, y, dx, dy, dz);
-	const Ray ray = ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
-	uint32_t stack[kMaxDepth];
-	Hit h;
-	if (fast_path_ok(cam.ox, cam.oy, cam.oz, ray))
-	{
-		FastWalker<COUNT> w;
-		w.start(root, miss_t, ray);
-		while (!w.iterate_staged(nodes_m1, depth, stack, s_nodes_m1, n_staged)) {}
-		h = w.hit;
-	}
-	else
-		h = traverse(nodes_m1, root, depth, miss_t, ray, stack);
-
-	const size_t i = static_cast<size_t>(r) * fr.W + x;
-	voxel[i] = h.voxel;
-	face[i] = static_cast<uint8_t>(h.face);
-	t[i] = h.t;
-	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
-}
-
-// Fixture kernels (SURVEY 8f.3): the noise evaluations of the demo's terrain set-up, one thread per column / voxel.
-// get_terrain_heigth over the whole map (test_och_h_octree.cpp:561-566, :587-592)
-__global__ void __launch_bounds__(256)
-fixture_heightmap_kernel(uint16_t* __restrict__ heights, int dim)
-{
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
-	if (x < dim) heights[static_cast<size_t>(y) * dim + x] = ort_noise::terrain_height(x, y, dim);
-}
-
-// remove(tree, splatter_noise(-0.5F, .., 1/16))'s dim^3 test (:735-743, :755-763) for the voxels at or below the
-// surface: bit (y * dim + x) of slab z = "carved".  A warp covers 32 consecutive x and writes one 32-bit word.
-__global__ void __launch_bounds__(256)
-fixture_carve_kernel(const uint16_t* __restrict__ heights, int dim, uint32_t* __restrict__ bits, size_t words32_per_slab)
-{
-	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
-	const bool carved = x < dim && z <= static_cast<int>(heights[static_cast<size_t>(y) * dim + x]) && ort_noise::carve_test(x, y, z);
-	const unsigned w = __ballot_sync(0xFFFFFFFFu, carved);
-	if ((threadIdx.x & 31u) == 0u && x < dim)
-		bits[static_cast<size_t>(z) * words32_per_slab + ((static_cast<size_t>(y) * dim + x) >> 5)] = w;
-}
-
-// Diagnostic: random 32-byte-sector gather over an L2-resident buffer -- the memory-side ceiling of a
-// traversal whose nodes live in L2 (one 4-byte child read moves one sector).  Independent loads, 8 in
-// flight per thread, addresses from a counter hash so that L1 cannot help.
-__global__ void __launch_bounds__(256)
-gather_peak_kernel(const uint32_t* __restrict__ buf, uint32_t n_sectors, uint32_t iters, uint32_t* __restrict__ sink)
-{
-	uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
-	uint32_t acc = 0;
-	for (uint32_t i = 0; i < iters; ++i)
-	{
-		uint32_t v[8];
-#pragma unroll
-		for (int k = 0; k < 8; ++k)
-		{
-			x = x * 1664525u + 1013904223u;
-			const uint32_t s = __umulhi(x ^ (x >> 15), n_sectors);            // uniform in [0, n_sectors)
-			v[k] = __ldg(buf + (static_cast<size_t>(s) << 3) + (x & 7u));
-		}
-#pragma unroll
-		for (int k = 0; k < 8; ++k) acc ^= v[k];
-	}
-	if (acc == 0x9E3779B9u) *sink = acc;                                      // keep the loads alive
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -535,25 +238,28 @@ gather_peak_kernel(const uint32_t* __restrict__ buf, uint32_t n_sectors, uint32_
 // rays, a lot on incoherent rays (BASELINE config 3: 10 PUSHes on average, 600 worst case).
 // FRAME = true enumerates the pixels of the strip in 8x4 tile order (index = 32 * tile + lane-in-tile) so
 // that consecutive indices stay spatially coherent.
+// The resumable walker is LeanWalker (its parent stack is the thread's shared-memory column); a ray outside its
+// preconditions is walked to the end right away when it is drawn (FastWalker / traverse()), like any other rare case.
+// `counter` is the launch's own work counter (a ring of them lives in the context, so launches on different streams
+// never share one).
 // ------------------------------------------------------------------------------------------------
 
 constexpr unsigned kBatch = 128;    // ray indices a warp draws per atomicAdd
 
-// MINB = minimum resident blocks per SM the compiler must allow for (register budget): 1 -> 47 registers, 57 %
-// occupancy; 6 -> 40 registers (a few spilled words), 75 %; 8 -> 32 registers, 100 %.
+// MINB = minimum resident blocks per SM the compiler must allow for (register budget)
 template<bool COUNT, bool FRAME, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB)
-trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, RcpTable rt,
-                        const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, Camera cam, FrameRows fr,
+trace_persistent_kernel(const Dag g, const float* __restrict__ o3, int o_stride, const float* __restrict__ d3, Camera cam, FrameRows fr,
                         unsigned long long n, unsigned long long* __restrict__ counter, int low_water,
                         uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
+	extern __shared__ uint32_t s_stack[];
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned lt_mask = (1u << lane) - 1u;
-	const unsigned tiles_x = FRAME ? (fr.W + 7) / 8 : 0;
+	const unsigned tiles_x = FRAME ? (fr.W + 7) / 8 : 1;
+	const LeanStack<kLeanShift> st{ lean_stack_base(s_stack, g.depth) };
 
-	uint32_t stack[kMaxDepth];
-	FastWalker<COUNT> w;
+	LeanWalker<COUNT> w;
 	bool active = false;
 	size_t out = 0;                              // where this lane's result goes
 	unsigned long long next = 0, end = 0;        // the warp's current batch (uniform)
@@ -611,14 +317,14 @@ trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 				}
 				if (valid)
 				{
-					const Ray ray = ray_setup(rt, ox, oy, oz, dx, dy, dz);
-					if (fast_path_ok(ox, oy, oz, ray))
+					const Ray ray = ray_setup(g.rt, ox, oy, oz, dx, dy, dz, g.plane_mask);
+					if (fast_path_ok(ox, oy, oz, ray) && lean_path_ok(ray))
 					{
-						w.start(root, miss_t, ray);
+						w.start(g.root, ray);
 						active = true;
 					}
 					else
-						store(out, traverse(nodes_m1, root, depth, miss_t, ray, stack));       // out-of-domain ray: the generic walk, right away
+						store(out, traverse_variant<1, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, ox, oy, oz, ray));   // rare ray: walked to the end right away
 				}
 			}
 			next += avail;
@@ -631,7 +337,7 @@ trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 		// ---- traverse until too few lanes are busy ---------------------------------------------
 		for (;;)
 		{
-			if (active && w.iterate(nodes_m1, depth, stack))
+			if (active && w.round(g.base_biased, g.leaf_dimf, g.miss_t, st))
 			{
 				store(out, w.hit);
 				active = false;
@@ -641,6 +347,83 @@ trace_persistent_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, in
 				break;
 		}
 	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// multi-GPU strip gather (ort_mg_*): received strips -> their rows of the assembled frame
+// ------------------------------------------------------------------------------------------------
+
+// A rank's strip block holds its tiles back to back (tile k of the strip = frame tile rank + k * world, tile_rows rows
+// each) in three sections of max_n entries: voxel u32 | t f32 | face u8 (max_n = pixels of the longest strip, a
+// multiple of 4 because W is).  The consumer holds one block per rank, `pitch` bytes apart, in rank order.
+// One thread moves 4 pixels of all three outputs: grid = (ceil(max_n / 4 / 256), world).
+struct StripMap
+{
+	int W, H, tile_rows, world;
+	unsigned long long max_n, pitch;
+};
+
+__global__ void __launch_bounds__(256)
+unpack_strips_kernel(uint4* __restrict__ voxel, uint4* __restrict__ t, uint32_t* __restrict__ face, const char* __restrict__ blocks, StripMap m)
+{
+	const int W4 = m.W >> 2;
+	const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;     // 4-pixel group within the strip
+	if (i * 4 >= m.max_n) return;
+	const int rk = static_cast<int>(blockIdx.y);
+	const int r = static_cast<int>(i / W4), x4 = static_cast<int>(i % W4);
+	const int tile = r / m.tile_rows, in_tile = r % m.tile_rows;
+	const int y = (rk + tile * m.world) * m.tile_rows + in_tile;
+	if (y >= m.H) return;                                                            // past the rank's last tile / the frame's last row
+	const char* blk = blocks + static_cast<size_t>(rk) * m.pitch;
+	const size_t o = static_cast<size_t>(y) * W4 + x4;
+	voxel[o] = reinterpret_cast<const uint4*>(blk)[i];
+	t[o] = reinterpret_cast<const uint4*>(blk + m.max_n * 4)[i];
+	face[o] = reinterpret_cast<const uint32_t*>(blk + m.max_n * 8)[i];
+}
+
+// Fixture kernels (SURVEY 8f.3): the noise evaluations of the demo's terrain set-up, one thread per column / voxel.
+// get_terrain_heigth over the whole map (test_och_h_octree.cpp:561-566, :587-592)
+__global__ void __launch_bounds__(256)
+fixture_heightmap_kernel(uint16_t* __restrict__ heights, int dim)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+	if (x < dim) heights[static_cast<size_t>(y) * dim + x] = ort_noise::terrain_height(x, y, dim);
+}
+
+// remove(tree, splatter_noise(-0.5F, .., 1/16))'s dim^3 test (:735-743, :755-763) for the voxels at or below the
+// surface: bit (y * dim + x) of slab z = "carved".  A warp covers 32 consecutive x and writes one 32-bit word.
+__global__ void __launch_bounds__(256)
+fixture_carve_kernel(const uint16_t* __restrict__ heights, int dim, uint32_t* __restrict__ bits, size_t words32_per_slab)
+{
+	const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, z = blockIdx.z;
+	const bool carved = x < dim && z <= static_cast<int>(heights[static_cast<size_t>(y) * dim + x]) && ort_noise::carve_test(x, y, z);
+	const unsigned w = __ballot_sync(0xFFFFFFFFu, carved);
+	if ((threadIdx.x & 31u) == 0u && x < dim)
+		bits[static_cast<size_t>(z) * words32_per_slab + ((static_cast<size_t>(y) * dim + x) >> 5)] = w;
+}
+
+// Diagnostic: random 32-byte-sector gather over an L2-resident buffer -- the memory-side ceiling of a
+// traversal whose nodes live in L2 (one 4-byte child read moves one sector).  Independent loads, 8 in
+// flight per thread, addresses from a counter hash so that L1 cannot help.
+__global__ void __launch_bounds__(256)
+gather_peak_kernel(const uint32_t* __restrict__ buf, uint32_t n_sectors, uint32_t iters, uint32_t* __restrict__ sink)
+{
+	uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+	uint32_t acc = 0;
+	for (uint32_t i = 0; i < iters; ++i)
+	{
+		uint32_t v[8];
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+		{
+			x = x * 1664525u + 1013904223u;
+			const uint32_t s = __umulhi(x ^ (x >> 15), n_sectors);            // uniform in [0, n_sectors)
+			v[k] = __ldg(buf + (static_cast<size_t>(s) << 3) + (x & 7u));
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k) acc ^= v[k];
+	}
+	if (acc == 0x9E3779B9u) *sink = acc;                                      // keep the loads alive
 }
 
 }  // namespace ort

@@ -63,9 +63,10 @@ struct Ray
 	uint32_t px, py, pz;     // pos (float bit patterns in [1,2))
 	uint32_t inv;            // inv_signs
 	uint32_t idx;
+	uint32_t t0or;           // OR over the axes of bits(fma(o_a, coef_a, bias_a)): the sign bit tells whether a t value can ever be negative (LeanWalker)
 };
 
-__device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, int a, float& coef, float& bias, uint32_t& pos, uint32_t& inv, uint32_t& idx)
+__device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, int a, float& coef, float& bias, uint32_t& pos, uint32_t& inv, uint32_t& idx, uint32_t& t0or, uint32_t plane_mask)
 {
 	const bool sg = 0.0f < d;                                                  // :310
 	inv |= static_cast<uint32_t>(sg) << a;                                     // :322
@@ -75,16 +76,22 @@ __device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, in
 	bias = __uint_as_float(__float_as_uint(__fmul_rn(coef, oa)) ^ 0x80000000u); // :318
 	pos = __float_as_uint(oa) & 0x3FC00000u;                                   // :320
 	idx |= static_cast<uint32_t>(pos == 0x3FC00000u) << a;                     // :324
+	// t of the plane through the origin itself -- it only exists as a cell plane when the origin lies on the finest
+	// level's grid, i.e. when its mantissa bits below that level (plane_mask) are clear (see LeanWalker / lean_path_ok)
+	if ((__float_as_uint(oa) & plane_mask) == 0u)
+		t0or |= __float_as_uint(__fmaf_rn(oa, coef, bias));
 }
 
-__device__ __forceinline__ Ray ray_setup(const RcpTable rt, float ox, float oy, float oz, float dx, float dy, float dz)
+// plane_mask = (1 << (23 - depth)) - 1, the mantissa bits below the finest level's grid (0: treat every origin as on-grid)
+__device__ __forceinline__ Ray ray_setup(const RcpTable rt, float ox, float oy, float oz, float dx, float dy, float dz, uint32_t plane_mask = 0u)
 {
 	Ray r;
 	r.inv = 0;
 	r.idx = 0;
-	ray_axis(rt, ox, dx, 0, r.cx, r.bx, r.px, r.inv, r.idx);
-	ray_axis(rt, oy, dy, 1, r.cy, r.by, r.py, r.inv, r.idx);
-	ray_axis(rt, oz, dz, 2, r.cz, r.bz, r.pz, r.inv, r.idx);
+	r.t0or = 0;
+	ray_axis(rt, ox, dx, 0, r.cx, r.bx, r.px, r.inv, r.idx, r.t0or, plane_mask);
+	ray_axis(rt, oy, dy, 1, r.cy, r.by, r.py, r.inv, r.idx, r.t0or, plane_mask);
+	ray_axis(rt, oz, dz, 2, r.cz, r.bz, r.pz, r.inv, r.idx, r.t0or, plane_mask);
 	return r;
 }
 
@@ -365,166 +372,8 @@ struct FastWalker
 	}
 };
 
-// ------------------------------------------------------------------------------------------------
-// Tight variant.  Same decisions and the same FMAs as FastWalker; what changes is bookkeeping that the SASS of
-// FastWalker's loop showed to be avoidable (profiles/r1_v4_ncu_full.md: the loop is issue-bound, so every
-// instruction of the round counts):
-//   * the node is carried as its word index (id * 8): the child-slot address is one LOP3 (node8 | (idx ^ inv))
-//     plus the 64-bit scale-add, and a parent-stack entry is node8 | idx (the low three bits are free), so POP
-//     restores node and idx with two masks and ids are no longer squeezed below 2^29 by the stack format
-//     (the 32-bit word index still caps ids at 2^29);
-//   * the step to the sibling is three predicated FADDs instead of an if / else-if ladder;
-//   * the child index after a descend is assembled from the three compares without a branch.
-// ------------------------------------------------------------------------------------------------
-template<bool COUNT>
-struct TightWalker
-{
-	uint32_t node8, idx, inv, mti;
-	int      level;
-	float    px, py, pz, dimf, tmin;
-	float    cx, cy, cz, bx, by, bz;
-	float    miss_t;
-	Hit      hit;
-
-	__device__ __forceinline__ void start(uint32_t root, float miss_time, const Ray& r)
-	{
-		node8 = root << 3;
-		miss_t = miss_time;
-		level = 1;
-		idx = r.idx;
-		inv = r.inv;
-		px = __uint_as_float(r.px); py = __uint_as_float(r.py); pz = __uint_as_float(r.pz);
-		dimf = 0.5f;
-		tmin = 0.0f;
-		mti = 8;
-		hit.npush = 0;
-		cx = r.cx; cy = r.cy; cz = r.cz; bx = r.bx; by = r.by; bz = r.bz;
-		const float ninf = __uint_as_float(0xFF800000u);      // degenerate axes: see FastWalker
-		if (cx == ninf) { cx = 0.0f; bx = ninf; }
-		if (cy == ninf) { cy = 0.0f; by = ninf; }
-		if (cz == ninf) { cz = 0.0f; bz = ninf; }
-	}
-
-	__device__ __forceinline__ void miss()
-	{
-		hit.voxel = 0;
-		hit.face = 6;
-		hit.t = miss_t;
-	}
-
-	// PUSH's load (och_h_octree.h:344)
-	__device__ __forceinline__ uint32_t load_child(const uint32_t* __restrict__ nodes_m1)
-	{
-		if (COUNT) ++hit.npush;
-		return __ldg(nodes_m1 + (node8 | (idx ^ inv)));
-	}
-
-	// PUSH with a non-empty child: HIT at the last level (returns true), else go down one level
-	__device__ __forceinline__ bool descend(uint32_t child, int depth, uint32_t* stack)
-	{
-		if (level == depth)
-		{
-			hit.voxel = child;
-			hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
-			hit.t = tmin;
-			return true;
-		}
-		stack[level - 1] = node8 | idx;
-		++level;
-		node8 = child << 3;
-		dimf *= 0.5f;
-		const float mx = px + dimf, my = py + dimf, mz = pz + dimf;          // exact
-		const bool ux = __fmaf_rn(mx, cx, bx) >= tmin;
-		const bool uy = __fmaf_rn(my, cy, by) >= tmin;
-		const bool uz = __fmaf_rn(mz, cz, bz) >= tmin;
-		px = ux ? mx : px;
-		py = uy ? my : py;
-		pz = uz ? mz : pz;
-		idx = static_cast<uint32_t>(ux) | (static_cast<uint32_t>(uy) << 1) | (static_cast<uint32_t>(uz) << 2);
-		return false;
-	}
-
-	// PUSH with an empty child: STEP to the sibling across the nearest exit plane, POPping as far as needed;
-	// returns true on MISS
-	__device__ __forceinline__ bool advance(const uint32_t* stack)
-	{
-		bool ax, ay;
-		for (;;)
-		{
-			const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
-			const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
-			const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
-			const uint32_t tyz = min(ty, tz);
-			ax = tx <= tyz;                                                     // unsigned argmin, ties -> x, y, z (:388-406)
-			ay = !ax && ty <= tz;
-			tmin = __uint_as_float(min(tx, tyz));
-			mti = ax ? 1u : (ay ? 2u : 4u);
-
-			if (idx & mti)
-				break;                                                          // a sibling lies that way
-
-			if (((tx | ty | tz) & 0x80000000u) == 0u)
-			{
-				// multi-level POP (proof in FastWalker::advance)
-				const uint32_t pa = __float_as_uint(ax ? px : (ay ? py : pz));
-				level -= __ffs(static_cast<int>(pa >> (24 - level)));
-				if (level == 0)
-				{
-					miss();
-					return true;
-				}
-				const uint32_t keep = 0xFFFFFFFFu << (23 - level);
-				px = __uint_as_float(__float_as_uint(px) & keep);
-				py = __uint_as_float(__float_as_uint(py) & keep);
-				pz = __uint_as_float(__float_as_uint(pz) & keep);
-				dimf = __uint_as_float(static_cast<uint32_t>(127 - level) << 23);
-				const uint32_t e = stack[level - 1];
-				node8 = e & ~7u;
-				idx = e & 7u;                                                   // bit a* is set there
-				break;
-			}
-
-			if (--level == 0)
-			{
-				miss();
-				return true;
-			}
-			if (idx & 1u) px -= dimf;                                           // back to the parent's corner
-			if (idx & 2u) py -= dimf;
-			if (idx & 4u) pz -= dimf;
-			dimf += dimf;
-			const uint32_t e = stack[level - 1];
-			node8 = e & ~7u;
-			idx = e & 7u;
-		}
-
-		// step to the sibling across the exit plane (exact: the bit is set)
-		const bool az = !(ax | ay);
-		if (ax) px -= dimf;
-		if (ay) py -= dimf;
-		if (az) pz -= dimf;
-		idx ^= mti;
-		return false;
-	}
-};
-
-// ------------------------------------------------------------------------------------------------
-// ALU-lean variant ("PipeWalker").  Probe kernels (ort_kernels.cuh, variants 8-11) showed how the loop is bound:
-// six extra FMA-pipe instructions per round cost +7.9 %, six extra ALU-pipe instructions +16.7 % -- an ALU-pipe
-// instruction (LOP3, SEL, FSEL, ISETP, FSETP, VIMNMX, SHF ...: one warp instruction per two cycles) costs twice an
-// FMA-pipe one.  Same decisions and the same t values as FastWalker; the bookkeeping moves off the ALU pipe:
-//   * child pick after a descend: `set.ge.f32` yields 1.0f / 0.0f, the position takes the half step by an exact
-//     FMA (p + u * size) and the child-slot index is accumulated in float, already XORed with inv_signs:
-//     idx' = inv + sum_a w_a u_a with w_a = +-2^a, kept as F = 2^23 + idx' (every partial sum is a small integer at
-//     ulp 1, so the FMAs are exact).  bits(F) = 0x4B000000 | idx' goes straight into the 64-bit address IMAD; the
-//     constant is folded into the base pointer.  No FSETP / FSEL / SEL / LOP3 for the pick;
-//   * a sibling step is three predicated FADD pairs (position, F);
-//   * the parent stack holds node id and F in two local arrays -- POP restores both with loads, no unpacking;
-//   * multi-level POP: the position bits below the current level are zero and the current level's bit on the exit
-//     axis is clear (that is why we pop), so the ancestor to resume at is simply the LOWEST set bit b of the exit
-//     axis' position word (the exponent's lowest bit is the sentinel for "through the root"):  b = pa & -pa,
-//     positions &= -b, cell size = as_float(0x3F800000 | b) - 1, level = 23 - flo(b).
-// ------------------------------------------------------------------------------------------------
+// child pick without predicates: set.ge.f32 and a 2^23 'magic' float that carries the slot index (LeanWalker; PipeWalker in
+// ort_trace_experiments.cuh)
 constexpr uint32_t kMagicBits = 0x4B000000u;     // bits of 8388608.0f = 2^23
 
 __device__ __forceinline__ float set_ge(float a, float b)    // 1.0f if a >= b (ordered) else 0.0f -- one instruction
@@ -538,148 +387,179 @@ __device__ __forceinline__ float set_ge(float a, float b)    // 1.0f if a >= b (
 #endif
 }
 
-template<bool COUNT>
-struct PipeWalker
+// ------------------------------------------------------------------------------------------------
+// Lean variant (round 2, the default for frames).  Same decisions, same FMAs, same t values as FastWalker; built from
+// what round 1's profile said about the loop: it is bound by warp-instruction issue (5.8 eligible warps per cycle,
+// ALU pipe at half rate), so every instruction of the round counts, ALU-pipe instructions twice.
+//   * ONE word of state for "where am I": w = node * 8 + ((idx ^ inv_signs) | 2^23-magic), the word offset of the
+//     current child slot.  The PUSH load is base[w] (one IMAD.WIDE + LDG), a parent-stack entry is w itself (no
+//     packing on the way in, no unpacking on the way out), the sibling step is w ^= min_t_idx, and the sibling test reads
+//     bit a* of (w ^ inv).  The child pick after a descend needs no predicate: set.ge.f32 gives 1.0f / 0.0f, position and
+//     slot index take the half step through exact FMAs (FMA pipe, full rate), and bits(F) = magic | idx' is added to
+//     child * 8 by the same IMAD that scales the id; the magic constant is folded into the base pointer on the host.
+//   * no `level` register: the size of the current node's children (dimf = 2^-level) says it all.  HIT test: dimf ==
+//     2^-depth.  Parent-stack address: the exponent field of dimf, scaled by a shift (one LEA.HI), into a per-thread
+//     column of shared memory (no 64-bit local addressing, no unpack).  POP restores dimf from the lowest set position
+//     bit and finds its stack entry the same way.
+//   * no negative-t branch in the loop.  FastWalker tests "is a negative t in play" before every multi-level POP and
+//     carries the reference's one-level POP sequence for that case.  A t value is fma(X, coef, bias) for a cell plane
+//     X on the ray's side of the (mirrored) origin o: X <= o.  For X < o the exact value |coef| * (o - X) - e, with e the
+//     rounding error of bias = -(coef * o), is positive, because o - X >= 2^-23 and |e| < 2^-23 * |coef|; coef = -0
+//     (huge |d|) gives t = +0 and an overflowing bias gives t = +inf.  So a negative t can only be the t of the plane
+//     through the origin itself, X == o, and that one value per axis is computed at ray set-up (Ray::t0or).  Rays
+//     whose three values are sign-clear and whose three reciprocals are regular (no -inf: d = +-0 / denormal) can
+//     never see a negative t: they take this walker, the others take FastWalker (exact for those, as before).
+// ------------------------------------------------------------------------------------------------
+
+// parent stack of one thread.  Device: a column of shared memory, entry of level L (children of size 2^-L) at byte
+// address base + (bits(2^-L) >> SHIFT), i.e. exponent field (127 - L) scaled by the column pitch 2^(23 - SHIFT) bytes.
+// Host emulation: a plain array indexed by the exponent field.
+template<int SHIFT>
+struct LeanStack
 {
-	uint32_t node, inv, mti;
-	int      level;
-	float    F;                      // 2^23 + ((child index) ^ inv)
+#ifdef ORT_HOST_EMU
+	uint32_t* e;                                     // kMaxDepth entries
+	__device__ __forceinline__ void store(float dimf, uint32_t w) const { e[(__float_as_uint(dimf) >> 23) - (127u - kMaxDepth)] = w; }
+	__device__ __forceinline__ uint32_t load(float dimf) const { return e[(__float_as_uint(dimf) >> 23) - (127u - kMaxDepth)]; }
+#else
+	uint32_t base;                                   // shared-space byte address, biased by the lowest exponent in use
+	__device__ __forceinline__ void store(float dimf, uint32_t w) const
+	{
+		asm volatile("st.shared.u32 [%0], %1;" :: "r"(base + (__float_as_uint(dimf) >> SHIFT)), "r"(w) : "memory");
+	}
+	__device__ __forceinline__ uint32_t load(float dimf) const
+	{
+		uint32_t w;
+		asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(base + (__float_as_uint(dimf) >> SHIFT)) : "memory");
+		return w;
+	}
+#endif
+};
+
+template<bool COUNT>
+struct LeanWalker
+{
+	uint32_t w, mti;
 	float    px, py, pz, dimf, tmin;
 	float    cx, cy, cz, bx, by, bz;
-	float    wx, wy, wz, c0;         // idx' = inv + wx*ux + wy*uy + wz*uz;  c0 = 2^23 + inv
-	float    miss_t;
+	float    wx, wy, wz, c0;         // slot index of a picked child = inv + wx*ux + wy*uy + wz*uz;  c0 = 2^23 + inv (PipeWalker)
 	Hit      hit;
 
-	__device__ __forceinline__ void start(uint32_t root, float miss_time, const Ray& r)
+	__device__ __forceinline__ void start(uint32_t root, const Ray& r)
 	{
-		node = root;
-		miss_t = miss_time;
-		level = 1;
-		inv = r.inv;
+		w = root * 8u + (kMagicBits | (r.idx ^ r.inv));
 		px = __uint_as_float(r.px); py = __uint_as_float(r.py); pz = __uint_as_float(r.pz);
 		dimf = 0.5f;
 		tmin = 0.0f;
 		mti = 8;
 		hit.npush = 0;
 		cx = r.cx; cy = r.cy; cz = r.cz; bx = r.bx; by = r.by; bz = r.bz;
-		const float ninf = __uint_as_float(0xFF800000u);      // degenerate axes: see FastWalker
-		if (cx == ninf) { cx = 0.0f; bx = ninf; }
-		if (cy == ninf) { cy = 0.0f; by = ninf; }
-		if (cz == ninf) { cz = 0.0f; bz = ninf; }
-		wx = (inv & 1u) ? -1.0f : 1.0f;
-		wy = (inv & 2u) ? -2.0f : 2.0f;
-		wz = (inv & 4u) ? -4.0f : 4.0f;
-		c0 = __uint_as_float(kMagicBits | inv);
-		F = __uint_as_float(kMagicBits | (r.idx ^ inv));
+		wx = (r.inv & 1u) ? -1.0f : 1.0f;
+		wy = (r.inv & 2u) ? -2.0f : 2.0f;
+		wz = (r.inv & 4u) ? -4.0f : 4.0f;
+		c0 = __uint_as_float(kMagicBits | r.inv);
 	}
 
-	__device__ __forceinline__ void miss()
-	{
-		hit.voxel = 0;
-		hit.face = 6;
-		hit.t = miss_t;
-	}
-
-	// PUSH's load (och_h_octree.h:344).  base_biased = address of nodes_m1 minus 4 * kMagicBits (computed on the host),
-	// so that bits(F) = kMagicBits | idx' can be used as the word offset as it is: two 64-bit IMADs, no logic op
+	// PUSH's load (och_h_octree.h:344).  base_biased = address of nodes_m1 minus 4 * kMagicBits
 	__device__ __forceinline__ uint32_t load_child(unsigned long long base_biased)
 	{
 		if (COUNT) ++hit.npush;
-		const unsigned long long a = base_biased + static_cast<unsigned long long>(node) * 32ull + static_cast<unsigned long long>(__float_as_uint(F)) * 4ull;
-		return __ldg(reinterpret_cast<const uint32_t*>(a));
+		return __ldg(reinterpret_cast<const uint32_t*>(base_biased + static_cast<unsigned long long>(w) * 4ull));
 	}
 
-	// PUSH with a non-empty child: HIT at the last level (returns true), else go down one level
-	__device__ __forceinline__ bool descend(uint32_t child, int depth, uint32_t* stack_n, float* stack_f)
+	// PUSH with a non-empty child (:346-376): HIT at the last level (returns true), else go down one level.
+	// leaf_dimf = 2^-depth
+	template<class STACK>
+	__device__ __forceinline__ bool descend(uint32_t child, float leaf_dimf, const STACK st)
 	{
-		if (level == depth)
+		if (dimf == leaf_dimf)                                                      // :346 HIT
 		{
+			const uint32_t inv = __float_as_uint(c0);
 			hit.voxel = child;
 			hit.face = (mti >> 1) + 3u * ((inv & mti) == 0u);
 			hit.t = tmin;
 			return true;
 		}
-		stack_n[level - 1] = node;
-		stack_f[level - 1] = F;
-		++level;
-		node = child;
-		dimf *= 0.5f;
-		const float ux = set_ge(__fmaf_rn(px + dimf, cx, bx), tmin);            // px + dimf is exact
+		st.store(dimf, w);                                                          // :357
+		dimf *= 0.5f;                                                               // :361
+		const float ux = set_ge(__fmaf_rn(px + dimf, cx, bx), tmin);                // :363-367; px + dimf is exact
 		const float uy = set_ge(__fmaf_rn(py + dimf, cy, by), tmin);
 		const float uz = set_ge(__fmaf_rn(pz + dimf, cz, bz), tmin);
-		px = __fmaf_rn(ux, dimf, px);                                              // exact: + size or + 0
+		px = __fmaf_rn(ux, dimf, px);                                               // :371-373, exact: + size or + 0
 		py = __fmaf_rn(uy, dimf, py);
 		pz = __fmaf_rn(uz, dimf, pz);
-		F = __fmaf_rn(uz, wz, __fmaf_rn(uy, wy, __fmaf_rn(ux, wx, c0)));           // exact small integers at ulp 1
+		const float F = __fmaf_rn(uz, wz, __fmaf_rn(uy, wy, __fmaf_rn(ux, wx, c0)));   // exact small integers at ulp 1
+		w = child * 8u + __float_as_uint(F);
 		return false;
 	}
 
-	// PUSH with an empty child: STEP to the sibling across the nearest exit plane, POPping as far as needed;
-	// returns true on MISS
-	__device__ __forceinline__ bool advance(const uint32_t* stack_n, const float* stack_f)
+	// PUSH with an empty child: STEP (:378-419) to the sibling across the nearest exit plane, POPping (:421-446) as far as
+	// needed; returns true on MISS.  All t are non-negative here (see above), so the unsigned order of the reference is
+	// the order of the values and the multi-level POP (proof in FastWalker::advance) always applies.
+	template<class STACK>
+	__device__ __forceinline__ bool advance(float miss_t, const STACK st)
 	{
-		bool ax, ay;
-		for (;;)
+		const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
+		const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
+		const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
+		const uint32_t tyz = min(ty, tz);
+		const bool ax = tx <= tyz;                                                  // argmin, ties -> x, y, z
+		const bool ay = !ax && ty <= tz;
+		tmin = __uint_as_float(min(tx, tyz));
+		mti = 4u;
+		if (ay) mti = 2u;
+		if (ax) mti = 1u;
+
+		if (((w ^ __float_as_uint(c0)) & mti) == 0u)                                // :410 no sibling that way
 		{
-			const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
-			const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
-			const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
-			const uint32_t tyz = min(ty, tz);
-			ax = tx <= tyz;                                                     // unsigned argmin, ties -> x, y, z (:388-406)
-			ay = !ax && ty <= tz;
-			tmin = __uint_as_float(min(tx, tyz));
-			mti = 4u;
-			if (ay) mti = 2u;
-			if (ax) mti = 1u;
-
-			if (((__float_as_uint(F) ^ inv) & mti) != 0u)
-				break;                                                          // a sibling lies that way
-
-			if (((tx | ty | tz) & 0x80000000u) == 0u)
+			// The position bits below the current level are zero and the current level's bit on the exit axis is clear
+			// (that is why we pop), so the ancestor to resume at is the LOWEST set bit b of the exit axis' position word;
+			// the exponent's lowest bit (127 is odd) is the sentinel for "popped through the root".
+			uint32_t pa = __float_as_uint(pz);
+			if (ay) pa = __float_as_uint(py);
+			if (ax) pa = __float_as_uint(px);
+			const uint32_t b = pa & (0u - pa);
+			if (b == 0x00800000u)                                                   // :423
 			{
-				// multi-level POP (proof of the shortcut in FastWalker::advance; the bit trick is explained above)
-				uint32_t pa = __float_as_uint(pz);
-				if (ay) pa = __float_as_uint(py);
-				if (ax) pa = __float_as_uint(px);
-				const uint32_t b = pa & (0u - pa);
-				if (b == 0x00800000u)
-				{
-					miss();                                                         // popped through the root
-					return true;
-				}
-				const uint32_t keep = 0u - b;
-				px = __uint_as_float(__float_as_uint(px) & keep);
-				py = __uint_as_float(__float_as_uint(py) & keep);
-				pz = __uint_as_float(__float_as_uint(pz) & keep);
-				dimf = __uint_as_float(0x3F800000u | b) - 1.0f;                 // b * 2^-23, exact
-				level = __clz(static_cast<int>(b)) - 8;                         // 23 - flo(b)
-				node = stack_n[level - 1];
-				F = stack_f[level - 1];                                         // bit a* (un-XORed) is set there
-				break;
-			}
-
-			// a negative or -inf t is in play: the reference's sequence verbatim, one level at a time
-			if (--level == 0)
-			{
-				miss();
+				hit.voxel = 0;
+				hit.face = 6;
+				hit.t = miss_t;
 				return true;
 			}
-			const uint32_t u = __float_as_uint(F) ^ inv;
-			if (u & 1u) px -= dimf;                                             // back to the parent's corner
-			if (u & 2u) py -= dimf;
-			if (u & 4u) pz -= dimf;
-			dimf += dimf;
-			node = stack_n[level - 1];
-			F = stack_f[level - 1];
+			const uint32_t keep = 0u - b;                                           // drop the position bits of the levels left
+			px = __uint_as_float(__float_as_uint(px) & keep);
+			py = __uint_as_float(__float_as_uint(py) & keep);
+			pz = __uint_as_float(__float_as_uint(pz) & keep);
+			dimf = __uint_as_float(0x3F800000u | b) - 1.0f;                         // b * 2^-23, exact
+			w = st.load(dimf);                                                      // bit a* of its index is set
 		}
 
-		// step to the sibling across the exit plane (exact: the bit is set)
-		if (ax) { px -= dimf; F -= wx; }
-		else if (ay) { py -= dimf; F -= wy; }
-		else { pz -= dimf; F -= wz; }
+		// step to the sibling across the exit plane (:414-419; exact: the bit is set)
+		if (ax) px -= dimf;
+		if (ay) py -= dimf;
+		if (!(ax | ay)) pz -= dimf;
+		w ^= mti;
 		return false;
 	}
+
+	// One round of the reference's PUSH label plus the STEP / POP work that follows an empty slot.  Returns true when
+	// the ray is finished (result in `hit`).
+	template<class STACK>
+	__device__ __forceinline__ bool round(unsigned long long base_biased, float leaf_dimf, float miss_t, const STACK st)
+	{
+		const uint32_t child = load_child(base_biased);
+		return child ? descend(child, leaf_dimf, st) : advance(miss_t, st);
+	}
 };
+
+// LeanWalker's preconditions on top of fast_path_ok: no degenerate axis (coef regular, i.e. below -inf as unsigned bits)
+// and no negative t at the planes through the origin (Ray::t0or; the argument is in LeanWalker's header).
+__device__ __forceinline__ bool lean_path_ok(const Ray& r)
+{
+	const uint32_t ninf = 0xFF800000u;
+	const uint32_t cx = __float_as_uint(r.cx), cy = __float_as_uint(r.cy), cz = __float_as_uint(r.cz);
+	return (max(cx, max(cy, cz)) < ninf) & ((r.t0or & 0x80000000u) == 0u);
+}
 
 template<bool COUNT>
 __device__ __forceinline__ Hit traverse_fast(const uint32_t* __restrict__ nodes_m1, uint32_t root, int depth, float miss_t, const Ray& r, uint32_t* stack)

@@ -3,14 +3,95 @@ frames cut into cyclic tile strips.  The trace itself needs no collective; NCCL 
 as in BASELINE.json's north_star: broadcasting the DAG / its edit deltas from the rank that owns the host table,
 and gathering finished strips where the assembled frame is wanted.
 
-Everything here is backend-agnostic (nccl with CUDA tensors on the GPU box, gloo with CPU tensors in the CPU
-tests): the functions take an `apply` callback instead of touching a device themselves.
+Two layers:
+  * `MultiGpu` -- the library's own communicator (include/ort_b200.h, ort_mg_*): NCCL inside libort_b200.so, strips
+    traced into a ring of slots, sent on a dedicated stream, unpacked at their final rows on the consumer.  This is
+    the product path on GPUs; torch.distributed only carries the 128-byte NCCL id at start-up.
+  * the functions below it -- backend-agnostic helpers (nccl with CUDA tensors, gloo with CPU tensors in the CPU
+    tests) that take an `apply` callback instead of touching a device themselves; `gather_strips` is the simple
+    torch.distributed gather kept as the checker of the library's.
 """
 from __future__ import annotations
 
 import numpy as np
 import torch
 import torch.distributed as dist
+
+
+# ---- the library's communicator ------------------------------------------------------------------------
+
+class MultiGpu:
+    """ort_mg_* (include/ort_b200.h): the communicator of one rank's TraceContext.  The NCCL id travels over the
+    torch.distributed process group that launched the job (any backend); everything after that is the library's."""
+
+    def __init__(self, ctx, rank: int | None = None, world: int | None = None):
+        import ctypes as C
+        from ._lib import check, lib
+        self.L, self.ctx = lib(), ctx
+        self.rank = dist.get_rank() if rank is None else rank
+        self.world = dist.get_world_size() if world is None else world
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if self.world > 1:
+            if self.rank == 0:
+                raw = (C.c_char * 128)()
+                check(self.L.ort_mg_unique_id(raw))
+                idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+            dev = torch.device("cuda", ctx.device) if dist.get_backend() == "nccl" else torch.device("cpu")
+            t = idbuf.to(dev)
+            dist.broadcast(t, src=0)
+            idbuf = t.cpu()
+        self._id = bytes(idbuf.numpy().tobytes())
+        h = C.c_void_p()
+        check(self.L.ort_mg_create(C.byref(h), ctx.h, self.rank, self.world, self._id), ctx.h)
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ort_mg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        from ._lib import check
+        check(rc, self.ctx.h)
+
+    def strip_rows(self, H: int, tile_rows: int = 8, rank: int | None = None) -> int:
+        return self.L.ort_mg_strip_rows(self.rank if rank is None else rank, self.world, H, tile_rows)
+
+    def broadcast_update(self, update, src: int = 0):
+        """update (on src; None elsewhere): (ids | None, nodes8, root, is_full) as HOctree.take_delta() returns it."""
+        if self.rank == src:
+            ids, nodes8, root, is_full = update
+            nodes8 = np.ascontiguousarray(nodes8, np.uint32)
+            ids = None if ids is None else np.ascontiguousarray(ids, np.uint32)
+            n = int(nodes8.shape[0])
+            self._ck(self.L.ort_mg_broadcast_update(self.h, None if ids is None else ids.ctypes.data, nodes8.ctypes.data if n else None, n, int(root), int(bool(is_full)), src))
+        else:
+            self._ck(self.L.ort_mg_broadcast_update(self.h, None, None, 0, 0, 0, src))
+        return self.ctx.node_count
+
+    def trace_frame_gather(self, pos, rot, fov_factor, W, H, tile_rows=8, dst=0, d_vox=None, d_face=None, d_t=None):
+        """Enqueue: trace this rank's strips and gather the frame into dst's device tensors (None elsewhere)."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        rot = np.ascontiguousarray(rot, np.float32)
+        ptr = lambda x: None if x is None else x.data_ptr()
+        self._ck(self.L.ort_mg_trace_frame_gather(self.h, pos.ctypes.data, rot.ctypes.data, float(fov_factor), W, H, tile_rows, dst, ptr(d_vox), ptr(d_face), ptr(d_t)))
+
+    def sync(self):
+        self._ck(self.L.ort_mg_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.ort_mg_stream(self.h)
+
+    @property
+    def wire_bytes(self) -> float:
+        return float(self.L.ort_mg_wire_bytes(self.h))
 
 
 # ---- host placement ------------------------------------------------------------------------------------
@@ -82,7 +163,8 @@ def broadcast_update(update, apply, device="cpu", src: int = 0):
     update (on src; ignored elsewhere): (ids | None, nodes8[n,8], root, is_full) as HOctree.take_delta()
     returns it.  apply(ids_or_None, nodes8, root, is_full) is called on every rank (src included) with
     tensors on `device` -- e.g. ctx.upload_full / ctx.upload_delta with device pointers.
-    One header broadcast + one payload broadcast: [ids[n] | nodes8[n*8]] as uint32 (int32 on the wire)."""
+    One header broadcast + one payload broadcast: [ids[n] padded to 4 words | nodes8[n*8]] as uint32 (int32 on the
+    wire).  ort_upload_delta returns only after its scatter has read the payload, so the tensor may be recycled."""
     rank = dist.get_rank() if dist.is_initialized() else 0
     world = dist.get_world_size() if dist.is_initialized() else 1
     hdr = torch.zeros(3, dtype=torch.int64, device=device)
@@ -93,9 +175,10 @@ def broadcast_update(update, apply, device="cpu", src: int = 0):
     if world > 1:
         dist.broadcast(hdr, src=src)
     n, root, is_full = int(hdr[0]), int(hdr[1]), bool(hdr[2])
-    words = n * 8 + (0 if is_full else n)
+    n_ids = 0 if is_full else (n + 3) // 4 * 4          # the ids section is padded to 16 bytes so that the rows stay 16-byte aligned
+    words = n * 8 + n_ids
     if rank == src:
-        parts = [] if is_full else [np.ascontiguousarray(ids, np.uint32)]
+        parts = [] if is_full else [np.ascontiguousarray(ids, np.uint32), np.zeros(n_ids - n, np.uint32)]
         parts.append(np.ascontiguousarray(nodes8, np.uint32).reshape(-1))
         payload = torch.from_numpy(np.concatenate(parts).view(np.int32)).to(device) if words else torch.zeros(0, dtype=torch.int32, device=device)
     else:
@@ -109,7 +192,7 @@ def broadcast_update(update, apply, device="cpu", src: int = 0):
     if is_full:
         apply(None, payload.view(-1, 8), root, True)
     else:
-        apply(payload[:n], payload[n:].view(-1, 8), root, False)
+        apply(payload[:n], payload[n_ids:].view(-1, 8), root, False)
     return n, is_full
 
 

@@ -41,6 +41,19 @@ def golden():
     return load
 
 
+PRODUCT_VARIANTS = (0, 1, 2, 13)                       # traverse(), FastWalker, persistent lane refill, LeanWalker tiers (default)
+EXPERIMENT_VARIANTS = (3, 4, 5, 6, 7, 12, 14, 15)      # csrc/ort_experiments.cuh, only in libort_b200_exp.so
+
+
+def frame_variants(ort):
+    """The frame-kernel variants the loaded library carries: the product's, plus the experiments when the measurement
+    build is loaded (ORT_B200_EXPERIMENTS=1, see tests/test_experiments.py)."""
+    v = list(PRODUCT_VARIANTS)
+    if b"experiments" in ort.lib().ort_version():
+        v += list(EXPERIMENT_VARIANTS)
+    return tuple(v)
+
+
 def same_bits(a, b):
     a = np.ascontiguousarray(a)
     b = np.ascontiguousarray(b)

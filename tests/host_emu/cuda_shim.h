@@ -56,5 +56,6 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __clz(int x) { return x ? __builtin_clz(static_cast<unsigned>(x)) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+struct uint4 { uint32_t x, y, z, w; };
 using std::min;
 using std::max;

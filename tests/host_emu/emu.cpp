@@ -4,6 +4,7 @@
 // the test into tests/host_emu/_build/; never part of libort_b200.so.
 #include "cuda_shim.h"
 #include "../../octree_ray_tracing_b200/csrc/ort_trace.cuh"
+#include "../../octree_ray_tracing_b200/csrc/ort_trace_experiments.cuh"
 
 #include <cstddef>
 #include <omp.h>
@@ -15,9 +16,11 @@ struct Stats
 	unsigned long long rounds_by_level[ort::kMaxDepth + 2];   // child-slot loads issued with the walker at that level
 	unsigned long long rays, slow_path_rays;                  // slow path: rays outside FastWalker's preconditions
 	unsigned long long oob_loads;                             // loads outside the node array / reciprocal table (cuda_shim.h)
+	unsigned long long lean_rays;                             // walker 13: rays that took LeanWalker (the rest: FastWalker / traverse)
 };
 
-// walker ids follow ort_set_option("variant"): 0 baseline traverse(), 1 FastWalker, 5 TightWalker, 7 PipeWalker
+// walker ids follow ort_set_option("variant"): 0 baseline traverse(), 1 FastWalker, 5 TightWalker, 7 PipeWalker,
+// 13 the round-2 tiers (LeanWalker first), 14 FlatWalker, 15 V4Walker (both on LeanWalker's tiers)
 template<bool COUNT>
 ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, float miss_t, float ox, float oy, float oz, const ort::Ray& ray,
               Stats* st)
@@ -42,6 +45,38 @@ ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, fl
 				break;
 		}
 		return w.hit;
+	}
+	if (walker == 13 || walker == 14 || walker == 15)
+	{
+		// round-2 tiers as in ort::trace_ray: LeanWalker (or an experiment round on its state) where no t can be
+		// negative, FastWalker otherwise
+		if (ort::lean_path_ok(ray))
+		{
+			if (st) ++st->lean_rays;
+			uint32_t lstack[ort::kMaxDepth] = {};
+			const ort::LeanStack<0> ls{ lstack };
+			const unsigned long long base_biased = reinterpret_cast<unsigned long long>(nodes_m1) - 4ull * ort::kMagicBits;
+			const float leaf_dimf = std::ldexp(1.0f, -depth);
+			if (walker == 14)
+			{
+				ort::FlatWalker<COUNT> w;
+				w.start(root, ray);
+				while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
+				return w.hit;
+			}
+			if (walker == 15)
+			{
+				ort::V4Walker<COUNT> w;
+				w.start(root, ray);
+				while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
+				return w.hit;
+			}
+			ort::LeanWalker<COUNT> w;
+			w.start(root, ray);
+			while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
+			return w.hit;
+		}
+		return walk<COUNT>(1, nodes_m1, root, depth, miss_t, ox, oy, oz, ray, nullptr);
 	}
 	if (walker == 5)
 	{
@@ -87,7 +122,7 @@ void set_bounds(const uint32_t* nodes8, size_t n_rows, const uint32_t* rcp_tab, 
 void merge(Stats* dst, const Stats& s)
 {
 	for (int i = 0; i < ort::kMaxDepth + 2; ++i) dst->rounds_by_level[i] += s.rounds_by_level[i];
-	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays; dst->oob_loads += s.oob_loads;
+	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays; dst->oob_loads += s.oob_loads; dst->lean_rays += s.lean_rays;
 }
 
 }  // namespace
@@ -112,7 +147,7 @@ int emu_trace_rays(const uint32_t* nodes8, size_t n_rows, int index_base, int ha
 		{
 			const float* o = o3 + static_cast<size_t>(i) * o_stride;
 			const float* d = d3 + static_cast<size_t>(i) * 3;
-			const ort::Ray r = ort::ray_setup(rt, o[0], o[1], o[2], d[0], d[1], d[2]);
+			const ort::Ray r = ort::ray_setup(rt, o[0], o[1], o[2], d[0], d[1], d[2], (1u << (23 - depth)) - 1u);
 			ort::Hit h;
 			if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
 			else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr)
@@ -157,7 +192,7 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 			{
 				float dx, dy, dz;
 				ort::camera_ray(cam, x, ort::frame_row(fr, r), dx, dy, dz);
-				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz);
+				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, (1u << (23 - depth)) - 1u);
 				ort::Hit h;
 				if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
 				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr)

@@ -17,11 +17,11 @@ SANITIZE = os.environ.get("ORT_EMU_SANITIZE", "") == "1"      # tools/sanitize_h
 SO = os.path.join(HERE, "_build", "libort_emu_san.so" if SANITIZE else "libort_emu.so")
 _lib = None
 
-STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads"]
+STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads", "lean_rays"]
 
 
 def build(force: bool = False) -> str:
-    deps = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h"), os.path.join(CSRC, "ort_trace.cuh")]
+    deps = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h"), os.path.join(CSRC, "ort_trace.cuh"), os.path.join(CSRC, "ort_trace_experiments.cuh")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
     os.makedirs(os.path.dirname(SO), exist_ok=True)

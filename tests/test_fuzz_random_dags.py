@@ -90,7 +90,7 @@ def test_cuda_path_vs_oracle_on_random_dags(ort, oc):
         ctx = ctxs.setdefault(depth, ort.TraceContext(depth))
         ctx.upload_full(nodes8, root)
         want = oc.trace_rays(nodes8, root, depth, o, d, rcp_tab=tab, nthreads=4, want_counts=True)
-        for variant, rays_variant in ((1, 2), (1, 1), (0, 1), (7, 1)):
+        for variant, rays_variant in ((13, 2), (13, 1), (1, 1), (0, 1)):
             ctx.set_option("variant", variant)
             ctx.set_option("rays_variant", rays_variant)
             got = ctx.trace_rays(o, d, want_npush=True)

@@ -250,8 +250,9 @@ def test_depth12_4k_properties(ort, oc, ncpu):
 
 
 def test_kernel_variants_agree(ort, golden):
-    """Baseline walk (variant 0), fast walk (1), persistent lane-refill (2) and the shared-memory staging
-    experiment (3) are the same function."""
+    """Baseline walk (variant 0), round 1's fast walk (1), persistent lane refill (2), the round-2 tiers (13) -- and, in
+    the measurement build, every experiment kernel -- are the same function."""
+    from conftest import frame_variants
     g = golden("d8_tunnels")
     ctx = ort.TraceContext(8)
     ctx.upload_full(g["nodes8"], int(g["root"]))
@@ -259,7 +260,7 @@ def test_kernel_variants_agree(ort, golden):
     pos, rot, fov = g["poseC_pos"], g["poseC_rot"], float(g["poseC_fov"])
     ref = None
     ctx.set_option("smem_levels", 215)                  # variant 3 stages the first 215 nodes (levels 1-4 of this DAG)
-    for variant in (0, 1, 2, 3, 4, 5, 6, 7, 12):
+    for variant in frame_variants(ort):
         ctx.set_option("variant", variant)
         got = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
         part = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=64, tile_rows=8, tile_step=3)
@@ -269,10 +270,10 @@ def test_kernel_variants_agree(ort, golden):
         assert_same_hits(got, ref, f"frame variant {variant}")
         assert np.array_equal(got[3], ref[3]), f"npush differs in variant {variant}"
         assert_same_hits(part, [x.reshape(H, W)[rows].ravel() for x in ref[:3]], f"tiles variant {variant}")
-    ctx.set_option("variant", 1)
     for k in ("rand", "edge"):
         outs = []
-        for rv in (1, 2):
+        for variant, rv in ((0, 1), (1, 1), (13, 1), (13, 2)):
+            ctx.set_option("variant", variant)
             ctx.set_option("rays_variant", rv)
             for lw in ((20,) if rv == 1 else (0, 12, 31)):
                 ctx.set_option("low_water", lw)
@@ -471,7 +472,7 @@ def test_degenerate_rays_and_corner_cameras_vs_oracle(ort, oc, ncpu):
     direction components, origins outside [1,2)^3, on-plane origins and -- found by tests/test_host_emu.py -- a
     coordinate of exactly 1.0f travelled in the positive direction (mirrored to 2.0f, masked position bits 0).
     Explicit-ray kernels (one-shot and persistent) and frame kernels (camera on the cube's corner / faces)."""
-    from conftest import degenerate_rays
+    from conftest import degenerate_rays, frame_variants
     depth = 8
     T = ort.HOctree(19, depth)
     ort.harness.build_terrain(T, tunnels=True)
@@ -482,7 +483,7 @@ def test_degenerate_rays_and_corner_cameras_vs_oracle(ort, oc, ncpu):
     want = oc.trace_rays(nodes8, root, depth, O, D, rcp_tab=tab, nthreads=ncpu, want_counts=True)
     T.sync()
     ctx = T.ctx
-    for variant, rays_variant in ((0, 1), (1, 1), (1, 2), (5, 1), (7, 1)):
+    for variant, rays_variant in ((0, 1), (1, 1), (13, 1), (13, 2)):
         ctx.set_option("variant", variant)
         ctx.set_option("rays_variant", rays_variant)
         got = ctx.trace_rays(O, D, want_npush=True)
@@ -494,9 +495,9 @@ def test_degenerate_rays_and_corner_cameras_vs_oracle(ort, oc, ncpu):
         rot, fov = oc.camera_coeffs(yaw, pitch)
         d = oc.gen_rays(rot, fov, W, H)
         wv, wf, wt, wn, _ = oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=ncpu, want_counts=True)
-        for variant in (0, 1, 2, 5, 7, 12):
+        for variant in frame_variants(ort):
             ctx.set_option("variant", variant)
             got = ctx.trace_frame(np.array(pos, np.float32), rot, fov, W, H, want_npush=True)
             assert_same_hits(got, (wv, wf, wt), f"camera at {pos}, variant {variant}")
             assert np.array_equal(got[3], wn), f"camera at {pos}, variant {variant}: PUSH counts"
-    ctx.set_option("variant", 1)
+    ctx.set_option("variant", 13)

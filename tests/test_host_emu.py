@@ -15,7 +15,7 @@ from conftest import assert_same_hits, degenerate_rays
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
 
-WALKERS = (0, 1, 5, 7)
+WALKERS = (0, 1, 5, 7, 13, 14, 15)     # ort_set_option("variant") ids: traverse(), FastWalker, TightWalker, PipeWalker, LeanWalker tiers, FlatWalker, V4Walker
 POSES = {"A": ((1.5, 1.5, 1.5), 0.0, 0.0), "B": ((1.5, 1.5, 1.5), 0.7, -0.6), "C": ((1.1, 1.1, 1.4), 0.785, -0.3)}
 
 
@@ -195,6 +195,47 @@ def test_device_walkers_at_extreme_depths(emu, ort, oc, depth, log2cap):
         got = emu.trace_rays(nodes8, root, depth, o, d, walker=walker, want_npush=True)
         assert_same_hits(got, want, f"depth {depth}, walker {walker}")
         assert np.array_equal(got[3], want[3]), f"depth {depth}, walker {walker}: PUSH counts"
+
+
+@pytest.mark.parametrize("depth,log2cap", [(12, 18), (16, 18)])
+def test_lean_tier_split_with_origins_on_the_finest_grid(emu, ort, oc, depth, log2cap):
+    """LeanWalker drops FastWalker's negative-t branch; the tier test (ort::lean_path_ok) must send every ray that can
+    see a negative t to FastWalker.  A negative t needs the origin ON a cell plane of the finest level with a product
+    o * coef that does not fit 24 bits (13+ significant origin bits x the 12-bit RCPPS result), i.e. depth >= 12: origins
+    are snapped to the depth's grid (and, for some, to coarser grids), per axis and for all axes.  Both tiers must
+    be populated and every ray must equal the oracle bit for bit, PUSH counts included."""
+    rs = np.random.RandomState(7 + depth)
+    dim = 1 << depth
+    T = ort.HOctree(log2cap, depth, device=None)
+    n = 3000
+    pts = rs.randint(0, dim, (n, 3))
+    pts[: n // 2] = dim // 2 + rs.randint(-60, 60, (n // 2, 3))
+    T.set_many(np.concatenate([pts, rs.randint(1, 5, (n, 1))], 1).astype(np.uint32))
+    nodes8, root, _ = T.flatten()
+    m = 40000
+    o = rs.uniform(1.001, 1.999, (m, 3))
+    snap = rs.randint(0, 4, (m, 3))                          # per axis: 0 free, 1 finest grid, 2 a grid 3 levels up, 3 finest grid
+    for k, q in ((1, dim), (2, dim >> 3), (3, dim)):
+        sel = snap == k
+        o[sel] = 1.0 + np.round((o[sel] - 1.0) * q) / q
+    o = o.astype(np.float32)
+    target = (1.0 + (pts[rs.randint(0, n, m)] + rs.uniform(0, 1, (m, 3))) / dim).astype(np.float32)
+    d = target - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d = d.astype(np.float32)
+    tab = emu.default_rcp_table()
+    want = oc.trace_rays(nodes8, root, depth, o, d, rcp_tab=tab, nthreads=4, want_counts=True)
+    assert (want[0] != 0).sum() > m // 20
+    got = emu.trace_rays(nodes8, root, depth, o, d, walker=13, want_npush=True, want_stats=True)
+    assert_same_hits(got, want, f"depth {depth}, tiered walk")
+    assert np.array_equal(got[3], want[3]), f"depth {depth}: PUSH counts"
+    st = got[4]
+    assert 0 < st["lean_rays"] < st["rays"] - st["slow_path_rays"], "both tiers must have takers"
+    # off-grid origins do not need the FastWalker tier (apart from the odd ray with a degenerate direction component or an origin the shift moved onto the grid)
+    o2 = (o + np.float32(2.0 ** -22)).astype(np.float32)
+    got2 = emu.trace_rays(nodes8, root, depth, o2, d, walker=13, want_stats=True)
+    assert got2[3]["lean_rays"] >= 0.99 * (got2[3]["rays"] - got2[3]["slow_path_rays"])
+    assert_same_hits(got2, oc.trace_rays(nodes8, root, depth, o2, d, rcp_tab=tab, nthreads=4), f"depth {depth}, off-grid origins")
 
 
 def test_device_camera_rays_equal_the_oracle_rays(emu, oc):
