@@ -11,11 +11,14 @@ fixed, no data-path collective).
     python bench.py --impl reference [...]                         # the reference's own CPU sse_trace
 
 One JSON line on stdout (rank 0).  `value`: device-resident throughput (outputs stay in HBM; L2 is
-flushed before every frame).  `e2e`: the same frames through the public host-buffer entry point
-(ort_trace_frame: camera in, voxel/face/t out to pinned host memory, copies inside the timed region).
-`roofline`: algorithmic bytes (32 B per child-slot load + 9 B of output per ray) over the
-measured kernel time against the measured HBM copy peak.  `cpu_baseline`: the reference's CPU trace
-(oracle/_ref when present, else the oracle port) on the host cores, same rays.
+flushed before every step).  `parity`: the timed frames against the CPU checker, in the same run.
+`e2e`: the same frames through the public host-buffer entry point (ort_trace_frame: camera in, voxel/face/t out to
+pinned host memory, copies inside the timed region), next to what the host can ingest from all ranks at once.
+`roofline`: the bound that binds -- warp-instruction issue -- with the instruction count from the committed ncu
+capture (used only if it was taken from the kernel sources this run uses), the SIMT picture measured in-run, and the
+memory-side figures (SURVEY.md 8d's byte model as a rate, compulsory and measured HBM / L2 traffic as fractions).
+`with_gather` (N > 1): frames assembled on their consumer by the library's NCCL gather.  `cpu_baseline`: the
+reference's CPU trace (oracle/_ref when present, else the oracle port) on the host cores, all rays of a step.
 """
 from __future__ import annotations
 
@@ -54,41 +57,22 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the frame kernel, from the last committed
-    `ncu --set full` capture (profiles/traffic.json, written by tools/ncu_summary.py --traffic)."""
+def ncu_capture():
+    """The committed `ncu --set full` capture of the step's three frame launches (profiles/traffic.json, written by
+    tools/ncu_summary.py --traffic) -- but only if it was taken from the kernel sources this run uses: the file carries
+    the hash of those sources, and on a mismatch every number that would come from it is reported as null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p))["dram_bytes_per_launch"]
+        cap = json.load(open(p))
     except Exception:
-        return None
-
-
-def issue_roofline(ctx, clocks, ms_per_step, world):
-    """The bound that actually binds: warp instructions issued per second against the chip's issue peak
-    (SMs x 4 schedulers x SM clock), instructions per step from the committed ncu capture."""
-    inst = warp_instructions_per_step()
-    mhz = (clocks or {}).get("sm_mhz")
-    if not inst or not mhz:
-        return None
-    import torch
-    sms = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
-    peak = sms * 4 * mhz * 1e6
-    achieved = inst / (ms_per_step * 1e-3)          # each rank issues one GPU's share: 3 full frames' worth per step
-    return {"achieved": round(achieved / 1e9, 1), "peak": round(peak / 1e9, 1), "unit": "G warp-instr/s", "frac": round(achieved / peak, 4),
-            "warp_instructions_per_step_per_gpu": inst, "sms": sms,
-            "source": "smsp__inst_executed.sum of the three frame launches in profiles/traffic.json (ncu --set full)"}
-
-
-def warp_instructions_per_step():
-    """smsp__inst_executed.sum of the step's frame launches (poses A, B, C) from the same ncu capture -- a property of
-    the kernel build and the scene, not of the run."""
-    p = os.path.join(ROOT, "profiles", "traffic.json")
-    try:
-        v = json.load(open(p))["warp_instructions_per_launch"]
-        return int(sum(v)) if len(v) == len(POSE_NAMES) else None
-    except Exception:
-        return None
+        return None, "profiles/traffic.json missing"
+    from octree_ray_tracing_b200.build import kernel_source_hash
+    have, want = cap.get("kernel_source_sha16"), kernel_source_hash()
+    if have != want:
+        return None, f"profiles/traffic.json is a capture of other kernel sources (sha16 {have}, running {want}): not used"
+    if len(cap.get("warp_instructions_per_launch", [])) != len(POSE_NAMES):
+        return None, "profiles/traffic.json does not hold the three frame launches of a step"
+    return cap, f"profiles/traffic.json (ncu --set full, kernel sources sha16 {want})"
 
 
 class ClockSampler(threading.Thread):
@@ -150,7 +134,7 @@ def run_product(args):
     import torch
     import torch.distributed as dist
     import octree_ray_tracing_b200 as ort
-    from octree_ray_tracing_b200 import harness
+    from octree_ray_tracing_b200 import harness, multi_gpu
 
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
@@ -162,24 +146,25 @@ def run_product(args):
     torch.cuda.set_device(local_rank)
     numa_bound = False
     if world > 1 and not args.no_numa:
-        from octree_ray_tracing_b200 import multi_gpu as _mg
-        numa_bound = _mg.bind_to_gpu_numa(physical_gpu_index(local_rank))
+        numa_bound = multi_gpu.bind_to_gpu_numa(physical_gpu_index(local_rank))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    from octree_ray_tracing_b200 import multi_gpu
-
-    # rank 0 owns the host table: it builds the DAG and broadcasts the flattened nodes (NCCL); every rank
-    # uploads its replica from the received device buffer.
+    # rank 0 owns the host table: it builds the DAG; the library's communicator (ort_mg_*, NCCL inside libort_b200.so)
+    # broadcasts the flattened nodes and every rank uploads its replica from the received device buffer.
     t0 = time.time()
     ctx = ort.TraceContext(DEPTH, device=local_rank, node_capacity=1 << 21)
+    mg = multi_gpu.MultiGpu(ctx, rank, world) if world > 1 else None
     tree = None
-    update = None
     if rank == 0:
         tree = ort.HOctree(LOG2CAP, DEPTH, device=None)
         harness.build_terrain(tree)
-        update = tree.take_delta()
-    n_up, _ = multi_gpu.broadcast_update(update, multi_gpu.context_applier(ctx), device=torch.device("cuda", local_rank))
+    if mg is not None:
+        n_up = mg.broadcast_update(tree.take_delta() if rank == 0 else None)
+    else:
+        ids, nodes8_up, root_up, _full = tree.take_delta()
+        ctx.upload_full(nodes8_up, root_up)
+        n_up = ctx.node_count
     ctx.sync()
     if args.variant is not None:
         ctx.set_option("variant", args.variant)
@@ -212,7 +197,7 @@ def run_product(args):
         if world != 1 or not args.quick:
             raise SystemExit("bench.py: --as-rank is a single-GPU measurement aid and needs --quick")
         prank, pworld = (int(x) for x in args.as_rank.split("/"))
-    y0, rows, _frame_rows = multi_gpu.strip_rows(prank, pworld, H, TILE_ROWS)
+    y0, rows, frame_rows = multi_gpu.strip_rows(prank, pworld, H, TILE_ROWS)
     n_local = rows * W
     frames_per_step = len(cams) * pworld
     rays_per_step_total = frames_per_step * W * H          # all ranks together
@@ -220,7 +205,7 @@ def run_product(args):
 
     own = torch.cuda.ExternalStream(ctx.stream, device=local_rank)
     # frames in flight: small strips need more of them to hide launch tails, but too many concurrent launches dilute
-    # the L1 locality of each (measured: 2 GPUs 3/4/6 streams -> 28.2/28.2/26.5, 4 GPUs 4/6/8 -> 54.0/52.1/53.2, 8 GPUs 5/8/12 -> 101.8/104.5/102.3 Grays/s)
+    # the L1 locality of each (measured in round 1: 2 GPUs 3/4/6 streams -> 28.2/28.2/26.5, 4 GPUs 4/6/8 -> 54.0/52.1/53.2, 8 GPUs 5/8/12 -> 101.8/104.5/102.3 Grays/s)
     NS = args.streams or (3 if pworld == 1 else (4 if pworld <= 4 else 8))
     streams = [torch.cuda.Stream(device=local_rank) for _ in range(NS)]
     outs = [(torch.empty(n_local, dtype=torch.int32, device="cuda"), torch.empty(n_local, dtype=torch.uint8, device="cuda"),
@@ -233,15 +218,20 @@ def run_product(args):
     def frame(cam, out=outs[0], npush=None):
         ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, y0, rows, TILE_ROWS, pworld, out[0], out[1], out[2], npush)
 
-    # algorithmic bytes: PUSH counts from an (untimed) counting pass -- identical to the oracle's counts (tests)
+    # algorithmic bytes: PUSH counts from an (untimed) counting pass -- identical to the oracle's counts (tests).  The same
+    # pass yields the SIMT picture of the round loop: a warp (8 x 4 pixel tile) runs as many rounds as its longest ray.
     pushes = 0
     hits = 0
+    warp_rounds = 0
     with torch.cuda.stream(own):
         for cam in cams:
             frame(cam, outs[0], dn)
             own.synchronize()
-            pushes += int((dn.to(torch.int64) & 0xFFFF).sum().item())
+            cnt = (dn.to(torch.int32) & 0xFFFF).view(rows, W)
+            pushes += int(cnt.sum().item())
             hits += int((dv != 0).sum().item())
+            if rows % 4 == 0 and W % 8 == 0:
+                warp_rounds += int(cnt.view(rows // 4, 4, W // 8, 8).amax(dim=(1, 3)).sum().item())
     pushes_per_step_local = pushes * pworld
     bytes_per_step_local = 32 * pushes_per_step_local + 9 * rays_per_step_local
     step_cams = [cam for _rep in range(pworld) for cam in cams]
@@ -335,6 +325,13 @@ def run_product(args):
     launches = ctx.launch_count - launches0
     kernel_ms = sum(a.elapsed_time(b) for a, b in evs)
 
+    # Parity of the TIMED frames: the output buffers still hold the last frames the timed loop wrote -- buffer j the frame
+    # k = the largest index with k % NS == j, i.e. pose k % 3 of the step.  Every 8th row of each (this rank's strip rows)
+    # goes to the CPU checker: the reference's own sse_trace (oracle/_ref) where it travelled, else the oracle port.
+    parity = None
+    if args.launch == "streams" and not args.no_cpu:
+        parity = parity_of_timed_frames(ort, tree, n_up, ctx, mg, world, rank, outs, NS, len(step_cams), cams, frame_rows, torch, dist)
+
     # per-launch view of the same work: serialised launches, each timed alone
     serial_launches(1, True)
     barrier()
@@ -358,7 +355,7 @@ def run_product(args):
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
                           "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]],
-                          "tile_rows": TILE_ROWS, "streams": NS,
+                          "tile_rows": TILE_ROWS, "streams": NS, "parity": parity,
                           "as_rank": (f"{prank}/{pworld}: value = what {pworld} GPUs would total if every rank ran like this one" if args.as_rank else None)})
         return None
 
@@ -410,23 +407,66 @@ def run_product(args):
     barrier()
     e2e_sync_s = time.perf_counter() - e0
 
-    # strips -> rank 0 over NCCL (what a harness that wants the assembled frame pays on top of `value`)
-    gather = None
-    if world > 1:
-        def gather_step():
-            with torch.cuda.stream(own):
-                for cam in step_cams:
-                    frame(cam)
-                    for buf in (dv, dt, df):
-                        multi_gpu.gather_strips(buf, world, H, W, TILE_ROWS, dst=0)
-        gather_step()
-        barrier()
-        g0 = time.perf_counter()
-        g_steps = max(1, min(args.steps, 5))
-        for _ in range(g_steps):
-            gather_step()
-        barrier()
-        gather = (time.perf_counter() - g0) / g_steps
+    # What the host can take from all GPUs of the box AT ONCE: every rank copies a 256 MiB device buffer to pinned host
+    # memory, all ranks together, timed on the device.  The e2e figure cannot exceed (sum over ranks) / 9 B per ray.
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    probe_h.copy_(probe_d, non_blocking=True)
+    barrier()
+    pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pa.record()
+    for _ in range(4):
+        probe_h.copy_(probe_d, non_blocking=True)
+    pb.record()
+    barrier()
+    d2h_gbs_local = 4 * (256 << 20) / (pa.elapsed_time(pb) * 1e-3) / 1e9
+    del probe_d, probe_h
+
+    # Frames assembled on their consumer (ort_mg_trace_frame_gather: strips traced into a ring of slots, ONE NCCL message
+    # per rank and frame on the communicator's stream, unpacked at their final rows on the consumer).  Two consumer
+    # layouts: round robin (frame k of the step is consumed on rank k mod N -- the weak-scaling shape: N times the frames,
+    # N consumers) and everything on rank 0 (one consumer for N times the frames: bound by one GPU's NVLink ingest).
+    gather = {}
+    if mg is not None:
+        fv = torch.empty(W * H, dtype=torch.int32, device="cuda")
+        ff = torch.empty(W * H, dtype=torch.uint8, device="cuda")
+        ft = torch.empty(W * H, dtype=torch.float32, device="cuda")
+
+        def gather_step(mode):
+            for k, cam in enumerate(step_cams):
+                dst = k % world if mode == "round_robin" else 0
+                mine = dst == rank
+                mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=dst, d_vox=fv if mine else None, d_face=ff if mine else None, d_t=ft if mine else None)
+
+        g_steps = max(1, min(args.steps, 10))
+        for mode in ("round_robin", "rank0"):
+            gather_step(mode)
+            mg.sync()
+            barrier()
+            w0 = mg.wire_bytes
+            g0 = time.perf_counter()
+            for _ in range(g_steps):
+                gather_step(mode)
+            mg.sync()
+            barrier()
+            gather[mode] = ((time.perf_counter() - g0) / g_steps, (mg.wire_bytes - w0) / g_steps)
+        # one frame at a time, nothing in flight: the latency of "trace my strips + gather" for a single frame
+        lat = []
+        for cam in cams:
+            barrier()
+            g0 = time.perf_counter()
+            mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=0, d_vox=fv if rank == 0 else None, d_face=ff if rank == 0 else None, d_t=ft if rank == 0 else None)
+            mg.sync()
+            barrier()
+            lat.append(time.perf_counter() - g0)
+        gather["latency"] = lat
+        # the last assembled frame (pose C, consumer rank 0) against the single-GPU trace of the same frame on rank 0
+        if rank == 0:
+            full = (torch.empty(W * H, dtype=torch.int32, device="cuda"), torch.empty(W * H, dtype=torch.uint8, device="cuda"), torch.empty(W * H, dtype=torch.float32, device="cuda"))
+            cam = cams[-1]
+            ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, 0, H, 1, 1, full[0], full[1], full[2], None)
+            ctx.sync()
+            gather["assembled_equals_single_gpu"] = bool(torch.equal(full[0], fv) and torch.equal(full[1], ff) and torch.equal(full[2].view(torch.int32), ft.view(torch.int32)))
 
     # shaded frames (the pixels update_image draws): 4 B per ray cross PCIe instead of 9
     cols, _ = harness.parse_voxels(harness.DEMO_VOXELS)
@@ -454,27 +494,82 @@ def run_product(args):
     gather_hbm = ctx.measure_gather_peak(4 << 30) if rank == 0 else 0.0
 
     # max over ranks
+    g_rr, g_r0 = gather.get("round_robin", (0.0, 0.0)), gather.get("rank0", (0.0, 0.0))
+    g_lat = max(gather.get("latency", [0.0]))
+    d2h_sum = d2h_gbs_local
     if world > 1:
-        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, gather, rgba_s, e2e_sync_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms, warm_ms, e2e_s, wall, gather, rgba_s, e2e_sync_s = (float(x) for x in tt.tolist())
-        cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local], dtype=torch.float64, device="cuda")
+        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms = (float(x) for x in tt.tolist())
+        cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local, d2h_gbs_local, g_rr[1], g_r0[1]], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
         pushes_per_ray_all = float(cnt[2].item()) / rays_per_step_total
+        d2h_sum = float(cnt[3].item())
+        wire_rr, wire_r0 = float(cnt[4].item()) / 2, float(cnt[5].item()) / 2           # every message is counted by its sender and its receiver
+        wmax = torch.tensor([g_r0[1]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(wmax, op=dist.ReduceOp.MAX)
+        ingest_r0 = float(wmax.item())                                                  # the consumer's share (rank 0 receives everything)
     else:
         launches_all = launches
         pushes_per_ray_all = pushes_per_step_local / rays_per_step_local
+        g_rr_s = g_r0_s = 0.0
+        wire_rr = wire_r0 = ingest_r0 = 0.0
 
     result = None
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_per_step = kernel_ms / args.steps
-        value = rays_per_step_total / (ms_per_step * 1e-3) / 1e6
+        value_trace = rays_per_step_total / (ms_per_step * 1e-3) / 1e6
         n_launch_local = args.steps * frames_per_step
         avg_launch_s = kernel_ms * 1e-3 / n_launch_local      # effective: launches of a step overlap
-        achieved = (bytes_per_step_local / frames_per_step) / avg_launch_s / 1e9
+        algorithmic_rate = (bytes_per_step_local / frames_per_step) / avg_launch_s / 1e9
         e2e_val = rays_per_step_total * e2e_steps / e2e_s / 1e6
+        cap, cap_src = ncu_capture()
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        mhz = (clocks or {}).get("sm_mhz")
+        issue_peak = sms * 4 * mhz * 1e6 if mhz else None
+        inst_per_step = int(sum(cap["warp_instructions_per_launch"])) if cap else None       # one GPU's share of a step = 3 full frames' worth
+        issue_achieved = inst_per_step / (ms_per_step * 1e-3) if inst_per_step else None
+        # compulsory HBM traffic of a launch: every output byte once + the DAG once (it does not fit L1, it does fit L2)
+        compulsory = 9 * n_local + int(n_up) * 32
+        roofline = {
+            "bound": "issue",
+            "achieved": round(issue_achieved / 1e9, 1) if issue_achieved else None,
+            "peak": round(issue_peak / 1e9, 1) if issue_peak else None,
+            "unit": "G warp-instr/s",
+            "frac": round(issue_achieved / issue_peak, 4) if issue_achieved and issue_peak else None,
+            "traffic": cap["dram_bytes_per_launch"] if cap else None,
+            "kernel": "ort::trace_frame_kernel<13,false> (LeanWalker tiers)" if args.variant in (None, 13) else f"variant {args.variant}",
+            "peak_source": f"{sms} SMs x 4 schedulers x {mhz} MHz (SM clock sampled through NVML during the timed region)",
+            "warp_instructions_per_step_per_gpu": inst_per_step,
+            "counters_source": cap_src,
+            "avg_launch_ms": round(avg_launch_s * 1e3, 4),
+            "why_issue": "the DAG is cache resident (ncu: L1 hit ~90 %, DRAM traffic ~1 % of the algorithmic bytes, DRAM and L2 throughput a few % of peak) and every scheduler has ~6 eligible "
+                         "warps per cycle: the kernel is bound by warp-instruction issue, so that is the roofline it is held against; the memory-side figures are listed under `memory`",
+            "simt": {"lane_rounds_per_ray": round(pushes / (len(cams) * n_local), 3),
+                     "warp_rounds_per_warp": round(warp_rounds / (len(cams) * n_local / 32), 3) if warp_rounds else None,
+                     "lanes_busy_per_warp_round": round(pushes / warp_rounds, 2) if warp_rounds else None,
+                     "active_threads_per_warp_instruction_ncu": cap.get("active_threads_per_warp_instruction") if cap else None,
+                     "note": "measured in this run from per-ray PUSH counts (untimed counting pass): a warp = an 8x4 pixel tile runs as many rounds as its longest ray"},
+            "memory": {
+                "algorithmic_bytes_per_launch": int(bytes_per_step_local / frames_per_step),
+                "algorithmic_rate_gbs": round(algorithmic_rate, 1),
+                "algorithmic_note": "SURVEY 8d's byte model: 32 B per child-slot load (PUSH) + 9 B of output per ray, over the measured launch time.  ~90 % of those loads are L1 hits, "
+                                    "so this rate is NOT bytes that left the SM and is not a fraction of anything",
+                "hbm_peak_gbs": peak, "hbm_peak_source": peak_src,
+                "compulsory_bytes_per_launch": compulsory,
+                "compulsory_hbm_frac": round(compulsory / avg_launch_s / 1e9 / peak, 4),
+                "dram_bytes_per_launch_ncu": cap["dram_bytes_per_launch"] if cap else None,
+                "dram_hbm_frac_ncu": round(cap["dram_bytes_per_launch"] / avg_launch_s / 1e9 / peak, 4) if cap else None,
+                "l2_bytes_per_launch_ncu": int(np.mean(cap["l2_sectors_per_launch"]) * 32) if cap and cap.get("l2_sectors_per_launch") else None,
+                "l2_sector_gather_peak_gbs": round(gather_l2, 1), "hbm_sector_gather_peak_gbs": round(gather_hbm, 1),
+                "l2_gather_frac_ncu": round(float(np.mean(cap["l2_sectors_per_launch"])) * 32 / avg_launch_s / 1e9 / gather_l2, 4) if cap and cap.get("l2_sectors_per_launch") and gather_l2 else None,
+                "how": "ort_measure_gather_peak: independent random 4-B loads, one 32-B sector each, over a buffer of the DAG's size (L2-resident) / 4 GiB (HBM-resident); "
+                       "ncu figures from the capture named in counters_source",
+            },
+        }
+        value = value_trace
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -493,6 +588,7 @@ def run_product(args):
                 "hit_fraction": round(hits / (len(cams) * n_local), 4),
                 "timing": "sum of CUDA-event intervals around each step (start after the flush, end after all streams joined), max over ranks",
             },
+            "parity": parity,
             "serial": {"value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s",
                        "note": "same frames on ONE stream, one event interval per launch, L2 flushed before every launch",
                        "per_launch_ms": [round(x, 4) for x in serial_per_launch[-len(step_cams):]]},
@@ -504,38 +600,91 @@ def run_product(args):
                            "enqueued back to back and ort_sync() ends the step; chunk kernels on 3 streams, D2H on the copy engine",
                     "per_call_sync": {"value": round(rays_per_step_total * e2e_steps / e2e_sync_s / 1e6, 2), "unit": "Mrays/s",
                                       "note": "same frames, every ort_trace_frame call returns with its results on the host"},
-                    "pcie_floor_note": "9 B/ray over PCIe Gen5 x16 (56.9 GB/s D2H measured on these boxes) caps this path at 6.3 Grays/s per GPU",
+                    "host_ingest_peak_gbs": round(d2h_sum, 1),
+                    "host_ingest_note": f"measured in this run: all {world} rank(s) copy 256 MiB device -> pinned host at the same time (sum over ranks); "
+                                        f"at 9 B per ray this caps e2e at {d2h_sum / 9 * 1e3:.0f} Mrays/s on this box",
+                    "frac_of_host_ingest": round(e2e_val * 9 / 1e3 / d2h_sum, 4) if d2h_sum else None,
                     "hits_last_frame": e2e_check},
             "e2e_rgba": {"value": round(rays_per_step_total * e2e_steps / rgba_s / 1e6, 2), "unit": "Mrays/s",
                          "d2h_bytes_per_step": frames_per_step * n_local * 4,
                          "api": "ort_trace_frame_rgba: trace_pixel's colour lookup fused into the kernel, one uint32 pixel per ray to pinned host memory"},
             "gpu_launches": launches_all,
-            "roofline": {
-                "bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4),
-                "traffic": traffic_per_launch(), "peak_source": peak_src, "kernel": "ort::trace_frame_kernel<1,false,false>",
-                "algorithmic_bytes_per_launch": int(bytes_per_step_local / frames_per_step),
-                "avg_launch_ms": round(avg_launch_s * 1e3, 4),
-                "sector_gather_peak": {"l2_resident_gbs": round(gather_l2, 1), "hbm_resident_gbs": round(gather_hbm, 1),
-                                       "frac_of_l2_resident": round(achieved / gather_l2, 4) if gather_l2 else None,
-                                       "how": "ort_measure_gather_peak: independent random 4-B loads, one 32-B sector each, buffer = DAG size / 4 GiB"},
-                "note": "algorithmic bytes = 32 B per child-slot load (PUSH) + 9 B output per ray (SURVEY 8d). The 44 MiB DAG is cache resident "
-                        "(ncu: L1 hit 93 %, DRAM traffic ~1 % of the algorithmic bytes), so frac > 1 against the HBM copy peak is expected; "
-                        "the kernel is bound by instruction issue (ncu: issue slots 83 % busy), see DESIGN.md section 4",
-                "issue": issue_roofline(ctx, clocks, ms_per_step, world),
-            },
+            "roofline": roofline,
             "clocks": clocks,
             "wall_s_timed_region": round(wall, 3),
         }
-        if gather is not None:
-            result["with_gather"] = {"value": round(rays_per_step_total / gather / 1e6, 2), "unit": "Mrays/s",
-                                     "note": "trace + NCCL gather of every frame's strips (voxel, t, face) to rank 0, wall clock, max over ranks"}
+        if mg is not None:
+            result["with_gather"] = {
+                "value": round(rays_per_step_total / g_rr_s / 1e6, 2), "unit": "Mrays/s",
+                "frac_of_value": round(rays_per_step_total / g_rr_s / 1e6 / value_trace, 4),
+                "consumers": "round robin: frame k of the step is assembled on rank k mod N (N times the frames, N consumers)",
+                "wire_bytes_per_step": int(wire_rr), "wire_gbs_aggregate": round(wire_rr / g_rr_s / 1e9, 1),
+                "api": "ort_mg_trace_frame_gather (NCCL inside libort_b200.so): strips traced into a ring of 3 slots on the trace stream, one ncclSend per rank and frame on the "
+                       "communicator's stream, unpack kernel writes final rows on the consumer; wall clock over whole steps, max over ranks",
+                "rank0_only": {"value": round(rays_per_step_total / g_r0_s / 1e6, 2), "unit": "Mrays/s",
+                               "note": "every frame assembled on rank 0: one GPU's NVLink ingest carries (N-1)/N of ALL frames",
+                               "rank0_ingest_bytes_per_step": int(ingest_r0), "rank0_ingest_gbs": round(ingest_r0 / g_r0_s / 1e9, 1)},
+                "strong_scaling_single_frame": {"latency_ms": round(g_lat * 1e3, 3), "value": round(W * H / g_lat / 1e6, 2), "unit": "Mrays/s",
+                                                "note": "ONE 4K frame traced by N GPUs and assembled on rank 0, nothing else in flight (worst pose), wall clock"},
+                "assembled_equals_single_gpu": gather.get("assembled_equals_single_gpu"),
+            }
+            result["no_gather"] = {"value": round(value_trace, 2), "unit": "Mrays/s", "note": "= value: strips stay on the GPU that traced them"}
         if world == 1 and not args.no_cpu:
-            result["cpu_baseline"] = cpu_baseline(tree, sample_tiles=4)
+            result["cpu_baseline"] = cpu_baseline(tree)
         emit(result)
+    if mg is not None:
+        mg.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return result
+
+
+def parity_of_timed_frames(ort, tree, n_nodes, ctx, mg, world, rank, outs, NS, n_frames, cams, frame_rows, torch, dist):
+    """Compare what the timed loop left in its output buffers with the CPU checker (every rank its own strip rows; the
+    counts are summed over ranks).  The DAG reaches the other ranks' checkers as plain data (torch broadcast)."""
+    import numpy as _np
+    from oracle import oracle as oc
+    if world > 1:
+        meta = torch.zeros(1, dtype=torch.int64, device="cuda")
+        nodes8 = root = None
+        if rank == 0:
+            nodes8, root, _ = tree.flatten()
+            meta[0] = root
+        dist.broadcast(meta, src=0)
+        nn = torch.from_numpy(nodes8.view(_np.int32)).cuda() if rank == 0 else torch.empty((int(n_nodes), 8), dtype=torch.int32, device="cuda")
+        dist.broadcast(nn, src=0)
+        nodes8, root = nn.cpu().numpy().view(_np.uint32), int(meta[0])
+        del nn
+    else:
+        nodes8, root, _ = tree.flatten()
+    kind, fn = cpu_tracer(nodes8, root)
+    cores = os.cpu_count() or 1
+    tot = {"rays": 0, "voxel_mismatch": 0, "face_mismatch": 0, "t_bitwise_mismatch": 0}
+    poses_seen = set()
+    for j in range(min(NS, n_frames)):
+        k = max(kk for kk in range(n_frames) if kk % NS == j)
+        cam = cams[k % len(cams)]
+        poses_seen.add(POSE_NAMES[k % len(cams)])
+        local = _np.arange(3, len(frame_rows), 8)                          # every 8th row of this rank's strip
+        sel = torch.from_numpy((local[:, None] * W + _np.arange(W)[None, :]).ravel()).cuda()
+        gv = outs[j][0][sel].cpu().numpy().view(_np.uint32)
+        gf = outs[j][1][sel].cpu().numpy()
+        gt = outs[j][2][sel].cpu().numpy().view(_np.uint32)
+        d = _np.concatenate([oc.gen_rays(cam[1], cam[2], W, H, int(frame_rows[r]), int(frame_rows[r]) + 1) for r in local])
+        wv, wf, wt = fn(cam[0], d, cores)
+        tot["rays"] += int(gv.size)
+        tot["voxel_mismatch"] += int((gv != wv).sum())
+        tot["face_mismatch"] += int((gf != wf).sum())
+        tot["t_bitwise_mismatch"] += int((gt != wt.view(_np.uint32)).sum())
+    if world > 1:
+        c = torch.tensor([tot[k] for k in ("rays", "voxel_mismatch", "face_mismatch", "t_bitwise_mismatch")], dtype=torch.int64, device="cuda")
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        tot = dict(zip(("rays", "voxel_mismatch", "face_mismatch", "t_bitwise_mismatch"), (int(x) for x in c.tolist())))
+    tot["poses"] = sorted(poses_seen)
+    tot["checker"] = f"{kind}: " + ("the reference's own sse_trace (oracle/_ref)" if kind == "reference" else "oracle port (oracle/och_oracle.c)")
+    tot["what"] = "the frames the TIMED loop left in its output buffers, every 8th row of each rank's strip, bitwise (voxel, face, t)"
+    return tot
 
 
 # ------------------------------------------------------------------------------------------------
@@ -565,23 +714,30 @@ def sample_rays(sample_tiles: int):
     return out
 
 
-def cpu_baseline(tree, sample_tiles: int):
+CPU_LAYOUT = ("compact level-ordered node array (the product's flatten) imported into the reference's nodes[]: 44 MiB contiguous instead of "
+              "1.44 M nodes hashed over a 512 MiB table -- this favours the CPU arm; the traced function is the reference's own sse_trace")
+
+
+def cpu_baseline(tree):
+    """The reference's CPU trace over the WHOLE ray set of a step (3 poses x 3840x2160), all host cores."""
     nodes8, root, _ = tree.flatten()
     kind, fn = cpu_tracer(nodes8, root)
     cores = os.cpu_count() or 1
-    rays = sample_rays(sample_tiles)
+    rays = sample_rays(1)
     n = sum(d.shape[0] for _, d in rays)
     fn(rays[0][0], rays[0][1][:100000], cores)          # warm-up
+    reps = 3
     t0 = time.perf_counter()
-    for o, d in rays:
-        fn(o, d, cores)
-    dt = time.perf_counter() - t0
+    for _ in range(reps):
+        for o, d in rays:
+            fn(o, d, cores)
+    dt = (time.perf_counter() - t0) / reps
     t1 = time.perf_counter()
     fn(rays[1][0], rays[1][1][: 1 << 20], 1)
     one = (1 << 20) / (time.perf_counter() - t1) / 1e6
     return {"value": round(n / dt / 1e6, 2), "unit": "Mrays/s", "cores": cores, "kind": kind,
-            "sample": f"every {sample_tiles}th 8-row tile of the 3 poses' 4K frames ({n} rays), {cores} threads",
-            "one_thread_mrays": round(one, 2)}
+            "sample": f"all rays of a step: the 3 poses' full 4K frames ({n} rays), {reps} passes, {cores} threads",
+            "cpu_layout": CPU_LAYOUT, "one_thread_mrays": round(one, 2)}
 
 
 def run_reference(args):
@@ -595,8 +751,7 @@ def run_reference(args):
     nodes8, root, _ = tree.flatten()
     kind, fn = cpu_tracer(nodes8, root)
     cores = os.cpu_count() or 1
-    sample_tiles = 4
-    rays = sample_rays(sample_tiles)
+    rays = sample_rays(1)                                   # every ray of the product arm's step (N = 1 share)
     n = sum(d.shape[0] for _, d in rays)
 
     def step():
@@ -610,14 +765,14 @@ def run_reference(args):
         step()
     dt = time.perf_counter() - t0
     value = n * args.steps / dt / 1e6
-    sample = f"every {sample_tiles}th 8-row tile of the 3 poses' 4K frames ({n} rays per step), {cores} threads"
+    sample = f"all rays of a step: the 3 poses' full 4K frames ({n} rays per step), {cores} threads"
     emit({
         "impl": "reference", "metric": METRIC, "value": round(value, 3), "unit": "Mrays/s",
         "n_gpus": int(os.environ.get("WORLD_SIZE", args.gpus)), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32+u32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample, "rays_per_step": n},
-        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample},
+        "config": {"workload": WORKLOAD, "frames_per_step": len(rays), "rays_per_step": n, "sample": sample, "cpu_layout": CPU_LAYOUT},
+        "cpu_baseline": {"value": round(value, 3), "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample, "cpu_layout": CPU_LAYOUT},
         "e2e": {"value": round(value, 3), "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     })

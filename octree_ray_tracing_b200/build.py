@@ -34,6 +34,19 @@ NVCC_FLAGS = [
 ]
 
 
+def kernel_source_hash() -> str:
+    """sha256[:16] over the sources and flags that decide the trace kernels' machine code (the per-ray walk and the
+    kernels around it).  ncu captures are tied to it (profiles/traffic.json): a number read from a capture of OTHER
+    code must not end up in a bench line."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in ("ort_trace.cuh", "ort_kernels.cuh"):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
 def nvcc() -> str:
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
         if cand and os.path.exists(cand):

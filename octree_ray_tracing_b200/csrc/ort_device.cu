@@ -68,7 +68,7 @@ struct ort_ctx
 	int opt_smem_levels = -1;
 	int opt_block = 256;
 	int opt_tile_shape = 0;
-	int opt_persist_blocks = 6;         // explicit rays, persistent kernel: resident blocks per SM the build is capped for (1 / 6 / 8)
+	int opt_persist_blocks = 1;         // explicit rays, persistent kernel: 1 = uncapped build (default), 6 / 8 = builds capped for that many resident blocks per SM
 	int opt_band_rotate = -1;           // frames: the 16-row band that is scheduled first; -1 = the horizon band (horizon_band())
 	int opt_zero_copy = 0;              // pinned host outputs: 1 = the kernel stores straight into mapped host memory
 	int opt_frame_chunks = 0;           // host-buffer frames: launches per frame (0 = automatic)
@@ -565,8 +565,9 @@ int ort_trace_rays_async(ort_ctx* c, const float* o3, int o_stride, const float*
 		const unsigned long long need = (n + 255) / 256;
 		const ort::Camera cam0{};
 		const ort::FrameRows fr0{};
-		// the build capped at 40 registers (6 resident blocks per SM) is the default; 8 = the 32-register build, 1 = uncapped
-		const int per_sm = npush ? 0 : (c->opt_persist_blocks == 8 ? 8 : (c->opt_persist_blocks == 1 ? 0 : 6));
+		// the uncapped build is the default (16.7 M incoherent rays: 1.58 ms; capped for 6 / 8 resident blocks per SM: 1.67 / 1.83 ms,
+		// profiles/r2_config3_rays_vs_reference.json)
+		const int per_sm = npush ? 0 : (c->opt_persist_blocks == 8 ? 8 : (c->opt_persist_blocks == 6 ? 6 : 0));
 		const unsigned long long cap_blocks = per_sm ? static_cast<unsigned long long>(c->sm_count) * per_sm : static_cast<unsigned long long>(c->max_blocks_rays);
 		const unsigned pb = static_cast<unsigned>(need < cap_blocks ? need : cap_blocks);
 		if (npush)            ort::trace_persistent_kernel<true, false><<<pb, 256, smem, c->stream>>>(dag, o3, o_stride, d3, cam0, fr0, n, counter, c->opt_low_water, voxel, face, t, npush);

@@ -3,7 +3,7 @@
 // decisions in DESIGN.md section 4 can be re-measured; the product library does not carry them.  Selected through
 // ort_set_option("variant", n): 3 shared-memory staging of the top levels, 4 deferred phases, 5 / 6 TightWalker,
 // 7 PipeWalker, 8-11 pipe probes, 12 persistent warps over tiles, 14 straight-line (predicated) round, 15 128-bit half-node
-// fetches; options "tile_shape" / "block" select other warp tiles and block heights of the round-1 default kernel.
+// fetches, 16 / 17 while-while loop shapes, 18 local-memory parent stack, 19 a 40-register budget; options "tile_shape" / "block" select other warp tiles and block heights of the round-1 default kernel.
 // Included by ort_device.cu after the context definition.
 #pragma once
 
@@ -335,10 +335,22 @@ trace_frame_staged_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, 
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
-// Variants 14 / 15: FlatWalker (straight-line round) and V4Walker (128-bit half-node fetch) in the product kernel's
-// shape -- same tile mapping, same tiers, same shared-memory parent stack; only the round differs.
-template<template<bool> class WALKER, bool COUNT>
-__global__ void __launch_bounds__(256)
+// Variants 14 - 19: experiments in the product kernel's shape -- same tile mapping, same tiers; what differs is the
+// round (WALKER: FlatWalker = straight-line round, V4Walker = 128-bit half-node fetch, LeanWalker = the product's), the
+// loop shape (LOOP 0: one child load, then descend OR advance, as the product; 1: "while-while", every lane advances
+// over empty slots until it holds a child, then the warp descends together; 2: every lane descends while it finds
+// children, then advances once), where the parent stack lives (LOCAL_STACK: a local-memory array instead of the
+// shared-memory column) and the register budget (MINB resident blocks per SM).
+template<int SHIFT>
+struct LocalLeanStack
+{
+	uint32_t* e;                                     // kMaxDepth entries of local memory
+	__device__ __forceinline__ void store(float dimf, uint32_t w) const { e[(__float_as_uint(dimf) >> 23) - (127u - kMaxDepth)] = w; }
+	__device__ __forceinline__ uint32_t load(float dimf) const { return e[(__float_as_uint(dimf) >> 23) - (127u - kMaxDepth)]; }
+};
+
+template<template<bool> class WALKER, bool COUNT, int LOOP, bool LOCAL_STACK, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 trace_frame_walker_kernel(const Dag g, Camera cam, FrameRows fr,
                           uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
@@ -355,8 +367,35 @@ trace_frame_walker_kernel(const Dag g, Camera cam, FrameRows fr,
 	{
 		WALKER<COUNT> w;
 		w.start(g.root, ray);
-		const LeanStack<kLeanShift> st{ lean_stack_base(s_stack, g.depth) };
-		while (!w.round(g.base_biased, g.leaf_dimf, g.miss_t, st)) {}
+		uint32_t lstack[kMaxDepth];
+		auto run = [&](auto st) {
+			if (LOOP == 1)
+			{
+				for (;;)
+				{
+					uint32_t child;
+					bool done = false;
+					while ((child = w.load_child(g.base_biased)) == 0u)
+						if (w.advance(g.miss_t, st)) { done = true; break; }
+					if (done || w.descend(child, g.leaf_dimf, st)) break;
+				}
+			}
+			else if (LOOP == 2)
+			{
+				for (;;)
+				{
+					uint32_t child;
+					bool done = false;
+					while ((child = w.load_child(g.base_biased)) != 0u)
+						if (w.descend(child, g.leaf_dimf, st)) { done = true; break; }
+					if (done || w.advance(g.miss_t, st)) break;
+				}
+			}
+			else
+				while (!w.round(g.base_biased, g.leaf_dimf, g.miss_t, st)) {}
+		};
+		if (LOCAL_STACK) run(LocalLeanStack<0>{ lstack });
+		else             run(LeanStack<kLeanShift>{ lean_stack_base(s_stack, g.depth) });
 		h = w.hit;
 	}
 	else
@@ -439,11 +478,16 @@ static int launch_frame_experiment(ort_ctx* c, const ort::Dag& g, const ort::Cam
 			ort::trace_frame_staged_kernel<false><<<g2, 1024, smem, c->stream>>>(nodes_m1, g.root, g.depth, g.miss_t, rt, cam, fr, n_staged, voxel, face, t, npush);
 		}
 	}
-	else if ((v == 14 || v == 15) && lean_capable(c))
+	else if (v >= 14 && v <= 19 && lean_capable(c))
 	{
-		const size_t smem = ort::lean_smem_bytes(g.depth);
-		auto k = v == 14 ? (npush ? ort::trace_frame_walker_kernel<ort::FlatWalker, true> : ort::trace_frame_walker_kernel<ort::FlatWalker, false>)
-		                 : (npush ? ort::trace_frame_walker_kernel<ort::V4Walker, true> : ort::trace_frame_walker_kernel<ort::V4Walker, false>);
+		// 14 straight-line round, 15 128-bit fetches, 16 while-while, 17 descend-while, 18 parent stack in local memory,
+		// 19 register budget of 6 resident blocks per SM (40 registers)
+		const size_t smem = v == 18 ? 0 : ort::lean_smem_bytes(g.depth);
+#define ORT_WALKER_KERNEL(W, L, LS, MB) (npush ? ort::trace_frame_walker_kernel<W, true, L, LS, MB> : ort::trace_frame_walker_kernel<W, false, L, LS, MB>)
+		auto k = v == 14 ? ORT_WALKER_KERNEL(ort::FlatWalker, 0, false, 1) : v == 15 ? ORT_WALKER_KERNEL(ort::V4Walker, 0, false, 1)
+		       : v == 16 ? ORT_WALKER_KERNEL(ort::LeanWalker, 1, false, 1) : v == 17 ? ORT_WALKER_KERNEL(ort::LeanWalker, 2, false, 1)
+		       : v == 18 ? ORT_WALKER_KERNEL(ort::LeanWalker, 0, true, 1) : ORT_WALKER_KERNEL(ort::LeanWalker, 0, false, 6);
+#undef ORT_WALKER_KERNEL
 		k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
 	}
 	else if (v == 1 && (c->opt_tile_shape != 0 || c->opt_block == 128 || c->opt_block == 64))

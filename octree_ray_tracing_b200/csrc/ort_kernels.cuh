@@ -80,6 +80,9 @@ __device__ __forceinline__ uint32_t lean_stack_base(const uint32_t* s_stack, int
 	return static_cast<uint32_t>(__cvta_generic_to_shared(s_stack)) + threadIdx.x * 4u - (static_cast<uint32_t>(128 - depth) << (23 - kLeanShift));
 }
 
+// Loop shape of the lean tier ("descend-while"): a lane keeps descending while the slot it lands on holds a child and
+// only then takes ONE advance (step / pop) -- measured against the plain "one load, then descend or advance" round and
+// the "advance-while" shape on the bench step: 18.57 vs 18.38 vs 18.34 Grays/s (profiles/r2_loop_shapes.json).
 template<int VARIANT, bool COUNT>
 __device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float oz, float dx, float dy, float dz, const uint32_t* s_stack)
 {
@@ -89,7 +92,14 @@ __device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float
 		LeanWalker<COUNT> w;
 		w.start(g.root, ray);
 		const LeanStack<kLeanShift> st{ lean_stack_base(s_stack, g.depth) };
-		while (!w.round(g.base_biased, g.leaf_dimf, g.miss_t, st)) {}
+		for (;;)
+		{
+			uint32_t child;
+			bool done = false;
+			while ((child = w.load_child(g.base_biased)) != 0u)
+				if (w.descend(child, g.leaf_dimf, st)) { done = true; break; }
+			if (done || w.advance(g.miss_t, st)) break;
+		}
 		return w.hit;
 	}
 	return traverse_variant<VARIANT, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, ox, oy, oz, ray);
@@ -131,8 +141,10 @@ __device__ __forceinline__ bool frame_pixel(const FrameRows& fr, unsigned block_
 	return x < fr.W && r < fr.rows;
 }
 
+// (register budget: 6 resident blocks per SM = 40 registers; the 32-register build reloads the node base pointer from the
+// constant bank every round and measures 1-2 % slower, although it fits 8 blocks)
 template<int VARIANT, bool COUNT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
                    uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
 {
@@ -173,7 +185,7 @@ struct FrameJobBatch
 };
 
 template<int VARIANT, bool COUNT>          // COUNT: some job of the batch wants per-ray PUSH counts (jobs without an npush pointer skip the store)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 trace_frames_kernel(const Dag g, const __grid_constant__ FrameJobBatch batch)
 {
 	extern __shared__ uint32_t s_stack[];
@@ -208,7 +220,7 @@ struct Palette
 };
 
 template<int VARIANT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 trace_frame_rgba_kernel(const Dag g, Camera cam, FrameRows fr, Palette pal, uint32_t* __restrict__ rgba)
 {
 	extern __shared__ uint32_t s_stack[];

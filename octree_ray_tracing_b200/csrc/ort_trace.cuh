@@ -494,18 +494,18 @@ struct LeanWalker
 	}
 
 	// PUSH with an empty child: STEP (:378-419) to the sibling across the nearest exit plane, POPping (:421-446) as far as
-	// needed; returns true on MISS.  All t are non-negative here (see above), so the unsigned order of the reference is
-	// the order of the values and the multi-level POP (proof in FastWalker::advance) always applies.
+	// needed; returns true on MISS.  All t are non-negative and none is NaN here (see above): the reference's unsigned
+	// order of the bit patterns is the order of the float values, so the argmin is a float min3 + two equality tests
+	// (ties -> x, then y, as :388-406), and the multi-level POP (proof in FastWalker::advance) always applies.
 	template<class STACK>
 	__device__ __forceinline__ bool advance(float miss_t, const STACK st)
 	{
-		const uint32_t tx = __float_as_uint(__fmaf_rn(px, cx, bx));
-		const uint32_t ty = __float_as_uint(__fmaf_rn(py, cy, by));
-		const uint32_t tz = __float_as_uint(__fmaf_rn(pz, cz, bz));
-		const uint32_t tyz = min(ty, tz);
-		const bool ax = tx <= tyz;                                                  // argmin, ties -> x, y, z
-		const bool ay = !ax && ty <= tz;
-		tmin = __uint_as_float(min(tx, tyz));
+		const float tx = __fmaf_rn(px, cx, bx);
+		const float ty = __fmaf_rn(py, cy, by);
+		const float tz = __fmaf_rn(pz, cz, bz);
+		tmin = fminf(tx, fminf(ty, tz));
+		const bool ax = tx == tmin;
+		const bool ay = !ax && ty == tmin;
 		mti = 4u;
 		if (ay) mti = 2u;
 		if (ax) mti = 1u;
@@ -518,7 +518,8 @@ struct LeanWalker
 			uint32_t pa = __float_as_uint(pz);
 			if (ay) pa = __float_as_uint(py);
 			if (ax) pa = __float_as_uint(px);
-			const uint32_t b = pa & (0u - pa);
+			const uint32_t na = 0u - pa;
+			const uint32_t b = pa & na;
 			if (b == 0x00800000u)                                                   // :423
 			{
 				hit.voxel = 0;
@@ -526,11 +527,11 @@ struct LeanWalker
 				hit.t = miss_t;
 				return true;
 			}
-			const uint32_t keep = 0u - b;                                           // drop the position bits of the levels left
+			const uint32_t keep = pa | na;                                          // = -b: drops the position bits of the levels left
 			px = __uint_as_float(__float_as_uint(px) & keep);
 			py = __uint_as_float(__float_as_uint(py) & keep);
 			pz = __uint_as_float(__float_as_uint(pz) & keep);
-			dimf = __uint_as_float(0x3F800000u | b) - 1.0f;                         // b * 2^-23, exact
+			dimf = __uint_as_float(b) * 0x1p126f;                                   // b * 2^-23 (b as a denormal x 2^126), exact
 			w = st.load(dimf);                                                      // bit a* of its index is set
 		}
 

@@ -396,7 +396,7 @@ def ref():
     return _ref
 
 
-REF_CONFIGS = [(12, 4), (16, 6), (19, 8), (22, 10), (24, 12)]
+REF_CONFIGS = [(12, 4), (16, 6), (19, 8), (22, 10), (24, 12), (25, 13), (25, 14)]   # the last two: trace-only (import_compact) for the depth-13 / 14 parity tests
 
 
 class RefTree:

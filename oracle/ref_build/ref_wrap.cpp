@@ -130,7 +130,7 @@ void trace_batch_t(const tree_iface* ti, const float* o3, int o_stride, const fl
 	for (auto& th : pool) th.join();
 }
 
-#define OCHREF_CONFIGS(X) X(12, 4) X(16, 6) X(19, 8) X(22, 10) X(24, 12)
+#define OCHREF_CONFIGS(X) X(12, 4) X(16, 6) X(19, 8) X(22, 10) X(24, 12) X(25, 13) X(25, 14)
 
 }
 

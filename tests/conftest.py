@@ -42,7 +42,7 @@ def golden():
 
 
 PRODUCT_VARIANTS = (0, 1, 2, 13)                       # traverse(), FastWalker, persistent lane refill, LeanWalker tiers (default)
-EXPERIMENT_VARIANTS = (3, 4, 5, 6, 7, 12, 14, 15)      # csrc/ort_experiments.cuh, only in libort_b200_exp.so
+EXPERIMENT_VARIANTS = (3, 4, 5, 6, 7, 12, 14, 15, 16, 17, 18, 19)      # csrc/ort_experiments.cuh, only in libort_b200_exp.so
 
 
 def frame_variants(ort):

@@ -57,5 +57,6 @@ static inline int __clz(int x) { return x ? __builtin_clz(static_cast<unsigned>(
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 struct uint4 { uint32_t x, y, z, w; };
+using std::fminf;
 using std::min;
 using std::max;

@@ -59,8 +59,22 @@ def traffic(rep, out_json):
             b += float(r[i]) * scale[units[i]]
         tot.append(b)
     inst = [int(float(r[hdr.index("smsp__inst_executed.sum")])) for r in data] if "smsp__inst_executed.sum" in hdr else []
+
+    def col(key, conv=float):
+        return [conv(r[hdr.index(key)]) for r in data] if key in hdr else []
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from octree_ray_tracing_b200.build import kernel_source_hash
     json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "per_launch": [int(x) for x in tot],
-               "warp_instructions_per_launch": inst, "source": rep,
+               "warp_instructions_per_launch": inst,
+               "l2_sectors_per_launch": [int(x) for x in col("lts__t_sectors.sum")],
+               "l1_hit_pct": col("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": col("lts__t_sector_hit_rate.pct"),
+               "active_threads_per_warp_instruction": col("smsp__thread_inst_executed_per_inst_executed.ratio"),
+               "issue_active_pct": col("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+               "kernel_time_us": col("gpu__time_duration.sum"),
+               "source": rep, "kernel_source_sha16": kernel_source_hash(),
+               "note": "written by tools/ncu_summary.py --traffic from an `ncu --set full` capture of the three frame launches (poses A, B, C) of one bench step; "
+                       "bench.py uses it only while kernel_source_sha16 equals the hash of the sources it runs",
                "kernels": [r[hdr.index("Kernel Name")].split("(")[0] for r in data]}, open(out_json, "w"), indent=1)
 
 
