@@ -311,6 +311,58 @@ def run_product(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def measure_gather():
+        # Frames assembled on their consumer (ort_mg_trace_frame_gather: strips traced into a ring of slots, ONE NCCL message
+        # per rank and frame on the communicator's stream, unpacked at their final rows on the consumer).  Two consumer
+        # layouts: round robin (frame k of the step is consumed on rank k mod N -- the weak-scaling shape: N times the frames,
+        # N consumers) and everything on rank 0 (one consumer for N times the frames: bound by one GPU's NVLink ingest).
+        gather = {}
+        if mg is not None:
+            fv = torch.empty(W * H, dtype=torch.int32, device="cuda")
+            ff = torch.empty(W * H, dtype=torch.uint8, device="cuda")
+            ft = torch.empty(W * H, dtype=torch.float32, device="cuda")
+
+            def gather_step(mode):
+                for k, cam in enumerate(step_cams):
+                    dst = k % world if mode == "round_robin" else 0
+                    mine = dst == rank
+                    mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=dst, d_vox=fv if mine else None, d_face=ff if mine else None, d_t=ft if mine else None)
+
+            g_steps = max(1, min(args.steps, 10))
+            # (consumers, frames per wire operation): per-frame messages, and the whole step's strips as one NCCL group
+            for mode, grp in (("round_robin", 1), ("round_robin", len(step_cams)), ("rank0", len(step_cams))):
+                mg.set_group(grp)
+                gather_step(mode)
+                mg.sync()
+                barrier()
+                w0 = mg.wire_bytes
+                g0 = time.perf_counter()
+                for _ in range(g_steps):
+                    gather_step(mode)
+                mg.sync()
+                barrier()
+                gather[(mode, grp)] = ((time.perf_counter() - g0) / g_steps, (mg.wire_bytes - w0) / g_steps)
+            mg.set_group(1)
+            # one frame at a time, nothing in flight: the latency of "trace my strips + gather" for a single frame
+            lat = []
+            for cam in cams:
+                barrier()
+                g0 = time.perf_counter()
+                mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=0, d_vox=fv if rank == 0 else None, d_face=ff if rank == 0 else None, d_t=ft if rank == 0 else None)
+                mg.sync()
+                barrier()
+                lat.append(time.perf_counter() - g0)
+            gather["latency"] = lat
+            # the last assembled frame (pose C, consumer rank 0) against the single-GPU trace of the same frame on rank 0
+            if rank == 0:
+                full = (torch.empty(W * H, dtype=torch.int32, device="cuda"), torch.empty(W * H, dtype=torch.uint8, device="cuda"), torch.empty(W * H, dtype=torch.float32, device="cuda"))
+                cam = cams[-1]
+                ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, 0, H, 1, 1, full[0], full[1], full[2], None)
+                ctx.sync()
+                gather["assembled_equals_single_gpu"] = bool(torch.equal(full[0], fv) and torch.equal(full[1], ff) and torch.equal(full[2].view(torch.int32), ft.view(torch.int32)))
+
+        return gather
+
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
 
@@ -343,10 +395,17 @@ def run_product(args):
     if args.quick:
         sampler.stop()
         ms = kernel_ms / args.steps
+        gq = None
         if world > 1:
-            tq = torch.tensor([ms, serial_ms], dtype=torch.float64, device="cuda")
+            g = measure_gather()
+            keys = sorted(k for k in g if isinstance(k, tuple))
+            tq = torch.tensor([ms, serial_ms] + [g[k][0] for k in keys] + [max(g["latency"])], dtype=torch.float64, device="cuda")
             dist.all_reduce(tq, op=dist.ReduceOp.MAX)
             ms, serial_ms = float(tq[0]), float(tq[1])
+            gq = {f"{k[0]}_group{k[1]}_Mrays/s": round(rays_per_step_total / float(tq[2 + i]) / 1e6, 1) for i, k in enumerate(keys)}
+            gq["single_frame_latency_ms"] = round(float(tq[-1]) * 1e3, 3)
+            gq["assembled_equals_single_gpu"] = g.get("assembled_equals_single_gpu")
+            mg.close()
             dist.barrier()
             dist.destroy_process_group()
         if rank != 0:
@@ -355,7 +414,7 @@ def run_product(args):
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
                           "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]],
-                          "tile_rows": TILE_ROWS, "streams": NS, "parity": parity,
+                          "tile_rows": TILE_ROWS, "streams": NS, "parity": parity, "gather": gq,
                           "as_rank": (f"{prank}/{pworld}: value = what {pworld} GPUs would total if every rank ran like this one" if args.as_rank else None)})
         return None
 
@@ -422,51 +481,7 @@ def run_product(args):
     d2h_gbs_local = 4 * (256 << 20) / (pa.elapsed_time(pb) * 1e-3) / 1e9
     del probe_d, probe_h
 
-    # Frames assembled on their consumer (ort_mg_trace_frame_gather: strips traced into a ring of slots, ONE NCCL message
-    # per rank and frame on the communicator's stream, unpacked at their final rows on the consumer).  Two consumer
-    # layouts: round robin (frame k of the step is consumed on rank k mod N -- the weak-scaling shape: N times the frames,
-    # N consumers) and everything on rank 0 (one consumer for N times the frames: bound by one GPU's NVLink ingest).
-    gather = {}
-    if mg is not None:
-        fv = torch.empty(W * H, dtype=torch.int32, device="cuda")
-        ff = torch.empty(W * H, dtype=torch.uint8, device="cuda")
-        ft = torch.empty(W * H, dtype=torch.float32, device="cuda")
-
-        def gather_step(mode):
-            for k, cam in enumerate(step_cams):
-                dst = k % world if mode == "round_robin" else 0
-                mine = dst == rank
-                mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=dst, d_vox=fv if mine else None, d_face=ff if mine else None, d_t=ft if mine else None)
-
-        g_steps = max(1, min(args.steps, 10))
-        for mode in ("round_robin", "rank0"):
-            gather_step(mode)
-            mg.sync()
-            barrier()
-            w0 = mg.wire_bytes
-            g0 = time.perf_counter()
-            for _ in range(g_steps):
-                gather_step(mode)
-            mg.sync()
-            barrier()
-            gather[mode] = ((time.perf_counter() - g0) / g_steps, (mg.wire_bytes - w0) / g_steps)
-        # one frame at a time, nothing in flight: the latency of "trace my strips + gather" for a single frame
-        lat = []
-        for cam in cams:
-            barrier()
-            g0 = time.perf_counter()
-            mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=0, d_vox=fv if rank == 0 else None, d_face=ff if rank == 0 else None, d_t=ft if rank == 0 else None)
-            mg.sync()
-            barrier()
-            lat.append(time.perf_counter() - g0)
-        gather["latency"] = lat
-        # the last assembled frame (pose C, consumer rank 0) against the single-GPU trace of the same frame on rank 0
-        if rank == 0:
-            full = (torch.empty(W * H, dtype=torch.int32, device="cuda"), torch.empty(W * H, dtype=torch.uint8, device="cuda"), torch.empty(W * H, dtype=torch.float32, device="cuda"))
-            cam = cams[-1]
-            ctx.trace_frame_async(cam[0], cam[1], cam[2], W, H, 0, H, 1, 1, full[0], full[1], full[2], None)
-            ctx.sync()
-            gather["assembled_equals_single_gpu"] = bool(torch.equal(full[0], fv) and torch.equal(full[1], ff) and torch.equal(full[2].view(torch.int32), ft.view(torch.int32)))
+    gather = measure_gather()
 
     # shaded frames (the pixels update_image draws): 4 B per ray cross PCIe instead of 9
     cols, _ = harness.parse_voxels(harness.DEMO_VOXELS)
@@ -494,13 +509,15 @@ def run_product(args):
     gather_hbm = ctx.measure_gather_peak(4 << 30) if rank == 0 else 0.0
 
     # max over ranks
-    g_rr, g_r0 = gather.get("round_robin", (0.0, 0.0)), gather.get("rank0", (0.0, 0.0))
+    n_step_frames = len(step_cams)
+    g_rr, g_r0 = gather.get(("round_robin", n_step_frames), (0.0, 0.0)), gather.get(("rank0", n_step_frames), (0.0, 0.0))
+    g_rr1 = gather.get(("round_robin", 1), (0.0, 0.0))
     g_lat = max(gather.get("latency", [0.0]))
     d2h_sum = d2h_gbs_local
     if world > 1:
-        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1[0]], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms = (float(x) for x in tt.tolist())
+        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1_s = (float(x) for x in tt.tolist())
         cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local, d2h_gbs_local, g_rr[1], g_r0[1]], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
@@ -513,7 +530,7 @@ def run_product(args):
     else:
         launches_all = launches
         pushes_per_ray_all = pushes_per_step_local / rays_per_step_local
-        g_rr_s = g_r0_s = 0.0
+        g_rr_s = g_r0_s = g_rr1_s = 0.0
         wire_rr = wire_r0 = ingest_r0 = 0.0
 
     result = None
@@ -618,9 +635,12 @@ def run_product(args):
                 "value": round(rays_per_step_total / g_rr_s / 1e6, 2), "unit": "Mrays/s",
                 "frac_of_value": round(rays_per_step_total / g_rr_s / 1e6 / value_trace, 4),
                 "consumers": "round robin: frame k of the step is assembled on rank k mod N (N times the frames, N consumers)",
+                "wire": f"ort_mg_set_group({n_step_frames}): the strips of a step's {n_step_frames} frames leave in ONE NCCL group (an all-to-all-shaped exchange) that overlaps the next step's traces",
                 "wire_bytes_per_step": int(wire_rr), "wire_gbs_aggregate": round(wire_rr / g_rr_s / 1e9, 1),
-                "api": "ort_mg_trace_frame_gather (NCCL inside libort_b200.so): strips traced into a ring of 3 slots on the trace stream, one ncclSend per rank and frame on the "
-                       "communicator's stream, unpack kernel writes final rows on the consumer; wall clock over whole steps, max over ranks",
+                "per_frame_messages": {"value": round(rays_per_step_total / g_rr1_s / 1e6, 2), "unit": "Mrays/s",
+                                       "note": "ort_mg_set_group(1): every frame's strips leave as soon as they are traced (one small point-to-point NCCL operation per frame)"},
+                "api": "ort_mg_trace_frame_gather (NCCL inside libort_b200.so): strips traced into a ring of blocks on the trace stream, ncclSend / ncclRecv on the "
+                       "communicator's stream, one unpack kernel per frame writes final rows on the consumer; wall clock over whole steps, max over ranks",
                 "rank0_only": {"value": round(rays_per_step_total / g_r0_s / 1e6, 2), "unit": "Mrays/s",
                                "note": "every frame assembled on rank 0: one GPU's NVLink ingest carries (N-1)/N of ALL frames",
                                "rank0_ingest_bytes_per_step": int(ingest_r0), "rank0_ingest_gbs": round(ingest_r0 / g_r0_s / 1e9, 1)},

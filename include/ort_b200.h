@@ -184,14 +184,24 @@ int ort_mg_strip_rows(int rank, int world, int H, int tile_rows);
 int ort_mg_broadcast_update(ort_mg* mg, const uint32_t* ids, const uint32_t* nodes8, size_t n, uint32_t root, int is_full, int src);
 /* Collective: trace this rank's strips of a W x H frame and gather the frame on rank dst, whose voxel / face / t are
  * device buffers of W * H entries (ignored on the other ranks).  W % 4 == 0.  Enqueue only: the trace runs on
- * ort_stream(ctx), send / receive / unpack on the communicator's own stream, strips in a ring of three slots, so the
- * trace of the next frame overlaps the wire time of this one.  ort_mg_sync() returns when every frame queued so far
+ * ort_stream(ctx), send / receive / unpack on the communicator's own stream, strips in a ring of blocks, so the
+ * traces of the next frames overlap the wire time of these.  ort_mg_sync() returns when every frame queued so far
  * is complete. */
 int ort_mg_trace_frame_gather(ort_mg* mg, const float pos[3], const float rot[9], float fov_factor, int W, int H, int tile_rows, int dst,
                               uint32_t* voxel, uint8_t* face, float* t);
+/* Collective setting: frames per wire operation.  1 (default): the strips of every frame leave as soon as they are traced
+ * (lowest latency).  n > 1: the strips of n consecutive frames leave in ONE NCCL group -- fewer, larger, all-to-all-shaped
+ * exchanges that NCCL spreads over all peers and channels at once (highest throughput when many frames are in flight);
+ * ort_mg_flush() sends a partial group, ort_mg_sync() flushes and waits. */
+int ort_mg_set_group(ort_mg* mg, int frames);
+int ort_mg_flush(ort_mg* mg);
+/* Streams the strips are traced on in turn (1..8; default 4, 8 from five ranks on): a strip launch ends with the latency
+ * tail of its longest rays, and only launches on different streams overlap that tail with the bulk of the next one. */
+int ort_mg_set_trace_streams(ort_mg* mg, int n);
 int ort_mg_sync(ort_mg* mg);
 void* ort_mg_stream(ort_mg* mg);                     /* the cudaStream_t of the gather (for event timing) */
 double ort_mg_wire_bytes(const ort_mg* mg);          /* bytes this rank has sent + received for gathers so far */
+uint64_t ort_mg_wire_ops(const ort_mg* mg);          /* NCCL groups issued for gathers so far */
 
 int   ort_sync(ort_ctx* ctx);
 void* ort_stream(ort_ctx* ctx);                 /* the cudaStream_t all work of ctx is queued on */

@@ -360,6 +360,14 @@ int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_set_rcp_table: need a table of 2^1..2^23 entries");
 	DeviceGuard g(c->device);
 	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	{
+		// every entry is the reciprocal of a number in [1, 2): exponent field 126 or 127 (ort::rcp_model relies on it)
+		std::vector<uint32_t> host(static_cast<size_t>(1) << log2n);
+		ORT_CUDA(c, cudaMemcpy(host.data(), tab, host.size() * 4, cudaMemcpyDefault));
+		for (size_t k = 0; k < host.size(); ++k)
+			if (((host[k] >> 23) | 1u) != 127u)
+				return ort_fail(c, ORT_ERR_INVALID, "ort_set_rcp_table: entry %zu (0x%08x) is not in (0.5, 1]: not a reciprocal table of [1, 2)", k, host[k]);
+	}
 	if (c->rcp_log2n != log2n)
 	{
 		cudaFree(c->d_rcp);
@@ -489,7 +497,7 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 // trace
 // ------------------------------------------------------------------------------------------------
 
-static ort::Camera make_camera(const float pos[3], const float rot[9], float fov_factor, int W, int H);
+static ort::Camera make_camera(const ort_ctx* c, const float pos[3], const float rot[9], float fov_factor, int W, int H);
 
 // Which 16-row band of the launch should be scheduled first.  A launch ends when its longest rays do, and those are
 // the grazing rays at the top of the downward-looking part of the picture (farthest terrain); rows above the horizon
@@ -513,7 +521,7 @@ static int horizon_band(const ort::Camera& cam, int W, int y0, int rows, int til
 	return 0;
 }
 
-static ort::Camera make_camera(const float pos[3], const float rot[9], float fov_factor, int W, int H)
+static ort::Camera make_camera(const ort_ctx* c, const float pos[3], const float rot[9], float fov_factor, int W, int H)
 {
 	ort::Camera cam;
 	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
@@ -522,6 +530,7 @@ static ort::Camera make_camera(const float pos[3], const float rot[9], float fov
 	cam.aspect = static_cast<float>(W) / static_cast<float>(H);   // test_och_h_octree.cpp:89
 	cam.vfx = 2.0F / static_cast<float>(W);                       // :91
 	cam.vfy = 2.0F / static_cast<float>(H);                       // :93
+	cam.origin_flags = ort::camera_origin_flags(pos[0], pos[1], pos[2], (1u << (23 - c->depth)) - 1u);
 	return cam;
 }
 
@@ -610,7 +619,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	if (!c->has_root)
 		return launch_miss(c, n, voxel, face, t, npush);
 	const ort::Dag dag = make_dag(c);
-	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
+	const ort::Camera cam = make_camera(c, pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape, rotate, ort::tile_shift_of(tile_rows) };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
@@ -688,7 +697,7 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 			const ort_frame_job& j = jobs[i];
 			if (!j.rows) continue;
 			ort::FrameJob& d = batch.job[n++];
-			d.cam = make_camera(j.pos, j.rot, j.fov_factor, j.W, j.H);
+			d.cam = make_camera(c, j.pos, j.rot, j.fov_factor, j.W, j.H);
 			const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((j.rows + 15) / 16) : horizon_band(d.cam, j.W, j.y0, j.rows, j.tile_rows, j.tile_step);
 			d.fr = ort::FrameRows{ j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, 0, rotate, ort::tile_shift_of(j.tile_rows) };
 			d.voxel = j.voxel; d.face = j.face; d.t = j.t; d.npush = j.npush;
@@ -970,7 +979,7 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
 		return ORT_OK;
 	}
 	const ort::Dag dag = make_dag(c);
-	const ort::Camera cam = make_camera(pos, rot, fov_factor, W, H);
+	const ort::Camera cam = make_camera(c, pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, rotate, ort::tile_shift_of(tile_rows) };
 	switch (walk_variant(c))

@@ -83,11 +83,13 @@ __device__ __forceinline__ uint32_t lean_stack_base(const uint32_t* s_stack, int
 // Loop shape of the lean tier ("descend-while"): a lane keeps descending while the slot it lands on holds a child and
 // only then takes ONE advance (step / pop) -- measured against the plain "one load, then descend or advance" round and
 // the "advance-while" shape on the bench step: 18.57 vs 18.38 vs 18.34 Grays/s (profiles/r2_loop_shapes.json).
+// The walk of one ray from its set-up state.  origin_ok: the origin part of fast_path_ok holds (tested per ray for
+// explicit rays, known for the whole launch for camera frames).
 template<int VARIANT, bool COUNT>
-__device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float oz, float dx, float dy, float dz, const uint32_t* s_stack)
+__device__ __forceinline__ Hit walk_ray(const Dag& g, float ox, float oy, float oz, const Ray& ray, bool origin_ok, const uint32_t* s_stack)
 {
-	const Ray ray = ray_setup(g.rt, ox, oy, oz, dx, dy, dz, VARIANT == kLean ? g.plane_mask : 0u);
-	if (VARIANT == kLean && fast_path_ok(ox, oy, oz, ray) && lean_path_ok(ray))
+	// lean tier: origin inside the cube, no degenerate axis, no negative t possible
+	if (VARIANT == kLean && origin_ok && lean_path_ok(ray))
 	{
 		LeanWalker<COUNT> w;
 		w.start(g.root, ray);
@@ -103,6 +105,24 @@ __device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float
 		return w.hit;
 	}
 	return traverse_variant<VARIANT, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, ox, oy, oz, ray);
+}
+
+// explicit ray: every ray has its own origin, the origin tests run per ray
+template<int VARIANT, bool COUNT>
+__device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float oz, float dx, float dy, float dz, const uint32_t* s_stack)
+{
+	const Ray ray = ray_setup(g.rt, ox, oy, oz, dx, dy, dz, VARIANT == kLean ? g.plane_mask : 0u);
+	return walk_ray<VARIANT, COUNT>(g, ox, oy, oz, ray, VARIANT == kLean && origin_in_cube(ox, oy, oz, ray), s_stack);
+}
+
+// camera ray: the origin facts were established once on the host (Camera::origin_flags)
+template<int VARIANT, bool COUNT>
+__device__ __forceinline__ Hit trace_camera_ray(const Dag& g, const Camera& cam, float dx, float dy, float dz, const uint32_t* s_stack)
+{
+	if (VARIANT != kLean)
+		return trace_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, dx, dy, dz, s_stack);
+	const Ray ray = ray_setup_camera(g.rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, cam.origin_flags);
+	return walk_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, ray, (cam.origin_flags & kOriginInCube) != 0u, s_stack);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -155,7 +175,7 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
-	const Hit h = trace_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, dx, dy, dz, s_stack);
+	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, cam, dx, dy, dz, s_stack);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
@@ -199,7 +219,7 @@ trace_frames_kernel(const Dag g, const __grid_constant__ FrameJobBatch batch)
 
 	float dx, dy, dz;
 	camera_ray(jb.cam, x, y, dx, dy, dz);
-	const Hit h = trace_ray<VARIANT, COUNT>(g, jb.cam.ox, jb.cam.oy, jb.cam.oz, dx, dy, dz, s_stack);
+	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, jb.cam, dx, dy, dz, s_stack);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	jb.voxel[i] = h.voxel;
@@ -230,7 +250,7 @@ trace_frame_rgba_kernel(const Dag g, Camera cam, FrameRows fr, Palette pal, uint
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
-	const Hit h = trace_ray<VARIANT, false>(g, cam.ox, cam.oy, cam.oz, dx, dy, dz, s_stack);
+	const Hit h = trace_camera_ray<VARIANT, false>(g, cam, dx, dy, dz, s_stack);
 
 	uint32_t px;
 	if (h.face == 6u) px = pal.exit_rgba;
@@ -330,7 +350,7 @@ trace_persistent_kernel(const Dag g, const float* __restrict__ o3, int o_stride,
 				if (valid)
 				{
 					const Ray ray = ray_setup(g.rt, ox, oy, oz, dx, dy, dz, g.plane_mask);
-					if (fast_path_ok(ox, oy, oz, ray) && lean_path_ok(ray))
+					if (origin_in_cube(ox, oy, oz, ray) && lean_path_ok(ray))
 					{
 						w.start(g.root, ray);
 						active = true;

@@ -7,12 +7,15 @@
 // system one), so single-GPU users need no NCCL at all.  Included at the end of ort_device.cu.
 //
 // Gather data path, per frame and rank r (all on the device, nothing touches the host):
-//   trace stream : ort_trace_frame_async -> strip slot s = [voxel u32 | t f32 | face u8] of r's cyclic tiles
-//   comm stream  : waits for the trace (event); ONE ncclSend of the whole slot to the consumer rank; the consumer posts
-//                  world-1 ncclRecv into its staging ring in the same group, then three unpack kernels move every rank's
-//                  tiles to their final rows of the caller's frame buffers (its own strip straight from its trace slot).
-//   The slots form a ring (kSlots): the trace of frame k+1 runs while frame k is on the wire; a slot is reused only after
-//   its send (and, on the consumer, its unpack) has completed -- ordered by events, no host synchronisation.
+//   trace stream : ort_trace_frame_async -> a strip block [voxel u32 | t f32 | face u8] of r's cyclic tiles, taken from a
+//                  ring of blocks (on the consumer: the block of its own rank inside the frame's staging area)
+//   comm stream  : every `group` frames (ort_mg_set_group, default 1) ONE NCCL group moves all pending strips -- a sender
+//                  posts one ncclSend per frame, a consumer world-1 ncclRecv per frame -- and one unpack kernel per
+//                  consumed frame writes every rank's tiles to their final rows of the caller's frame buffers.
+//   The rings hold 2 x group blocks: the traces of the next group run while this group is on the wire; a block is reused
+//   only after its send (on the consumer: its unpack) has completed -- ordered by events, no host synchronisation.
+//   group = 1 gives the lowest latency per frame; a larger group turns many small point-to-point messages into one
+//   all-to-all-shaped exchange that NCCL spreads over all peers and channels at once.
 #pragma once
 
 #include <dlfcn.h>
@@ -74,7 +77,24 @@ NcclApi* nccl_api(std::string* why)
 	return &api;
 }
 
-constexpr int kSlots = 3;                        // frames in flight between trace and wire
+struct MgFrame                                     // a traced frame whose strips have not been put on the wire yet
+{
+	int W, H, tile_rows, dst;
+	size_t max_n;
+	char* sb;                                      // this rank's strip block
+	char* blocks;                                  // consumer: the frame's world blocks (rank order), else null
+	uint32_t* voxel; uint8_t* face; float* t;      // consumer: the caller's frame buffers
+	int slot;                                      // ring slot to release (sender ring or consumer ring)
+};
+
+struct MgRing                                      // blocks handed out round robin, each guarded by an event
+{
+	char* base = nullptr;
+	size_t slot_bytes = 0;
+	int n = 0, next = 0;
+	std::vector<cudaEvent_t> ev_free;
+	std::vector<char> used;
+};
 
 }  // namespace
 
@@ -84,16 +104,23 @@ struct ort_mg
 	NcclApi* api = nullptr;
 	ncclComm_t comm = nullptr;
 	int rank = 0, world = 1;
+	int group = 1;                                 // frames per wire operation
 	cudaStream_t comm_stream = nullptr;
-	cudaEvent_t  ev_traced[kSlots] = {};         // slot's strip has been traced (trace stream)
-	cudaEvent_t  ev_free[kSlots] = {};           // slot's strip has left / has been unpacked (comm stream)
-	bool         slot_used[kSlots] = {};
-	int          next_slot = 0;
-	size_t pitch = 0;                                          // bytes of one strip block (the longest strip's)
-	char*  d_strips = nullptr;  size_t strip_bytes = 0;        // sender: kSlots strip blocks of this rank
-	char*  d_stage = nullptr;   size_t stage_bytes = 0;        // consumer: kSlots x world strip blocks, rank order (its own among them)
+	// Strips are traced on a few streams in turn: a strip launch ends with the latency tail of its longest rays, and only
+	// launches on different streams overlap that tail with the bulk of the next one (one stream: 28.7, four: 35.2 Grays/s
+	// on two GPUs).  Every trace is forked from / joined to the context's stream, which stays the ordering timeline for
+	// uploads.
+	static constexpr int kMaxTraceStreams = 8;
+	int          n_trace_streams = 4, next_trace_stream = 0;
+	cudaStream_t trace_stream[kMaxTraceStreams] = {};
+	cudaEvent_t  ev_traced[kMaxTraceStreams] = {};     // the stream's pending strips have been traced
+	bool         trace_stream_dirty[kMaxTraceStreams] = {};
+	cudaEvent_t  ev_fork = nullptr;
+	size_t pitch = 0;                              // bytes of one strip block (the longest strip's)
+	MgRing send_ring, recv_ring;                   // sender: blocks of this rank; consumer: world blocks per frame
+	std::vector<MgFrame> pending;
 	uint32_t* d_update = nullptr; size_t update_words = 0;     // broadcast payload of ort_mg_broadcast_update
-	uint64_t frames = 0;
+	uint64_t frames = 0, wire_ops = 0;
 	double   wire_bytes = 0;                                   // bytes this rank sent + received for gathers
 };
 
@@ -120,6 +147,78 @@ int mg_strip_rows(int rank, int world, int H, int tile_rows)
 
 // a strip block of n pixels: voxel u32 [n] | t f32 [n] | face u8 [n]  (n is a multiple of 4: W % 4 == 0)
 inline size_t mg_block_bytes(size_t n) { return n * 9; }
+
+void mg_ring_free(MgRing& r)
+{
+	cudaFree(r.base);
+	for (cudaEvent_t e : r.ev_free) cudaEventDestroy(e);
+	r = MgRing{};
+}
+
+// (re)build a ring of n slots of slot_bytes; the caller has made sure nothing is in flight
+int mg_ring_alloc(ort_mg* m, MgRing& r, int n, size_t slot_bytes)
+{
+	mg_ring_free(r);
+	ORT_CUDA(m->ctx, cudaMalloc(&r.base, slot_bytes * n));
+	r.slot_bytes = slot_bytes;
+	r.n = n;
+	r.ev_free.assign(n, nullptr);
+	r.used.assign(n, 0);
+	for (int i = 0; i < n; ++i) ORT_CUDA(m->ctx, cudaEventCreateWithFlags(&r.ev_free[i], cudaEventDisableTiming));
+	return ORT_OK;
+}
+
+// put the pending frames on the wire: one NCCL group, then the consumers' unpack kernels, then the blocks are released
+int mg_flush(ort_mg* m)
+{
+	ort_ctx* c = m->ctx;
+	if (m->pending.empty()) return ORT_OK;
+	for (int i = 0; i < m->n_trace_streams; ++i)
+		if (m->trace_stream_dirty[i])
+		{
+			ORT_CUDA(c, cudaStreamWaitEvent(m->comm_stream, m->ev_traced[i], 0));
+			m->trace_stream_dirty[i] = false;
+		}
+	const int world = m->world, rank = m->rank;
+	if (world > 1)
+	{
+		ORT_NCCL(m, m->api->GroupStart());
+		for (const MgFrame& f : m->pending)
+		{
+			const size_t bytes = mg_block_bytes(f.max_n);
+			if (!f.blocks)
+			{
+				ORT_NCCL(m, m->api->Send(f.sb, bytes, ort_ncclUint8, f.dst, m->comm, m->comm_stream));
+				m->wire_bytes += static_cast<double>(bytes);
+			}
+			else
+				for (int r = 0; r < world; ++r)
+				{
+					if (r == rank) continue;
+					ORT_NCCL(m, m->api->Recv(f.blocks + static_cast<size_t>(r) * m->pitch, bytes, ort_ncclUint8, r, m->comm, m->comm_stream));
+					m->wire_bytes += static_cast<double>(bytes);
+				}
+		}
+		ORT_NCCL(m, m->api->GroupEnd());
+		++m->wire_ops;
+	}
+	for (const MgFrame& f : m->pending)
+	{
+		MgRing& ring = f.blocks ? m->recv_ring : m->send_ring;
+		if (f.blocks)
+		{
+			// every rank's tiles -> their rows of the frame, one launch
+			const ort::StripMap map{ f.W, f.H, f.tile_rows, world, f.max_n, m->pitch };
+			const dim3 grid(static_cast<unsigned>((f.max_n / 4 + 255) / 256), static_cast<unsigned>(world));
+			ort::unpack_strips_kernel<<<grid, 256, 0, m->comm_stream>>>(reinterpret_cast<uint4*>(f.voxel), reinterpret_cast<uint4*>(f.t), reinterpret_cast<uint32_t*>(f.face), f.blocks, map);
+			++c->launches;
+		}
+		ORT_CUDA(c, cudaEventRecord(ring.ev_free[f.slot], m->comm_stream));
+	}
+	ORT_CUDA(c, cudaGetLastError());
+	m->pending.clear();
+	return ORT_OK;
+}
 
 }  // namespace
 
@@ -151,10 +250,12 @@ int ort_mg_create(ort_mg** out, ort_ctx* ctx, int rank, int world, const void* i
 	DeviceGuard g(ctx->device);
 	const int rc = [&]() -> int {
 		ORT_CUDA(ctx, cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
-		for (int i = 0; i < kSlots; ++i)
+		ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+		m->n_trace_streams = world > 4 ? 8 : 4;
+		for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i)
 		{
+			ORT_CUDA(ctx, cudaStreamCreateWithFlags(&m->trace_stream[i], cudaStreamNonBlocking));
 			ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_traced[i], cudaEventDisableTiming));
-			ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_free[i], cudaEventDisableTiming));
 		}
 		if (world > 1)
 		{
@@ -185,14 +286,15 @@ int ort_mg_destroy(ort_mg* m)
 	DeviceGuard g(m->ctx->device);
 	if (m->comm_stream) cudaStreamSynchronize(m->comm_stream);
 	if (m->comm && m->api) m->api->CommDestroy(m->comm);
-	cudaFree(m->d_strips);
-	cudaFree(m->d_stage);
+	mg_ring_free(m->send_ring);
+	mg_ring_free(m->recv_ring);
 	cudaFree(m->d_update);
-	for (int i = 0; i < kSlots; ++i)
+	for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i)
 	{
+		if (m->trace_stream[i]) { cudaStreamSynchronize(m->trace_stream[i]); cudaStreamDestroy(m->trace_stream[i]); }
 		if (m->ev_traced[i]) cudaEventDestroy(m->ev_traced[i]);
-		if (m->ev_free[i]) cudaEventDestroy(m->ev_free[i]);
 	}
+	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
 	if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
 	delete m;
 	return ORT_OK;
@@ -225,9 +327,15 @@ int ort_mg_broadcast_update(ort_mg* m, const uint32_t* ids, const uint32_t* node
 	enter(c);
 	if (src < 0 || src >= m->world || (m->rank == src && n && (!nodes8 || (!is_full && !ids))))
 		return ort_fail(c, ORT_ERR_INVALID, "ort_mg_broadcast_update: bad arguments");
+	DeviceGuard g(c->device);
+	{
+		// the update changes the array every strip trace in flight reads: they finish first
+		const int rc = mg_flush(m);
+		if (rc != ORT_OK) return rc;
+		for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i) ORT_CUDA(c, cudaStreamSynchronize(m->trace_stream[i]));
+	}
 	if (m->world == 1)
 		return is_full ? ort_upload_full(c, nodes8, n, root) : ort_upload_delta(c, ids, nodes8, n, root);
-	DeviceGuard g(c->device);
 	// header: n, root, is_full (through the same payload buffer: 4 words)
 	auto ensure = [&](size_t words) -> int {
 		if (words <= m->update_words) return ORT_OK;
@@ -287,76 +395,94 @@ int ort_mg_trace_frame_gather(ort_mg* m, const float pos[3], const float rot[9],
 	const size_t pitch = align_up(mg_block_bytes(max_n), 256);
 	const bool consumer = rank == dst;
 
-	// a rank that sends keeps kSlots blocks; the consumer keeps kSlots x world (one per rank, its own among them)
-	const size_t need = pitch * kSlots * (consumer ? world : 1);
-	char*& pool = consumer ? m->d_stage : m->d_strips;
-	size_t& pool_bytes = consumer ? m->stage_bytes : m->strip_bytes;
-	if (need > pool_bytes || pitch != m->pitch)
+	// rings of 2 x group blocks (at least 3): a sender's hold one strip block per slot, a consumer's world blocks per slot
+	const int want_slots = std::max(3, 2 * m->group);
+	MgRing& ring = consumer ? m->recv_ring : m->send_ring;
+	const size_t slot_bytes = pitch * (consumer ? world : 1);
+	if (pitch != m->pitch || ring.n < want_slots || ring.slot_bytes != slot_bytes)
 	{
+		int rc = mg_flush(m);                                              // (collective discipline: every rank changes geometry at the same frame)
+		if (rc != ORT_OK) return rc;
 		ORT_CUDA(c, cudaDeviceSynchronize());
 		if (pitch != m->pitch)
 		{
-			cudaFree(m->d_strips); m->d_strips = nullptr; m->strip_bytes = 0;
-			cudaFree(m->d_stage); m->d_stage = nullptr; m->stage_bytes = 0;
+			mg_ring_free(m->send_ring);
+			mg_ring_free(m->recv_ring);
 			m->pitch = pitch;
 		}
-		cudaFree(pool); pool = nullptr; pool_bytes = 0;
-		ORT_CUDA(c, cudaMalloc(&pool, need));
-		pool_bytes = need;
-		for (int i = 0; i < kSlots; ++i) m->slot_used[i] = false;
+		rc = mg_ring_alloc(m, ring, want_slots, slot_bytes);
+		if (rc != ORT_OK) return rc;
 	}
 
-	const int slot = m->next_slot;
-	m->next_slot = (m->next_slot + 1) % kSlots;
-	char* blocks = consumer ? m->d_stage + static_cast<size_t>(slot) * world * pitch : nullptr;      // consumer: this frame's blocks, rank order
-	char* sb = consumer ? blocks + static_cast<size_t>(rank) * pitch : m->d_strips + static_cast<size_t>(slot) * pitch;
+	const int slot = ring.next;
+	ring.next = (ring.next + 1) % ring.n;
+	char* blocks = consumer ? ring.base + static_cast<size_t>(slot) * slot_bytes : nullptr;          // consumer: this frame's blocks, rank order
+	char* sb = consumer ? blocks + static_cast<size_t>(rank) * pitch : ring.base + static_cast<size_t>(slot) * slot_bytes;
 	uint32_t* sv = reinterpret_cast<uint32_t*>(sb);
 	float*    st = reinterpret_cast<float*>(sb + max_n * 4);
 	uint8_t*  sf = reinterpret_cast<uint8_t*>(sb + max_n * 8);
 
-	// trace into the slot once its previous contents have left (a sender's block) / have been unpacked (the consumer's)
-	cudaStream_t ts = c->stream;
-	if (m->slot_used[slot]) ORT_CUDA(c, cudaStreamWaitEvent(ts, m->ev_free[slot], 0));
+	// trace into the block once its previous contents have left (a sender's block) / have been unpacked (a consumer's), on
+	// the next trace stream; the context's stream is the timeline: the trace starts after what is queued there (an
+	// upload)
+	cudaStream_t user = c->stream;
+	const int tsi = m->next_trace_stream;
+	m->next_trace_stream = (m->next_trace_stream + 1) % m->n_trace_streams;
+	cudaStream_t ts = m->trace_stream[tsi];
+	ORT_CUDA(c, cudaEventRecord(m->ev_fork, user));
+	ORT_CUDA(c, cudaStreamWaitEvent(ts, m->ev_fork, 0));
+	if (ring.used[slot]) ORT_CUDA(c, cudaStreamWaitEvent(ts, ring.ev_free[slot], 0));
+	ring.used[slot] = 1;
 	if (my_rows)
 	{
+		c->stream = ts;
 		const int rc = ort_trace_frame_async(c, pos, rot, fov_factor, W, H, rank * tile_rows, my_rows, tile_rows, world, sv, sf, st, nullptr);
+		c->stream = user;
 		if (rc != ORT_OK) return rc;
 	}
-	ORT_CUDA(c, cudaEventRecord(m->ev_traced[slot], ts));
-	ORT_CUDA(c, cudaStreamWaitEvent(m->comm_stream, m->ev_traced[slot], 0));
-
-	// the wire: one message per (rank -> dst) pair -- the whole block, sections at fixed offsets
-	if (world > 1)
-	{
-		ORT_NCCL(m, m->api->GroupStart());
-		if (!consumer)
-		{
-			ORT_NCCL(m, m->api->Send(sb, mg_block_bytes(max_n), ort_ncclUint8, dst, m->comm, m->comm_stream));
-			m->wire_bytes += static_cast<double>(mg_block_bytes(max_n));
-		}
-		else
-			for (int r = 0; r < world; ++r)
-			{
-				if (r == dst) continue;
-				ORT_NCCL(m, m->api->Recv(blocks + static_cast<size_t>(r) * pitch, mg_block_bytes(max_n), ort_ncclUint8, r, m->comm, m->comm_stream));
-				m->wire_bytes += static_cast<double>(mg_block_bytes(max_n));
-			}
-		ORT_NCCL(m, m->api->GroupEnd());
-	}
-
-	// consumer: every rank's tiles -> their rows of the frame, one launch
-	if (consumer)
-	{
-		const ort::StripMap map{ W, H, tile_rows, world, max_n, pitch };
-		const dim3 grid(static_cast<unsigned>((max_n / 4 + 255) / 256), static_cast<unsigned>(world));
-		ort::unpack_strips_kernel<<<grid, 256, 0, m->comm_stream>>>(reinterpret_cast<uint4*>(voxel), reinterpret_cast<uint4*>(t), reinterpret_cast<uint32_t*>(face), blocks, map);
-		++c->launches;
-		ORT_CUDA(c, cudaGetLastError());
-	}
-	ORT_CUDA(c, cudaEventRecord(m->ev_free[slot], m->comm_stream));
-	m->slot_used[slot] = true;
+	ORT_CUDA(c, cudaEventRecord(m->ev_traced[tsi], ts));
+	m->trace_stream_dirty[tsi] = true;
+	// (no join back into the context's stream here: the next frame's fork would then wait for this trace and the strips
+	// would run one after the other; ort_mg_sync() and ort_mg_broadcast_update() wait for the trace streams instead)
+	m->pending.push_back(MgFrame{ W, H, tile_rows, dst, max_n, sb, blocks, voxel, face, t, slot });
 	++m->frames;
+	if (static_cast<int>(m->pending.size()) >= m->group)
+		return mg_flush(m);
 	return ORT_OK;
+}
+
+// Frames per wire operation (collective setting: the same on every rank; takes effect at the next frame).  1 (default):
+// every frame's strips leave as soon as they are traced.  n > 1: the strips of n consecutive frames leave in ONE NCCL
+// group -- fewer, larger, all-to-all-shaped exchanges; ort_mg_flush() / ort_mg_sync() send a partial group.
+int ort_mg_set_group(ort_mg* m, int frames)
+{
+	if (!m || frames < 1 || frames > 256) return ort_fail(m ? m->ctx : nullptr, ORT_ERR_INVALID, "ort_mg_set_group: 1..256 frames");
+	enter(m->ctx);
+	DeviceGuard g(m->ctx->device);
+	const int rc = mg_flush(m);
+	m->group = frames;
+	return rc;
+}
+
+// Streams the strips are traced on in turn (1..8; default 4, 8 from five ranks on): more of them hide the latency tails of
+// small strip launches, too many dilute each launch's cache locality.
+int ort_mg_set_trace_streams(ort_mg* m, int n)
+{
+	if (!m || n < 1 || n > ort_mg::kMaxTraceStreams) return ort_fail(m ? m->ctx : nullptr, ORT_ERR_INVALID, "ort_mg_set_trace_streams: 1..8 streams");
+	enter(m->ctx);
+	DeviceGuard g(m->ctx->device);
+	const int rc = mg_flush(m);
+	m->n_trace_streams = n;
+	m->next_trace_stream = 0;
+	return rc;
+}
+
+int ort_mg_flush(ort_mg* m)
+{
+	if (!m) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_mg_flush: null communicator");
+	enter(m->ctx);
+	DeviceGuard g(m->ctx->device);
+	return mg_flush(m);
 }
 
 // all frames queued so far are complete on their consumers (and this rank's strips have left)
@@ -365,11 +491,15 @@ int ort_mg_sync(ort_mg* m)
 	if (!m) return ort_fail(nullptr, ORT_ERR_INVALID, "ort_mg_sync: null communicator");
 	enter(m->ctx);
 	DeviceGuard g(m->ctx->device);
+	const int rc = mg_flush(m);
+	if (rc != ORT_OK) return rc;
 	ORT_CUDA(m->ctx, cudaStreamSynchronize(m->ctx->stream));
+	for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i) ORT_CUDA(m->ctx, cudaStreamSynchronize(m->trace_stream[i]));
 	ORT_CUDA(m->ctx, cudaStreamSynchronize(m->comm_stream));
 	return ORT_OK;
 }
 
 double ort_mg_wire_bytes(const ort_mg* m) { return m ? m->wire_bytes : 0.0; }
+uint64_t ort_mg_wire_ops(const ort_mg* m) { return m ? m->wire_ops : 0; }
 
 }  // extern "C"

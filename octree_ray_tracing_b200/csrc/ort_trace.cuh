@@ -14,6 +14,7 @@
 #pragma once
 
 #include <cstdint>
+#include <cstring>
 #ifndef ORT_HOST_EMU          // tests/host_emu compiles this header for the host with its own stand-ins for the intrinsics
 #include <cuda_runtime.h>
 #endif
@@ -28,19 +29,22 @@ struct RcpTable
 	int shift;             // 23 - log2n
 };
 
+// RCPPS as a table function: the top log2n mantissa bits pick the entry, the exponent is handled
+// arithmetically.  Every entry is the reciprocal of a number in [1, 2), i.e. lies in (0.5, 1] with exponent field 126 or
+// 127 -- ort_set_rcp_table() refuses tables that break this -- which is what lets the common case run without a check
+// on the result's exponent.
 __device__ __forceinline__ uint32_t rcp_model(const RcpTable rt, uint32_t x)
 {
-	const uint32_t sign = x & 0x80000000u;
-	const uint32_t e = (x >> 23) & 0xFFu;
-	const uint32_t m = x & 0x7FFFFFu;
-	if (e - 1u < 252u)
+	const uint32_t xe = x & 0x7F800000u;                                   // the exponent field e, in place
+	if (xe - 0x00800000u < 0x7E000000u)
 	{
-		// common case: the result exponent field (>= 126 - 125 = 1 for Intel's table) cannot underflow
-		const uint32_t r = __ldg(rt.tab + (m >> rt.shift));
-		const int re = static_cast<int>(r >> 23) - (static_cast<int>(e) - 127);
-		if (re > 0) return sign | (r - ((e - 127u) << 23));
-		return sign;
+		// e in 1..252: result exponent field = (126 | 127) - (e - 127) >= 1, no underflow; r - ((e - 127) << 23) in one add
+		const uint32_t r = __ldg(rt.tab + ((x & 0x7FFFFFu) >> rt.shift));
+		return (x & 0x80000000u) | (r + 0x3F800000u - xe);
 	}
+	const uint32_t sign = x & 0x80000000u;
+	const uint32_t e = xe >> 23;
+	const uint32_t m = x & 0x7FFFFFu;
 	if (e == 255u) return m ? (x | 0x00400000u) : sign;      // NaN stays NaN, inf -> 0
 	if (e == 0u) return sign | 0x7F800000u;                  // 0 and denormals -> inf
 	const uint32_t r = __ldg(rt.tab + (m >> rt.shift));
@@ -66,7 +70,12 @@ struct Ray
 	uint32_t t0or;           // OR over the axes of bits(fma(o_a, coef_a, bias_a)): the sign bit tells whether a t value can ever be negative (LeanWalker)
 };
 
-__device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, int a, float& coef, float& bias, uint32_t& pos, uint32_t& inv, uint32_t& idx, uint32_t& t0or, uint32_t plane_mask)
+// t0or: the t of the plane through the origin itself only exists as a cell plane when the origin coordinate lies on the
+// finest level's grid, i.e. when its mantissa bits below that level (plane_mask) are clear (see LeanWalker /
+// lean_path_ok).  CAMERA = false: tested per ray with `arg` = plane_mask.  CAMERA = true: the rays of a launch share the
+// origin, `arg` != 0 says "on the grid" for the whole launch (a warp-uniform branch; camera_origin_flags()).
+template<bool CAMERA>
+__device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, int a, float& coef, float& bias, uint32_t& pos, uint32_t& inv, uint32_t& idx, uint32_t& t0or, uint32_t arg)
 {
 	const bool sg = 0.0f < d;                                                  // :310
 	inv |= static_cast<uint32_t>(sg) << a;                                     // :322
@@ -76,9 +85,7 @@ __device__ __forceinline__ void ray_axis(const RcpTable rt, float o, float d, in
 	bias = __uint_as_float(__float_as_uint(__fmul_rn(coef, oa)) ^ 0x80000000u); // :318
 	pos = __float_as_uint(oa) & 0x3FC00000u;                                   // :320
 	idx |= static_cast<uint32_t>(pos == 0x3FC00000u) << a;                     // :324
-	// t of the plane through the origin itself -- it only exists as a cell plane when the origin lies on the finest
-	// level's grid, i.e. when its mantissa bits below that level (plane_mask) are clear (see LeanWalker / lean_path_ok)
-	if ((__float_as_uint(oa) & plane_mask) == 0u)
+	if (CAMERA ? arg != 0u : (__float_as_uint(oa) & arg) == 0u)
 		t0or |= __float_as_uint(__fmaf_rn(oa, coef, bias));
 }
 
@@ -89,9 +96,22 @@ __device__ __forceinline__ Ray ray_setup(const RcpTable rt, float ox, float oy, 
 	r.inv = 0;
 	r.idx = 0;
 	r.t0or = 0;
-	ray_axis(rt, ox, dx, 0, r.cx, r.bx, r.px, r.inv, r.idx, r.t0or, plane_mask);
-	ray_axis(rt, oy, dy, 1, r.cy, r.by, r.py, r.inv, r.idx, r.t0or, plane_mask);
-	ray_axis(rt, oz, dz, 2, r.cz, r.bz, r.pz, r.inv, r.idx, r.t0or, plane_mask);
+	ray_axis<false>(rt, ox, dx, 0, r.cx, r.bx, r.px, r.inv, r.idx, r.t0or, plane_mask);
+	ray_axis<false>(rt, oy, dy, 1, r.cy, r.by, r.py, r.inv, r.idx, r.t0or, plane_mask);
+	ray_axis<false>(rt, oz, dz, 2, r.cz, r.bz, r.pz, r.inv, r.idx, r.t0or, plane_mask);
+	return r;
+}
+
+// the rays of a camera frame: origin_flags = camera_origin_flags() of the shared origin (bits 0-2: coordinate on the grid)
+__device__ __forceinline__ Ray ray_setup_camera(const RcpTable rt, float ox, float oy, float oz, float dx, float dy, float dz, uint32_t origin_flags)
+{
+	Ray r;
+	r.inv = 0;
+	r.idx = 0;
+	r.t0or = 0;
+	ray_axis<true>(rt, ox, dx, 0, r.cx, r.bx, r.px, r.inv, r.idx, r.t0or, origin_flags & 1u);
+	ray_axis<true>(rt, oy, dy, 1, r.cy, r.by, r.py, r.inv, r.idx, r.t0or, origin_flags & 2u);
+	ray_axis<true>(rt, oz, dz, 2, r.cz, r.bz, r.pz, r.inv, r.idx, r.t0or, origin_flags & 4u);
 	return r;
 }
 
@@ -553,8 +573,15 @@ struct LeanWalker
 	}
 };
 
-// LeanWalker's preconditions on top of fast_path_ok: no degenerate axis (coef regular, i.e. below -inf as unsigned bits)
-// and no negative t at the planes through the origin (Ray::t0or; the argument is in LeanWalker's header).
+// the origin part of fast_path_ok: origin inside [1,2)^3 and a start position in [1,2)^3 (see there)
+__device__ __forceinline__ bool origin_in_cube(float ox, float oy, float oz, const Ray& r)
+{
+	return in_unit_cube(ox, oy, oz) & ((r.px & r.py & r.pz & 0x3F800000u) == 0x3F800000u);
+}
+
+// LeanWalker's preconditions on top of origin_in_cube: no degenerate axis (every coef regular, i.e. below -inf as unsigned
+// bits -- which also rules out NaN) and no negative t at the planes through the origin (Ray::t0or; the argument is in
+// LeanWalker's header).  Together they imply fast_path_ok.
 __device__ __forceinline__ bool lean_path_ok(const Ray& r)
 {
 	const uint32_t ninf = 0xFF800000u;
@@ -621,7 +648,32 @@ struct Camera
 	float r[9];
 	float fov;
 	float aspect, vfx, vfy;
+	uint32_t origin_flags;   // camera_origin_flags(): what holds for EVERY ray of the frame because they share the origin
 };
+
+// Origin facts of a camera frame, computed once on the host instead of once per ray:
+//   bits 0-2  coordinate a lies on the finest level's grid (its mantissa bits below that level are clear) -- only then
+//             does a cell plane pass through the origin and the t0 test of the lean tier apply (Ray::t0or);
+//   bit 3     the origin passes fast_path_ok's origin tests for every direction: all coordinates in [1, 2) and none
+//             exactly 1.0f (which mirrors to 2.0f on an axis travelled in the positive direction and leaves the cube).
+constexpr uint32_t kOriginInCube = 8u;
+inline uint32_t camera_origin_flags(float ox, float oy, float oz, uint32_t plane_mask)
+{
+	const float o[3] = { ox, oy, oz };
+	uint32_t f = kOriginInCube;
+	for (int a = 0; a < 3; ++a)
+	{
+		uint32_t b;
+#ifdef ORT_HOST_EMU
+		b = __float_as_uint(o[a]);
+#else
+		memcpy(&b, &o[a], 4);
+#endif
+		if ((b >> 23) != 127u || b == 0x3F800000u) f &= ~kOriginInCube;
+		if ((b & plane_mask) == 0u) f |= 1u << a;       // (3 - o has the same low mantissa bits clear as o, for o in [1, 2))
+	}
+	return f;
+}
 
 __device__ __forceinline__ void camera_ray(const Camera& c, int x, int y, float& dx, float& dy, float& dz)
 {

@@ -82,6 +82,13 @@ class MultiGpu:
         ptr = lambda x: None if x is None else x.data_ptr()
         self._ck(self.L.ort_mg_trace_frame_gather(self.h, pos.ctypes.data, rot.ctypes.data, float(fov_factor), W, H, tile_rows, dst, ptr(d_vox), ptr(d_face), ptr(d_t)))
 
+    def set_group(self, frames: int):
+        """Frames per wire operation (the same on every rank): 1 = lowest latency, n = one NCCL group per n frames."""
+        self._ck(self.L.ort_mg_set_group(self.h, frames))
+
+    def flush(self):
+        self._ck(self.L.ort_mg_flush(self.h))
+
     def sync(self):
         self._ck(self.L.ort_mg_sync(self.h))
 

@@ -23,9 +23,48 @@ struct Stats
 // 13 the round-2 tiers (LeanWalker first), 14 FlatWalker, 15 V4Walker (both on LeanWalker's tiers)
 template<bool COUNT>
 ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, float miss_t, float ox, float oy, float oz, const ort::Ray& ray,
-              Stats* st)
+              Stats* st, int origin_flags = -1)
 {
 	uint32_t stack[ort::kMaxDepth];
+	if (walker >= 13 && walker <= 15)
+	{
+		// the kernels' tier test (ort::trace_ray): origin facts known for the launch (camera frames) or tested per ray;
+		// LeanWalker (or an experiment round on its state) where no t can be negative, FastWalker / traverse() otherwise
+		const bool origin_ok = origin_flags >= 0 ? (origin_flags & static_cast<int>(ort::kOriginInCube)) != 0 : ort::origin_in_cube(ox, oy, oz, ray);
+		if (!(origin_ok && ort::lean_path_ok(ray)))
+			return walk<COUNT>(1, nodes_m1, root, depth, miss_t, ox, oy, oz, ray, st);
+		if (st) ++st->lean_rays;
+		uint32_t lstack[ort::kMaxDepth] = {};
+		const ort::LeanStack<0> ls{ lstack };
+		const unsigned long long base_biased = reinterpret_cast<unsigned long long>(nodes_m1) - 4ull * ort::kMagicBits;
+		const float leaf_dimf = std::ldexp(1.0f, -depth);
+		if (walker == 14)
+		{
+			ort::FlatWalker<COUNT> w;
+			w.start(root, ray);
+			while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
+			return w.hit;
+		}
+		if (walker == 15)
+		{
+			ort::V4Walker<COUNT> w;
+			w.start(root, ray);
+			while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
+			return w.hit;
+		}
+		// the product's loop shape (ort::trace_ray): descend while there are children, then one advance
+		ort::LeanWalker<COUNT> w;
+		w.start(root, ray);
+		for (;;)
+		{
+			uint32_t child;
+			bool done = false;
+			while ((child = w.load_child(base_biased)) != 0u)
+				if (w.descend(child, leaf_dimf, ls)) { done = true; break; }
+			if (done || w.advance(miss_t, ls)) break;
+		}
+		return w.hit;
+	}
 	if (walker == 0 || !ort::fast_path_ok(ox, oy, oz, ray))
 	{
 		if (st) ++st->slow_path_rays;
@@ -45,38 +84,6 @@ ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, fl
 				break;
 		}
 		return w.hit;
-	}
-	if (walker == 13 || walker == 14 || walker == 15)
-	{
-		// round-2 tiers as in ort::trace_ray: LeanWalker (or an experiment round on its state) where no t can be
-		// negative, FastWalker otherwise
-		if (ort::lean_path_ok(ray))
-		{
-			if (st) ++st->lean_rays;
-			uint32_t lstack[ort::kMaxDepth] = {};
-			const ort::LeanStack<0> ls{ lstack };
-			const unsigned long long base_biased = reinterpret_cast<unsigned long long>(nodes_m1) - 4ull * ort::kMagicBits;
-			const float leaf_dimf = std::ldexp(1.0f, -depth);
-			if (walker == 14)
-			{
-				ort::FlatWalker<COUNT> w;
-				w.start(root, ray);
-				while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
-				return w.hit;
-			}
-			if (walker == 15)
-			{
-				ort::V4Walker<COUNT> w;
-				w.start(root, ray);
-				while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
-				return w.hit;
-			}
-			ort::LeanWalker<COUNT> w;
-			w.start(root, ray);
-			while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
-			return w.hit;
-		}
-		return walk<COUNT>(1, nodes_m1, root, depth, miss_t, ox, oy, oz, ray, nullptr);
 	}
 	if (walker == 5)
 	{
@@ -180,6 +187,8 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 	cam.aspect = static_cast<float>(W) / static_cast<float>(H);
 	cam.vfx = 2.0F / static_cast<float>(W);
 	cam.vfy = 2.0F / static_cast<float>(H);
+	cam.origin_flags = ort::camera_origin_flags(cam.ox, cam.oy, cam.oz, (1u << (23 - depth)) - 1u);
+	const int oflags = static_cast<int>(cam.origin_flags);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, 0, ort::tile_shift_of(tile_rows) };
 	Stats total{};
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
@@ -192,11 +201,11 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 			{
 				float dx, dy, dz;
 				ort::camera_ray(cam, x, ort::frame_row(fr, r), dx, dy, dz);
-				const ort::Ray ray = ort::ray_setup(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, (1u << (23 - depth)) - 1u);
+				const ort::Ray ray = ort::ray_setup_camera(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, cam.origin_flags);
 				ort::Hit h;
 				if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
-				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr)
-				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr);
+				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags)
+				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags);
 				++st.rays;
 				const size_t i = static_cast<size_t>(r) * W + x;
 				voxel[i] = h.voxel;

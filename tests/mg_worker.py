@@ -78,7 +78,9 @@ for k in range(2):
     if rank == 0:
         tree.set_box(100 + 20 * k, 128, 70, 17 + k, 1 + k)
     nodes8, root = ship()
-    check_frames(nodes8, root, f"delta {k}")
+    mg.set_group((2, 5)[k])           # grouped wire operations: 2 frames per NCCL group (one partial group per sync), then 5 (every sync sends a partial group)
+    check_frames(nodes8, root, f"delta {k}, group {(2, 5)[k]}")
+mg.set_group(1)
 wire = mg.wire_bytes
 dist.barrier()
 if rank == 0:
