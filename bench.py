@@ -322,15 +322,22 @@ def run_product(args):
             ff = torch.empty(W * H, dtype=torch.uint8, device="cuda")
             ft = torch.empty(W * H, dtype=torch.float32, device="cuda")
 
-            def gather_step(mode):
+            def jobs_of(mode):
+                js = []
                 for k, cam in enumerate(step_cams):
                     dst = k % world if mode == "round_robin" else 0
                     mine = dst == rank
-                    mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=dst, d_vox=fv if mine else None, d_face=ff if mine else None, d_t=ft if mine else None)
+                    js.append((cam[0], cam[1], cam[2], W, H, TILE_ROWS, dst, fv if mine else None, ff if mine else None, ft if mine else None))
+                return mg.make_jobs(js)
+            step_jobs = {mode: jobs_of(mode) for mode in ("round_robin", "rank0")}
+
+            def gather_step(mode):
+                mg.trace_frames_gather(step_jobs[mode])         # the step's frames in one call (ort_mg_trace_frames_gather)
 
             g_steps = max(1, min(args.steps, 10))
             # (consumers, frames per wire operation): per-frame messages, and the whole step's strips as one NCCL group
-            for mode, grp in (("round_robin", 1), ("round_robin", len(step_cams)), ("rank0", len(step_cams))):
+            for mode, grp, tr in (("round_robin", 1, 1), ("round_robin", len(step_cams), 1), ("rank0", len(step_cams), 1), ("round_robin", len(step_cams), 0)):
+                mg.set_transport(tr)
                 mg.set_group(grp)
                 gather_step(mode)
                 mg.sync()
@@ -341,10 +348,16 @@ def run_product(args):
                     gather_step(mode)
                 mg.sync()
                 barrier()
-                gather[(mode, grp)] = ((time.perf_counter() - g0) / g_steps, (mg.wire_bytes - w0) / g_steps)
+                if tr == 1:
+                    gather["transport"] = mg.transport
+                gather[(mode, grp) if tr == 1 else (mode + "_nccl_sendrecv", grp)] = ((time.perf_counter() - g0) / g_steps, (mg.wire_bytes - w0) / g_steps)
+            mg.set_transport(1)
             mg.set_group(1)
             # one frame at a time, nothing in flight: the latency of "trace my strips + gather" for a single frame
             lat = []
+            for cam in cams[:1]:                    # (untimed: the settings above rebuild the rings at the next frame)
+                mg.trace_frame_gather(cam[0], cam[1], cam[2], W, H, tile_rows=TILE_ROWS, dst=0, d_vox=fv if rank == 0 else None, d_face=ff if rank == 0 else None, d_t=ft if rank == 0 else None)
+                mg.sync()
             for cam in cams:
                 barrier()
                 g0 = time.perf_counter()
@@ -512,12 +525,13 @@ def run_product(args):
     n_step_frames = len(step_cams)
     g_rr, g_r0 = gather.get(("round_robin", n_step_frames), (0.0, 0.0)), gather.get(("rank0", n_step_frames), (0.0, 0.0))
     g_rr1 = gather.get(("round_robin", 1), (0.0, 0.0))
+    g_rrn = gather.get(("round_robin_nccl_sendrecv", n_step_frames), (0.0, 0.0))
     g_lat = max(gather.get("latency", [0.0]))
     d2h_sum = d2h_gbs_local
     if world > 1:
-        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1[0]], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1[0], g_rrn[0]], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1_s = (float(x) for x in tt.tolist())
+        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1_s, g_rrn_s = (float(x) for x in tt.tolist())
         cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local, d2h_gbs_local, g_rr[1], g_r0[1]], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
@@ -530,7 +544,7 @@ def run_product(args):
     else:
         launches_all = launches
         pushes_per_ray_all = pushes_per_step_local / rays_per_step_local
-        g_rr_s = g_r0_s = g_rr1_s = 0.0
+        g_rr_s = g_r0_s = g_rr1_s = g_rrn_s = 0.0
         wire_rr = wire_r0 = ingest_r0 = 0.0
 
     result = None
@@ -586,11 +600,13 @@ def run_product(args):
                        "ncu figures from the capture named in counters_source",
             },
         }
-        value = value_trace
+        # N > 1: the headline is the throughput WITH the gather (frames assembled on their consumers inside the library);
+        # the trace-only figure stands beside it (no_gather).  N = 1 assembles nothing: the frame is already whole.
+        value = rays_per_step_total / g_rr_s / 1e6 if mg is not None else value_trace
         result = {
             "metric": METRIC, "value": round(value, 2), "unit": "Mrays/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": round((g_rr_s * 1e3) if mg is not None else ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32+u32", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD, "frames_per_step": frames_per_step, "rays_per_step": rays_per_step_total,
@@ -603,7 +619,9 @@ def run_product(args):
                 "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
                 "pushes_per_ray": round(pushes_per_ray_all, 3),
                 "hit_fraction": round(hits / (len(cams) * n_local), 4),
-                "timing": "sum of CUDA-event intervals around each step (start after the flush, end after all streams joined), max over ranks",
+                "timing": ("value: wall clock over whole steps of trace + gather (ort_mg_trace_frames_gather ... ort_mg_sync), barrier + synchronize on both sides, max over ranks; "
+                           "no_gather / roofline: sum of CUDA-event intervals around each step, max over ranks" if mg is not None else
+                           "sum of CUDA-event intervals around each step (start after the flush, end after all streams joined), max over ranks"),
             },
             "parity": parity,
             "serial": {"value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2), "unit": "Mrays/s",
@@ -633,14 +651,18 @@ def run_product(args):
         if mg is not None:
             result["with_gather"] = {
                 "value": round(rays_per_step_total / g_rr_s / 1e6, 2), "unit": "Mrays/s",
-                "frac_of_value": round(rays_per_step_total / g_rr_s / 1e6 / value_trace, 4),
+                "frac_of_no_gather": round(rays_per_step_total / g_rr_s / 1e6 / value_trace, 4),
                 "consumers": "round robin: frame k of the step is assembled on rank k mod N (N times the frames, N consumers)",
-                "wire": f"ort_mg_set_group({n_step_frames}): the strips of a step's {n_step_frames} frames leave in ONE NCCL group (an all-to-all-shaped exchange) that overlaps the next step's traces",
+                "wire": f"ort_mg_set_group({n_step_frames}): the strips of a step's {n_step_frames} frames leave in ONE wire operation that overlaps the next step's traces",
                 "wire_bytes_per_step": int(wire_rr), "wire_gbs_aggregate": round(wire_rr / g_rr_s / 1e9, 1),
+                "transport": ("peer copies: every strip block moves with one cudaMemcpyAsync on the copy engines into the consumer's staging area (CUDA IPC mapping), one 4-byte ncclAllReduce per wire operation orders it"
+                              if gather.get("transport") == 1 else "NCCL ncclSend / ncclRecv (CUDA IPC not available between the ranks)"),
+                "nccl_sendrecv_transport": {"value": round(rays_per_step_total / g_rrn_s / 1e6, 2), "unit": "Mrays/s",
+                                            "note": "the same exchange with ort_mg_set_transport(0): NCCL's copy kernels share the SMs with the issue-bound trace kernels"},
                 "per_frame_messages": {"value": round(rays_per_step_total / g_rr1_s / 1e6, 2), "unit": "Mrays/s",
-                                       "note": "ort_mg_set_group(1): every frame's strips leave as soon as they are traced (one small point-to-point NCCL operation per frame)"},
-                "api": "ort_mg_trace_frame_gather (NCCL inside libort_b200.so): strips traced into a ring of blocks on the trace stream, ncclSend / ncclRecv on the "
-                       "communicator's stream, one unpack kernel per frame writes final rows on the consumer; wall clock over whole steps, max over ranks",
+                                       "note": "ort_mg_set_group(1): every frame's strips leave as soon as they are traced (one wire operation per frame)"},
+                "api": "ort_mg_trace_frame_gather (inside libort_b200.so): strips traced into a ring of blocks on 4-8 trace streams, moved on the communicator's "
+                       "stream, one unpack kernel per frame writes final rows on the consumer; wall clock over whole steps, max over ranks",
                 "rank0_only": {"value": round(rays_per_step_total / g_r0_s / 1e6, 2), "unit": "Mrays/s",
                                "note": "every frame assembled on rank 0: one GPU's NVLink ingest carries (N-1)/N of ALL frames",
                                "rank0_ingest_bytes_per_step": int(ingest_r0), "rank0_ingest_gbs": round(ingest_r0 / g_r0_s / 1e9, 1)},
@@ -648,7 +670,8 @@ def run_product(args):
                                                 "note": "ONE 4K frame traced by N GPUs and assembled on rank 0, nothing else in flight (worst pose), wall clock"},
                 "assembled_equals_single_gpu": gather.get("assembled_equals_single_gpu"),
             }
-            result["no_gather"] = {"value": round(value_trace, 2), "unit": "Mrays/s", "note": "= value: strips stay on the GPU that traced them"}
+            result["no_gather"] = {"value": round(value_trace, 2), "unit": "Mrays/s", "ms_per_step": round(ms_per_step, 4),
+                                   "note": "trace only: every rank's strips stay on the GPU that traced them (round 1's headline); L2 flushed before every step, CUDA events"}
         if world == 1 and not args.no_cpu:
             result["cpu_baseline"] = cpu_baseline(tree)
         emit(result)

@@ -189,12 +189,31 @@ int ort_mg_broadcast_update(ort_mg* mg, const uint32_t* ids, const uint32_t* nod
  * is complete. */
 int ort_mg_trace_frame_gather(ort_mg* mg, const float pos[3], const float rot[9], float fov_factor, int W, int H, int tile_rows, int dst,
                               uint32_t* voxel, uint8_t* face, float* t);
+/* The same for a sequence of frames in one call (the cameras of a rig, the frames of a step); fields as the arguments above. */
+typedef struct ort_mg_frame_job
+{
+	float pos[3];
+	float rot[9];
+	float fov_factor;
+	int   W, H, tile_rows, dst;
+	uint32_t* voxel;
+	uint8_t*  face;
+	float*    t;
+} ort_mg_frame_job;
+int ort_mg_trace_frames_gather(ort_mg* mg, const ort_mg_frame_job* jobs, int n_jobs);
 /* Collective setting: frames per wire operation.  1 (default): the strips of every frame leave as soon as they are traced
  * (lowest latency).  n > 1: the strips of n consecutive frames leave in ONE NCCL group -- fewer, larger, all-to-all-shaped
  * exchanges that NCCL spreads over all peers and channels at once (highest throughput when many frames are in flight);
  * ort_mg_flush() sends a partial group, ort_mg_sync() flushes and waits. */
 int ort_mg_set_group(ort_mg* mg, int frames);
 int ort_mg_flush(ort_mg* mg);
+/* Collective setting: how the strips travel.  1 (default): peer copies -- every rank maps the other ranks' receive rings
+ * (CUDA IPC) and a strip block moves with one cudaMemcpyAsync on the copy engines over NVLink, no SM involved; NCCL
+ * carries one 4-byte all-reduce per wire operation for the ordering.  Falls back to 0 where CUDA IPC is unavailable.
+ * 0: NCCL ncclSend / ncclRecv (its copy kernels share the SMs with the trace kernels).  ort_mg_transport() returns what
+ * is in use after the first frame.  The environment variable ORT_MG_TRANSPORT presets it. */
+int ort_mg_set_transport(ort_mg* mg, int transport);
+int ort_mg_transport(const ort_mg* mg);
 /* Streams the strips are traced on in turn (1..8; default 4, 8 from five ranks on): a strip launch ends with the latency
  * tail of its longest rays, and only launches on different streams overlap that tail with the bulk of the next one. */
 int ort_mg_set_trace_streams(ort_mg* mg, int n);

@@ -115,8 +115,11 @@ _SIGS = {
     "ort_mg_trace_frame_gather": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
     "ort_mg_set_group": (C.c_int, [_vp, C.c_int]),
     "ort_mg_flush": (C.c_int, [_vp]),
+    "ort_mg_set_transport": (C.c_int, [_vp, C.c_int]),
+    "ort_mg_transport": (C.c_int, [_vp]),
     "ort_mg_set_trace_streams": (C.c_int, [_vp, C.c_int]),
     "ort_mg_wire_ops": (C.c_uint64, [_vp]),
+    "ort_mg_trace_frames_gather": (C.c_int, [_vp, _vp, C.c_int]),
     "ort_mg_sync": (C.c_int, [_vp]),
     "ort_mg_stream": (_vp, [_vp]),
     "ort_mg_wire_bytes": (C.c_double, [_vp]),

@@ -16,6 +16,19 @@
 //   only after its send (on the consumer: its unpack) has completed -- ordered by events, no host synchronisation.
 //   group = 1 gives the lowest latency per frame; a larger group turns many small point-to-point messages into one
 //   all-to-all-shaped exchange that NCCL spreads over all peers and channels at once.
+//
+// Two transports for the strips (ort_mg_set_transport; the choice is collective):
+//   0  NCCL point-to-point: ncclSend / ncclRecv as described above.  NCCL's copy kernels share the SMs with the trace
+//      kernels of the next frames -- which are bound by instruction issue, so the wire runs at a fraction of its idle
+//      rate and the traces slow down (2 GPUs: 0.82 of the trace-only throughput, 8 GPUs: 0.80).
+//   1  peer copies (default where CUDA IPC works): every rank maps every other rank's receive ring (cudaIpc*MemHandle,
+//      exchanged once per geometry through NCCL) and a sender's strip block travels with ONE cudaMemcpyAsync on the copy
+//      engines over NVLink straight into its place in the consumer's staging area -- no SM is involved.  NCCL carries only
+//      the synchronisation: one 4-byte ncclAllReduce per wire operation after the copies.  It is a rendezvous of all
+//      ranks' comm streams, which gives both orderings the rings need: a consumer unpacks after every sender's copies of
+//      this operation have landed (they precede the sender's all-reduce in stream order), and a sender overwrites a
+//      staging slot two operations later, after the consumer's unpack of the slot's previous frame (which precedes the
+//      consumer's NEXT all-reduce, which the sender's own next all-reduce cannot complete without).
 #pragma once
 
 #include <dlfcn.h>
@@ -26,7 +39,8 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;                       // 0 = ncclSuccess
-enum { ort_ncclUint8 = 1, ort_ncclUint32 = 3 };
+enum { ort_ncclUint8 = 1, ort_ncclInt32 = 2, ort_ncclUint32 = 3 };
+enum { ort_ncclSum = 0, ort_ncclMin = 3 };
 
 struct NcclApi
 {
@@ -39,6 +53,8 @@ struct NcclApi
 	ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	const char*  (*GetErrorString)(ncclResult_t) = nullptr;
 	ncclResult_t (*GetVersion)(int*) = nullptr;
 };
@@ -68,6 +84,8 @@ NcclApi* nccl_api(std::string* why)
 			ORT_NCCL_SYM(Send, "ncclSend");
 			ORT_NCCL_SYM(Recv, "ncclRecv");
 			ORT_NCCL_SYM(Broadcast, "ncclBroadcast");
+			ORT_NCCL_SYM(AllReduce, "ncclAllReduce");
+			ORT_NCCL_SYM(AllGather, "ncclAllGather");
 			ORT_NCCL_SYM(GetErrorString, "ncclGetErrorString");
 			ORT_NCCL_SYM(GetVersion, "ncclGetVersion");
 #undef ORT_NCCL_SYM
@@ -85,6 +103,7 @@ struct MgFrame                                     // a traced frame whose strip
 	char* blocks;                                  // consumer: the frame's world blocks (rank order), else null
 	uint32_t* voxel; uint8_t* face; float* t;      // consumer: the caller's frame buffers
 	int slot;                                      // ring slot to release (sender ring or consumer ring)
+	int rslot;                                     // the frame's slot in its consumer's receive ring (the same number on every rank)
 };
 
 struct MgRing                                      // blocks handed out round robin, each guarded by an event
@@ -92,8 +111,7 @@ struct MgRing                                      // blocks handed out round ro
 	char* base = nullptr;
 	size_t slot_bytes = 0;
 	int n = 0, next = 0;
-	std::vector<cudaEvent_t> ev_free;
-	std::vector<char> used;
+	std::vector<int> op_of_slot;                   // the wire operation that releases the slot (index into ort_mg::ev_op), -1: never used
 };
 
 }  // namespace
@@ -116,9 +134,25 @@ struct ort_mg
 	cudaEvent_t  ev_traced[kMaxTraceStreams] = {};     // the stream's pending strips have been traced
 	bool         trace_stream_dirty[kMaxTraceStreams] = {};
 	cudaEvent_t  ev_fork = nullptr;
+	// peer copies of one wire operation are spread over a few streams so that several copy engines work at once
+	static constexpr int kCopyStreams = 4;
+	cudaStream_t copy_stream[kCopyStreams] = {};
+	cudaEvent_t  ev_copied[kCopyStreams] = {};
+	cudaEvent_t  ev_ready = nullptr;                   // the comm stream has seen the traces of the pending frames
+	// one completion event per wire operation, a ring of them: a block is reused after the operation that carried its
+	// previous contents (and, on a consumer, unpacked them) -- at most two operations back, the rings hold 2 x group blocks
+	static constexpr int kOpEvents = 8;
+	cudaEvent_t  ev_op[kOpEvents] = {};
+	int          next_op = 0;
+	bool         forked = false;                       // the trace streams have seen the context's stream since the last wire operation
 	size_t pitch = 0;                              // bytes of one strip block (the longest strip's)
 	MgRing send_ring, recv_ring;                   // sender: blocks of this rank; consumer: world blocks per frame
 	std::vector<MgFrame> pending;
+	int  transport_pref = 1;                       // 1: peer copies over CUDA IPC if every rank can map every ring, 0: NCCL send / recv
+	bool peer_copies = false;                      // what the current rings use (agreed by all ranks)
+	std::vector<char*> peer_recv_base;             // [world] the other ranks' receive rings, mapped into this process
+	std::vector<uint64_t> consumed;                // [world] frames consumed on each rank so far (the same count on every rank)
+	int* d_flag = nullptr;                         // the 4 bytes of the all-reduce
 	uint32_t* d_update = nullptr; size_t update_words = 0;     // broadcast payload of ort_mg_broadcast_update
 	uint64_t frames = 0, wire_ops = 0;
 	double   wire_bytes = 0;                                   // bytes this rank sent + received for gathers
@@ -151,7 +185,6 @@ inline size_t mg_block_bytes(size_t n) { return n * 9; }
 void mg_ring_free(MgRing& r)
 {
 	cudaFree(r.base);
-	for (cudaEvent_t e : r.ev_free) cudaEventDestroy(e);
 	r = MgRing{};
 }
 
@@ -162,10 +195,62 @@ int mg_ring_alloc(ort_mg* m, MgRing& r, int n, size_t slot_bytes)
 	ORT_CUDA(m->ctx, cudaMalloc(&r.base, slot_bytes * n));
 	r.slot_bytes = slot_bytes;
 	r.n = n;
-	r.ev_free.assign(n, nullptr);
-	r.used.assign(n, 0);
-	for (int i = 0; i < n; ++i) ORT_CUDA(m->ctx, cudaEventCreateWithFlags(&r.ev_free[i], cudaEventDisableTiming));
+	r.op_of_slot.assign(n, -1);
 	return ORT_OK;
+}
+
+void mg_unmap_peers(ort_mg* m)
+{
+	for (int r = 0; r < static_cast<int>(m->peer_recv_base.size()); ++r)
+		if (m->peer_recv_base[r] && r != m->rank) cudaIpcCloseMemHandle(m->peer_recv_base[r]);
+	m->peer_recv_base.assign(m->world, nullptr);
+	m->peer_copies = false;
+}
+
+// Collective: every rank exports its receive ring and maps everybody else's.  All ranks end up with the same answer
+// (peer_copies on or off): a rank that cannot export or map makes everybody fall back to NCCL send / recv.
+int mg_map_peers(ort_mg* m)
+{
+	ort_ctx* c = m->ctx;
+	const int world = m->world, rank = m->rank;
+	mg_unmap_peers(m);
+	if (world == 1 || !m->transport_pref) return ORT_OK;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	char* d_handles = nullptr;
+	ORT_CUDA(c, cudaMalloc(&d_handles, 64 * static_cast<size_t>(world)));
+	cudaIpcMemHandle_t mine;
+	int ok = cudaIpcGetMemHandle(&mine, m->recv_ring.base) == cudaSuccess;
+	if (!ok) { cudaGetLastError(); std::memset(&mine, 0, sizeof mine); }
+	std::vector<cudaIpcMemHandle_t> all(world);
+	const int rc = [&]() -> int {
+		ORT_CUDA(c, cudaMemcpyAsync(d_handles + 64 * static_cast<size_t>(rank), &mine, 64, cudaMemcpyHostToDevice, m->comm_stream));
+		ORT_NCCL(m, m->api->AllGather(d_handles + 64 * static_cast<size_t>(rank), d_handles, 64, ort_ncclUint8, m->comm, m->comm_stream));
+		ORT_CUDA(c, cudaMemcpyAsync(all.data(), d_handles, 64 * static_cast<size_t>(world), cudaMemcpyDeviceToHost, m->comm_stream));
+		ORT_CUDA(c, cudaStreamSynchronize(m->comm_stream));
+		for (int r = 0; r < world && ok; ++r)
+		{
+			if (r == rank) { m->peer_recv_base[r] = m->recv_ring.base; continue; }
+			void* p = nullptr;
+			if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+			m->peer_recv_base[r] = static_cast<char*>(p);
+		}
+		// agree: peer copies only if every rank mapped every ring
+		ORT_CUDA(c, cudaMemcpyAsync(m->d_flag, &ok, 4, cudaMemcpyHostToDevice, m->comm_stream));
+		ORT_NCCL(m, m->api->AllReduce(m->d_flag, m->d_flag, 1, ort_ncclInt32, ort_ncclMin, m->comm, m->comm_stream));
+		int all_ok = 0;
+		ORT_CUDA(c, cudaMemcpyAsync(&all_ok, m->d_flag, 4, cudaMemcpyDeviceToHost, m->comm_stream));
+		ORT_CUDA(c, cudaStreamSynchronize(m->comm_stream));
+		if (all_ok) m->peer_copies = true;
+		else
+		{
+			mg_unmap_peers(m);
+			static bool said = false;
+			if (!said && rank == 0) { said = true; std::fprintf(stderr, "ort_b200: note: CUDA IPC is not available between the ranks; the strip gather uses NCCL send / recv\n"); }
+		}
+		return ORT_OK;
+	}();
+	cudaFree(d_handles);
+	return rc;
 }
 
 // put the pending frames on the wire: one NCCL group, then the consumers' unpack kernels, then the blocks are released
@@ -173,14 +258,49 @@ int mg_flush(ort_mg* m)
 {
 	ort_ctx* c = m->ctx;
 	if (m->pending.empty()) return ORT_OK;
-	for (int i = 0; i < m->n_trace_streams; ++i)
+	for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i)
 		if (m->trace_stream_dirty[i])
 		{
+			ORT_CUDA(c, cudaEventRecord(m->ev_traced[i], m->trace_stream[i]));
 			ORT_CUDA(c, cudaStreamWaitEvent(m->comm_stream, m->ev_traced[i], 0));
 			m->trace_stream_dirty[i] = false;
 		}
+	m->forked = false;
 	const int world = m->world, rank = m->rank;
-	if (world > 1)
+	if (world > 1 && m->peer_copies)
+	{
+		// transport 1: the copy engines move the blocks, one 4-byte all-reduce orders everything (see the file header).
+		// The copies of this operation fan out over a few streams (several engines, several destinations at once) and
+		// join the comm stream again before the all-reduce.
+		int n_copies = 0;
+		for (const MgFrame& f : m->pending) n_copies += f.blocks ? 0 : 1;
+		const int n_cs = std::min<int>(ort_mg::kCopyStreams, n_copies);
+		if (n_cs > 1)
+		{
+			ORT_CUDA(c, cudaEventRecord(m->ev_ready, m->comm_stream));
+			for (int i = 0; i < n_cs; ++i) ORT_CUDA(c, cudaStreamWaitEvent(m->copy_stream[i], m->ev_ready, 0));
+		}
+		int k = 0;
+		for (const MgFrame& f : m->pending)
+		{
+			if (f.blocks) continue;
+			const size_t bytes = mg_block_bytes(f.max_n);
+			char* dst = m->peer_recv_base[f.dst] + static_cast<size_t>(f.rslot) * m->recv_ring.slot_bytes + static_cast<size_t>(rank) * m->pitch;
+			ORT_CUDA(c, cudaMemcpyAsync(dst, f.sb, bytes, cudaMemcpyDeviceToDevice, n_cs > 1 ? m->copy_stream[k++ % n_cs] : m->comm_stream));
+			m->wire_bytes += static_cast<double>(bytes);
+		}
+		if (n_cs > 1)
+			for (int i = 0; i < n_cs; ++i)
+			{
+				ORT_CUDA(c, cudaEventRecord(m->ev_copied[i], m->copy_stream[i]));
+				ORT_CUDA(c, cudaStreamWaitEvent(m->comm_stream, m->ev_copied[i], 0));
+			}
+		for (const MgFrame& f : m->pending)
+			if (f.blocks) m->wire_bytes += static_cast<double>(mg_block_bytes(f.max_n)) * (world - 1);
+		ORT_NCCL(m, m->api->AllReduce(m->d_flag, m->d_flag, 1, ort_ncclInt32, ort_ncclSum, m->comm, m->comm_stream));
+		++m->wire_ops;
+	}
+	else if (world > 1)
 	{
 		ORT_NCCL(m, m->api->GroupStart());
 		for (const MgFrame& f : m->pending)
@@ -202,6 +322,8 @@ int mg_flush(ort_mg* m)
 		ORT_NCCL(m, m->api->GroupEnd());
 		++m->wire_ops;
 	}
+	const int op = m->next_op;
+	m->next_op = (m->next_op + 1) % ort_mg::kOpEvents;
 	for (const MgFrame& f : m->pending)
 	{
 		MgRing& ring = f.blocks ? m->recv_ring : m->send_ring;
@@ -213,8 +335,9 @@ int mg_flush(ort_mg* m)
 			ort::unpack_strips_kernel<<<grid, 256, 0, m->comm_stream>>>(reinterpret_cast<uint4*>(f.voxel), reinterpret_cast<uint4*>(f.t), reinterpret_cast<uint32_t*>(f.face), f.blocks, map);
 			++c->launches;
 		}
-		ORT_CUDA(c, cudaEventRecord(ring.ev_free[f.slot], m->comm_stream));
+		ring.op_of_slot[f.slot] = op;
 	}
+	ORT_CUDA(c, cudaEventRecord(m->ev_op[op], m->comm_stream));        // releases every block of this operation
 	ORT_CUDA(c, cudaGetLastError());
 	m->pending.clear();
 	return ORT_OK;
@@ -251,6 +374,18 @@ int ort_mg_create(ort_mg** out, ort_ctx* ctx, int rank, int world, const void* i
 	const int rc = [&]() -> int {
 		ORT_CUDA(ctx, cudaStreamCreateWithFlags(&m->comm_stream, cudaStreamNonBlocking));
 		ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+		ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_ready, cudaEventDisableTiming));
+		for (int i = 0; i < ort_mg::kOpEvents; ++i) ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_op[i], cudaEventDisableTiming));
+		for (int i = 0; i < ort_mg::kCopyStreams; ++i)
+		{
+			ORT_CUDA(ctx, cudaStreamCreateWithFlags(&m->copy_stream[i], cudaStreamNonBlocking));
+			ORT_CUDA(ctx, cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+		}
+		ORT_CUDA(ctx, cudaMalloc(&m->d_flag, 4));
+		ORT_CUDA(ctx, cudaMemset(m->d_flag, 0, 4));
+		m->peer_recv_base.assign(world, nullptr);
+		m->consumed.assign(world, 0);
+		if (const char* e = std::getenv("ORT_MG_TRANSPORT")) m->transport_pref = std::atoi(e) != 0;
 		m->n_trace_streams = world > 4 ? 8 : 4;
 		for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i)
 		{
@@ -285,16 +420,33 @@ int ort_mg_destroy(ort_mg* m)
 	if (!m) return ORT_OK;
 	DeviceGuard g(m->ctx->device);
 	if (m->comm_stream) cudaStreamSynchronize(m->comm_stream);
+	const bool had_peers = m->peer_copies;
+	mg_unmap_peers(m);
+	if (had_peers && m->comm && m->api && m->d_flag)
+	{
+		// (collective, like ncclCommDestroy: a receive ring is freed only after every rank has dropped its mapping of it)
+		if (m->api->AllReduce(m->d_flag, m->d_flag, 1, ort_ncclInt32, ort_ncclSum, m->comm, m->comm_stream) == 0)
+			cudaStreamSynchronize(m->comm_stream);
+	}
 	if (m->comm && m->api) m->api->CommDestroy(m->comm);
+	mg_unmap_peers(m);
 	mg_ring_free(m->send_ring);
 	mg_ring_free(m->recv_ring);
 	cudaFree(m->d_update);
+	cudaFree(m->d_flag);
 	for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i)
 	{
 		if (m->trace_stream[i]) { cudaStreamSynchronize(m->trace_stream[i]); cudaStreamDestroy(m->trace_stream[i]); }
 		if (m->ev_traced[i]) cudaEventDestroy(m->ev_traced[i]);
 	}
 	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+	if (m->ev_ready) cudaEventDestroy(m->ev_ready);
+	for (int i = 0; i < ort_mg::kOpEvents; ++i) if (m->ev_op[i]) cudaEventDestroy(m->ev_op[i]);
+	for (int i = 0; i < ort_mg::kCopyStreams; ++i)
+	{
+		if (m->copy_stream[i]) { cudaStreamSynchronize(m->copy_stream[i]); cudaStreamDestroy(m->copy_stream[i]); }
+		if (m->ev_copied[i]) cudaEventDestroy(m->ev_copied[i]);
+	}
 	if (m->comm_stream) cudaStreamDestroy(m->comm_stream);
 	delete m;
 	return ORT_OK;
@@ -395,27 +547,49 @@ int ort_mg_trace_frame_gather(ort_mg* m, const float pos[3], const float rot[9],
 	const size_t pitch = align_up(mg_block_bytes(max_n), 256);
 	const bool consumer = rank == dst;
 
-	// rings of 2 x group blocks (at least 3): a sender's hold one strip block per slot, a consumer's world blocks per slot
+	// Rings of 2 x group slots (at least 3): the send ring holds one strip block per slot, the receive ring world blocks
+	// per slot (one per rank, the consumer's own among them).  Every rank keeps both -- with peer copies a rank's
+	// receive ring is written by the others -- and every rank hands out the receive slots of every consumer in the same
+	// order (consumed[dst]), so a sender knows where its block goes.  Geometry changes are collective: all ranks see
+	// the same frames.
 	const int want_slots = std::max(3, 2 * m->group);
-	MgRing& ring = consumer ? m->recv_ring : m->send_ring;
-	const size_t slot_bytes = pitch * (consumer ? world : 1);
-	if (pitch != m->pitch || ring.n < want_slots || ring.slot_bytes != slot_bytes)
+	if (pitch != m->pitch || m->send_ring.n != want_slots || m->recv_ring.n != want_slots)
 	{
-		int rc = mg_flush(m);                                              // (collective discipline: every rank changes geometry at the same frame)
+		int rc = mg_flush(m);
 		if (rc != ORT_OK) return rc;
-		ORT_CUDA(c, cudaDeviceSynchronize());
-		if (pitch != m->pitch)
+		rc = ort_mg_sync(m);                                               // nothing in flight on any stream of this rank ...
+		if (rc != ORT_OK) return rc;
+		enter(c);
+		if (world > 1)
 		{
-			mg_ring_free(m->send_ring);
-			mg_ring_free(m->recv_ring);
-			m->pitch = pitch;
+			ORT_NCCL(m, m->api->AllReduce(m->d_flag, m->d_flag, 1, ort_ncclInt32, ort_ncclSum, m->comm, m->comm_stream));   // ... nor on any other rank's
+			ORT_CUDA(c, cudaStreamSynchronize(m->comm_stream));
 		}
-		rc = mg_ring_alloc(m, ring, want_slots, slot_bytes);
+		mg_unmap_peers(m);
+		if (world > 1)
+		{
+			// a ring is freed only after every rank has dropped its mapping of it
+			ORT_NCCL(m, m->api->AllReduce(m->d_flag, m->d_flag, 1, ort_ncclInt32, ort_ncclSum, m->comm, m->comm_stream));
+			ORT_CUDA(c, cudaStreamSynchronize(m->comm_stream));
+		}
+		m->pitch = pitch;
+		rc = mg_ring_alloc(m, m->send_ring, want_slots, pitch);
+		if (rc == ORT_OK) rc = mg_ring_alloc(m, m->recv_ring, want_slots, pitch * world);
+		if (rc == ORT_OK) rc = mg_map_peers(m);
 		if (rc != ORT_OK) return rc;
+		std::fill(m->consumed.begin(), m->consumed.end(), 0);
 	}
 
-	const int slot = ring.next;
-	ring.next = (ring.next + 1) % ring.n;
+	const int rslot = static_cast<int>(m->consumed[dst] % static_cast<uint64_t>(m->recv_ring.n));
+	++m->consumed[dst];
+	MgRing& ring = consumer ? m->recv_ring : m->send_ring;
+	const size_t slot_bytes = ring.slot_bytes;
+	int slot = rslot;
+	if (!consumer)
+	{
+		slot = ring.next;
+		ring.next = (ring.next + 1) % ring.n;
+	}
 	char* blocks = consumer ? ring.base + static_cast<size_t>(slot) * slot_bytes : nullptr;          // consumer: this frame's blocks, rank order
 	char* sb = consumer ? blocks + static_cast<size_t>(rank) * pitch : ring.base + static_cast<size_t>(slot) * slot_bytes;
 	uint32_t* sv = reinterpret_cast<uint32_t*>(sb);
@@ -426,13 +600,17 @@ int ort_mg_trace_frame_gather(ort_mg* m, const float pos[3], const float rot[9],
 	// the next trace stream; the context's stream is the timeline: the trace starts after what is queued there (an
 	// upload)
 	cudaStream_t user = c->stream;
+	if (!m->forked)
+	{
+		// once per wire operation: the trace streams see what is queued on the context's stream (an upload)
+		ORT_CUDA(c, cudaEventRecord(m->ev_fork, user));
+		for (int i = 0; i < m->n_trace_streams; ++i) ORT_CUDA(c, cudaStreamWaitEvent(m->trace_stream[i], m->ev_fork, 0));
+		m->forked = true;
+	}
 	const int tsi = m->next_trace_stream;
 	m->next_trace_stream = (m->next_trace_stream + 1) % m->n_trace_streams;
 	cudaStream_t ts = m->trace_stream[tsi];
-	ORT_CUDA(c, cudaEventRecord(m->ev_fork, user));
-	ORT_CUDA(c, cudaStreamWaitEvent(ts, m->ev_fork, 0));
-	if (ring.used[slot]) ORT_CUDA(c, cudaStreamWaitEvent(ts, ring.ev_free[slot], 0));
-	ring.used[slot] = 1;
+	if (ring.op_of_slot[slot] >= 0) ORT_CUDA(c, cudaStreamWaitEvent(ts, m->ev_op[ring.op_of_slot[slot]], 0));
 	if (my_rows)
 	{
 		c->stream = ts;
@@ -440,14 +618,26 @@ int ort_mg_trace_frame_gather(ort_mg* m, const float pos[3], const float rot[9],
 		c->stream = user;
 		if (rc != ORT_OK) return rc;
 	}
-	ORT_CUDA(c, cudaEventRecord(m->ev_traced[tsi], ts));
 	m->trace_stream_dirty[tsi] = true;
-	// (no join back into the context's stream here: the next frame's fork would then wait for this trace and the strips
-	// would run one after the other; ort_mg_sync() and ort_mg_broadcast_update() wait for the trace streams instead)
-	m->pending.push_back(MgFrame{ W, H, tile_rows, dst, max_n, sb, blocks, voxel, face, t, slot });
+	// (no join back into the context's stream: the next fork would then wait for this trace and the strips would run one
+	// after the other; ort_mg_sync() and ort_mg_broadcast_update() wait for the trace streams instead)
+	m->pending.push_back(MgFrame{ W, H, tile_rows, dst, max_n, sb, blocks, voxel, face, t, slot, rslot });
 	++m->frames;
 	if (static_cast<int>(m->pending.size()) >= m->group)
 		return mg_flush(m);
+	return ORT_OK;
+}
+
+// A sequence of frames in one call (a render loop's step: several cameras, or the frames of a benchmark step).
+int ort_mg_trace_frames_gather(ort_mg* m, const ort_mg_frame_job* jobs, int n_jobs)
+{
+	if (!m || n_jobs < 0 || (n_jobs && !jobs)) return ort_fail(m ? m->ctx : nullptr, ORT_ERR_INVALID, "ort_mg_trace_frames_gather: bad arguments");
+	for (int i = 0; i < n_jobs; ++i)
+	{
+		const ort_mg_frame_job& j = jobs[i];
+		const int rc = ort_mg_trace_frame_gather(m, j.pos, j.rot, j.fov_factor, j.W, j.H, j.tile_rows, j.dst, j.voxel, j.face, j.t);
+		if (rc != ORT_OK) return rc;
+	}
 	return ORT_OK;
 }
 
@@ -476,6 +666,22 @@ int ort_mg_set_trace_streams(ort_mg* m, int n)
 	m->next_trace_stream = 0;
 	return rc;
 }
+
+// Collective setting: how the strips travel.  1 (default): peer copies on the copy engines through CUDA IPC mappings of
+// the receive rings (NCCL carries a 4-byte all-reduce per wire operation); falls back to 0 when some rank cannot map a
+// ring.  0: NCCL ncclSend / ncclRecv.  Takes effect at the next frame (the rings are rebuilt).  ort_mg_transport()
+// tells what is in use.
+int ort_mg_set_transport(ort_mg* m, int transport)
+{
+	if (!m || (transport != 0 && transport != 1)) return ort_fail(m ? m->ctx : nullptr, ORT_ERR_INVALID, "ort_mg_set_transport: 0 (NCCL send / recv) or 1 (peer copies)");
+	enter(m->ctx);
+	DeviceGuard g(m->ctx->device);
+	const int rc = mg_flush(m);
+	m->transport_pref = transport;
+	m->pitch = 0;                                  // forces the (collective) ring set-up at the next frame
+	return rc;
+}
+int ort_mg_transport(const ort_mg* m) { return m ? (m->peer_copies ? 1 : 0) : -1; }
 
 int ort_mg_flush(ort_mg* m)
 {

@@ -82,12 +82,43 @@ class MultiGpu:
         ptr = lambda x: None if x is None else x.data_ptr()
         self._ck(self.L.ort_mg_trace_frame_gather(self.h, pos.ctypes.data, rot.ctypes.data, float(fov_factor), W, H, tile_rows, dst, ptr(d_vox), ptr(d_face), ptr(d_t)))
 
+    def make_jobs(self, jobs):
+        """jobs: iterable of (pos, rot, fov_factor, W, H, tile_rows, dst, d_vox, d_face, d_t) -> a reusable job array for
+        trace_frames_gather (the tensors must stay alive while the array is in use)."""
+        import ctypes as C
+
+        class Job(C.Structure):
+            _fields_ = [("pos", C.c_float * 3), ("rot", C.c_float * 9), ("fov_factor", C.c_float), ("W", C.c_int), ("H", C.c_int), ("tile_rows", C.c_int), ("dst", C.c_int),
+                        ("voxel", C.c_void_p), ("face", C.c_void_p), ("t", C.c_void_p)]
+        jobs = list(jobs)
+        arr = (Job * len(jobs))()
+        for a, (pos, rot, fov, W, H, tile_rows, dst, dv, df, dt) in zip(arr, jobs):
+            a.pos[:] = [float(x) for x in np.asarray(pos, np.float32).ravel()]
+            a.rot[:] = [float(x) for x in np.asarray(rot, np.float32).ravel()]
+            a.fov_factor, a.W, a.H, a.tile_rows, a.dst = float(fov), W, H, tile_rows, dst
+            a.voxel = None if dv is None else dv.data_ptr()
+            a.face = None if df is None else df.data_ptr()
+            a.t = None if dt is None else dt.data_ptr()
+        return arr
+
+    def trace_frames_gather(self, job_array):
+        """Enqueue a sequence of frames (make_jobs) in one call."""
+        self._ck(self.L.ort_mg_trace_frames_gather(self.h, job_array, len(job_array)))
+
     def set_group(self, frames: int):
         """Frames per wire operation (the same on every rank): 1 = lowest latency, n = one NCCL group per n frames."""
         self._ck(self.L.ort_mg_set_group(self.h, frames))
 
     def flush(self):
         self._ck(self.L.ort_mg_flush(self.h))
+
+    def set_transport(self, transport: int):
+        """1: peer copies on the copy engines (CUDA IPC), 0: NCCL send / recv.  Collective; takes effect at the next frame."""
+        self._ck(self.L.ort_mg_set_transport(self.h, transport))
+
+    @property
+    def transport(self) -> int:
+        return self.L.ort_mg_transport(self.h)
 
     def sync(self):
         self._ck(self.L.ort_mg_sync(self.h))

@@ -74,16 +74,28 @@ def check_frames(nodes8, root, what):
 
 nodes8, root = ship()
 check_frames(nodes8, root, "full upload")
+transports = {mg.transport}
+assert os.environ.get("ORT_MG_TRANSPORT") is not None or mg.transport in (0, 1)
 for k in range(2):
     if rank == 0:
         tree.set_box(100 + 20 * k, 128, 70, 17 + k, 1 + k)
     nodes8, root = ship()
     mg.set_group((2, 5)[k])           # grouped wire operations: 2 frames per NCCL group (one partial group per sync), then 5 (every sync sends a partial group)
     check_frames(nodes8, root, f"delta {k}, group {(2, 5)[k]}")
+# the other transport (NCCL send / recv where the default was peer copies), grouped and per frame
+mg.set_transport(0)
+mg.set_group(3)
+check_frames(nodes8, root, "NCCL send/recv transport, group 3")
+transports.add(mg.transport)
+assert mg.transport == 0
 mg.set_group(1)
+check_frames(nodes8, root, "NCCL send/recv transport, group 1")
+mg.set_transport(1)
+check_frames(nodes8, root, "peer-copy transport again, group 1")
+transports.add(mg.transport)
 wire = mg.wire_bytes
 dist.barrier()
 if rank == 0:
-    print(f"MG-OK world={world} nccl={ort.lib().ort_mg_nccl_version()} wire_bytes_rank0={wire:.0f}")
+    print(f"MG-OK world={world} nccl={ort.lib().ort_mg_nccl_version()} transports_used={sorted(transports)} wire_bytes_rank0={wire:.0f}")
 mg.close()
 dist.destroy_process_group()
