@@ -344,6 +344,12 @@ void     ort_octree_sync_stats(const ort_octree* tree, uint64_t* nodes_uploaded,
 
 /* heights[y*dim+x] = get_terrain_heigth(x, y) with och::simplex_n(0.5F) (:561-566) */
 void ort_fixture_heightmap(int depth, uint16_t* heights, int nthreads);
+/* The demo's alternative terrain noise: heights[y*dim+x] = get_terrain_heigth(x, y) with the commented line
+ * `terrain_noise.Evaluate(px, py)` (test_och_h_octree.cpp:568), terrain_noise = OpenSimplexNoise(seed), seed 8789 in the
+ * demo (:33); 2-D OpenSimplex as vendored by the reference (opensimplex.h:222-289, :338-386), double precision. */
+void ort_fixture_heightmap_opensimplex(int depth, int64_t seed, uint16_t* heights, int nthreads);
+/* OpenSimplexNoise(seed).Evaluate(x, y) for n points (xy = n pairs) -- the function the heightmap above samples */
+void ort_opensimplex2(int64_t seed, const double* xy, size_t n, double* out);
 /* Same voxel content as initialize_h_octree (solid stone below the heightmap, grass/dark-grass
  * top chosen by grass[y*dim+x], two dirt layers, optional simplex tunnels) but built bottom-up
  * with memoisation, so depth 12-14 take seconds.  The DAG is canonical, so it equals the

@@ -100,6 +100,8 @@ _SIGS = {
     "ort_octree_sync": (C.c_int, [_vp]),
     "ort_octree_sync_stats": (None, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]),
     "ort_fixture_heightmap": (None, [C.c_int, _vp, C.c_int]),
+    "ort_fixture_heightmap_opensimplex": (None, [C.c_int, C.c_int64, _vp, C.c_int]),
+    "ort_opensimplex2": (None, [C.c_int64, _vp, C.c_size_t, _vp]),
     "ort_fixture_build_terrain": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "ort_fixture_build_terrain_ex": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, _vp]),
     "ort_fixture_heightmap_gpu": (C.c_int, [_vp, C.c_int, _vp]),

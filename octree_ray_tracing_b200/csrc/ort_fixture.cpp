@@ -17,6 +17,7 @@
 // register_node calls add up to (saturating at 2^32-1 instead of wrapping for depth >= 13).
 #include "ort_internal.h"
 #include "ort_noise.h"
+#include "ort_opensimplex.h"
 
 #include <algorithm>
 #include <atomic>
@@ -447,6 +448,22 @@ void ort_fixture_heightmap(int depth, uint16_t* heights, int nthreads)
 			heights[static_cast<size_t>(y) * dim + x] = ort_noise::terrain_height(x, y, dim);
 		}
 	});
+}
+
+void ort_fixture_heightmap_opensimplex(int depth, int64_t seed, uint16_t* heights, int nthreads)
+{
+	const int dim = 1 << depth;
+	const ort_noise::OpenSimplex2 noise(seed);
+	parallel_rows(dim, nthreads, [&](int y) {
+		for (int x = 0; x < dim; ++x)
+			heights[static_cast<size_t>(y) * dim + x] = ort_noise::terrain_height_opensimplex(noise, x, y, dim);
+	});
+}
+
+void ort_opensimplex2(int64_t seed, const double* xy, size_t n, double* out)
+{
+	const ort_noise::OpenSimplex2 noise(seed);
+	for (size_t i = 0; i < n; ++i) out[i] = noise(xy[2 * i], xy[2 * i + 1]);
 }
 
 int ort_fixture_build_terrain(ort_tree* tree, const uint16_t* heights, const uint8_t* grass, int tunnels, int nthreads)

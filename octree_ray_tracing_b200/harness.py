@@ -17,12 +17,29 @@ POSES = {
 }
 
 
-def heightmap(depth: int, nthreads: int | None = None) -> np.ndarray:
-    """get_terrain_heigth over the whole map (test_och_h_octree.cpp:561-566, :587-592)."""
+def heightmap(depth: int, nthreads: int | None = None, noise: str = "simplex") -> np.ndarray:
+    """get_terrain_heigth over the whole map (test_och_h_octree.cpp:561-566, :587-592).  noise: "simplex" = the live code's
+    och::simplex_n(0.5F) (:566), "opensimplex" = the commented alternative OpenSimplexNoise(8789) (:33, :568)."""
     dim = 1 << depth
     h = np.zeros((dim, dim), np.uint16)
-    lib().ort_fixture_heightmap(depth, _p(h), nthreads or os.cpu_count() or 1)
+    if noise == "opensimplex":
+        lib().ort_fixture_heightmap_opensimplex(depth, OPENSIMPLEX_SEED, _p(h), nthreads or os.cpu_count() or 1)
+    elif noise == "simplex":
+        lib().ort_fixture_heightmap(depth, _p(h), nthreads or os.cpu_count() or 1)
+    else:
+        raise ValueError("noise must be 'simplex' or 'opensimplex'")
     return h
+
+
+OPENSIMPLEX_SEED = 8789          # terrain_noise(8789), test_och_h_octree.cpp:33
+
+
+def opensimplex2(xy, seed: int = OPENSIMPLEX_SEED) -> np.ndarray:
+    """OpenSimplexNoise(seed).Evaluate(x, y) (opensimplex.h:338-386) for an (n, 2) float64 array."""
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    out = np.zeros(len(xy), np.float64)
+    lib().ort_opensimplex2(seed, _p(xy), len(xy), _p(out))
+    return out
 
 
 def grass_bits(depth: int, seed: int = 1) -> np.ndarray:
@@ -50,7 +67,7 @@ def carve_bitmap_gpu(ctx, depth: int, heights: np.ndarray) -> np.ndarray:
     return bits
 
 
-def build_terrain(tree: HOctree, heights=None, grass=None, tunnels: bool = False, nthreads: int | None = None, gpu: bool | None = None):
+def build_terrain(tree: HOctree, heights=None, grass=None, tunnels: bool = False, nthreads: int | None = None, gpu: bool | None = None, noise: str = "simplex"):
     """initialize_h_octree's voxel content (:767-787) through the memoising builder.  gpu: evaluate the noise (heightmap,
     tunnel bitmap) with the CUDA fixture kernels of the tree's context; default: whenever the tree has a context and the
     depth allows (>= 5).  The host threads do it otherwise -- same bits either way."""
@@ -60,7 +77,7 @@ def build_terrain(tree: HOctree, heights=None, grass=None, tunnels: bool = False
     if gpu and ctx is None:
         raise ValueError("build_terrain(gpu=True) needs a tree with a device context")
     if heights is None:
-        heights = heightmap_gpu(ctx, tree.depth) if gpu else heightmap(tree.depth, nthreads)
+        heights = heightmap_gpu(ctx, tree.depth) if (gpu and noise == "simplex") else heightmap(tree.depth, nthreads, noise)
     else:
         heights = np.ascontiguousarray(heights, np.uint16)
     grass = grass_bits(tree.depth) if grass is None else np.ascontiguousarray(grass, np.uint8)

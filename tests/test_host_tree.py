@@ -362,3 +362,30 @@ def test_host_rcp_probe_matches_builtin_table_on_this_host(ort, oc):
         assert np.array_equal(tab, builtin)
     else:                                               # another vendor: a finer table must exist
         assert any(ort.host_rcp_table(k)[1] == 0 for k in (12, 14, 16, 20, 23))
+
+
+def test_opensimplex_heightmap_option_against_the_reference_class(ort, oc, golden):
+    """The demo's alternative terrain noise (OpenSimplexNoise(8789), test_och_h_octree.cpp:33, :568): the product's
+    restatement (csrc/ort_opensimplex.h) equals golden values minted from the UNMODIFIED reference class bit for bit --
+    sample points for two seeds and the depth-6 heightmap -- and, where oracle/_ref exists, the class itself on fresh
+    points and seeds.  A terrain built from that heightmap is the heightmap again when read back through at()."""
+    g = golden("opensimplex_8789")
+    assert np.array_equal(ort.harness.opensimplex2(g["xy"], 8789).view(np.uint64), g["v8789"].view(np.uint64))
+    assert np.array_equal(ort.harness.opensimplex2(g["xy"][:2000], -123456789).view(np.uint64), g["v_neg"].view(np.uint64))
+    depth = int(g["depth"])
+    h = ort.harness.heightmap(depth, noise="opensimplex")
+    assert np.array_equal(h, g["heights"])
+    assert not np.array_equal(h, ort.harness.heightmap(depth))              # a different terrain than the live simplex_n one
+    if oc.have_ref():
+        rs = np.random.RandomState(3)
+        xy = rs.uniform(-100, 100, (50000, 2))
+        for seed in (8789, 0, 1, 2**40 + 3):
+            want = np.zeros(len(xy))
+            oc.ref().ochref_opensimplex2(seed, xy.ctypes.data, len(xy), want.ctypes.data)
+            assert np.array_equal(ort.harness.opensimplex2(xy, seed).view(np.uint64), want.view(np.uint64)), seed
+    T = ort.HOctree(16, depth, device=None)
+    ort.harness.build_terrain(T, noise="opensimplex")
+    rs = np.random.RandomState(1)
+    for x, y in rs.randint(0, 1 << depth, (200, 2)):
+        z = int(h[y, x])
+        assert T.at(int(x), int(y), z) in (2, 3) and T.at(int(x), int(y), z + 1) == 0 and T.at(int(x), int(y), max(z - 3, 0)) == 1
