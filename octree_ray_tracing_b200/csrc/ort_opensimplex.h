@@ -2,8 +2,8 @@
 // the 2-D contribution tables :246-289, Evaluate(x, y) :338-386), restated for the fixture builder: the demo's
 // alternative heightmap noise `terrain_noise(8789)` (test_och_h_octree.cpp:33, the commented line :568).  Host only,
 // double precision, every operation in the reference's order (the translation units are compiled without contraction),
-// so the heights are the reference's bit for bit -- tests/test_oracle.py holds it to the real class where oracle/_ref
-// exists, tests/golden/opensimplex_8789.npz pins it elsewhere.
+// so the heights are the reference's bit for bit -- the CPU tests hold it to the real class where the compiled reference
+// is present, tests/golden/opensimplex_8789.npz pins it elsewhere.
 #pragma once
 
 #include <cstdint>
