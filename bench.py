@@ -232,6 +232,22 @@ def run_product(args):
             hits += int((dv != 0).sum().item())
             if rows % 4 == 0 and W % 8 == 0:
                 warp_rounds += int(cnt.view(rows // 4, 4, W // 8, 8).amax(dim=(1, 3)).sum().item())
+    # the rounds the timed kernels actually run: with the beam start (csrc/ort_beam.cuh) most rays re-enter their walk at the
+    # tile's lower bound, or end as a MISS at once -- counted by the same kind of pass with option count_beam
+    pushes_run, warp_rounds_run = pushes, warp_rounds
+    beam_levels = [ctx.beam_level(cam[0], cam[1], cam[2], W, H) for cam in cams]
+    if any(beam_levels):
+        ctx.set_option("count_beam", 1)
+        pushes_run = warp_rounds_run = 0
+        with torch.cuda.stream(own):
+            for cam in cams:
+                frame(cam, outs[0], dn)
+                own.synchronize()
+                cnt = (dn.to(torch.int32) & 0xFFFF).view(rows, W)
+                pushes_run += int(cnt.sum().item())
+                if rows % 4 == 0 and W % 8 == 0:
+                    warp_rounds_run += int(cnt.view(rows // 4, 4, W // 8, 8).amax(dim=(1, 3)).sum().item())
+        ctx.set_option("count_beam", 0)
     pushes_per_step_local = pushes * pworld
     bytes_per_step_local = 32 * pushes_per_step_local + 9 * rays_per_step_local
     step_cams = [cam for _rep in range(pworld) for cam in cams]
@@ -425,7 +441,8 @@ def run_product(args):
             return None
         emit({"quick": True, "value": round(rays_per_step_total / (ms * 1e-3) / 1e6, 2), "unit": "Mrays/s", "ms_per_step": round(ms, 4),
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
-                          "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3), "launches": launches,
+                          "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3),
+                          "rounds_run_per_ray": round(pushes_run / (len(cams) * n_local), 3), "beam_levels": beam_levels, "launches": launches,
                           "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]],
                           "tile_rows": TILE_ROWS, "streams": NS, "parity": parity, "gather": gq,
                           "as_rank": (f"{prank}/{pworld}: value = what {pworld} GPUs would total if every rank ran like this one" if args.as_rank else None)})
@@ -560,7 +577,7 @@ def run_product(args):
         sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
         mhz = (clocks or {}).get("sm_mhz")
         issue_peak = sms * 4 * mhz * 1e6 if mhz else None
-        inst_per_step = int(sum(cap["warp_instructions_per_launch"])) if cap else None       # one GPU's share of a step = 3 full frames' worth
+        inst_per_step = int(sum(cap["warp_instructions_per_launch"]) + sum(cap.get("march_warp_instructions_per_launch", []))) if cap else None   # one GPU's share of a step = 3 full frames' worth (+ their marches)
         issue_achieved = inst_per_step / (ms_per_step * 1e-3) if inst_per_step else None
         # compulsory HBM traffic of a launch: every output byte once + the DAG once (it does not fit L1, it does fit L2)
         compulsory = 9 * n_local + int(n_up) * 32
@@ -571,18 +588,21 @@ def run_product(args):
             "unit": "G warp-instr/s",
             "frac": round(issue_achieved / issue_peak, 4) if issue_achieved and issue_peak else None,
             "traffic": cap["dram_bytes_per_launch"] if cap else None,
-            "kernel": "ort::trace_frame_kernel<13,false> (LeanWalker tiers)" if args.variant in (None, 13) else f"variant {args.variant}",
+            "kernel": ("ort::trace_frame_kernel<13,false,true> (LeanWalker tiers, beam start) + ort::beam_start_kernel" if any(beam_levels) else
+                       "ort::trace_frame_kernel<13,false,false> (LeanWalker tiers)") if args.variant in (None, 13) else f"variant {args.variant}",
             "peak_source": f"{sms} SMs x 4 schedulers x {mhz} MHz (SM clock sampled through NVML during the timed region)",
             "warp_instructions_per_step_per_gpu": inst_per_step,
             "counters_source": cap_src,
             "avg_launch_ms": round(avg_launch_s * 1e3, 4),
             "why_issue": "the DAG is cache resident (ncu: L1 hit ~90 %, DRAM traffic ~1 % of the algorithmic bytes, DRAM and L2 throughput a few % of peak) and every scheduler has ~6 eligible "
                          "warps per cycle: the kernel is bound by warp-instruction issue, so that is the roofline it is held against; the memory-side figures are listed under `memory`",
-            "simt": {"lane_rounds_per_ray": round(pushes / (len(cams) * n_local), 3),
-                     "warp_rounds_per_warp": round(warp_rounds / (len(cams) * n_local / 32), 3) if warp_rounds else None,
-                     "lanes_busy_per_warp_round": round(pushes / warp_rounds, 2) if warp_rounds else None,
+            "simt": {"lane_rounds_per_ray": round(pushes_run / (len(cams) * n_local), 3),
+                     "warp_rounds_per_warp": round(warp_rounds_run / (len(cams) * n_local / 32), 3) if warp_rounds_run else None,
+                     "lanes_busy_per_warp_round": round(pushes_run / warp_rounds_run, 2) if warp_rounds_run else None,
+                     "reference_walk": {"lane_rounds_per_ray": round(pushes / (len(cams) * n_local), 3),
+                                        "warp_rounds_per_warp": round(warp_rounds / (len(cams) * n_local / 32), 3) if warp_rounds else None},
                      "active_threads_per_warp_instruction_ncu": cap.get("active_threads_per_warp_instruction") if cap else None,
-                     "note": "measured in this run from per-ray PUSH counts (untimed counting pass): a warp = an 8x4 pixel tile runs as many rounds as its longest ray"},
+                     "note": "measured in this run from per-ray round counts (untimed counting passes, with and without the beam start): a warp = an 8x4 pixel tile runs as many rounds as its longest ray"},
             "memory": {
                 "algorithmic_bytes_per_launch": int(bytes_per_step_local / frames_per_step),
                 "algorithmic_rate_gbs": round(algorithmic_rate, 1),
@@ -618,6 +638,9 @@ def run_product(args):
                               if args.launch == "batch" else f"{NS} streams: the frames of a step are queued round-robin so launch tails overlap"),
                 "dag_nodes": int(n_up), "dag_mib": round(n_up * 32 / 2**20, 1),
                 "pushes_per_ray": round(pushes_per_ray_all, 3),
+                "beam_start": {"grid_level_per_pose": beam_levels, "rounds_run_per_ray": round(pushes_run / (len(cams) * n_local), 3),
+                               "note": "pushes_per_ray counts the reference walk (och_h_octree.h:344 executions, what the byte model of SURVEY 8d is stated in); the kernels "
+                                       "start every 8x4 tile at a proven lower bound of its rays' hit times (csrc/ort_beam.cuh) and run rounds_run_per_ray -- same outputs, see parity"},
                 "hit_fraction": round(hits / (len(cams) * n_local), 4),
                 "timing": ("value: wall clock over whole steps of trace + gather (ort_mg_trace_frames_gather ... ort_mg_sync), barrier + synchronize on both sides, max over ranks; "
                            "no_gather / roofline: sum of CUDA-event intervals around each step, max over ranks" if mg is not None else

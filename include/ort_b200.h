@@ -241,8 +241,24 @@ uint64_t ort_launch_count(const ort_ctx* ctx);
  * early and the cheap sky rows fill the end of the launch).  Kernel selection for A/B measurements: "variant"
  * (frames: 0 baseline walk, 1 fast walk = default, 2 persistent lane-refill, 3 upper levels staged in shared memory,
  * 4 deferred phases, 5 tight bookkeeping, 6 while-while), "rays_variant" (explicit rays: 1 one thread per ray,
- * 2 persistent lane-refill = default), "low_water", "smem_levels", "tile_shape", "block". */
+ * 2 persistent lane-refill = default), "low_water", "smem_levels", "tile_shape", "block".
+ * Beam start of camera frames (csrc/ort_beam.cuh): "beam" (1 = default: every 8 x 4 pixel tile of a frame launch starts
+ * its rays at a lower bound of their hit times taken from a coarse grid of the DAG, and rays that provably leave the
+ * cube unhindered end as a MISS without a round -- same outputs bit for bit, fewer PUSH rounds; 0 = every ray walks from
+ * its origin like och_h_octree.h:292-447), "beam_level" (force a coarser grid level, measurement), "count_beam"
+ * (launches that return PUSH counts normally walk from the origin so that the counts are the reference's; 1 = they
+ * use the beam start too and count the loads actually issued). */
 int ort_set_option(ort_ctx* ctx, const char* key, int value);
+
+/* Introspection of the beam start.  ort_beam_level: the grid level (3..7) frame launches of this camera geometry would
+ * use on ctx, 0 = they run without a beam start (pixels too coarse for the coarsest grid, rot not a rotation, option
+ * off, ...).  ort_beam_grid: the level-`level` grid of the DAG currently on the device, (2^level)^3 bytes to host
+ * memory, index (z * N + y) * N + x: 0 = some cell among the 27 around this one holds a voxel, j > 0 = the level-j cell
+ * around this one has no such cell.  Both are for tests and tools; tracing needs neither. */
+int ort_beam_level(ort_ctx* ctx, const float pos[3], const float rot[9], float fov_factor, int W, int H);
+int ort_beam_grid(ort_ctx* ctx, int level, uint8_t* skip_out);
+/* number of beam grids built on ctx since creation (one per DAG version and level in use) */
+uint64_t ort_beam_builds(const ort_ctx* ctx);
 
 /* Diagnostic for roofline reports: throughput of random 32-byte-sector gathers (independent 4-byte loads, 8 in
  * flight per thread, full occupancy) over a `bytes`-sized buffer on ctx's GPU, in GB/s of sectors moved.  With

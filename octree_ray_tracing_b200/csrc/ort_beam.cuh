@@ -1,0 +1,204 @@
+// ort_beam.cuh -- conservative beam start for camera frames (round 2): skip the part of every ray's walk that runs
+// through space the whole 8 x 4 pixel tile provably sees as empty, without changing a single output bit.
+//
+// Where the rounds go.  On the bench frames (depth 12, 4K) 60 % of the rays leave the cube without a hit and the others
+// spend 35-58 % of their PUSH rounds in levels 1-3: the walk from the camera through the coarse empty cells above the
+// terrain.  Those rounds are the same for all rays of a tile, but SIMT already issues them once per warp -- only not
+// running them saves anything (tools/beam/beam_model.py: 19.7 / 30.3 / 37.6 rounds per ray -> 6.7 / 17.0 / 21.8).
+//
+// Two pieces.
+//
+// (1) Re-entry (LeanWalker::start_at).  For a ray of the lean tier (no degenerate axis, no negative t, finite bias) let
+//     e_1 <= e_2 <= ... be the exit times the reference computes in its STEPs at the empty slots S_1, S_2, ... it visits
+//     (och_h_octree.h:378-406).  t_a(X) = fma(X, coef_a, bias_a) is a non-increasing function of the plane coordinate X
+//     (rounding is monotone), and every exit plane of the cell entered after a STEP has t >= the STEP's tmin, so the e_i
+//     never decrease.  Take any tau > 0 that is not later than the ray's hit time (its cube exit time for a MISS) and let i
+//     be the first index with e_i >= tau.  Descending from the root with the reference's own child test `t_mid >= tmin`
+//     (:363-373) at tmin = tau reaches exactly S_i, through the same nodes:
+//       - where the reference's cell is the upper half on axis a (mid plane m not crossed): t_a(m) >= t_a(exit plane of
+//         S_i on a) >= e_i >= tau, so the test picks the upper half;
+//       - where it is the lower half, the reference either failed the test at some earlier tmin (t_a(m) < e_q <= e_{i-1}
+//         < tau, or t_a(m) < 0 during the first descents), or stepped across m at e_q = t_a(m) <= e_{i-1} < tau, or the
+//         half was picked from the origin's bits at level 1 (:320-324: m = 1.5 lies behind the origin, t_a(m) <= 0 < tau):
+//         the test picks the lower half.
+//     So the slot word, the position, the cell size and every parent-stack entry (the slot word of each ancestor) are
+//     the reference's; the STEP that follows overwrites tmin and min_t_idx before anything reads them, and from there on
+//     the two walks are the same instruction stream.  tau beyond the cube exit time means the ray ends as a MISS without
+//     a round.  A re-entry that reaches a voxel without a single STEP can only mean tau was later than the hit time:
+//     the kernel then walks the ray again from the start (a guard; the bound below rules it out).
+//
+// (2) The bound (beam_march).  The reference does not trace the ray (o, d) but, up to 2^-22 in space, the straight ray
+//     (o, d') with d'_a = 1 / |coef_a|: RCPPS is a 12-bit reciprocal (relative error eps_r, measured from the table).  At
+//     its hit time the point o + t_hit d' lies within 2^-22 of the hit voxel (every entry plane of the voxel has t <=
+//     t_hit, every exit plane t >= t_hit).  Let R bound |d' - d_c| over the rays of a tile, d_c the direction through the
+//     tile's centre: R = (half diagonal of the tile in the image plane) / fov + eps_r + rounding.  A level-k grid cell has
+//     size s = 2^-k; take the largest k with t_max R + slack <= 0.7 s (t_max = 1.75 > sqrt(3): no ray stays longer in the
+//     cube).  Then, at equal parameter t, every ray of the tile is in one of the 27 cells around the cell of the
+//     central ray.  `skip` holds, for every level-k cell, 0 if any of its 27 neighbours contains a non-empty level-k cell
+//     of the DAG ("dilated-occupied"), else the coarsest level j <= k whose cell around it is dilated-empty throughout.
+//     Marching the central ray through that grid (one load per step, the steps as large as the empty cells) gives the
+//     first parameter tau_c at which it is inside a dilated-occupied cell: no ray of the tile can hit anything before
+//     tau_c.  The march samples 2^-19 past every exit plane instead of tracking cell indices; the cells it can miss that
+//     way are clipped by less than the slack.  tau = tau_c (1 - 2^-12) - 2^-17.
+//
+// What this buys is measured in profiles/ (r2_beam_*); what it costs is one byte grid per DAG version (built lazily by
+// four small kernels, 8^k bytes) and one march per tile (a separate launch, one thread per tile).
+#pragma once
+
+#include <cmath>
+
+#include "ort_trace.cuh"
+
+namespace ort {
+
+constexpr int kBeamMinLevel = 3;      // below this the grid says nothing (8 cells per axis)
+constexpr int kBeamMaxLevel = 7;      // 128^3 bytes = 2 MiB
+constexpr int kBeamMaxSteps = 256;
+
+struct BeamGrid
+{
+	const uint8_t* skip;   // (2^k)^3 bytes, index (z * N + y) * N + x, world axes
+	int k;
+};
+
+// Level for a launch: the largest k in [kBeamMinLevel, min(depth, kBeamMaxLevel)] whose cells are wider than the tile's
+// beam wherever a ray of this origin can be inside the cube, or 0.  tile_radius = R above, t_max = the longest stay of a
+// ray in the cube (host side, double precision).
+inline int beam_level_for(double tile_radius, int depth, double t_max = 1.75)
+{
+	const int hi = depth < kBeamMaxLevel ? depth : kBeamMaxLevel;
+	for (int k = hi; k >= kBeamMinLevel; --k)
+		if (t_max * tile_radius + 3e-5 <= 0.7 / static_cast<double>(1 << k))
+			return k;
+	return 0;
+}
+
+// Longest stay in the cube [1,2]^3 of a ray from (ox, oy, oz) inside it: the distance to the farthest corner, widened
+// for the reference's clock (t = length / |d'|, |d'| within eps_r of 1).
+inline double beam_t_max(double ox, double oy, double oz, double rcp_eps)
+{
+	const double fx = ox - 1.0 > 2.0 - ox ? ox - 1.0 : 2.0 - ox, fy = oy - 1.0 > 2.0 - oy ? oy - 1.0 : 2.0 - oy, fz = oz - 1.0 > 2.0 - oz ? oz - 1.0 : 2.0 - oz;
+	return std::sqrt(fx * fx + fy * fy + fz * fz) * (1.0 + 2.0 * rcp_eps + 1e-5) + 1e-5;
+}
+
+// R for the 8 x 4 pixel tiles of a camera frame.  The rays are M (u, v, fov)^T normalised (camera_ray), M the caller's
+// rotation: with M orthonormal to 1e-3 two rays differ by at most 1.01 |(du, dv)| / fov.  Returns a negative number
+// when the camera gives no bound (fov <= 0, M not a rotation).
+inline double beam_tile_radius(const Camera& c, double rcp_eps)
+{
+	if (!(c.fov > 0.0f)) return -1.0;
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j)
+		{
+			double dot = 0;                                   // columns i, j of M
+			for (int r = 0; r < 3; ++r) dot += static_cast<double>(c.r[3 * r + i]) * c.r[3 * r + j];
+			const double dev = dot - (i == j ? 1.0 : 0.0);
+			if (!(dev < 1e-3 && dev > -1e-3)) return -1.0;
+		}
+	const double du = 3.5 * static_cast<double>(c.aspect) * c.vfx, dv = 1.5 * static_cast<double>(c.vfy);   // tile centre to the farthest pixel centre: 3.5 x 1.5 pixels
+	return 1.01 * std::sqrt(du * du + dv * dv) / c.fov + rcp_eps + 1e-6;
+}
+
+// Largest relative error of a reciprocal table over its bins: entry i serves the mantissas [i, i + 1) / n of [1, 2).
+inline double rcp_table_rel_error(const uint32_t* tab, int log2n)
+{
+	const size_t n = static_cast<size_t>(1) << log2n;
+	double worst = 0;
+	for (size_t i = 0; i < n; ++i)
+	{
+		uint32_t b = tab[i];
+		float r;
+#ifdef ORT_HOST_EMU
+		r = __uint_as_float(b);
+#else
+		memcpy(&r, &b, 4);
+#endif
+		const double lo = 1.0 + static_cast<double>(i) / n, hi = 1.0 + static_cast<double>(i + 1) / n;
+		const double e0 = r * lo - 1.0, e1 = r * hi - 1.0;
+		const double e = (e0 < 0 ? -e0 : e0) > (e1 < 0 ? -e1 : e1) ? (e0 < 0 ? -e0 : e0) : (e1 < 0 ? -e1 : e1);
+		if (e > worst) worst = e;
+	}
+	return worst;
+}
+
+// First parameter at which the ray o + t d (|d| = 1, o inside the cube) is inside a dilated-occupied cell of the grid, made
+// conservative; 0 when it starts in one; +inf when the whole tile has left the cube with nothing in sight.  Outside
+// the cube the grid continues as one ring of virtual cells that inherit the flag of the boundary cell next to them (the
+// inside cells around a virtual cell are among the 27 around that boundary cell): the tile's other rays may still be
+// inside while the central ray is up to one cell out, and not once it is further.
+__device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy, float oz, float dx, float dy, float dz)
+{
+	const int N = 1 << g.k;
+	const float fN = static_cast<float>(N), cell = 1.0f / fN;
+	const float inf = __uint_as_float(0x7F800000u);
+	const float ix_ = dx != 0.0f ? __fdiv_rn(1.0f, dx) : inf, iy_ = dy != 0.0f ? __fdiv_rn(1.0f, dy) : inf, iz_ = dz != 0.0f ? __fdiv_rn(1.0f, dz) : inf;
+	const float delta = 0x1p-19f;
+	float t = 0.0f;
+	for (int it = 0; it < kBeamMaxSteps; ++it)
+	{
+		const float ts = it ? __fadd_rn(t, delta) : 0.0f;
+		const float qx = __fmul_rn(__fsub_rn(__fmaf_rn(ts, dx, ox), 1.0f), fN), qy = __fmul_rn(__fsub_rn(__fmaf_rn(ts, dy, oy), 1.0f), fN),
+		            qz = __fmul_rn(__fsub_rn(__fmaf_rn(ts, dz, oz), 1.0f), fN);                      // position in cells
+		const float lim = __fadd_rn(fN, 1.0f);
+		if (!(qx >= -1.0f && qx < lim && qy >= -1.0f && qy < lim && qz >= -1.0f && qz < lim))
+			return it ? inf : 0.0f;                        // more than a cell outside (NaN: no beam start)
+		const int cx = static_cast<int>(floorf(qx)), cy = static_cast<int>(floorf(qy)), cz = static_cast<int>(floorf(qz));      // -1 .. N
+		const int bx = min(max(cx, 0), N - 1), by = min(max(cy, 0), N - 1), bz = min(max(cz, 0), N - 1);
+		const int s = g.skip[(static_cast<size_t>(bz) * N + by) * N + bx];
+		if (s == 0)
+			break;
+		// leave the level-s cell around the sample point (a virtual cell: that cell alone) through its nearest exit plane
+		const int sh = (cx == bx && cy == by && cz == bz) ? g.k - s : 0;
+		const float lx = __fmaf_rn(static_cast<float>((cx >> sh) << sh), cell, 1.0f), ly = __fmaf_rn(static_cast<float>((cy >> sh) << sh), cell, 1.0f),
+		            lz = __fmaf_rn(static_cast<float>((cz >> sh) << sh), cell, 1.0f);
+		const float w = static_cast<float>(1 << sh) * cell;
+		float te = inf;
+		if (dx != 0.0f) te = fminf(te, __fmul_rn(__fsub_rn(dx > 0.0f ? __fadd_rn(lx, w) : lx, ox), ix_));
+		if (dy != 0.0f) te = fminf(te, __fmul_rn(__fsub_rn(dy > 0.0f ? __fadd_rn(ly, w) : ly, oy), iy_));
+		if (dz != 0.0f) te = fminf(te, __fmul_rn(__fsub_rn(dz > 0.0f ? __fadd_rn(lz, w) : lz, oz), iz_));
+		t = te > t ? te : __fadd_rn(t, delta);             // always forward
+	}
+	// inside a dilated-occupied cell from t on (or out of steps): nothing before t
+	const float tau = __fsub_rn(__fmul_rn(t, 1.0f - 0x1p-12f), 0x1p-17f);
+	return tau > 0.0f ? tau : 0.0f;
+}
+
+// start time of the 8 x 4 pixel tile whose first pixel is (x0, y0) of the frame: the ray through the tile's centre
+__device__ __forceinline__ float beam_tile_start(const BeamGrid g, const Camera& c, int x0, int y0)
+{
+	const float xc = static_cast<float>(x0) + 3.5f, yc = static_cast<float>(y0) + 1.5f;
+	const float u = __fmul_rn(c.aspect, __fsub_rn(__fmul_rn(c.vfx, xc), 1.0f));
+	const float v = __fsub_rn(__fmul_rn(c.vfy, yc), 1.0f);
+	const float ru = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[0]), __fmul_rn(v, c.r[1])), __fmul_rn(c.fov, c.r[2]));
+	const float rv = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[3]), __fmul_rn(v, c.r[4])), __fmul_rn(c.fov, c.r[5]));
+	const float rw = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[6]), __fmul_rn(v, c.r[7])), __fmul_rn(c.fov, c.r[8]));
+	const float s = __fadd_rn(__fadd_rn(__fmul_rn(ru, ru), __fmul_rn(rv, rv)), __fmul_rn(rw, rw));
+	const float rm = __fdiv_rn(1.0f, __fsqrt_rn(s));
+	return beam_march(g, c.ox, c.oy, c.oz, __fmul_rn(rw, rm), __fmul_rn(ru, rm), __fmul_rn(-rv, rm));
+}
+
+// The lean tier with a beam start: `tau` as beam_tile_start() gave it for the ray's tile (0: none).  Returns true when
+// the result is already known (a MISS: the tile sees nothing before the ray has left the cube); otherwise the walker
+// stands at the re-entry state (or at the ordinary start).  beam_used tells the caller to check the guard afterwards.
+template<bool COUNT>
+__device__ __forceinline__ bool lean_start(LeanWalker<COUNT>& w, uint32_t root, const Ray& r, float tau, float miss_t, bool& beam_used)
+{
+	beam_used = false;
+	if (tau > 0.0f && fmaxf(r.bx, fmaxf(r.by, r.bz)) < __uint_as_float(0x7F800000u))
+	{
+		w.start_at(root, r, tau);
+		if (tau > w.cube_exit_time())
+		{
+			w.hit.voxel = 0;
+			w.hit.face = 6;
+			w.hit.t = miss_t;
+			return true;
+		}
+		beam_used = true;
+		return false;
+	}
+	w.start(root, r);
+	return false;
+}
+
+}  // namespace ort

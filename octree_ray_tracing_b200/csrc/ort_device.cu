@@ -58,6 +58,21 @@ struct ort_ctx
 	// staging (grown on demand)
 	void*  d_stage = nullptr;  size_t d_stage_bytes = 0;   // device side of host-pointer calls
 
+	// beam start (ort_beam.cuh): per level k one byte grid of the current DAG, built on demand by the first frame launch
+	// that needs it.  Two buffers per level, used in turn, so that launches still reading the grid of the previous DAG
+	// version (on other streams) are not overwritten by a rebuild.
+	uint8_t* d_beam_skip[8][2] = {};
+	int      beam_gen[8] = {};          // buffer of level k in use
+	bool     beam_valid[8] = {};        // grid of level k describes the current DAG
+	uint8_t* d_beam_tmp = nullptr;      // occupancy + pyramid scratch of a build (largest level)
+	cudaEvent_t ev_beam = nullptr;      // last grid build done (builds share the scratch; launches on other streams wait for their grid)
+	bool     beam_built_once = false;
+	double   rcp_eps = 0;               // largest relative error of the reciprocal table in use
+	int opt_beam = 1;                   // 1: camera frames of the lean tier start at their tile's beam bound
+	int opt_beam_level = 0;             // 0: the finest level the tile size allows; else forced (measurement)
+	int opt_count_beam = 0;             // 1: launches that return PUSH counts use the beam start too (counts = loads actually issued)
+	uint64_t beam_builds = 0;
+
 	unsigned long long* d_counters = nullptr; // work counters of the persistent kernels: a ring, one per launch (kCounterRing)
 	unsigned next_counter = 0;
 	int max_blocks_rays = 0, max_blocks_frame = 0;
@@ -172,6 +187,12 @@ inline unsigned long long* next_counter(ort_ctx* c)
 // LeanWalker's slot words are node * 8 + 2^23-magic + index in 32 bits: ids stay below 0x16A00000
 inline bool lean_capable(const ort_ctx* c) { return c->n_nodes < 0x16000000u; }
 
+// the DAG changed: every beam grid is out of date (rebuilt by the next frame launch that wants one)
+inline void beam_invalidate(ort_ctx* c)
+{
+	for (int k = 0; k < 8; ++k) c->beam_valid[k] = false;
+}
+
 }  // namespace
 
 #include "ort_kernels.cuh"
@@ -199,6 +220,77 @@ inline int walk_variant(const ort_ctx* c)
 	if (c->opt_variant == 0) return 0;
 	if (c->opt_variant == 1 || !lean_capable(c)) return 1;
 	return ort::kLean;
+}
+
+// Beam start of a frame launch (ort_beam.cuh).  Returns the level of the grid the launch's tiles can be bounded with, or 0
+// when the launch runs without: option off, another walk selected, PUSH counts wanted (they count the reference's
+// rounds), a tile geometry the bound does not cover (warp tiles other than 8 x 4 pixels, cyclic tiles whose height is not
+// a multiple of 4 rows: the 4 rows of a warp tile would not be neighbours in the frame), an origin outside the lean
+// tier, a camera without a bound, or pixels too large for the coarsest grid.
+int beam_level(const ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& fr, bool counting)
+{
+	if (!c->opt_beam || c->opt_zero_copy || walk_variant(c) != ort::kLean || (counting && !c->opt_count_beam)) return 0;
+	if (fr.tile_shape != 0 || (fr.tile_step > 1 && fr.tile_rows % 4 != 0)) return 0;
+	if ((cam.origin_flags & ort::kOriginInCube) == 0u) return 0;
+	const double radius = ort::beam_tile_radius(cam, c->rcp_eps);
+	if (radius < 0) return 0;
+	int k = ort::beam_level_for(radius, c->depth, ort::beam_t_max(cam.ox, cam.oy, cam.oz, c->rcp_eps));
+	if (k && c->opt_beam_level >= ort::kBeamMinLevel && c->opt_beam_level < k) k = c->opt_beam_level;      // (only coarser: stays a bound)
+	return k;
+}
+
+// Make the level-k grid describe the current DAG; on return the launch stream is ordered after the build.
+int beam_ensure_grid(ort_ctx* c, int k)
+{
+	const size_t cells = static_cast<size_t>(1) << (3 * k);
+	if (!c->beam_valid[k])
+	{
+		if (!c->d_beam_tmp)
+		{
+			// occupancy of the finest level + the pyramid levels 1 .. kBeamMaxLevel
+			size_t bytes = static_cast<size_t>(1) << (3 * ort::kBeamMaxLevel);
+			for (int j = 1; j <= ort::kBeamMaxLevel; ++j) bytes += static_cast<size_t>(1) << (3 * j);
+			ORT_CUDA(c, cudaMalloc(&c->d_beam_tmp, bytes));
+		}
+		const int gen = c->beam_gen[k] ^ 1;
+		if (!c->d_beam_skip[k][gen]) ORT_CUDA(c, cudaMalloc(&c->d_beam_skip[k][gen], cells));
+		// builds share the scratch: one after the other, whatever streams ask for them
+		if (c->beam_built_once) ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_beam, 0));
+		uint8_t* occ = c->d_beam_tmp;
+		uint8_t* pyr = c->d_beam_tmp + (static_cast<size_t>(1) << (3 * ort::kBeamMaxLevel));
+		size_t off[ort::kBeamMaxLevel + 2] = {};
+		for (int j = 1; j <= k; ++j) off[j + 1] = off[j] + (static_cast<size_t>(1) << (3 * j));      // level j at off[j]
+		const ort::Dag dag = make_dag(c);
+		const unsigned blocks = static_cast<unsigned>((cells + 255) / 256);
+		ort::beam_occupancy_kernel<<<blocks, 256, 0, c->stream>>>(dag.nodes_m1, dag.root, k, occ);
+		ort::beam_dilate_kernel<<<blocks, 256, 0, c->stream>>>(occ, k, pyr + off[k]);
+		for (int j = k - 1; j >= 1; --j)
+			ort::beam_reduce_kernel<<<static_cast<unsigned>(((static_cast<size_t>(1) << (3 * j)) + 255) / 256), 256, 0, c->stream>>>(pyr + off[j + 1], j, pyr + off[j]);
+		ort::beam_skip_kernel<<<blocks, 256, 0, c->stream>>>(pyr, k, c->d_beam_skip[k][gen]);
+		c->launches += 3 + (k - 1);
+		ORT_CUDA(c, cudaGetLastError());
+		ORT_CUDA(c, cudaEventRecord(c->ev_beam, c->stream));
+		c->beam_built_once = true;
+		c->beam_gen[k] = gen;
+		c->beam_valid[k] = true;
+		++c->beam_builds;
+		return ORT_OK;
+	}
+	// built earlier, possibly on another stream
+	ORT_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_beam, 0));
+	return ORT_OK;
+}
+
+// the march over the tiles of one frame launch; `tile_word` = the output array that carries the start times
+int beam_launch_march(ort_ctx* c, int k, const ort::Camera& cam, const ort::FrameRows& fr, float* tile_word)
+{
+	const int rc = beam_ensure_grid(c, k);
+	if (rc != ORT_OK) return rc;
+	const unsigned tiles = static_cast<unsigned>(((fr.W + 7) / 8) * ((fr.rows + 3) / 4));
+	ort::beam_start_kernel<<<(tiles + 127) / 128, 128, 0, c->stream>>>(ort::BeamGrid{ c->d_beam_skip[k][c->beam_gen[k]], k }, cam, fr, tile_word);
+	++c->launches;
+	ORT_CUDA(c, cudaGetLastError());
+	return ORT_OK;
 }
 
 }  // namespace
@@ -264,6 +356,7 @@ int ort_create(ort_ctx** out, int device, int depth, uint32_t node_capacity)
 		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
 		ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
 		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		ORT_CUDA(nullptr, cudaEventCreateWithFlags(&c->ev_beam, cudaEventDisableTiming));
 		for (int i = 0; i < 3; ++i)
 		{
 			ORT_CUDA(nullptr, cudaStreamCreateWithFlags(&c->aux_stream[i], cudaStreamNonBlocking));
@@ -333,6 +426,9 @@ int ort_destroy(ort_ctx* c)
 	cudaFree(c->d_palette);
 	cudaFree(c->d_counters);
 	cudaFree(c->d_stage);
+	cudaFree(c->d_beam_tmp);
+	for (int k = 0; k < 8; ++k) { cudaFree(c->d_beam_skip[k][0]); cudaFree(c->d_beam_skip[k][1]); }
+	if (c->ev_beam) cudaEventDestroy(c->ev_beam);
 	for (int i = 0; i < 2; ++i)
 	{
 		if (c->ev_chunk[i]) cudaEventDestroy(c->ev_chunk[i]);
@@ -367,6 +463,7 @@ int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
 		for (size_t k = 0; k < host.size(); ++k)
 			if (((host[k] >> 23) | 1u) != 127u)
 				return ort_fail(c, ORT_ERR_INVALID, "ort_set_rcp_table: entry %zu (0x%08x) is not in (0.5, 1]: not a reciprocal table of [1, 2)", k, host[k]);
+		c->rcp_eps = ort::rcp_table_rel_error(host.data(), log2n);      // the beam start's bound widens with the table's error
 	}
 	if (c->rcp_log2n != log2n)
 	{
@@ -407,6 +504,7 @@ int ort_upload_full(ort_ctx* c, const uint32_t* nodes8, size_t n, uint32_t root)
 	c->index_base = 1;
 	c->has_root = root != 0;
 	c->miss_t = __builtin_inff();
+	beam_invalidate(c);
 	return ORT_OK;
 }
 
@@ -420,6 +518,7 @@ int ort_upload_pool(ort_ctx* c, const uint32_t* nodes8, size_t n)
 	c->index_base = 0;
 	c->has_root = true;
 	c->miss_t = 0.0F;                                     // och_octree.cpp:302
+	beam_invalidate(c);
 	return ORT_OK;
 }
 
@@ -490,6 +589,7 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 		c->root = root;
 		c->has_root = root != 0;
 	}
+	beam_invalidate(c);
 	return ORT_OK;
 }
 
@@ -647,12 +747,21 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 #endif
 	if (c->opt_variant != 0 && c->opt_variant != 1 && c->opt_variant != 2 && c->opt_variant != ort::kLean)
 		return bad_variant(c);
-#define ORT_LAUNCH_FRAME(V, C) ort::trace_frame_kernel<V, C><<<grid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, cam, fr, voxel, face, t, npush)
+	const int bk = beam_level(c, cam, fr, npush != nullptr);
+	if (bk)
+	{
+		const int rc = beam_launch_march(c, bk, cam, fr, t);
+		if (rc != ORT_OK) return rc;
+	}
+#define ORT_LAUNCH_FRAME(V, C, B) ort::trace_frame_kernel<V, C, B><<<grid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, cam, fr, voxel, face, t, npush)
 	switch (walk_variant(c))
 	{
-	case 0:  if (npush) ORT_LAUNCH_FRAME(0, true); else ORT_LAUNCH_FRAME(0, false); break;
-	case 1:  if (npush) ORT_LAUNCH_FRAME(1, true); else ORT_LAUNCH_FRAME(1, false); break;
-	default: if (npush) ORT_LAUNCH_FRAME(ort::kLean, true); else ORT_LAUNCH_FRAME(ort::kLean, false); break;
+	case 0:  if (npush) ORT_LAUNCH_FRAME(0, true, false); else ORT_LAUNCH_FRAME(0, false, false); break;
+	case 1:  if (npush) ORT_LAUNCH_FRAME(1, true, false); else ORT_LAUNCH_FRAME(1, false, false); break;
+	default:
+		if (bk) { if (npush) ORT_LAUNCH_FRAME(ort::kLean, true, true); else ORT_LAUNCH_FRAME(ort::kLean, false, true); }
+		else    { if (npush) ORT_LAUNCH_FRAME(ort::kLean, true, false); else ORT_LAUNCH_FRAME(ort::kLean, false, false); }
+		break;
 	}
 #undef ORT_LAUNCH_FRAME
 	++c->launches;
@@ -701,19 +810,49 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 			const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((j.rows + 15) / 16) : horizon_band(d.cam, j.W, j.y0, j.rows, j.tile_rows, j.tile_step);
 			d.fr = ort::FrameRows{ j.W, j.H, j.y0, j.rows, j.tile_rows, j.tile_step, 0, rotate, ort::tile_shift_of(j.tile_rows) };
 			d.voxel = j.voxel; d.face = j.face; d.t = j.t; d.npush = j.npush;
+			d.beam_k = 0;
 			gx = std::max(gx, static_cast<unsigned>((j.W + 15) / 16));
 			gy = std::max(gy, static_cast<unsigned>((j.rows + 15) / 16));
 		}
 		if (!n) break;
 		bool count = false;
 		for (int k = 0; k < n; ++k) count |= batch.job[k].npush != nullptr;
+		// beam start: all or nothing per batch (one kernel instantiation per launch)
+		bool beam = true;
+		unsigned max_tiles = 0;
+		for (int k = 0; k < n && beam; ++k)
+		{
+			ort::FrameJob& d = batch.job[k];
+			d.beam_k = beam_level(c, d.cam, d.fr, count);
+			beam = d.beam_k != 0;
+			max_tiles = std::max(max_tiles, static_cast<unsigned>(((d.fr.W + 7) / 8) * ((d.fr.rows + 3) / 4)));
+		}
+		if (beam)
+		{
+			ort::BeamGridSet grids{};
+			for (int k = 0; k < n; ++k)
+			{
+				const int bk = batch.job[k].beam_k;
+				const int rc = beam_ensure_grid(c, bk);
+				if (rc != ORT_OK) return rc;
+				grids.skip[bk] = c->d_beam_skip[bk][c->beam_gen[bk]];
+			}
+			ort::beam_start_batch_kernel<<<dim3((max_tiles + 127) / 128, static_cast<unsigned>(n)), 128, 0, c->stream>>>(grids, batch);
+			++c->launches;
+			ORT_CUDA(c, cudaGetLastError());
+		}
+		else
+			for (int k = 0; k < n; ++k) batch.job[k].beam_k = 0;
 		const dim3 bgrid(gx, gy, static_cast<unsigned>(n));
-#define ORT_LAUNCH_BATCH(V, C) ort::trace_frames_kernel<V, C><<<bgrid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, batch)
+#define ORT_LAUNCH_BATCH(V, C, B) ort::trace_frames_kernel<V, C, B><<<bgrid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, batch)
 		switch (walk_variant(c))
 		{
-		case 0:  if (count) ORT_LAUNCH_BATCH(0, true); else ORT_LAUNCH_BATCH(0, false); break;
-		case 1:  if (count) ORT_LAUNCH_BATCH(1, true); else ORT_LAUNCH_BATCH(1, false); break;
-		default: if (count) ORT_LAUNCH_BATCH(ort::kLean, true); else ORT_LAUNCH_BATCH(ort::kLean, false); break;
+		case 0:  if (count) ORT_LAUNCH_BATCH(0, true, false); else ORT_LAUNCH_BATCH(0, false, false); break;
+		case 1:  if (count) ORT_LAUNCH_BATCH(1, true, false); else ORT_LAUNCH_BATCH(1, false, false); break;
+		default:
+			if (beam) { if (count) ORT_LAUNCH_BATCH(ort::kLean, true, true); else ORT_LAUNCH_BATCH(ort::kLean, false, true); }
+			else      { if (count) ORT_LAUNCH_BATCH(ort::kLean, true, false); else ORT_LAUNCH_BATCH(ort::kLean, false, false); }
+			break;
 		}
 #undef ORT_LAUNCH_BATCH
 		++c->launches;
@@ -982,11 +1121,20 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
 	const ort::Camera cam = make_camera(c, pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, rotate, ort::tile_shift_of(tile_rows) };
+	const int bk = beam_level(c, cam, fr, false);
+	if (bk)
+	{
+		const int rc = beam_launch_march(c, bk, cam, fr, reinterpret_cast<float*>(d_rgba));
+		if (rc != ORT_OK) return rc;
+	}
 	switch (walk_variant(c))
 	{
 	case 0:  ort::trace_frame_rgba_kernel<0><<<grid, 256, 0, c->stream>>>(dag, cam, fr, pal, d_rgba); break;
 	case 1:  ort::trace_frame_rgba_kernel<1><<<grid, 256, 0, c->stream>>>(dag, cam, fr, pal, d_rgba); break;
-	default: ort::trace_frame_rgba_kernel<ort::kLean><<<grid, 256, ort::lean_smem_bytes(c->depth), c->stream>>>(dag, cam, fr, pal, d_rgba); break;
+	default:
+		if (bk) ort::trace_frame_rgba_kernel<ort::kLean, true><<<grid, 256, ort::lean_smem_bytes(c->depth), c->stream>>>(dag, cam, fr, pal, d_rgba);
+		else    ort::trace_frame_rgba_kernel<ort::kLean, false><<<grid, 256, ort::lean_smem_bytes(c->depth), c->stream>>>(dag, cam, fr, pal, d_rgba);
+		break;
 	}
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
@@ -1130,6 +1278,9 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
 		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<ort::kLean, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
 	}
+	else if (!std::strcmp(key, "beam")) c->opt_beam = value;
+	else if (!std::strcmp(key, "beam_level")) c->opt_beam_level = value;
+	else if (!std::strcmp(key, "count_beam")) c->opt_count_beam = value;
 	else if (!std::strcmp(key, "defer_sync")) c->opt_defer_sync = value;
 	else if (!std::strcmp(key, "frame_chunks")) c->opt_frame_chunks = value;
 	else if (!std::strcmp(key, "rays_chunk")) c->opt_rays_chunk = value;
@@ -1137,6 +1288,32 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	else return ort_fail(c, ORT_ERR_INVALID, "ort_set_option: unknown key '%s'", key);
 	return ORT_OK;
 }
+
+int ort_beam_level(ort_ctx* c, const float pos[3], const float rot[9], float fov_factor, int W, int H)
+{
+	enter(c);
+	if (!c || !pos || !rot || W <= 0 || H <= 0) return 0;
+	const ort::Camera cam = make_camera(c, pos, rot, fov_factor, W, H);
+	const ort::FrameRows fr{ W, H, 0, H, 1, 1, c->opt_tile_shape, 0, 0 };
+	return beam_level(c, cam, fr, false);
+}
+
+int ort_beam_grid(ort_ctx* c, int level, uint8_t* skip_out)
+{
+	enter(c);
+	if (!c || !skip_out || level < 1 || level > ort::kBeamMaxLevel || level > c->depth)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_beam_grid: level must be 1..min(depth, %d)", ort::kBeamMaxLevel);
+	if (!c->has_root)
+		return ort_fail(c, ORT_ERR_INVALID, "ort_beam_grid: no DAG on the device");
+	DeviceGuard g(c->device);
+	const int rc = beam_ensure_grid(c, level);
+	if (rc != ORT_OK) return rc;
+	ORT_CUDA(c, cudaMemcpyAsync(skip_out, c->d_beam_skip[level][c->beam_gen[level]], static_cast<size_t>(1) << (3 * level), cudaMemcpyDeviceToHost, c->stream));
+	ORT_CUDA(c, cudaStreamSynchronize(c->stream));
+	return ORT_OK;
+}
+
+uint64_t ort_beam_builds(const ort_ctx* c) { return c ? c->beam_builds : 0; }
 
 int ort_measure_gather_peak(ort_ctx* c, size_t bytes, double* gb_per_s)
 {

@@ -10,6 +10,7 @@
 
 #include "ort_noise.h"
 #include "ort_trace.cuh"
+#include "ort_beam.cuh"
 
 namespace ort {
 
@@ -86,21 +87,32 @@ __device__ __forceinline__ uint32_t lean_stack_base(const uint32_t* s_stack, int
 // The walk of one ray from its set-up state.  origin_ok: the origin part of fast_path_ok holds (tested per ray for
 // explicit rays, known for the whole launch for camera frames).
 template<int VARIANT, bool COUNT>
-__device__ __forceinline__ Hit walk_ray(const Dag& g, float ox, float oy, float oz, const Ray& ray, bool origin_ok, const uint32_t* s_stack)
+__device__ __forceinline__ Hit walk_ray(const Dag& g, float ox, float oy, float oz, const Ray& ray, bool origin_ok, const uint32_t* s_stack, float tau = 0.0f)
 {
 	// lean tier: origin inside the cube, no degenerate axis, no negative t possible
 	if (VARIANT == kLean && origin_ok && lean_path_ok(ray))
 	{
 		LeanWalker<COUNT> w;
-		w.start(g.root, ray);
 		const LeanStack<kLeanShift> st{ lean_stack_base(s_stack, g.depth) };
+		// tau > 0: the tile's beam start (ort_beam.cuh) -- re-enter the walk there, or end as a MISS right away
+		bool beam_used;
+		if (lean_start(w, g.root, ray, tau, g.miss_t, beam_used))
+			return w.hit;
 		for (;;)
 		{
-			uint32_t child;
-			bool done = false;
-			while ((child = w.load_child(g.base_biased)) != 0u)
-				if (w.descend(child, g.leaf_dimf, st)) { done = true; break; }
-			if (done || w.advance(g.miss_t, st)) break;
+			for (;;)
+			{
+				uint32_t child;
+				bool done = false;
+				while ((child = w.load_child(g.base_biased)) != 0u)
+					if (w.descend(child, g.leaf_dimf, st)) { done = true; break; }
+				if (done || w.advance(g.miss_t, st)) break;
+			}
+			// guard of the beam start: a voxel reached without a single STEP (min_t_idx untouched) means tau was not a
+			// lower bound of this ray's hit time -- walk it from the start (an origin inside a solid voxel never gets tau > 0)
+			if (!(beam_used && w.mti == 8u)) break;
+			beam_used = false;
+			w.start(g.root, ray);
 		}
 		return w.hit;
 	}
@@ -117,12 +129,12 @@ __device__ __forceinline__ Hit trace_ray(const Dag& g, float ox, float oy, float
 
 // camera ray: the origin facts were established once on the host (Camera::origin_flags)
 template<int VARIANT, bool COUNT>
-__device__ __forceinline__ Hit trace_camera_ray(const Dag& g, const Camera& cam, float dx, float dy, float dz, const uint32_t* s_stack)
+__device__ __forceinline__ Hit trace_camera_ray(const Dag& g, const Camera& cam, float dx, float dy, float dz, const uint32_t* s_stack, float tau = 0.0f)
 {
 	if (VARIANT != kLean)
 		return trace_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, dx, dy, dz, s_stack);
 	const Ray ray = ray_setup_camera(g.rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, cam.origin_flags);
-	return walk_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, ray, (cam.origin_flags & kOriginInCube) != 0u, s_stack);
+	return walk_ray<VARIANT, COUNT>(g, cam.ox, cam.oy, cam.oz, ray, (cam.origin_flags & kOriginInCube) != 0u, s_stack, tau);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -161,27 +173,56 @@ __device__ __forceinline__ bool frame_pixel(const FrameRows& fr, unsigned block_
 	return x < fr.W && r < fr.rows;
 }
 
+// Beam start of the thread's 8 x 4 tile: beam_start_kernel left it in the output word of the tile's first pixel (nobody but
+// the tile's own warp touches that word, and the warp reads it here before any of its lanes can have stored a result).
+// All 32 lanes take part, also those outside the frame.
+__device__ __forceinline__ float read_tile_start(const FrameRows& fr, const float* tile_word, int x, int r)
+{
+	const int x0 = x & ~7, r0 = r & ~3;
+	float tau = 0.0f;
+	if (x0 < fr.W && r0 < fr.rows)
+		tau = tile_word[static_cast<size_t>(r0) * fr.W + x0];
+	__syncwarp();
+	return tau;
+}
+
 // (register budget: 6 resident blocks per SM = 40 registers; the 32-register build reloads the node base pointer from the
 // constant bank every round and measures 1-2 % slower, although it fits 8 blocks)
-template<int VARIANT, bool COUNT>
+// BEAM: the launch was preceded by beam_start_kernel over the same rows and the same `t` array.
+template<int VARIANT, bool COUNT, bool BEAM = false>
 __global__ void __launch_bounds__(256, 6)
 trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
-                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* __restrict__ t, uint16_t* __restrict__ npush)
+                   uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* t, uint16_t* __restrict__ npush)
 {
 	extern __shared__ uint32_t s_stack[];
 	int x, r;
-	if (!frame_pixel(fr, blockIdx.y, gridDim.y, x, r)) return;
+	const bool inside = frame_pixel(fr, blockIdx.y, gridDim.y, x, r);
+	const float tau = BEAM ? read_tile_start(fr, t, x, r) : 0.0f;
+	if (!inside) return;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
-	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, cam, dx, dy, dz, s_stack);
+	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, cam, dx, dy, dz, s_stack, tau);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
+// The march of the beam start (ort_beam.cuh), one thread per 8 x 4 pixel tile of the rows a frame launch traces: the tile's
+// start time goes into the output word of its first pixel -- `t` for the voxel / face / t kernels, the pixel for the
+// shaded kernel -- where the trace kernel picks it up.
+__global__ void __launch_bounds__(128)
+beam_start_kernel(const BeamGrid grid, Camera cam, FrameRows fr, float* __restrict__ tile_word)
+{
+	const int tiles_x = (fr.W + 7) >> 3, tiles_y = (fr.rows + 3) >> 2;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= tiles_x * tiles_y) return;
+	const int x0 = (i % tiles_x) * 8, r0 = (i / tiles_x) * 4;
+	tile_word[static_cast<size_t>(r0) * fr.W + x0] = beam_tile_start(grid, cam, x0, frame_row(fr, r0));
 }
 
 // Several frame jobs in ONE launch (blockIdx.z = job): strips of different frames, or the views of a multi-camera
@@ -197,6 +238,7 @@ struct FrameJob
 	uint8_t*  face;
 	float*    t;
 	uint16_t* npush;    // may be null
+	int       beam_k;   // level of the beam grid this job's tile starts come from (0: the job runs without)
 };
 
 struct FrameJobBatch
@@ -204,7 +246,7 @@ struct FrameJobBatch
 	FrameJob job[kMaxJobs];
 };
 
-template<int VARIANT, bool COUNT>          // COUNT: some job of the batch wants per-ray PUSH counts (jobs without an npush pointer skip the store)
+template<int VARIANT, bool COUNT, bool BEAM = false>          // COUNT: some job of the batch wants per-ray PUSH counts (jobs without an npush pointer skip the store)
 __global__ void __launch_bounds__(256, 6)
 trace_frames_kernel(const Dag g, const __grid_constant__ FrameJobBatch batch)
 {
@@ -214,18 +256,39 @@ trace_frames_kernel(const Dag g, const __grid_constant__ FrameJobBatch batch)
 	const unsigned bands = static_cast<unsigned>((fr.rows + 15) >> 4);
 	if (blockIdx.y >= bands) return;                                    // the grid is sized for the largest job
 	int x, r;
-	if (!frame_pixel(fr, blockIdx.y, bands, x, r)) return;
+	const bool inside = frame_pixel(fr, blockIdx.y, bands, x, r);
+	const float tau = BEAM ? read_tile_start(fr, jb.t, x, r) : 0.0f;
+	if (!inside) return;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(jb.cam, x, y, dx, dy, dz);
-	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, jb.cam, dx, dy, dz, s_stack);
+	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, jb.cam, dx, dy, dz, s_stack, tau);
 
 	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	jb.voxel[i] = h.voxel;
 	jb.face[i] = static_cast<uint8_t>(h.face);
 	jb.t[i] = h.t;
 	if (COUNT && jb.npush) jb.npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
+// the march for every job of a batch (blockIdx.y = job); grids[k] = the context's grid of level k
+struct BeamGridSet
+{
+	const uint8_t* skip[kBeamMaxLevel + 1];
+};
+
+__global__ void __launch_bounds__(128)
+beam_start_batch_kernel(const BeamGridSet grids, const __grid_constant__ FrameJobBatch batch)
+{
+	const FrameJob& jb = batch.job[blockIdx.y];
+	if (!jb.beam_k) return;
+	const FrameRows& fr = jb.fr;
+	const int tiles_x = (fr.W + 7) >> 3, tiles_y = (fr.rows + 3) >> 2;
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= tiles_x * tiles_y) return;
+	const int x0 = (i % tiles_x) * 8, r0 = (i / tiles_x) * 4;
+	jb.t[static_cast<size_t>(r0) * fr.W + x0] = beam_tile_start(BeamGrid{ grids.skip[jb.beam_k], jb.beam_k }, jb.cam, x0, frame_row(fr, r0));
 }
 
 // Shading epilogue (tree_camera::trace_pixel, test_och_h_octree.cpp:76-84) fused into the frame kernel: the hit is
@@ -239,18 +302,20 @@ struct Palette
 	uint32_t exit_rgba, inside_rgba;
 };
 
-template<int VARIANT>
+template<int VARIANT, bool BEAM = false>
 __global__ void __launch_bounds__(256, 6)
-trace_frame_rgba_kernel(const Dag g, Camera cam, FrameRows fr, Palette pal, uint32_t* __restrict__ rgba)
+trace_frame_rgba_kernel(const Dag g, Camera cam, FrameRows fr, Palette pal, uint32_t* rgba)
 {
 	extern __shared__ uint32_t s_stack[];
 	int x, r;
-	if (!frame_pixel(fr, blockIdx.y, gridDim.y, x, r)) return;
+	const bool inside = frame_pixel(fr, blockIdx.y, gridDim.y, x, r);
+	const float tau = BEAM ? read_tile_start(fr, reinterpret_cast<const float*>(rgba), x, r) : 0.0f;
+	if (!inside) return;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
-	const Hit h = trace_camera_ray<VARIANT, false>(g, cam, dx, dy, dz, s_stack);
+	const Hit h = trace_camera_ray<VARIANT, false>(g, cam, dx, dy, dz, s_stack, tau);
 
 	uint32_t px;
 	if (h.face == 6u) px = pal.exit_rgba;
@@ -411,6 +476,79 @@ unpack_strips_kernel(uint4* __restrict__ voxel, uint4* __restrict__ t, uint32_t*
 	voxel[o] = reinterpret_cast<const uint4*>(blk)[i];
 	t[o] = reinterpret_cast<const uint4*>(blk + m.max_n * 4)[i];
 	face[o] = reinterpret_cast<const uint32_t*>(blk + m.max_n * 8)[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// beam grid (ort_beam.cuh): level-k occupancy of the DAG -> dilation -> empty-cell pyramid -> skip levels
+// ------------------------------------------------------------------------------------------------
+
+// one thread per level-k cell (index (z * N + y) * N + x): is anything below it?  Slot bit a = upper half on world axis a.
+__global__ void __launch_bounds__(256)
+beam_occupancy_kernel(const uint32_t* __restrict__ nodes_m1, uint32_t root, int k, uint8_t* __restrict__ occ)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (1u << (3 * k))) return;
+	const uint32_t m = (1u << k) - 1u, x = i & m, y = (i >> k) & m, z = i >> (2 * k);
+	uint32_t node = root, child = 1u;
+	for (int l = k - 1; l >= 0 && child; --l)
+	{
+		const uint32_t slot = ((x >> l) & 1u) | (((y >> l) & 1u) << 1) | (((z >> l) & 1u) << 2);
+		child = __ldg(nodes_m1 + (static_cast<size_t>(node) << 3) + slot);
+		node = child;
+	}
+	occ[i] = child != 0u;
+}
+
+// dil = 1 where any of the 27 cells around the cell is occupied
+__global__ void __launch_bounds__(256)
+beam_dilate_kernel(const uint8_t* __restrict__ occ, int k, uint8_t* __restrict__ dil)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (1u << (3 * k))) return;
+	const int N = 1 << k, x = i & (N - 1), y = (i >> k) & (N - 1), z = i >> (2 * k);
+	uint32_t any = 0;
+	for (int dz = -1; dz <= 1; ++dz)
+		for (int dy = -1; dy <= 1; ++dy)
+			for (int dx = -1; dx <= 1; ++dx)
+			{
+				const int xx = x + dx, yy = y + dy, zz = z + dz;
+				if (xx >= 0 && xx < N && yy >= 0 && yy < N && zz >= 0 && zz < N)
+					any |= occ[(static_cast<size_t>(zz) * N + yy) * N + xx];
+			}
+	dil[i] = any != 0u;
+}
+
+// level j of the pyramid from level j + 1: a cell is marked when any of its 8 children is
+__global__ void __launch_bounds__(256)
+beam_reduce_kernel(const uint8_t* __restrict__ fine, int j, uint8_t* __restrict__ coarse)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (1u << (3 * j))) return;
+	const int N = 1 << j, F = 2 * N, x = i & (N - 1), y = (i >> j) & (N - 1), z = i >> (2 * j);
+	uint32_t any = 0;
+	for (int c = 0; c < 8; ++c)
+		any |= fine[(static_cast<size_t>(2 * z + (c >> 2)) * F + (2 * y + ((c >> 1) & 1))) * F + (2 * x + (c & 1))];
+	coarse[i] = any != 0u;
+}
+
+// skip[cell] = 0 where the cell is dilated-occupied, else the coarsest level whose cell around it is unmarked.
+// pyr: the levels 1 .. k of the dilation pyramid back to back (level j at offset sum of 8^i for i in 1 .. j - 1)
+__global__ void __launch_bounds__(256)
+beam_skip_kernel(const uint8_t* __restrict__ pyr, int k, uint8_t* __restrict__ skip)
+{
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (1u << (3 * k))) return;
+	const uint32_t m = (1u << k) - 1u, x = i & m, y = (i >> k) & m, z = i >> (2 * k);
+	size_t off = 0;
+	int s = 0;
+	for (int j = 1; j <= k; ++j)
+	{
+		const int sh = k - j;
+		const size_t c = ((((static_cast<size_t>(z >> sh) << j) | (y >> sh)) << j) | (x >> sh));
+		if (!pyr[off + c]) { s = j; break; }
+		off += static_cast<size_t>(1) << (3 * j);
+	}
+	skip[i] = static_cast<uint8_t>(s);
 }
 
 // Fixture kernels: the noise evaluations of the demo's terrain set-up, one thread per column / voxel.

@@ -480,6 +480,33 @@ struct LeanWalker
 		c0 = __uint_as_float(kMagicBits | r.inv);
 	}
 
+	// Re-entry into the walk at time tau > 0 (beam start, ort_beam.cuh): descend from the root choosing, per axis, the
+	// half whose mid plane the ray has not crossed by tau -- the same `t_mid >= tmin` test descend() applies, with tmin =
+	// tau.  The caller continues with the ordinary loop; the first empty slot it meets is the empty slot S_i of the
+	// reference walk with the smallest exit time e_i >= tau (proof in ort_beam.cuh), with the same slot word, position,
+	// cell size and parent stack; advance() then overwrites tmin and mti before anything reads them.  The stack entry
+	// of level 0 does not exist, so the first half step is spelled out here instead of calling descend().
+	__device__ __forceinline__ void start_at(uint32_t root, const Ray& r, float tau)
+	{
+		start(root, r);
+		tmin = tau;
+		const float ux = set_ge(__fmaf_rn(1.5f, cx, bx), tau);
+		const float uy = set_ge(__fmaf_rn(1.5f, cy, by), tau);
+		const float uz = set_ge(__fmaf_rn(1.5f, cz, bz), tau);
+		px = __fmaf_rn(ux, 0.5f, 1.0f);
+		py = __fmaf_rn(uy, 0.5f, 1.0f);
+		pz = __fmaf_rn(uz, 0.5f, 1.0f);
+		const float F = __fmaf_rn(uz, wz, __fmaf_rn(uy, wy, __fmaf_rn(ux, wx, c0)));
+		w = root * 8u + __float_as_uint(F);
+	}
+
+	// the time the ray leaves the cube [1,2)^3: the exit time of the walk's last advance (the one that pops through the
+	// root) -- the smallest t of the three lower planes X = 1.0
+	__device__ __forceinline__ float cube_exit_time() const
+	{
+		return fminf(__fmaf_rn(1.0f, cx, bx), fminf(__fmaf_rn(1.0f, cy, by), __fmaf_rn(1.0f, cz, bz)));
+	}
+
 	// PUSH's load (och_h_octree.h:344).  base_biased = address of nodes_m1 minus 4 * kMagicBits
 	__device__ __forceinline__ uint32_t load_child(unsigned long long base_biased)
 	{

@@ -142,6 +142,23 @@ class TraceContext:
         self._ck(self.L.ort_measure_gather_peak(self.h, nbytes, C.byref(out)))
         return out.value
 
+    def beam_level(self, pos, rot, fov_factor: float, W: int, H: int) -> int:
+        """Grid level the beam start of W x H frames with this camera would use (0: none)."""
+        pos = np.ascontiguousarray(pos, np.float32)
+        rot = np.ascontiguousarray(rot, np.float32)
+        return int(self.L.ort_beam_level(self.h, _p(pos), _p(rot), fov_factor, W, H))
+
+    def beam_grid(self, level: int) -> np.ndarray:
+        """The level-`level` skip grid of the DAG on the device, (N, N, N) bytes indexed [z, y, x]."""
+        n = 1 << level
+        out = np.zeros((n, n, n), np.uint8)
+        self._ck(self.L.ort_beam_grid(self.h, level, _p(out)))
+        return out
+
+    @property
+    def beam_builds(self) -> int:
+        return self.L.ort_beam_builds(self.h)
+
     def set_stream(self, stream):
         """Queue subsequent work on a caller stream (a cudaStream_t as int, a torch.cuda.Stream, or None)."""
         if stream is not None and hasattr(stream, "cuda_stream"):

@@ -5,6 +5,9 @@
 #include "cuda_shim.h"
 #include "../../octree_ray_tracing_b200/csrc/ort_trace.cuh"
 #include "../../octree_ray_tracing_b200/csrc/ort_trace_experiments.cuh"
+#include "../../octree_ray_tracing_b200/csrc/ort_beam.cuh"
+
+#include <vector>
 
 #include <cstddef>
 #include <omp.h>
@@ -17,13 +20,14 @@ struct Stats
 	unsigned long long rays, slow_path_rays;                  // slow path: rays outside FastWalker's preconditions
 	unsigned long long oob_loads;                             // loads outside the node array / reciprocal table (cuda_shim.h)
 	unsigned long long lean_rays;                             // walker 13: rays that took LeanWalker (the rest: FastWalker / traverse)
+	unsigned long long beam_rays, beam_misses, beam_guard;    // beam start: rays re-entered at tau, rays ended as a MISS without a round, guard re-walks
 };
 
 // walker ids follow ort_set_option("variant"): 0 baseline traverse(), 1 FastWalker, 5 TightWalker, 7 PipeWalker,
 // 13 the round-2 tiers (LeanWalker first), 14 FlatWalker, 15 V4Walker (both on LeanWalker's tiers)
 template<bool COUNT>
 ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, float miss_t, float ox, float oy, float oz, const ort::Ray& ray,
-              Stats* st, int origin_flags = -1)
+              Stats* st, int origin_flags = -1, float tau = 0.0f)
 {
 	uint32_t stack[ort::kMaxDepth];
 	if (walker >= 13 && walker <= 15)
@@ -52,16 +56,30 @@ ort::Hit walk(int walker, const uint32_t* nodes_m1, uint32_t root, int depth, fl
 			while (!w.round(base_biased, leaf_dimf, miss_t, ls)) {}
 			return w.hit;
 		}
-		// the product's loop shape (ort::trace_ray): descend while there are children, then one advance
+		// the product's loop shape (ort::walk_ray): beam start or ordinary start, descend while there are children, then
+		// one advance; the beam guard re-walks from the start
 		ort::LeanWalker<COUNT> w;
-		w.start(root, ray);
+		bool beam_used;
+		if (ort::lean_start(w, root, ray, tau, miss_t, beam_used))
+		{
+			if (st) ++st->beam_misses;
+			return w.hit;
+		}
+		if (st && beam_used) ++st->beam_rays;
 		for (;;)
 		{
-			uint32_t child;
-			bool done = false;
-			while ((child = w.load_child(base_biased)) != 0u)
-				if (w.descend(child, leaf_dimf, ls)) { done = true; break; }
-			if (done || w.advance(miss_t, ls)) break;
+			for (;;)
+			{
+				uint32_t child;
+				bool done = false;
+				while ((child = w.load_child(base_biased)) != 0u)
+					if (w.descend(child, leaf_dimf, ls)) { done = true; break; }
+				if (done || w.advance(miss_t, ls)) break;
+			}
+			if (!(beam_used && w.mti == 8u)) break;
+			if (st) ++st->beam_guard;
+			beam_used = false;
+			w.start(root, ray);
 		}
 		return w.hit;
 	}
@@ -130,6 +148,7 @@ void merge(Stats* dst, const Stats& s)
 {
 	for (int i = 0; i < ort::kMaxDepth + 2; ++i) dst->rounds_by_level[i] += s.rounds_by_level[i];
 	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays; dst->oob_loads += s.oob_loads; dst->lean_rays += s.lean_rays;
+	dst->beam_rays += s.beam_rays; dst->beam_misses += s.beam_misses; dst->beam_guard += s.beam_guard;
 }
 
 }  // namespace
@@ -140,7 +159,7 @@ extern "C" {
 // och::octree pool (raw rows, root = row 0, index_base 0).  has_root = 0: empty tree, every ray is a MISS.
 int emu_trace_rays(const uint32_t* nodes8, size_t n_rows, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
                    const float* o3, int o_stride, const float* d3, size_t n, int walker,
-                   uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
+                   uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads, const float* tau)
 {
 	const uint32_t* nodes_m1 = nodes8 - 8 * static_cast<ptrdiff_t>(index_base);
 	const ort::RcpTable rt{rcp_tab, 23 - log2n};
@@ -157,8 +176,8 @@ int emu_trace_rays(const uint32_t* nodes8, size_t n_rows, int index_base, int ha
 			const ort::Ray r = ort::ray_setup(rt, o[0], o[1], o[2], d[0], d[1], d[2], (1u << (23 - depth)) - 1u);
 			ort::Hit h;
 			if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
-			else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr)
-			               : walk<false>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr);
+			else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr, -1, tau ? tau[i] : 0.0f)
+			               : walk<false>(walker, nodes_m1, root, depth, miss_t, o[0], o[1], o[2], r, stats_out ? &st : nullptr, -1, tau ? tau[i] : 0.0f);
 			++st.rays;
 			voxel[i] = h.voxel;
 			face[i] = static_cast<uint8_t>(h.face);
@@ -176,7 +195,8 @@ int emu_trace_rays(const uint32_t* nodes8, size_t n_rows, int index_base, int ha
 // camera rays generated like the frame kernels do (ort::camera_ray); rows as ort_trace_frame takes them (ort::frame_row)
 int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int has_root, uint32_t root, int depth, float miss_t, const uint32_t* rcp_tab, int log2n,
                     const float pos[3], const float rot[9], float fov, int W, int H, int y0, int rows, int tile_rows, int tile_step, int walker,
-                     uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads)
+                     uint32_t* voxel, uint8_t* face, float* t, uint16_t* npush, unsigned long long* stats_out, int nthreads,
+                     const uint8_t* beam_skip, int beam_k, float* tau_out)
 {
 	const uint32_t* nodes_m1 = nodes8 - 8 * static_cast<ptrdiff_t>(index_base);
 	const ort::RcpTable rt{rcp_tab, 23 - log2n};
@@ -202,10 +222,15 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 				float dx, dy, dz;
 				ort::camera_ray(cam, x, ort::frame_row(fr, r), dx, dy, dz);
 				const ort::Ray ray = ort::ray_setup_camera(rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, cam.origin_flags);
+				// beam start of the pixel's 8 x 4 tile, as beam_start_kernel computes it (the kernels: once per tile)
+				float tau = 0.0f;
+				if (beam_skip)
+					tau = ort::beam_tile_start(ort::BeamGrid{ beam_skip, beam_k }, cam, x & ~7, ort::frame_row(fr, r & ~3));
+				if (tau_out) tau_out[static_cast<size_t>(r) * W + x] = tau;
 				ort::Hit h;
 				if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
-				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags)
-				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags);
+				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags, tau)
+				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags, tau);
 				++st.rays;
 				const size_t i = static_cast<size_t>(r) * W + x;
 				voxel[i] = h.voxel;
@@ -222,6 +247,80 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 }
 
 int emu_stats_words(void) { return static_cast<int>(sizeof(Stats) / sizeof(unsigned long long)); }
+
+// The beam grid of level k for a DAG (ort_beam.cuh), computed the plain way on the host: occupancy by descending from the
+// root per cell, 27-neighbour dilation, OR pyramid, skip level.  skip: (2^k)^3 bytes.  The GPU kernels must produce the
+// same bytes (tests/test_gpu_beam.py).
+void emu_beam_grid(const uint32_t* nodes8, int index_base, uint32_t root, int k, uint8_t* skip)
+{
+	const uint32_t* nodes_m1 = nodes8 - 8 * static_cast<ptrdiff_t>(index_base);
+	const int N = 1 << k;
+	const size_t cells = static_cast<size_t>(N) * N * N;
+	std::vector<uint8_t> occ(cells), dil(cells);
+#pragma omp parallel for schedule(static)
+	for (long long i = 0; i < static_cast<long long>(cells); ++i)
+	{
+		const int x = static_cast<int>(i % N), y = static_cast<int>((i / N) % N), z = static_cast<int>(i / (static_cast<long long>(N) * N));
+		uint32_t node = root, child = 1;
+		for (int l = k - 1; l >= 0 && child; --l)
+		{
+			const uint32_t slot = ((x >> l) & 1) | (((y >> l) & 1) << 1) | (((z >> l) & 1) << 2);
+			child = nodes_m1[(static_cast<size_t>(node) << 3) + slot];
+			node = child;
+		}
+		occ[i] = child != 0;
+	}
+#pragma omp parallel for schedule(static)
+	for (long long i = 0; i < static_cast<long long>(cells); ++i)
+	{
+		const int x = static_cast<int>(i % N), y = static_cast<int>((i / N) % N), z = static_cast<int>(i / (static_cast<long long>(N) * N));
+		uint8_t any = 0;
+		for (int dz = -1; dz <= 1; ++dz) for (int dy = -1; dy <= 1; ++dy) for (int dx = -1; dx <= 1; ++dx)
+		{
+			const int xx = x + dx, yy = y + dy, zz = z + dz;
+			if (xx >= 0 && xx < N && yy >= 0 && yy < N && zz >= 0 && zz < N) any |= occ[(static_cast<size_t>(zz) * N + yy) * N + xx];
+		}
+		dil[i] = any;
+	}
+	// pyr[j]: level j of the OR pyramid over dil
+	std::vector<std::vector<uint8_t>> pyr(k + 1);
+	pyr[k] = dil;
+	for (int j = k - 1; j >= 1; --j)
+	{
+		const int M = 1 << j, F = 2 * M;
+		pyr[j].assign(static_cast<size_t>(M) * M * M, 0);
+		for (int z = 0; z < F; ++z) for (int y = 0; y < F; ++y) for (int x = 0; x < F; ++x)
+			pyr[j][(static_cast<size_t>(z / 2) * M + y / 2) * M + x / 2] |= pyr[j + 1][(static_cast<size_t>(z) * F + y) * F + x];
+	}
+#pragma omp parallel for schedule(static)
+	for (long long i = 0; i < static_cast<long long>(cells); ++i)
+	{
+		const int x = static_cast<int>(i % N), y = static_cast<int>((i / N) % N), z = static_cast<int>(i / (static_cast<long long>(N) * N));
+		int s = 0;
+		for (int j = 1; j <= k && !s; ++j)
+		{
+			const int sh = k - j, M = 1 << j;
+			if (!pyr[j][(static_cast<size_t>(z >> sh) * M + (y >> sh)) * M + (x >> sh)]) s = j;
+		}
+		skip[i] = static_cast<uint8_t>(s);
+	}
+}
+
+// the host-side choice of the grid level for a camera (ort::beam_tile_radius / beam_level_for), 0 = no beam start
+int emu_beam_level(const float pos[3], const float rot[9], float fov, int W, int H, int depth, const uint32_t* rcp_tab, int log2n)
+{
+	ort::Camera cam{};
+	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
+	for (int i = 0; i < 9; ++i) cam.r[i] = rot[i];
+	cam.fov = fov;
+	cam.aspect = static_cast<float>(W) / static_cast<float>(H);
+	cam.vfx = 2.0F / static_cast<float>(W);
+	cam.vfy = 2.0F / static_cast<float>(H);
+	const double eps = ort::rcp_table_rel_error(rcp_tab, log2n);
+	const double radius = ort::beam_tile_radius(cam, eps);
+	if (!(ort::camera_origin_flags(cam.ox, cam.oy, cam.oz, 0u) & ort::kOriginInCube)) return 0;
+	return radius < 0 ? 0 : ort::beam_level_for(radius, depth, ort::beam_t_max(cam.ox, cam.oy, cam.oz, eps));
+}
 
 }  // extern "C"
 

@@ -17,11 +17,11 @@ SANITIZE = os.environ.get("ORT_EMU_SANITIZE", "") == "1"      # tools/sanitize_h
 SO = os.path.join(HERE, "_build", "libort_emu_san.so" if SANITIZE else "libort_emu.so")
 _lib = None
 
-STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads", "lean_rays"]
+STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads", "lean_rays", "beam_rays", "beam_misses", "beam_guard"]
 
 
 def build(force: bool = False) -> str:
-    deps = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h"), os.path.join(CSRC, "ort_trace.cuh"), os.path.join(CSRC, "ort_trace_experiments.cuh")]
+    deps = [os.path.join(HERE, "emu.cpp"), os.path.join(HERE, "cuda_shim.h"), os.path.join(CSRC, "ort_trace.cuh"), os.path.join(CSRC, "ort_trace_experiments.cuh"), os.path.join(CSRC, "ort_beam.cuh")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
     os.makedirs(os.path.dirname(SO), exist_ok=True)
@@ -60,8 +60,9 @@ def _stats(raw):
     return d
 
 
-def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False):
-    """pool=True: nodes8 is an och::octree pool (raw rows, root = row 0; the caller passes miss_t=0.0)."""
+def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf, want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False, tau=None):
+    """pool=True: nodes8 is an och::octree pool (raw rows, root = row 0; the caller passes miss_t=0.0).
+    tau: per-ray re-entry times of the beam start (walker 13 only; 0 = ordinary start)."""
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
     d = np.ascontiguousarray(d, np.float32).reshape(-1, 3)
@@ -73,7 +74,8 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
     oob = lib().emu_trace_rays(_p(nodes8), C.c_size_t(nodes8.size // 8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
                          _p(o), o_stride, _p(d), C.c_size_t(n), walker,
-                         _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
+                         _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1,
+                         _p(None if tau is None else np.ascontiguousarray(tau, np.float32)))
     if oob and not allow_oob:
         raise MemoryError("host emulation: the walk loaded from outside the node array / reciprocal table")
     out = [vox, face, t]
@@ -84,8 +86,26 @@ def trace_rays(nodes8, root, depth, o, d, walker=1, rcp_tab=None, miss_t=np.inf,
     return tuple(out)
 
 
+def beam_grid(nodes8, root, k, pool=False) -> np.ndarray:
+    """The level-k skip grid of the beam start (csrc/ort_beam.cuh) for a DAG, computed on the host: (N, N, N) bytes [z, y, x]."""
+    nodes8 = np.ascontiguousarray(nodes8, np.uint32)
+    n = 1 << k
+    skip = np.zeros((n, n, n), np.uint8)
+    lib().emu_beam_grid(_p(nodes8), 0 if pool else 1, C.c_uint32(root), k, _p(skip))
+    return skip
+
+
+def beam_level(pos, rot, fov, W, H, depth, rcp_tab=None) -> int:
+    """The grid level the library would pick for this camera (0: no beam start)."""
+    tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
+    pos = np.ascontiguousarray(pos, np.float32)
+    rot = np.ascontiguousarray(rot, np.float32)
+    return int(lib().emu_beam_level(_p(pos), _p(rot), C.c_float(fov), W, H, depth, _p(tab), int(np.log2(len(tab)))))
+
+
 def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, tile_rows=1, tile_step=1, walker=1, rcp_tab=None, miss_t=np.inf,
-                want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False):
+                want_npush=False, want_stats=False, nthreads=None, pool=False, allow_oob=False, beam=None, want_tau=False):
+    """beam: a skip grid from beam_grid() -- the frame is traced with the beam start of every 8 x 4 tile (walker 13)."""
     nodes8 = np.ascontiguousarray(nodes8, np.uint32)
     tab = default_rcp_table() if rcp_tab is None else np.ascontiguousarray(rcp_tab, np.uint32)
     rows = H - y0 if rows is None else rows
@@ -94,9 +114,13 @@ def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, tile_
     vox = np.empty(n, np.uint32); face = np.empty(n, np.uint8); t = np.empty(n, np.float32)
     npush = np.empty(n, np.uint16) if want_npush else None
     stats = np.zeros(lib().emu_stats_words(), np.uint64) if want_stats else None
+    tau = np.zeros(n, np.float32) if want_tau else None
+    if beam is not None:
+        beam = np.ascontiguousarray(beam, np.uint8)
     oob = lib().emu_trace_frame(_p(nodes8), C.c_size_t(nodes8.size // 8), 0 if pool else 1, 1 if (pool or root) else 0, C.c_uint32(root), depth, C.c_float(miss_t), _p(tab), int(np.log2(len(tab))),
                           _p(pos), _p(rot), C.c_float(fov), W, H, y0, rows, tile_rows, tile_step, walker,
-                           _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1)
+                           _p(vox), _p(face), _p(t), _p(npush), _p(stats), nthreads or os.cpu_count() or 1,
+                           _p(beam), 0 if beam is None else int(np.log2(beam.shape[0])), _p(tau))
     if oob and not allow_oob:
         raise MemoryError("host emulation: the walk loaded from outside the node array / reciprocal table")
     out = [vox, face, t]
@@ -104,6 +128,8 @@ def trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=0, rows=None, tile_
         out.append(npush)
     if want_stats:
         out.append(_stats(stats))
+    if want_tau:
+        out.append(tau)
     return tuple(out)
 
 

@@ -1,0 +1,187 @@
+"""Beam start of camera frames (csrc/ort_beam.cuh) on the CPU: the device code (LeanWalker::start_at, lean_start, beam_march,
+beam_tile_start, the host-side level choice) compiled for the host by tests/host_emu and held against the oracle.
+
+Three claims are tested separately:
+  1. re-entry: for ANY tau in (0, hit time] (cube exit time for a MISS, anything beyond it included) the walk re-entered
+     at tau returns the oracle's voxel, face and hit time bit for bit;
+  2. the bound: the tile start times the march yields never exceed the hit time of any ray of the tile;
+  3. frames traced with the beam start equal the oracle, with fewer rounds, and the guard never fires.
+Test infrastructure only (the product has no CPU path)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_same_hits, degenerate_rays
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+
+POSES = {"A": ((1.5, 1.5, 1.5), 0.0, 0.0), "B": ((1.5, 1.5, 1.5), 0.7, -0.6), "C": ((1.1, 1.1, 1.4), 0.785, -0.3)}
+NCPU = max(1, min(16, os.cpu_count() or 1))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu as m
+    m.lib()
+    return m
+
+
+@pytest.fixture(scope="module")
+def scene(ort):
+    depth = 9
+    T = ort.HOctree(21, depth, device=None)
+    ort.harness.build_terrain(T, tunnels=True)
+    nodes8, root, _ = T.flatten()
+    return depth, nodes8, root
+
+
+def test_reentry_at_any_time_up_to_the_hit_equals_the_oracle(emu, ort, oc, scene):
+    """Claim 1.  Rays: random, degenerate (zero / denormal / NaN / inf components, on-plane and outside origins -- they
+    leave the lean tier and must ignore tau) and camera rays.  tau: random fractions of the hit time, the hit time itself,
+    the next float below it, other rays' hit times clipped to it, and for rays that MISS anything up to far beyond the cube."""
+    depth, nodes8, root = scene
+    tab = emu.default_rcp_table()
+    O, D = degenerate_rays(ort, depth)
+    rot, fov = oc.camera_coeffs(0.7, -0.6)
+    dc = oc.gen_rays(rot, fov, 320, 180)
+    O = np.concatenate([O, np.tile(np.array([[1.5, 1.5, 1.5]], np.float32), (len(dc), 1))])
+    D = np.concatenate([D, dc])
+    want = oc.trace_rays(nodes8, root, depth, O, D, rcp_tab=tab, nthreads=NCPU)
+    t_hit = want[2].copy()
+    rs = np.random.RandomState(5)
+    hit = want[0] != 0
+    miss = ~hit                                  # a MISS takes any tau; a hit at time 0 (origin inside a voxel) or NaN takes none: tau = 0
+    finite = hit & np.isfinite(t_hit) & (t_hit > 0)
+    taus = []
+    for frac in (1.0, 0.999999, 0.5, None, None):
+        f = rs.rand(len(D)).astype(np.float32) if frac is None else np.float32(frac)
+        tau = np.where(finite, t_hit * f, np.where(miss, (rs.rand(len(D)) * 4.0).astype(np.float32), 0)).astype(np.float32)
+        taus.append(tau)
+    taus.append(np.where(finite, np.nextafter(t_hit, np.float32(0)), np.where(miss, np.float32(1e-30), 0)).astype(np.float32))
+    taus.append(np.where(finite, np.minimum(t_hit, np.roll(np.where(finite, t_hit, 1.0), 1)), np.where(miss, np.float32(np.inf), 0)).astype(np.float32))
+    beam_rays = 0
+    for i, tau in enumerate(taus):
+        got = emu.trace_rays(nodes8, root, depth, O, D, walker=13, tau=tau, want_stats=True, nthreads=NCPU)
+        assert_same_hits(got, want, f"re-entry, tau set {i}")
+        assert got[3]["beam_guard"] == 0, "a tau that is a lower bound of the hit time must never trip the guard"
+        beam_rays += got[3]["beam_rays"] + got[3]["beam_misses"]
+    assert beam_rays > 500_000, "the lean-tier rays must actually have taken the beam start"
+
+
+def test_a_tau_beyond_the_hit_time_trips_the_guard_or_is_caught(emu, oc, scene):
+    """The guard is no proof of anything, but where it fires it must repair: a tau INSIDE the hit voxel (later than the hit
+    time, earlier than the voxel's exit) makes the re-entry land on the voxel without a STEP; the ray is walked again."""
+    depth, nodes8, root = scene
+    tab = emu.default_rcp_table()
+    rot, fov = oc.camera_coeffs(0.7, -0.6)
+    d = oc.gen_rays(rot, fov, 160, 90)
+    o = np.array([1.5, 1.5, 1.5], np.float32)
+    want = oc.trace_rays(nodes8, root, depth, o, d, rcp_tab=tab, nthreads=NCPU)
+    hit = want[0] != 0
+    tau = np.where(hit, want[2] * np.float32(1.0 + 2.0 ** -14), 0).astype(np.float32)      # ~ a tenth of a voxel further
+    got = emu.trace_rays(nodes8, root, depth, o, d, walker=13, tau=tau, want_stats=True, nthreads=NCPU)
+    assert got[3]["beam_guard"] > 0
+    fired_all_right = np.array_equal(got[0], want[0])          # rays landing in a solid voxel are repaired; the test scene has no one-voxel walls the others could skip
+    assert fired_all_right
+
+
+@pytest.mark.parametrize("depth,tunnels", [(6, True), (8, True), (10, False)])
+def test_march_is_a_lower_bound_and_beam_frames_equal_the_oracle(emu, ort, oc, depth, tunnels):
+    """Claims 2 and 3 on terrain scenes: the three bench poses, cameras in the corners of the cube, next to the terrain
+    and inside tunnels, several frame sizes (the grid level follows the pixel size), whole frames and cyclic strips."""
+    T = ort.HOctree(14 + depth, depth, device=None)
+    ort.harness.build_terrain(T, tunnels=tunnels)
+    nodes8, root, _ = T.flatten()
+    tab = emu.default_rcp_table()
+    cams = [POSES["A"], POSES["B"], POSES["C"],
+            ((1.02, 1.03, 1.9), 0.785, -0.9), ((1.97, 1.96, 1.95), 3.9, -0.5), ((1.5, 1.5, 1.999), 0.3, -1.5),
+            ((1.25, 1.75, 1.0 + 5.0 / 16.0 + 0.02), 1.1, -0.05), ((1.5, 1.5, 1.2), 2.0, 0.4), ((1.0625, 1.5, 1.5), 0.0, 0.0)]
+    grids = {}
+    seen_levels = set()
+    total_ref = total_beam = 0
+    for ci, (pos, yaw, pitch) in enumerate(cams):
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        for (W, H, y0, rows, tr, ts) in [(640, 360, 0, 360, 1, 1), (1920, 1080, 512, 40, 8, 2), (256, 144, 0, 144, 1, 1)][: 3 if ci < 4 else 1]:
+            k = emu.beam_level(pos, rot, fov, W, H, depth)
+            if k == 0:
+                continue
+            seen_levels.add(k)
+            if k not in grids:
+                grids[k] = emu.beam_grid(nodes8, root, k)
+            # the oracle on the same rows
+            frame_rows = [y0 + (r // tr) * tr * ts + r % tr for r in range(rows)] if ts > 1 else list(range(y0, y0 + rows))
+            d = np.concatenate([oc.gen_rays(rot, fov, W, H, y, y + 1) for y in frame_rows])
+            want = oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=NCPU, want_counts=True)
+            got = emu.trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=y0, rows=rows, tile_rows=tr, tile_step=ts, walker=13,
+                                  want_npush=True, want_stats=True, beam=grids[k], want_tau=True)
+            what = f"depth {depth}, camera {ci}, {W}x{H} rows {y0}+{rows} tiles {tr}/{ts}, level {k}"
+            assert_same_hits(got, want, what)
+            st, tau = got[4], got[5]
+            assert st["beam_guard"] == 0, what
+            hit = want[0] != 0
+            assert (tau[hit] <= want[2][hit]).all(), f"{what}: a tile start later than a hit time of the tile"
+            assert (got[3] <= want[3]).all() or (got[3].astype(np.int64) - want[3]).max() <= depth, what
+            total_ref += int(want[3].sum()); total_beam += int(got[3].sum())
+    assert seen_levels, "no camera got a beam level"
+    assert total_beam < 0.8 * total_ref, f"the beam start should save rounds ({total_beam} vs {total_ref})"
+
+
+def test_grid_properties_and_level_choice(emu, ort, oc, scene):
+    depth, nodes8, root = scene
+    for k in (3, 5, 7):
+        g = emu.beam_grid(nodes8, root, k)
+        n = 1 << k
+        assert g.shape == (n, n, n) and g.max() <= k
+        occ = g == 0
+        # a cell with skip level j: its whole level-j cell is free of marked cells, and the level j-1 cell is not
+        for j in range(1, k + 1):
+            sel = np.argwhere(g == j)[:200]
+            for z, y, x in sel:
+                sh = k - j
+                blk = occ[(z >> sh) << sh:((z >> sh) + 1) << sh, (y >> sh) << sh:((y >> sh) + 1) << sh, (x >> sh) << sh:((x >> sh) + 1) << sh]
+                assert not blk.any()
+                if j > 1:
+                    sh += 1
+                    blk = occ[(z >> sh) << sh:((z >> sh) + 1) << sh, (y >> sh) << sh:((y >> sh) + 1) << sh, (x >> sh) << sh:((x >> sh) + 1) << sh]
+                    assert blk.any()
+    # empty DAG region: the sky above the terrain is free at level 1 or 2
+    assert (emu.beam_grid(nodes8, root, 5)[-1] != 0).all()
+    # level choice: finer pixels -> finer grid; a camera in the corner sees longer rays -> coarser; no level for huge pixels,
+    # for a matrix that is no rotation, for an origin outside the cube
+    rot, fov = oc.camera_coeffs(0.7, -0.6)
+    c = (1.5, 1.5, 1.5)
+    assert emu.beam_level(c, rot, fov, 3840, 2160, 12) == 7
+    assert emu.beam_level((1.1, 1.1, 1.4), rot, fov, 3840, 2160, 12) == 7
+    corner = (1.02, 1.03, 1.97)
+    assert emu.beam_level(corner, rot, fov, 1920, 1080, 12) == 6          # longer rays: the beam is wider at their far end
+    lv = [emu.beam_level(corner, rot, fov, 240 << i, 135 << i, 12) for i in range(5)]
+    assert lv == sorted(lv) and lv[0] in (0, 3) and lv[-1] == 7, lv
+    assert emu.beam_level(c, rot, fov, 3840, 2160, 5) == 5
+    assert emu.beam_level(c, rot, fov, 64, 36, 12) == 0
+    assert emu.beam_level(c, rot * 1.01, fov, 3840, 2160, 12) == 0
+    assert emu.beam_level((2.5, 1.5, 1.5), rot, fov, 3840, 2160, 12) == 0
+    assert emu.beam_level(c, rot, 0.0, 3840, 2160, 12) == 0
+
+
+def test_beam_on_the_pool_octree_layout(emu, ort, oc):
+    """och::octree pool rows (root = row 0, MISS time 0.0F) take the same beam start."""
+    from oracle import oracle as ocm
+    depth = 7
+    P = ocm.OracleOctree(depth, 1 << 16)
+    rs = np.random.RandomState(3)
+    for _ in range(300):
+        x, y, z = rs.randint(0, 1 << depth, 3)
+        P.set(int(x), int(y), int(z) // 3, int(rs.randint(1, 5)))
+    pool = P.nodes().copy()
+    pos, rot_fov = (1.5, 1.5, 1.8), oc.camera_coeffs(0.4, -0.8)
+    rot, fov = rot_fov
+    W, H = 640, 360
+    k = emu.beam_level(pos, rot, fov, W, H, depth)
+    assert k > 0
+    grid = emu.beam_grid(pool, 0, k, pool=True)
+    want = emu.trace_frame(pool, 0, depth, pos, rot, fov, W, H, walker=0, miss_t=0.0, pool=True)
+    got = emu.trace_frame(pool, 0, depth, pos, rot, fov, W, H, walker=13, miss_t=0.0, pool=True, beam=grid, want_stats=True)
+    assert_same_hits(got, want, "pool layout with beam start")
+    assert got[3]["beam_rays"] + got[3]["beam_misses"] > 0 and got[3]["beam_guard"] == 0

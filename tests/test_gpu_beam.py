@@ -1,0 +1,189 @@
+"""Beam start of camera frames on the GPU (csrc/ort_beam.cuh, the beam_* kernels and the BEAM instantiations of the frame
+kernels), through the C ABI.  The claims the CPU suite holds the host emulation to (tests/test_beam.py) are repeated here
+on the device: same grid bytes, same outputs with the option on and off, equal to the reference / the oracle, fewer
+rounds, grids rebuilt after edits."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import assert_same_hits
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emu"))
+
+pytestmark = pytest.mark.gpu
+
+POSES = {"A": ((1.5, 1.5, 1.5), 0.0, 0.0), "B": ((1.5, 1.5, 1.5), 0.7, -0.6), "C": ((1.1, 1.1, 1.4), 0.785, -0.3)}
+NCPU = max(1, min(32, os.cpu_count() or 1))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    import emu as m
+    m.lib()
+    return m
+
+
+def test_gpu_grid_equals_host_grid_and_follows_edits(ort, emu):
+    depth = 9
+    T = ort.HOctree(21, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=True)
+    T.sync()
+    nodes8, root, _ = T.flatten()
+    for k in (3, 6, 7):
+        assert np.array_equal(T.ctx.beam_grid(k), emu.beam_grid(nodes8, root, k)), f"level {k}"
+    b0 = T.ctx.beam_builds
+    assert np.array_equal(T.ctx.beam_grid(6), emu.beam_grid(nodes8, root, 6)) and T.ctx.beam_builds == b0, "an unchanged DAG keeps its grid"
+    # a floating block high above the terrain: cells that were free at level 1 are marked now
+    T.set_box(300, 300, 470, 12, 3)
+    T.sync()
+    nodes8, root, _ = T.flatten()
+    for k in (6, 7, 3):
+        g = T.ctx.beam_grid(k)
+        assert np.array_equal(g, emu.beam_grid(nodes8, root, k)), f"level {k} after the edit"
+        assert g[(470 * (1 << k)) >> depth, (300 * (1 << k)) >> depth, (300 * (1 << k)) >> depth] == 0
+    assert T.ctx.beam_builds == b0 + 3
+    T.ctx.close()
+
+
+def test_bench_frames_beam_on_equals_beam_off_and_the_reference(ort, oc, emu):
+    """Depth 12, 3840x2160, poses A/B/C: every ray with the beam start == every ray without, sampled rows == the CPU
+    checker (the reference's own sse_trace where it travelled), and the rounds actually issued are the host emulation's."""
+    depth = 12
+    T = ort.HOctree(24, depth, device=0)
+    ort.harness.build_terrain(T)
+    T.sync()
+    ctx = T.ctx
+    nodes8, root, _ = T.flatten()
+    tab = emu.default_rcp_table()
+    W, H = 3840, 2160
+    if oc.have_ref():
+        R = oc.RefTree(24, depth)
+        R.import_compact(nodes8, root)
+        cpu = lambda o, d: R.trace(o, d, nthreads=NCPU)
+    else:
+        cpu = lambda o, d: oc.trace_rays(nodes8, root, depth, o, d, rcp_tab=tab, nthreads=NCPU)
+    tot_on = tot_off = 0
+    for name, (pos, yaw, pitch) in POSES.items():
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        assert ctx.beam_level(pos, rot, fov, W, H) == 7
+        ctx.set_option("beam", 0)
+        off = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
+        ctx.set_option("beam", 1)
+        l0 = ctx.launch_count
+        on = ctx.trace_frame(pos, rot, fov, W, H)
+        assert ctx.launch_count - l0 >= 2 * 8, "every chunk of the host-buffer frame is a march + a trace launch"
+        assert_same_hits(on, off, f"pose {name}: beam on vs off")
+        ys = np.arange(5, H, 54)
+        d = np.concatenate([oc.gen_rays(rot, fov, W, H, int(y), int(y) + 1) for y in ys])
+        want = cpu(np.array(pos, np.float32), d)
+        sel = (ys[:, None] * W + np.arange(W)[None, :]).ravel()
+        assert_same_hits(tuple(a[sel] for a in on), want, f"pose {name}: beam on vs the CPU checker")
+        # rounds: counted with the beam start, against the emulation of the same rows
+        ctx.set_option("count_beam", 1)
+        cnt = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)
+        ctx.set_option("count_beam", 0)
+        assert_same_hits(cnt, off, f"pose {name}: counting launch with beam")
+        tot_on += int(cnt[3].astype(np.int64).sum()); tot_off += int(off[3].astype(np.int64).sum())
+        if name == "C":
+            grid = emu.beam_grid(nodes8, root, 7)
+            e = emu.trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=1024, rows=64, walker=13, want_npush=True, beam=grid)
+            assert np.array_equal(e[3], cnt[3][1024 * W:(1024 + 64) * W]), "per-ray rounds with the beam start differ from the host emulation's"
+    assert tot_on < 0.6 * tot_off, (tot_on, tot_off)
+    ctx.close()
+
+
+def test_strips_rgba_batched_launches_and_small_frames(ort, oc, emu):
+    """Every frame entry point with the beam start against itself without: cyclic strips (tile heights 8 and 12; 6 is not
+    a multiple of 4 and runs without), shaded frames, the batched launch, device buffers, a depth-7 DAG (grid level =
+    depth), frames too coarse for any grid."""
+    import torch
+    depth = 10
+    T = ort.HOctree(22, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=True)
+    T.sync()
+    ctx = T.ctx
+    cols, _ = ort.harness.parse_voxels(ort.harness.DEMO_VOXELS)
+    ctx.set_palette(cols)
+    W, H = 1920, 1080
+    cams = [(np.array(p, np.float32),) + tuple(oc.camera_coeffs(y, pt)) for p, y, pt in POSES.values()]
+    cams.append((np.array([1.03, 1.96, 1.93], np.float32),) + tuple(oc.camera_coeffs(5.5, -0.7)))
+
+    def run(fn):
+        ctx.set_option("beam", 0)
+        a = fn()
+        ctx.set_option("beam", 1)
+        b = fn()
+        return a, b
+
+    for ci, (pos, rot, fov) in enumerate(cams):
+        for (y0, rows, tr, ts) in [(0, H, 1, 1), (8, 536, 8, 2), (24, 360, 12, 3), (6, 180, 6, 5), (17, 333, 1, 1)]:
+            a, b = run(lambda: ctx.trace_frame(pos, rot, fov, W, H, y0=y0, rows=rows, tile_rows=tr, tile_step=ts))
+            assert_same_hits(b, a, f"camera {ci}, rows {y0}+{rows}, tiles {tr}/{ts}")
+        a, b = run(lambda: ctx.trace_frame_rgba(pos, rot, fov, W, H))
+        assert np.array_equal(a, b), f"camera {ci}: shaded frame"
+        a, b = run(lambda: ctx.trace_frame_rgba(pos, rot, fov, W, H, y0=16, rows=256, tile_rows=16, tile_step=4))
+        assert np.array_equal(a, b), f"camera {ci}: shaded strip"
+        a, b = run(lambda: ctx.trace_frame(pos, rot, fov, 96, 54))
+        assert_same_hits(b, a, f"camera {ci}: 96x54 (no grid is coarse enough)")
+    assert ctx.beam_level(cams[0][0], cams[0][1], cams[0][2], 96, 54) == 0
+
+    # batched launch on device buffers: strips of all cameras in one launch, twice (beam off / on)
+    def batched():
+        outs, jobs = [], []
+        for k, (pos, rot, fov) in enumerate(cams):
+            rows = 8 * (((H // 8) - k % 2 + 1) // 2)
+            n = rows * W
+            o = (torch.empty(n, dtype=torch.int32, device="cuda"), torch.empty(n, dtype=torch.uint8, device="cuda"), torch.empty(n, dtype=torch.float32, device="cuda"))
+            outs.append(o)
+            jobs.append((pos, rot, fov, W, H, 8 * (k % 2), rows, 8, 2, o[0], o[1], o[2]))
+        ctx.trace_frames_async(jobs)
+        ctx.sync()
+        return [(o[0].cpu().numpy().view(np.uint32), o[1].cpu().numpy(), o[2].cpu().numpy()) for o in outs]
+    a, b = run(batched)
+    for k in range(len(cams)):
+        assert_same_hits(b[k], a[k], f"batched job {k}")
+    ctx.close()
+
+    depth = 7
+    T = ort.HOctree(18, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=True)
+    T.sync()
+    pos, rot, fov = cams[1]
+    assert T.ctx.beam_level(pos, rot, fov, 3840, 2160) == 7
+    T.ctx.set_option("beam", 0)
+    a = T.ctx.trace_frame(pos, rot, fov, 3840, 2160)
+    T.ctx.set_option("beam", 1)
+    b = T.ctx.trace_frame(pos, rot, fov, 3840, 2160)
+    assert_same_hits(b, a, "depth 7, grid level = depth")
+    T.ctx.close()
+
+
+def test_edit_loop_with_beam_start_vs_oracle(ort, oc, emu):
+    """Config 4's loop at 1080p: edit bursts (add above the terrain, carve below), delta upload, frame -- the grid must follow
+    every DAG version (a stale grid would start rays behind the new voxels)."""
+    depth = 8
+    T = ort.HOctree(20, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=False)
+    tab = emu.default_rcp_table()
+    pos, yaw, pitch = POSES["B"]
+    rot, fov = oc.camera_coeffs(yaw, pitch)
+    W, H = 1920, 1080
+    assert T.ctx.beam_level(pos, rot, fov, W, H) > 0
+    d = oc.gen_rays(rot, fov, W, H)
+    rs = np.random.RandomState(2)
+    builds = T.ctx.beam_builds
+    for it in range(6):
+        x, y = (int(v) for v in rs.randint(40, 200, 2))
+        if it % 2 == 0:
+            T.set_box(x, y, 150 + 10 * it, 14, 2)          # a block in the sky, between the camera and the terrain
+        else:
+            T.set_box(x, y, 60, 30, 0)                     # a pit
+        T.sync()
+        got = T.ctx.trace_frame(pos, rot, fov, W, H)
+        nodes8, root, _ = T.flatten()
+        want = oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=NCPU)
+        assert_same_hits(got, want, f"edit {it}")
+        assert T.ctx.beam_builds == builds + it + 1
+    T.ctx.close()

@@ -49,33 +49,40 @@ def traffic(rep, out_json):
     import json
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr, units, data = rows[0], rows[1], rows[2:]
+    hdr, units, all_rows = rows[0], rows[1], rows[2:]
+    name_i = hdr.index("Kernel Name")
+    # the frame launches of the step; the marches of the beam start (beam_start_kernel, one per frame) are listed beside them
+    data = [r for r in all_rows if "beam_start" not in r[name_i]]
+    march = [r for r in all_rows if "beam_start" in r[name_i]]
     scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = []
-    for r in data:
+
+    def dram(r):
         b = 0.0
         for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(k)
             b += float(r[i]) * scale[units[i]]
-        tot.append(b)
+        return b
+    tot = [dram(r) for r in data]
     inst = [int(float(r[hdr.index("smsp__inst_executed.sum")])) for r in data] if "smsp__inst_executed.sum" in hdr else []
 
-    def col(key, conv=float):
-        return [conv(r[hdr.index(key)]) for r in data] if key in hdr else []
+    def col(key, conv=float, rows_=None):
+        return [conv(r[hdr.index(key)]) for r in (data if rows_ is None else rows_)] if key in hdr else []
     import os
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from octree_ray_tracing_b200.build import kernel_source_hash
     json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "per_launch": [int(x) for x in tot],
                "warp_instructions_per_launch": inst,
+               "march_warp_instructions_per_launch": [int(x) for x in col("smsp__inst_executed.sum", float, march)],
+               "march_kernel_time_us": col("gpu__time_duration.sum", float, march),
                "l2_sectors_per_launch": [int(x) for x in col("lts__t_sectors.sum")],
                "l1_hit_pct": col("l1tex__t_sector_hit_rate.pct"), "l2_hit_pct": col("lts__t_sector_hit_rate.pct"),
                "active_threads_per_warp_instruction": col("smsp__thread_inst_executed_per_inst_executed.ratio"),
                "issue_active_pct": col("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                "kernel_time_us": col("gpu__time_duration.sum"),
                "source": rep, "kernel_source_sha16": kernel_source_hash(),
-               "note": "written by tools/ncu_summary.py --traffic from an `ncu --set full` capture of the three frame launches (poses A, B, C) of one bench step; "
-                       "bench.py uses it only while kernel_source_sha16 equals the hash of the sources it runs",
-               "kernels": [r[hdr.index("Kernel Name")].split("(")[0] for r in data]}, open(out_json, "w"), indent=1)
+               "note": "written by tools/ncu_summary.py --traffic from an `ncu --set full` capture of the frame launches (poses A, B, C; with the beam start also "
+                       "their three beam_start_kernel marches) of one bench step; bench.py uses it only while kernel_source_sha16 equals the hash of the sources it runs",
+               "kernels": [r[name_i].split("(")[0] for r in data]}, open(out_json, "w"), indent=1)
 
 
 def main():
