@@ -41,6 +41,10 @@
 //     tau_c.  The march samples 2^-19 past every exit plane instead of tracking cell indices; the cells it can miss that
 //     way are clipped by less than the slack.  tau = tau_c (1 - 2^-12) - 2^-17.
 //
+// (3) Tiles that see nothing.  When the central ray has left the cube by more than a cell without meeting a marked cell,
+//     every ray of the tile has left it too: tau = +inf.  If all rays of the tile are certain to be lean-tier rays
+//     (beam_tile_start), the trace kernel writes 32 MISSes and is done -- no camera ray, no reciprocals.
+//
 // What this buys is measured in profiles/ (r2_beam_*); what it costs is one byte grid per DAG version (built lazily by
 // four small kernels, 8^k bytes) and one march per tile (a separate launch, one thread per tile).
 #pragma once
@@ -126,7 +130,7 @@ inline double rcp_table_rel_error(const uint32_t* tab, int log2n)
 // the cube the grid continues as one ring of virtual cells that inherit the flag of the boundary cell next to them (the
 // inside cells around a virtual cell are among the 27 around that boundary cell): the tile's other rays may still be
 // inside while the central ray is up to one cell out, and not once it is further.
-__device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy, float oz, float dx, float dy, float dz)
+__device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy, float oz, float dx, float dy, float dz, int* steps = nullptr)
 {
 	const int N = 1 << g.k;
 	const float fN = static_cast<float>(N), cell = 1.0f / fN;
@@ -145,6 +149,7 @@ __device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy
 		const int cx = static_cast<int>(floorf(qx)), cy = static_cast<int>(floorf(qy)), cz = static_cast<int>(floorf(qz));      // -1 .. N
 		const int bx = min(max(cx, 0), N - 1), by = min(max(cy, 0), N - 1), bz = min(max(cz, 0), N - 1);
 		const int s = g.skip[(static_cast<size_t>(bz) * N + by) * N + bx];
+		if (steps) ++*steps;
 		if (s == 0)
 			break;
 		// leave the level-s cell around the sample point (a virtual cell: that cell alone) through its nearest exit plane
@@ -163,8 +168,18 @@ __device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy
 	return tau > 0.0f ? tau : 0.0f;
 }
 
-// start time of the 8 x 4 pixel tile whose first pixel is (x0, y0) of the frame: the ray through the tile's centre
-__device__ __forceinline__ float beam_tile_start(const BeamGrid g, const Camera& c, int x0, int y0)
+// A tile whose march ends with +inf has nothing in sight; if, on top of that, every ray of the tile is certain to be in
+// the lean tier, the trace kernel can end the whole tile as MISSes without setting up a single ray (kBeamAllMiss).
+// Certain means: the origin lies off the finest grid on all three axes (Ray::t0or stays 0; the host knows) and no
+// direction component of any ray of the tile can be zero or denormal -- every component of the central direction is at
+// least min_comp = 1.5 R + 1e-4 away from zero, R the tile radius.  Tiles that see nothing but cannot be certified get
+// kBeamNoneInSight: later than any cube exit time, so their lean-tier rays still end as a MISS one by one.
+constexpr uint32_t kBeamAllMissBits = 0x7F800000u;        // +inf
+constexpr float kBeamNoneInSight = 3.0e38f;
+
+// start time of the 8 x 4 pixel tile whose first pixel is (x0, y0) of the frame: the ray through the tile's centre.
+// min_comp <= 0: never certify.
+__device__ __forceinline__ float beam_tile_start(const BeamGrid g, const Camera& c, int x0, int y0, float min_comp = 0.0f, int* steps = nullptr)
 {
 	const float xc = static_cast<float>(x0) + 3.5f, yc = static_cast<float>(y0) + 1.5f;
 	const float u = __fmul_rn(c.aspect, __fsub_rn(__fmul_rn(c.vfx, xc), 1.0f));
@@ -174,7 +189,20 @@ __device__ __forceinline__ float beam_tile_start(const BeamGrid g, const Camera&
 	const float rw = __fadd_rn(__fadd_rn(__fmul_rn(u, c.r[6]), __fmul_rn(v, c.r[7])), __fmul_rn(c.fov, c.r[8]));
 	const float s = __fadd_rn(__fadd_rn(__fmul_rn(ru, ru), __fmul_rn(rv, rv)), __fmul_rn(rw, rw));
 	const float rm = __fdiv_rn(1.0f, __fsqrt_rn(s));
-	return beam_march(g, c.ox, c.oy, c.oz, __fmul_rn(rw, rm), __fmul_rn(ru, rm), __fmul_rn(-rv, rm));
+	const float dx = __fmul_rn(rw, rm), dy = __fmul_rn(ru, rm), dz = __fmul_rn(-rv, rm);
+	const float tau = beam_march(g, c.ox, c.oy, c.oz, dx, dy, dz, steps);
+	if (__float_as_uint(tau) != kBeamAllMissBits)
+		return tau;
+	const bool certain = min_comp > 0.0f && fminf(fabsf(dx), fminf(fabsf(dy), fabsf(dz))) >= min_comp;
+	return certain ? tau : kBeamNoneInSight;
+}
+
+// min_comp for a camera (host side): 0 when the origin is on the finest grid on some axis (its rays' tier depends on
+// the sign of a rounding residue, Ray::t0or)
+inline float beam_certify_min_comp(const Camera& c, double tile_radius)
+{
+	if ((c.origin_flags & 7u) != 0u) return 0.0f;
+	return static_cast<float>(1.5 * tile_radius + 1e-4);
 }
 
 // The lean tier with a beam start: `tau` as beam_tile_start() gave it for the ray's tile (0: none).  Returns true when

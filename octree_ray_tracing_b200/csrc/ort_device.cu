@@ -287,7 +287,8 @@ int beam_launch_march(ort_ctx* c, int k, const ort::Camera& cam, const ort::Fram
 	const int rc = beam_ensure_grid(c, k);
 	if (rc != ORT_OK) return rc;
 	const unsigned tiles = static_cast<unsigned>(((fr.W + 7) / 8) * ((fr.rows + 3) / 4));
-	ort::beam_start_kernel<<<(tiles + 127) / 128, 128, 0, c->stream>>>(ort::BeamGrid{ c->d_beam_skip[k][c->beam_gen[k]], k }, cam, fr, tile_word);
+	const float min_comp = ort::beam_certify_min_comp(cam, ort::beam_tile_radius(cam, c->rcp_eps));
+	ort::beam_start_kernel<<<(tiles + 127) / 128, 128, 0, c->stream>>>(ort::BeamGrid{ c->d_beam_skip[k][c->beam_gen[k]], k }, cam, fr, min_comp, tile_word);
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
@@ -824,6 +825,7 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 		{
 			ort::FrameJob& d = batch.job[k];
 			d.beam_k = beam_level(c, d.cam, d.fr, count);
+			d.beam_min_comp = ort::beam_certify_min_comp(d.cam, ort::beam_tile_radius(d.cam, c->rcp_eps));
 			beam = d.beam_k != 0;
 			max_tiles = std::max(max_tiles, static_cast<unsigned>(((d.fr.W + 7) / 8) * ((d.fr.rows + 3) / 4)));
 		}

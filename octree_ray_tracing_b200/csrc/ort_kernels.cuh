@@ -199,13 +199,22 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 	const bool inside = frame_pixel(fr, blockIdx.y, gridDim.y, x, r);
 	const float tau = BEAM ? read_tile_start(fr, t, x, r) : 0.0f;
 	if (!inside) return;
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	if (BEAM && __float_as_uint(tau) == kBeamAllMissBits)
+	{
+		// nothing in sight for the whole tile and every ray certain to be in the lean tier: 32 MISSes (och_h_octree.h:423-431)
+		voxel[i] = 0u;
+		face[i] = 6;
+		t[i] = g.miss_t;
+		if (COUNT) npush[i] = 0;
+		return;
+	}
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(cam, x, y, dx, dy, dz);
 	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, cam, dx, dy, dz, s_stack, tau);
 
-	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	voxel[i] = h.voxel;
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
@@ -216,13 +225,13 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 // start time goes into the output word of its first pixel -- `t` for the voxel / face / t kernels, the pixel for the
 // shaded kernel -- where the trace kernel picks it up.
 __global__ void __launch_bounds__(128)
-beam_start_kernel(const BeamGrid grid, Camera cam, FrameRows fr, float* __restrict__ tile_word)
+beam_start_kernel(const BeamGrid grid, Camera cam, FrameRows fr, float min_comp, float* __restrict__ tile_word)
 {
 	const int tiles_x = (fr.W + 7) >> 3, tiles_y = (fr.rows + 3) >> 2;
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= tiles_x * tiles_y) return;
 	const int x0 = (i % tiles_x) * 8, r0 = (i / tiles_x) * 4;
-	tile_word[static_cast<size_t>(r0) * fr.W + x0] = beam_tile_start(grid, cam, x0, frame_row(fr, r0));
+	tile_word[static_cast<size_t>(r0) * fr.W + x0] = beam_tile_start(grid, cam, x0, frame_row(fr, r0), min_comp);
 }
 
 // Several frame jobs in ONE launch (blockIdx.z = job): strips of different frames, or the views of a multi-camera
@@ -239,6 +248,7 @@ struct FrameJob
 	float*    t;
 	uint16_t* npush;    // may be null
 	int       beam_k;   // level of the beam grid this job's tile starts come from (0: the job runs without)
+	float     beam_min_comp;   // beam_certify_min_comp() of the job's camera
 };
 
 struct FrameJobBatch
@@ -259,13 +269,21 @@ trace_frames_kernel(const Dag g, const __grid_constant__ FrameJobBatch batch)
 	const bool inside = frame_pixel(fr, blockIdx.y, bands, x, r);
 	const float tau = BEAM ? read_tile_start(fr, jb.t, x, r) : 0.0f;
 	if (!inside) return;
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	if (BEAM && __float_as_uint(tau) == kBeamAllMissBits)
+	{
+		jb.voxel[i] = 0u;
+		jb.face[i] = 6;
+		jb.t[i] = g.miss_t;
+		if (COUNT && jb.npush) jb.npush[i] = 0;
+		return;
+	}
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
 	camera_ray(jb.cam, x, y, dx, dy, dz);
 	const Hit h = trace_camera_ray<VARIANT, COUNT>(g, jb.cam, dx, dy, dz, s_stack, tau);
 
-	const size_t i = static_cast<size_t>(r) * fr.W + x;
 	jb.voxel[i] = h.voxel;
 	jb.face[i] = static_cast<uint8_t>(h.face);
 	jb.t[i] = h.t;
@@ -288,7 +306,7 @@ beam_start_batch_kernel(const BeamGridSet grids, const __grid_constant__ FrameJo
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= tiles_x * tiles_y) return;
 	const int x0 = (i % tiles_x) * 8, r0 = (i / tiles_x) * 4;
-	jb.t[static_cast<size_t>(r0) * fr.W + x0] = beam_tile_start(BeamGrid{ grids.skip[jb.beam_k], jb.beam_k }, jb.cam, x0, frame_row(fr, r0));
+	jb.t[static_cast<size_t>(r0) * fr.W + x0] = beam_tile_start(BeamGrid{ grids.skip[jb.beam_k], jb.beam_k }, jb.cam, x0, frame_row(fr, r0), jb.beam_min_comp);
 }
 
 // Shading epilogue (tree_camera::trace_pixel, test_och_h_octree.cpp:76-84) fused into the frame kernel: the hit is
@@ -311,6 +329,11 @@ trace_frame_rgba_kernel(const Dag g, Camera cam, FrameRows fr, Palette pal, uint
 	const bool inside = frame_pixel(fr, blockIdx.y, gridDim.y, x, r);
 	const float tau = BEAM ? read_tile_start(fr, reinterpret_cast<const float*>(rgba), x, r) : 0.0f;
 	if (!inside) return;
+	if (BEAM && __float_as_uint(tau) == kBeamAllMissBits)
+	{
+		rgba[static_cast<size_t>(r) * fr.W + x] = pal.exit_rgba;
+		return;
+	}
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;

@@ -21,6 +21,7 @@ struct Stats
 	unsigned long long oob_loads;                             // loads outside the node array / reciprocal table (cuda_shim.h)
 	unsigned long long lean_rays;                             // walker 13: rays that took LeanWalker (the rest: FastWalker / traverse)
 	unsigned long long beam_rays, beam_misses, beam_guard;    // beam start: rays re-entered at tau, rays ended as a MISS without a round, guard re-walks
+	unsigned long long beam_tile_misses, beam_cert_wrong;     // rays of tiles ended as a whole; of those, rays that were NOT lean-tier rays (must be 0)
 };
 
 // walker ids follow ort_set_option("variant"): 0 baseline traverse(), 1 FastWalker, 5 TightWalker, 7 PipeWalker,
@@ -149,6 +150,7 @@ void merge(Stats* dst, const Stats& s)
 	for (int i = 0; i < ort::kMaxDepth + 2; ++i) dst->rounds_by_level[i] += s.rounds_by_level[i];
 	dst->rays += s.rays; dst->slow_path_rays += s.slow_path_rays; dst->oob_loads += s.oob_loads; dst->lean_rays += s.lean_rays;
 	dst->beam_rays += s.beam_rays; dst->beam_misses += s.beam_misses; dst->beam_guard += s.beam_guard;
+	dst->beam_tile_misses += s.beam_tile_misses; dst->beam_cert_wrong += s.beam_cert_wrong;
 }
 
 }  // namespace
@@ -209,6 +211,7 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 	cam.vfy = 2.0F / static_cast<float>(H);
 	cam.origin_flags = ort::camera_origin_flags(cam.ox, cam.oy, cam.oz, (1u << (23 - depth)) - 1u);
 	const int oflags = static_cast<int>(cam.origin_flags);
+	const float beam_min_comp = beam_skip ? ort::beam_certify_min_comp(cam, ort::beam_tile_radius(cam, ort::rcp_table_rel_error(rcp_tab, log2n))) : 0.0f;
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, 0, ort::tile_shift_of(tile_rows) };
 	Stats total{};
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
@@ -225,9 +228,19 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 				// beam start of the pixel's 8 x 4 tile, as beam_start_kernel computes it (the kernels: once per tile)
 				float tau = 0.0f;
 				if (beam_skip)
-					tau = ort::beam_tile_start(ort::BeamGrid{ beam_skip, beam_k }, cam, x & ~7, ort::frame_row(fr, r & ~3));
+					tau = ort::beam_tile_start(ort::BeamGrid{ beam_skip, beam_k }, cam, x & ~7, ort::frame_row(fr, r & ~3), beam_min_comp);
 				if (tau_out) tau_out[static_cast<size_t>(r) * W + x] = tau;
 				ort::Hit h;
+				if (beam_skip && __float_as_uint(tau) == ort::kBeamAllMissBits)
+				{
+					// the kernels' whole-tile MISS: no ray is set up.  The claim behind it -- every ray of the tile is a lean-tier
+					// ray -- is checked here, where the ray exists anyway.
+					h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0;
+					++st.beam_tile_misses;
+					if (!((oflags & static_cast<int>(ort::kOriginInCube)) && ort::lean_path_ok(ray) && fmaxf(ray.bx, fmaxf(ray.by, ray.bz)) < __uint_as_float(0x7F800000u)))
+						++st.beam_cert_wrong;
+				}
+				else
 				if (!has_root) { h.voxel = 0; h.face = 6; h.t = miss_t; h.npush = 0; }
 				else h = npush ? walk<true>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags, tau)
 				               : walk<false>(walker, nodes_m1, root, depth, miss_t, cam.ox, cam.oy, cam.oz, ray, stats_out ? &st : nullptr, oflags, tau);
@@ -307,6 +320,26 @@ void emu_beam_grid(const uint32_t* nodes8, int index_base, uint32_t root, int k,
 }
 
 // the host-side choice of the grid level for a camera (ort::beam_tile_radius / beam_level_for), 0 = no beam start
+// march statistics of a frame (a design aid): steps[tile] = grid lookups of the tile's march, tau[tile] = its start time
+void emu_beam_march_stats(const uint8_t* skip, int k, const float pos[3], const float rot[9], float fov, int W, int H, int* steps, float* tau)
+{
+	ort::Camera cam{};
+	cam.ox = pos[0]; cam.oy = pos[1]; cam.oz = pos[2];
+	for (int i = 0; i < 9; ++i) cam.r[i] = rot[i];
+	cam.fov = fov;
+	cam.aspect = static_cast<float>(W) / static_cast<float>(H);
+	cam.vfx = 2.0F / static_cast<float>(W);
+	cam.vfy = 2.0F / static_cast<float>(H);
+	const int tx = (W + 7) / 8, ty = (H + 3) / 4;
+#pragma omp parallel for schedule(static)
+	for (int i = 0; i < tx * ty; ++i)
+	{
+		int n = 0;
+		tau[i] = ort::beam_tile_start(ort::BeamGrid{ skip, k }, cam, (i % tx) * 8, (i / tx) * 4, 0.0f, &n);
+		steps[i] = n;
+	}
+}
+
 int emu_beam_level(const float pos[3], const float rot[9], float fov, int W, int H, int depth, const uint32_t* rcp_tab, int log2n)
 {
 	ort::Camera cam{};

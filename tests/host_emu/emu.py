@@ -17,7 +17,7 @@ SANITIZE = os.environ.get("ORT_EMU_SANITIZE", "") == "1"      # tools/sanitize_h
 SO = os.path.join(HERE, "_build", "libort_emu_san.so" if SANITIZE else "libort_emu.so")
 _lib = None
 
-STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads", "lean_rays", "beam_rays", "beam_misses", "beam_guard"]
+STAT_FIELDS = ["rays", "slow_path_rays", "oob_loads", "lean_rays", "beam_rays", "beam_misses", "beam_guard", "beam_tile_misses", "beam_cert_wrong"]
 
 
 def build(force: bool = False) -> str:

@@ -100,7 +100,7 @@ def test_march_is_a_lower_bound_and_beam_frames_equal_the_oracle(emu, ort, oc, d
             ((1.25, 1.75, 1.0 + 5.0 / 16.0 + 0.02), 1.1, -0.05), ((1.5, 1.5, 1.2), 2.0, 0.4), ((1.0625, 1.5, 1.5), 0.0, 0.0)]
     grids = {}
     seen_levels = set()
-    total_ref = total_beam = 0
+    total_ref = total_beam = tile_misses = 0
     for ci, (pos, yaw, pitch) in enumerate(cams):
         rot, fov = oc.camera_coeffs(yaw, pitch)
         for (W, H, y0, rows, tr, ts) in [(640, 360, 0, 360, 1, 1), (1920, 1080, 512, 40, 8, 2), (256, 144, 0, 144, 1, 1)][: 3 if ci < 4 else 1]:
@@ -120,11 +120,16 @@ def test_march_is_a_lower_bound_and_beam_frames_equal_the_oracle(emu, ort, oc, d
             assert_same_hits(got, want, what)
             st, tau = got[4], got[5]
             assert st["beam_guard"] == 0, what
+            assert st["beam_cert_wrong"] == 0, f"{what}: a tile was ended as a whole although some of its rays are not lean-tier rays"
+            on_grid = any(float(c) * (1 << depth) == int(float(c) * (1 << depth)) for c in pos)
+            assert not (on_grid and st["beam_tile_misses"]), f"{what}: an origin on the finest grid must not certify tiles"
+            tile_misses += st["beam_tile_misses"]
             hit = want[0] != 0
             assert (tau[hit] <= want[2][hit]).all(), f"{what}: a tile start later than a hit time of the tile"
             assert (got[3] <= want[3]).all() or (got[3].astype(np.int64) - want[3]).max() <= depth, what
             total_ref += int(want[3].sum()); total_beam += int(got[3].sum())
     assert seen_levels, "no camera got a beam level"
+    assert tile_misses > 10_000, "tiles that see nothing should end as a whole"
     assert total_beam < 0.8 * total_ref, f"the beam start should save rounds ({total_beam} vs {total_ref})"
 
 

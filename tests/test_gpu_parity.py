@@ -211,7 +211,10 @@ def test_device_pointer_entry_points(ort, oc, golden):
     ctx.sync()
     got = (dv[:m].cpu().numpy().view(np.uint32), df[:m].cpu().numpy(), dt[:m].cpu().numpy())
     assert_same_hits(got, (g["rand_vox"], g["rand_face"], g["rand_t"]), "async rays")
-    assert ctx.launch_count == 2
+    # one frame kernel + one rays kernel; with the beam start the frame also has its march and, once per DAG version, the
+    # grid build (occupancy, dilation, k - 1 pyramid levels, skip levels)
+    k = ctx.beam_level(g["poseB_pos"], g["poseB_rot"], float(g["poseB_fov"]), W, H)
+    assert ctx.launch_count == 2 + ((1 + 3 + (k - 1)) if k else 0)
 
 
 def test_depth12_4k_properties(ort, oc, ncpu):
