@@ -38,8 +38,9 @@
 //     of the DAG ("dilated-occupied"), else the coarsest level j <= k whose cell around it is dilated-empty throughout.
 //     Marching the central ray through that grid (one load per step, the steps as large as the empty cells) gives the
 //     first parameter tau_c at which it is inside a dilated-occupied cell: no ray of the tile can hit anything before
-//     tau_c.  The march samples 2^-19 past every exit plane instead of tracking cell indices; the cells it can miss that
-//     way are clipped by less than the slack.  tau = tau_c (1 - 2^-12) - 2^-17.
+//     tau_c.  The march samples 2^-19 past every exit plane instead of tracking cell indices, and lets the ray drift up to
+//     a 16th of a cell into a neighbour it runs along; the cells it can miss that way are clipped by less than the slack
+//     (0.3 s).  tau = tau_c (1 - 2^-12) - 2^-17.
 //
 // (3) Tiles that see nothing.  When the central ray has left the cube by more than a cell without meeting a marked cell,
 //     every ray of the tile has left it too: tau = +inf.  If all rays of the tile are certain to be lean-tier rays
@@ -57,7 +58,7 @@ namespace ort {
 
 constexpr int kBeamMinLevel = 3;      // below this the grid says nothing (8 cells per axis)
 constexpr int kBeamMaxLevel = 7;      // 128^3 bytes = 2 MiB
-constexpr int kBeamMaxSteps = 256;
+constexpr int kBeamMaxSteps = 64;       // a march that needs more ends early: its tile starts where the march stood
 
 struct BeamGrid
 {
@@ -157,10 +158,18 @@ __device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy
 		const float lx = __fmaf_rn(static_cast<float>((cx >> sh) << sh), cell, 1.0f), ly = __fmaf_rn(static_cast<float>((cy >> sh) << sh), cell, 1.0f),
 		            lz = __fmaf_rn(static_cast<float>((cz >> sh) << sh), cell, 1.0f);
 		const float w = static_cast<float>(1 << sh) * cell;
+		// Exit times of the three axes.  One that is not in the future (<= t) belongs to a plane the sample point sits on within
+		// rounding: the ray runs along it (or has just crossed it and the next sample will say so).  It is no exit; but while
+		// the ray may be drifting into the cell beyond that plane the step is kept so short that the drift stays below a 16th
+		// of a cell -- part of the slack of the bound, like the 2^-19 the samples are set past every plane.
+		const float ex = dx != 0.0f ? __fmul_rn(__fsub_rn(dx > 0.0f ? __fadd_rn(lx, w) : lx, ox), ix_) : inf;
+		const float ey = dy != 0.0f ? __fmul_rn(__fsub_rn(dy > 0.0f ? __fadd_rn(ly, w) : ly, oy), iy_) : inf;
+		const float ez = dz != 0.0f ? __fmul_rn(__fsub_rn(dz > 0.0f ? __fadd_rn(lz, w) : lz, oz), iz_) : inf;
+		const float drift = cell * 0.0625f;
 		float te = inf;
-		if (dx != 0.0f) te = fminf(te, __fmul_rn(__fsub_rn(dx > 0.0f ? __fadd_rn(lx, w) : lx, ox), ix_));
-		if (dy != 0.0f) te = fminf(te, __fmul_rn(__fsub_rn(dy > 0.0f ? __fadd_rn(ly, w) : ly, oy), iy_));
-		if (dz != 0.0f) te = fminf(te, __fmul_rn(__fsub_rn(dz > 0.0f ? __fadd_rn(lz, w) : lz, oz), iz_));
+		te = fminf(te, ex > t ? ex : __fmaf_rn(drift, fabsf(ix_), t));
+		te = fminf(te, ey > t ? ey : __fmaf_rn(drift, fabsf(iy_), t));
+		te = fminf(te, ez > t ? ez : __fmaf_rn(drift, fabsf(iz_), t));
 		t = te > t ? te : __fadd_rn(t, delta);             // always forward
 	}
 	// inside a dilated-occupied cell from t on (or out of steps): nothing before t
@@ -197,11 +206,49 @@ __device__ __forceinline__ float beam_tile_start(const BeamGrid g, const Camera&
 	return certain ? tau : kBeamNoneInSight;
 }
 
-// min_comp for a camera (host side): 0 when the origin is on the finest grid on some axis (its rays' tier depends on
-// the sign of a rounding residue, Ray::t0or)
-inline float beam_certify_min_comp(const Camera& c, double tile_radius)
+// significant bits of a float's mantissa (1 for a power of two, 24 at most)
+inline int float_sig_bits(float f)
 {
-	if ((c.origin_flags & 7u) != 0u) return 0.0f;
+	uint32_t b;
+#ifdef ORT_HOST_EMU
+	b = __float_as_uint(f);
+#else
+	memcpy(&b, &f, 4);
+#endif
+	uint32_t m = (b & 0x7FFFFFu) | 0x800000u;
+	int tz = 0;
+	while (!(m & 1u)) { m >>= 1; ++tz; }
+	return 24 - tz;
+}
+
+// largest number of significant bits among the entries of a reciprocal table (Intel's RCPPS: 12)
+inline int rcp_table_sig_bits(const uint32_t* tab, int log2n)
+{
+	int worst = 1;
+	for (size_t i = 0; i < (static_cast<size_t>(1) << log2n); ++i)
+	{
+		uint32_t m = (tab[i] & 0x7FFFFFu) | 0x800000u;
+		int tz = 0;
+		while (!(m & 1u)) { m >>= 1; ++tz; }
+		if (24 - tz > worst) worst = 24 - tz;
+	}
+	return worst;
+}
+
+// min_comp for a camera (host side), 0 = never certify.  An origin coordinate on the finest grid puts a cell plane through
+// the origin; its t is the rounding residue of bias = -(coef * o) and a negative one sends the ray to another tier
+// (Ray::t0or).  That cannot happen when the product is exact: coef has at most rcp_sig_bits significant bits (a property
+// of the table), the mirrored coordinate (o or 3 - o) a few, and a product of at most 24 bits is not rounded -- the residue
+// is +0 for every ray.  Otherwise the tier depends on the ray and the tile cannot be certified.
+inline float beam_certify_min_comp(const Camera& c, double tile_radius, int rcp_sig_bits)
+{
+	const float o[3] = { c.ox, c.oy, c.oz };
+	for (int a = 0; a < 3; ++a)
+		if (c.origin_flags & (1u << a))
+		{
+			const int so = float_sig_bits(o[a]), sm = float_sig_bits(3.0f - o[a]);      // 3 - o is exact for o in [1, 2)
+			if ((so > sm ? so : sm) + rcp_sig_bits > 24) return 0.0f;
+		}
 	return static_cast<float>(1.5 * tile_radius + 1e-4);
 }
 

@@ -68,6 +68,7 @@ struct ort_ctx
 	cudaEvent_t ev_beam = nullptr;      // last grid build done (builds share the scratch; launches on other streams wait for their grid)
 	bool     beam_built_once = false;
 	double   rcp_eps = 0;               // largest relative error of the reciprocal table in use
+	int      rcp_sig_bits = 24;         // most significant bits any of its entries has
 	int opt_beam = 1;                   // 1: camera frames of the lean tier start at their tile's beam bound
 	int opt_beam_level = 0;             // 0: the finest level the tile size allows; else forced (measurement)
 	int opt_count_beam = 0;             // 1: launches that return PUSH counts use the beam start too (counts = loads actually issued)
@@ -287,7 +288,7 @@ int beam_launch_march(ort_ctx* c, int k, const ort::Camera& cam, const ort::Fram
 	const int rc = beam_ensure_grid(c, k);
 	if (rc != ORT_OK) return rc;
 	const unsigned tiles = static_cast<unsigned>(((fr.W + 7) / 8) * ((fr.rows + 3) / 4));
-	const float min_comp = ort::beam_certify_min_comp(cam, ort::beam_tile_radius(cam, c->rcp_eps));
+	const float min_comp = ort::beam_certify_min_comp(cam, ort::beam_tile_radius(cam, c->rcp_eps), c->rcp_sig_bits);
 	ort::beam_start_kernel<<<(tiles + 127) / 128, 128, 0, c->stream>>>(ort::BeamGrid{ c->d_beam_skip[k][c->beam_gen[k]], k }, cam, fr, min_comp, tile_word);
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
@@ -465,6 +466,7 @@ int ort_set_rcp_table(ort_ctx* c, const uint32_t* tab, int log2n)
 			if (((host[k] >> 23) | 1u) != 127u)
 				return ort_fail(c, ORT_ERR_INVALID, "ort_set_rcp_table: entry %zu (0x%08x) is not in (0.5, 1]: not a reciprocal table of [1, 2)", k, host[k]);
 		c->rcp_eps = ort::rcp_table_rel_error(host.data(), log2n);      // the beam start's bound widens with the table's error
+		c->rcp_sig_bits = ort::rcp_table_sig_bits(host.data(), log2n);
 	}
 	if (c->rcp_log2n != log2n)
 	{
@@ -825,7 +827,7 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 		{
 			ort::FrameJob& d = batch.job[k];
 			d.beam_k = beam_level(c, d.cam, d.fr, count);
-			d.beam_min_comp = ort::beam_certify_min_comp(d.cam, ort::beam_tile_radius(d.cam, c->rcp_eps));
+			d.beam_min_comp = ort::beam_certify_min_comp(d.cam, ort::beam_tile_radius(d.cam, c->rcp_eps), c->rcp_sig_bits);
 			beam = d.beam_k != 0;
 			max_tiles = std::max(max_tiles, static_cast<unsigned>(((d.fr.W + 7) / 8) * ((d.fr.rows + 3) / 4)));
 		}

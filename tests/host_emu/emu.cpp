@@ -211,7 +211,7 @@ int emu_trace_frame(const uint32_t* nodes8, size_t n_rows, int index_base, int h
 	cam.vfy = 2.0F / static_cast<float>(H);
 	cam.origin_flags = ort::camera_origin_flags(cam.ox, cam.oy, cam.oz, (1u << (23 - depth)) - 1u);
 	const int oflags = static_cast<int>(cam.origin_flags);
-	const float beam_min_comp = beam_skip ? ort::beam_certify_min_comp(cam, ort::beam_tile_radius(cam, ort::rcp_table_rel_error(rcp_tab, log2n))) : 0.0f;
+	const float beam_min_comp = beam_skip ? ort::beam_certify_min_comp(cam, ort::beam_tile_radius(cam, ort::rcp_table_rel_error(rcp_tab, log2n)), ort::rcp_table_sig_bits(rcp_tab, log2n)) : 0.0f;
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, 0, ort::tile_shift_of(tile_rows) };
 	Stats total{};
 #pragma omp parallel num_threads(nthreads > 0 ? nthreads : 1)
