@@ -259,6 +259,10 @@ int ort_beam_level(ort_ctx* ctx, const float pos[3], const float rot[9], float f
 int ort_beam_grid(ort_ctx* ctx, int level, uint8_t* skip_out);
 /* number of beam grids built on ctx since creation (one per DAG version and level in use) */
 uint64_t ort_beam_builds(const ort_ctx* ctx);
+/* number of band schedules applied on ctx since creation (option "band_order", default 1: a frame launch records what each
+ * 16-row band cost, the next launches of the same view -- same camera, same rows -- schedule the most expensive bands
+ * first; results do not depend on it) */
+uint64_t ort_band_schedules(const ort_ctx* ctx);
 
 /* Diagnostic for roofline reports: throughput of random 32-byte-sector gathers (independent 4-byte loads, 8 in
  * flight per thread, full occupancy) over a `bytes`-sized buffer on ctx's GPU, in GB/s of sectors moved.  With

@@ -57,6 +57,7 @@ _SIGS = {
     "ort_beam_level": (C.c_int, [_vp, _vp, _vp, C.c_float, C.c_int, C.c_int]),
     "ort_beam_grid": (C.c_int, [_vp, C.c_int, _vp]),
     "ort_beam_builds": (C.c_uint64, [_vp]),
+    "ort_band_schedules": (C.c_uint64, [_vp]),
     "ort_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "ort_host_free": (C.c_int, [_vp]),
     "ort_camera_coeffs": (None, [C.c_float, C.c_float, _vp, C.POINTER(C.c_float)]),

@@ -22,6 +22,35 @@
 
 static thread_local std::string g_last_error;
 
+// Band schedule of a view (VERDICT r1 item 7 / DESIGN section 12.2).  A frame launch ends when its longest warps do -- rays
+// that graze a silhouette run hundreds of rounds -- so the 16-row bands that hold them should be scheduled first, and where
+// they are depends on the view.  The trace kernel records, per band, the longest time a warp was busy; the next launch of
+// the same view (same camera, same rows) schedules its bands by that measure, most expensive first.  Keyed by view so
+// that the cameras of a multi-camera loop do not poison each other.  Results never depend on it: any permutation of the
+// bands traces every pixel once.
+struct BandMap
+{
+	bool     used = false;
+	uint64_t stamp = 0;                 // last use (eviction)
+	float    cam[13] = {};              // pos, rot, fov
+	int      geo[6] = {};               // W, H, y0, rows, tile_rows, tile_step
+	int      bands = 0;
+	uint16_t* d_order[2] = { nullptr, nullptr };   // device schedules: launches read `cur`, a new one is uploaded into the other
+	unsigned* d_cost = nullptr;
+	unsigned* h_cost = nullptr;         // pinned
+	uint16_t* h_order = nullptr;        // pinned, 2 x bands
+	cudaEvent_t ev_cost = nullptr;      // the recorded costs have reached h_cost
+	cudaEvent_t ev_order = nullptr;     // d_order[cur] has been uploaded
+	cudaEvent_t ev_read[2] = { nullptr, nullptr };   // last launch reading d_order[i]
+	bool     read_any[2] = { false, false };
+	int      cur = -1;                  // -1: no schedule yet (band_rotate rule)
+	bool     recording = false;
+	int      applied = 0;               // schedules uploaded so far
+	int      since = 0;                 // launches since the last recording
+	int      seen = 0;                  // launches of this view so far
+};
+constexpr int kBandMaps = 64;
+
 struct ort_ctx
 {
 	int device = 0;
@@ -69,6 +98,10 @@ struct ort_ctx
 	bool     beam_built_once = false;
 	double   rcp_eps = 0;               // largest relative error of the reciprocal table in use
 	int      rcp_sig_bits = 24;         // most significant bits any of its entries has
+	BandMap band_maps[kBandMaps];
+	uint64_t band_stamp = 0;
+	int opt_band_order = 1;             // 1: frame launches schedule their bands by the costs recorded for the same view (BandMap)
+	uint64_t band_schedules = 0;        // schedules applied so far
 	int opt_beam = 1;                   // 1: camera frames of the lean tier start at their tile's beam bound
 	int opt_beam_level = 0;             // 0: the finest level the tile size allows; else forced (measurement)
 	int opt_count_beam = 0;             // 1: launches that return PUSH counts use the beam start too (counts = loads actually issued)
@@ -188,6 +221,17 @@ inline unsigned long long* next_counter(ort_ctx* c)
 // LeanWalker's slot words are node * 8 + 2^23-magic + index in 32 bits: ids stay below 0x16A00000
 inline bool lean_capable(const ort_ctx* c) { return c->n_nodes < 0x16000000u; }
 
+void band_map_release(BandMap& m)
+{
+	cudaFree(m.d_order[0]); cudaFree(m.d_order[1]); cudaFree(m.d_cost);
+	if (m.h_cost) cudaFreeHost(m.h_cost);
+	if (m.h_order) cudaFreeHost(m.h_order);
+	if (m.ev_cost) cudaEventDestroy(m.ev_cost);
+	if (m.ev_order) cudaEventDestroy(m.ev_order);
+	for (int i = 0; i < 2; ++i) if (m.ev_read[i]) cudaEventDestroy(m.ev_read[i]);
+	m = BandMap{};
+}
+
 // the DAG changed: every beam grid is out of date (rebuilt by the next frame launch that wants one)
 inline void beam_invalidate(ort_ctx* c)
 {
@@ -293,6 +337,134 @@ int beam_launch_march(ort_ctx* c, int k, const ort::Camera& cam, const ort::Fram
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
 	return ORT_OK;
+}
+
+// The band map of a view: found, or a slot taken over (a free one, else the least recently used).  A slot's buffers and
+// events are created once and kept across views, so that a moving camera -- a new view every frame -- costs a lookup and
+// nothing else.  nullptr when the launch has more bands than a slot holds or memory is short.
+constexpr int kBandCap = 2048;          // bands a slot can hold (32 768 rows)
+
+BandMap* band_map_for(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& fr)
+{
+	const float key[13] = { cam.ox, cam.oy, cam.oz, cam.r[0], cam.r[1], cam.r[2], cam.r[3], cam.r[4], cam.r[5], cam.r[6], cam.r[7], cam.r[8], cam.fov };
+	const int geo[6] = { fr.W, fr.H, fr.y0, fr.rows, fr.tile_rows, fr.tile_step };
+	const int bands = (fr.rows + 15) / 16;
+	if (bands > kBandCap) return nullptr;
+	BandMap* pick = nullptr;
+	for (BandMap& m : c->band_maps)
+		if (m.used && !std::memcmp(m.cam, key, sizeof key) && !std::memcmp(m.geo, geo, sizeof geo))
+		{
+			m.stamp = ++c->band_stamp;
+			return &m;
+		}
+	for (BandMap& m : c->band_maps)
+		if (!m.used) { pick = &m; break; }
+	if (!pick)
+	{
+		pick = &c->band_maps[0];
+		for (BandMap& m : c->band_maps)
+			if (m.stamp < pick->stamp) pick = &m;
+	}
+	BandMap& m = *pick;
+	if (m.used)
+	{
+		// the view that leaves may still have launches and copies in flight on its buffers
+		if (m.recording) cudaEventSynchronize(m.ev_cost);
+		for (int i = 0; i < 2; ++i) if (m.read_any[i]) cudaEventSynchronize(m.ev_read[i]);
+	}
+	if (!m.d_cost)
+	{
+		const bool ok = cudaMalloc(&m.d_order[0], kBandCap * 2) == cudaSuccess && cudaMalloc(&m.d_order[1], kBandCap * 2) == cudaSuccess &&
+		          cudaMalloc(&m.d_cost, kBandCap * 4) == cudaSuccess && cudaHostAlloc(&m.h_cost, kBandCap * 4, cudaHostAllocDefault) == cudaSuccess &&
+		          cudaHostAlloc(&m.h_order, kBandCap * 4, cudaHostAllocDefault) == cudaSuccess &&
+		          cudaEventCreateWithFlags(&m.ev_cost, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m.ev_order, cudaEventDisableTiming) == cudaSuccess &&
+		          cudaEventCreateWithFlags(&m.ev_read[0], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m.ev_read[1], cudaEventDisableTiming) == cudaSuccess;
+		if (!ok)
+		{
+			cudaGetLastError();
+			band_map_release(m);
+			return nullptr;
+		}
+	}
+	m.used = true;
+	m.stamp = ++c->band_stamp;
+	std::memcpy(m.cam, key, sizeof key);
+	std::memcpy(m.geo, geo, sizeof geo);
+	m.bands = bands;
+	m.read_any[0] = m.read_any[1] = false;
+	m.cur = -1;
+	m.recording = false;
+	m.applied = 0;
+	m.since = 0;
+	m.seen = 0;
+	return &m;
+}
+
+// Before a frame launch: apply the newest recorded schedule of the view (fr.band_order) and decide whether this launch
+// records (fr.band_cost).  Costs are recorded by the first launches of a view and refreshed now and then.
+void band_map_before(ort_ctx* c, BandMap* m, ort::FrameRows& fr)
+{
+	if (m->recording && cudaEventQuery(m->ev_cost) == cudaSuccess)
+	{
+		m->recording = false;
+		// most expensive band first (stable: equal costs keep the band_rotate order they were measured in)
+		const int nb = m->bands, nxt = m->cur == 0 ? 1 : 0;
+		uint16_t* ho = m->h_order + static_cast<size_t>(nxt) * kBandCap;
+		std::vector<int> idx(nb);
+		for (int b = 0; b < nb; ++b) idx[b] = (b + fr.band_rotate) % nb;
+		std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return m->h_cost[a] > m->h_cost[b]; });
+		for (int b = 0; b < nb; ++b) ho[b] = static_cast<uint16_t>(idx[b]);
+		// the buffer may still be read by launches of two schedules ago; the upload waits for them
+		bool fine = true;
+		if (m->read_any[nxt]) fine = cudaStreamWaitEvent(c->stream, m->ev_read[nxt], 0) == cudaSuccess;
+		fine = fine && cudaMemcpyAsync(m->d_order[nxt], ho, nb * 2, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+		       cudaEventRecord(m->ev_order, c->stream) == cudaSuccess;
+		if (fine)
+		{
+			m->cur = nxt;
+			++m->applied;
+			++c->band_schedules;
+		}
+		else
+			cudaGetLastError();
+	}
+	if (m->cur >= 0)
+	{
+		if (cudaStreamWaitEvent(c->stream, m->ev_order, 0) == cudaSuccess)      // uploaded on whatever stream asked first
+			fr.band_order = m->d_order[m->cur];
+		else
+			cudaGetLastError();
+	}
+	++m->since;
+	++m->seen;
+	// (a view seen for the first time records nothing: a camera that moves every frame never comes back to it)
+	if (!m->recording && m->seen >= 2 && (m->applied < 2 || m->since >= 64))
+	{
+		if (cudaMemsetAsync(m->d_cost, 0, m->bands * 4, c->stream) == cudaSuccess)
+			fr.band_cost = m->d_cost;
+		else
+			cudaGetLastError();
+	}
+}
+
+void band_map_after(ort_ctx* c, BandMap* m, const ort::FrameRows& fr)
+{
+	if (fr.band_order)
+	{
+		const int i = fr.band_order == m->d_order[0] ? 0 : 1;
+		if (cudaEventRecord(m->ev_read[i], c->stream) == cudaSuccess) m->read_any[i] = true;
+	}
+	if (fr.band_cost)
+	{
+		if (cudaMemcpyAsync(m->h_cost, m->d_cost, m->bands * 4, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+		    cudaEventRecord(m->ev_cost, c->stream) == cudaSuccess)
+		{
+			m->recording = true;
+			m->since = 0;
+		}
+		else
+			cudaGetLastError();
+	}
 }
 
 }  // namespace
@@ -428,6 +600,7 @@ int ort_destroy(ort_ctx* c)
 	cudaFree(c->d_palette);
 	cudaFree(c->d_counters);
 	cudaFree(c->d_stage);
+	for (BandMap& m : c->band_maps) band_map_release(m);
 	cudaFree(c->d_beam_tmp);
 	for (int k = 0; k < 8; ++k) { cudaFree(c->d_beam_skip[k][0]); cudaFree(c->d_beam_skip[k][1]); }
 	if (c->ev_beam) cudaEventDestroy(c->ev_beam);
@@ -724,7 +897,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 	const ort::Dag dag = make_dag(c);
 	const ort::Camera cam = make_camera(c, pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
-	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape, rotate, ort::tile_shift_of(tile_rows) };
+	ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, c->opt_tile_shape, rotate, ort::tile_shift_of(tile_rows) };
 	const dim3 grid((W + 15) / 16, (rows + 15) / 16);
 	const size_t smem = ort::lean_smem_bytes(c->depth);
 	if (c->opt_variant == 2 && lean_capable(c))
@@ -756,6 +929,9 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		const int rc = beam_launch_march(c, bk, cam, fr, t);
 		if (rc != ORT_OK) return rc;
 	}
+	// band schedule of this view (launches of 8 bands and more; the frame kernels of the product walks)
+	BandMap* bm = (c->opt_band_order && c->opt_band_rotate < 0 && grid.y >= 8 && grid.y < 65536 && c->opt_tile_shape == 0) ? band_map_for(c, cam, fr) : nullptr;
+	if (bm) band_map_before(c, bm, fr);
 #define ORT_LAUNCH_FRAME(V, C, B) ort::trace_frame_kernel<V, C, B><<<grid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, cam, fr, voxel, face, t, npush)
 	switch (walk_variant(c))
 	{
@@ -769,6 +945,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 #undef ORT_LAUNCH_FRAME
 	++c->launches;
 	ORT_CUDA(c, cudaGetLastError());
+	if (bm) band_map_after(c, bm, fr);
 	return ORT_OK;
 }
 
@@ -1282,6 +1459,7 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
 		ORT_CUDA(c, cudaFuncSetAttribute(ort::trace_frame_kernel<ort::kLean, false>, cudaFuncAttributePreferredSharedMemoryCarveout, value));
 	}
+	else if (!std::strcmp(key, "band_order")) c->opt_band_order = value;
 	else if (!std::strcmp(key, "beam")) c->opt_beam = value;
 	else if (!std::strcmp(key, "beam_level")) c->opt_beam_level = value;
 	else if (!std::strcmp(key, "count_beam")) c->opt_count_beam = value;
@@ -1318,6 +1496,7 @@ int ort_beam_grid(ort_ctx* c, int level, uint8_t* skip_out)
 }
 
 uint64_t ort_beam_builds(const ort_ctx* c) { return c ? c->beam_builds : 0; }
+uint64_t ort_band_schedules(const ort_ctx* c) { return c ? c->band_schedules : 0; }
 
 int ort_measure_gather_peak(ort_ctx* c, size_t bytes, double* gb_per_s)
 {

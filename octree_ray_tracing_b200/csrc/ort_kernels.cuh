@@ -166,8 +166,14 @@ trace_rays_kernel(const Dag g, const float* __restrict__ o3, int o_stride, const
 __device__ __forceinline__ bool frame_pixel(const FrameRows& fr, unsigned block_y, unsigned bands, int& x, int& r)
 {
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	unsigned by = block_y + static_cast<unsigned>(fr.band_rotate);
-	if (by >= bands) by -= bands;
+	unsigned by;
+	if (fr.band_order)
+		by = __ldg(fr.band_order + block_y);
+	else
+	{
+		by = block_y + static_cast<unsigned>(fr.band_rotate);
+		if (by >= bands) by -= bands;
+	}
 	x = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
 	r = static_cast<int>(by) * 16 + (warp >> 1) * 4 + (lane >> 3);
 	return x < fr.W && r < fr.rows;
@@ -209,6 +215,7 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 		if (COUNT) npush[i] = 0;
 		return;
 	}
+	const long long t_start = fr.band_cost ? clock64() : 0ll;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
@@ -219,6 +226,15 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+	if (fr.band_cost)
+	{
+		// what this band costs, for the schedule of the next launch of the same view: the longest a warp of the band was busy
+		// (a scheduling hint, nothing reads it for results; one atomic per warp where the lanes have reconverged)
+		const unsigned m = __activemask();
+		const unsigned dur = __reduce_max_sync(m, static_cast<unsigned>((clock64() - t_start) >> 4));
+		if ((threadIdx.x & 31u) == static_cast<unsigned>(__ffs(static_cast<int>(m)) - 1))
+			atomicMax(fr.band_cost + (r >> 4), dur);
+	}
 }
 
 // The march of the beam start (ort_beam.cuh), one thread per 8 x 4 pixel tile of the rows a frame launch traces: the tile's

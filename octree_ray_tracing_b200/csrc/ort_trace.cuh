@@ -724,6 +724,11 @@ struct FrameRows
 	int tile_shape;     // warp tile: 0 = 8x4, 1 = 16x2, 2 = 4x8 (trace_frame_kernel only)
 	int band_rotate;    // block row b is traced by blockIdx.y = (b - band_rotate) mod gridDim.y: which 16-row band starts first
 	int tile_shift;     // log2(tile_rows) + 1 when tile_rows is a power of two (the row mapping then needs no division), else 0
+	// band schedule from an earlier launch of the same view (ort_device.cu: BandMap): blockIdx.y = k traces band band_order[k]
+	// (a permutation of the launch's bands, most expensive first; null: the band_rotate rule), and every warp leaves the
+	// longest time one of its lanes took in band_cost[band] (null: not recorded)
+	const uint16_t* band_order;
+	unsigned*       band_cost;
 };
 
 // FrameRows::tile_shift for a tile height (host side)

@@ -159,6 +159,10 @@ class TraceContext:
     def beam_builds(self) -> int:
         return self.L.ort_beam_builds(self.h)
 
+    @property
+    def band_schedules(self) -> int:
+        return self.L.ort_band_schedules(self.h)
+
     def set_stream(self, stream):
         """Queue subsequent work on a caller stream (a cudaStream_t as int, a torch.cuda.Stream, or None)."""
         if stream is not None and hasattr(stream, "cuda_stream"):

@@ -187,3 +187,50 @@ def test_edit_loop_with_beam_start_vs_oracle(ort, oc, emu):
         assert_same_hits(got, want, f"edit {it}")
         assert T.ctx.beam_builds == builds + it + 1
     T.ctx.close()
+
+
+def test_band_schedule_changes_no_output(ort, oc):
+    """The band schedule of a view (recorded costs -> most expensive 16-row bands first) is a permutation of the launch's
+    blocks: frames traced before a schedule exists, while one is being recorded and after it is applied are the same,
+    for whole frames and strips, with and without the beam start, and other views keep their own schedules."""
+    import torch
+    depth = 10
+    T = ort.HOctree(22, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=True)
+    T.sync()
+    ctx = T.ctx
+    W, H = 1920, 1080
+    views = [(np.array(p, np.float32),) + tuple(oc.camera_coeffs(y, pt)) for p, y, pt in POSES.values()]
+    n = W * H
+    dv = torch.empty(n, dtype=torch.int32, device="cuda"); df = torch.empty(n, dtype=torch.uint8, device="cuda"); dt = torch.empty(n, dtype=torch.float32, device="cuda")
+
+    def frame(pos, rot, fov, y0=0, rows=H, tr=1, ts=1):
+        m = rows * W
+        ctx.trace_frame_async(pos, rot, fov, W, H, y0, rows, tr, ts, dv, df, dt)
+        ctx.sync()
+        torch.cuda.synchronize()
+        return dv[:m].cpu().numpy().view(np.uint32), df[:m].cpu().numpy(), dt[:m].cpu().numpy()
+
+    ctx.set_option("band_order", 0)
+    want = [frame(*v) for v in views]
+    want_strip = [frame(*v, y0=8, rows=536, tr=8, ts=2) for v in views]
+    assert ctx.band_schedules == 0
+    ctx.set_option("band_order", 1)
+    for rep in range(5):
+        for k, v in enumerate(views):
+            assert_same_hits(frame(*v), want[k], f"view {k}, repetition {rep}")
+            assert_same_hits(frame(*v, y0=8, rows=536, tr=8, ts=2), want_strip[k], f"strip of view {k}, repetition {rep}")
+    assert ctx.band_schedules >= 2 * len(views), "every repeated view should have had schedules applied"
+    s0 = ctx.band_schedules
+    ctx.set_option("beam", 0)
+    for rep in range(3):
+        for k, v in enumerate(views):
+            assert_same_hits(frame(*v), want[k], f"view {k} without beam, repetition {rep}")
+    # a camera that never repeats a view records nothing and applies nothing
+    s1 = ctx.band_schedules
+    for i in range(70):
+        rot, fov = oc.camera_coeffs(0.01 * i, -0.5)
+        frame(np.array([1.5, 1.5, 1.6], np.float32), rot, fov)
+    assert ctx.band_schedules == s1
+    assert s1 >= s0
+    ctx.close()
