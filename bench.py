@@ -401,6 +401,7 @@ def run_product(args):
     launches0 = ctx.launch_count
     wall0 = time.perf_counter()
     evs = timed_steps(args.steps, True)
+    host_enqueue_s = time.perf_counter() - wall0          # the host's share: queueing the steps' launches, nothing waited for
     barrier()
     wall = time.perf_counter() - wall0
     launches = ctx.launch_count - launches0
@@ -443,6 +444,7 @@ def run_product(args):
                           "serial_value": round(rays_per_step_total / (serial_ms / args.steps * 1e-3) / 1e6, 2),
                           "pushes_per_ray": round(pushes_per_step_local / rays_per_step_local, 3),
                           "rounds_run_per_ray": round(pushes_run / (len(cams) * n_local), 3), "beam_levels": beam_levels, "launches": launches,
+                          "host_enqueue_ms_per_step": round(host_enqueue_s / args.steps * 1e3, 4), "band_schedules": ctx.band_schedules,
                           "per_frame_ms_serial": [round(x, 4) for x in serial_per_launch[-len(step_cams):]],
                           "tile_rows": TILE_ROWS, "streams": NS, "parity": parity, "gather": gq,
                           "as_rank": (f"{prank}/{pworld}: value = what {pworld} GPUs would total if every rank ran like this one" if args.as_rank else None)})

@@ -402,7 +402,7 @@ BandMap* band_map_for(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& 
 
 // Before a frame launch: apply the newest recorded schedule of the view (fr.band_order) and decide whether this launch
 // records (fr.band_cost).  Costs are recorded by the first launches of a view and refreshed now and then.
-void band_map_before(ort_ctx* c, BandMap* m, ort::FrameRows& fr)
+void band_map_before(ort_ctx* c, BandMap* m, ort::FrameRows& fr, bool may_record)
 {
 	if (m->recording && cudaEventQuery(m->ev_cost) == cudaSuccess)
 	{
@@ -438,7 +438,7 @@ void band_map_before(ort_ctx* c, BandMap* m, ort::FrameRows& fr)
 	++m->since;
 	++m->seen;
 	// (a view seen for the first time records nothing: a camera that moves every frame never comes back to it)
-	if (!m->recording && m->seen >= 2 && (m->applied < 2 || m->since >= 64))
+	if (may_record && !m->recording && m->seen >= 2 && (m->applied < 2 || m->since >= 64))
 	{
 		if (cudaMemsetAsync(m->d_cost, 0, m->bands * 4, c->stream) == cudaSuccess)
 			fr.band_cost = m->d_cost;
@@ -930,16 +930,23 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		if (rc != ORT_OK) return rc;
 	}
 	// band schedule of this view (launches of 8 bands and more; the frame kernels of the product walks)
-	BandMap* bm = (c->opt_band_order && c->opt_band_rotate < 0 && grid.y >= 8 && grid.y < 65536 && c->opt_tile_shape == 0) ? band_map_for(c, cam, fr) : nullptr;
-	if (bm) band_map_before(c, bm, fr);
+	BandMap* bm = (c->opt_band_order && c->opt_band_rotate < 0 && grid.y >= 8 && grid.y < 65536 && c->opt_tile_shape == 0 && walk_variant(c) == ort::kLean)
+	                  ? band_map_for(c, cam, fr) : nullptr;
+	if (bm) band_map_before(c, bm, fr, npush == nullptr);
 #define ORT_LAUNCH_FRAME(V, C, B) ort::trace_frame_kernel<V, C, B><<<grid, 256, (V) == ort::kLean ? smem : 0, c->stream>>>(dag, cam, fr, voxel, face, t, npush)
 	switch (walk_variant(c))
 	{
 	case 0:  if (npush) ORT_LAUNCH_FRAME(0, true, false); else ORT_LAUNCH_FRAME(0, false, false); break;
 	case 1:  if (npush) ORT_LAUNCH_FRAME(1, true, false); else ORT_LAUNCH_FRAME(1, false, false); break;
 	default:
-		if (bk) { if (npush) ORT_LAUNCH_FRAME(ort::kLean, true, true); else ORT_LAUNCH_FRAME(ort::kLean, false, true); }
-		else    { if (npush) ORT_LAUNCH_FRAME(ort::kLean, true, false); else ORT_LAUNCH_FRAME(ort::kLean, false, false); }
+		if (fr.band_cost)
+		{
+			// (recording launches return no PUSH counts: band_map_before() leaves those alone)
+			if (bk) ort::trace_frame_kernel<ort::kLean, false, true, true><<<grid, 256, smem, c->stream>>>(dag, cam, fr, voxel, face, t, npush);
+			else    ort::trace_frame_kernel<ort::kLean, false, false, true><<<grid, 256, smem, c->stream>>>(dag, cam, fr, voxel, face, t, npush);
+		}
+		else if (bk) { if (npush) ORT_LAUNCH_FRAME(ort::kLean, true, true); else ORT_LAUNCH_FRAME(ort::kLean, false, true); }
+		else         { if (npush) ORT_LAUNCH_FRAME(ort::kLean, true, false); else ORT_LAUNCH_FRAME(ort::kLean, false, false); }
 		break;
 	}
 #undef ORT_LAUNCH_FRAME

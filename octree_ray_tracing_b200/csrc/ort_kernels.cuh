@@ -195,7 +195,9 @@ __device__ __forceinline__ float read_tile_start(const FrameRows& fr, const floa
 // (register budget: 6 resident blocks per SM = 40 registers; the 32-register build reloads the node base pointer from the
 // constant bank every round and measures 1-2 % slower, although it fits 8 blocks)
 // BEAM: the launch was preceded by beam_start_kernel over the same rows and the same `t` array.
-template<int VARIANT, bool COUNT, bool BEAM = false>
+// RECORD: the launch measures what its bands cost (FrameRows::band_cost) -- a separate instantiation, because the clock
+// value kept across the walk costs the ordinary kernel four registers and a tenth of its speed.
+template<int VARIANT, bool COUNT, bool BEAM = false, bool RECORD = false>
 __global__ void __launch_bounds__(256, 6)
 trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
                    uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* t, uint16_t* __restrict__ npush)
@@ -215,7 +217,7 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 		if (COUNT) npush[i] = 0;
 		return;
 	}
-	const long long t_start = fr.band_cost ? clock64() : 0ll;
+	const long long t_start = RECORD ? clock64() : 0ll;
 	const int y = frame_row(fr, r);
 
 	float dx, dy, dz;
@@ -226,7 +228,7 @@ trace_frame_kernel(const Dag g, Camera cam, FrameRows fr,
 	face[i] = static_cast<uint8_t>(h.face);
 	t[i] = h.t;
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
-	if (fr.band_cost)
+	if (RECORD)
 	{
 		// what this band costs, for the schedule of the next launch of the same view: the longest a warp of the band was busy
 		// (a scheduling hint, nothing reads it for results; one atomic per warp where the lanes have reconverged)
