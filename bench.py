@@ -367,6 +367,18 @@ def run_product(args):
                 if tr == 1:
                     gather["transport"] = mg.transport
                 gather[(mode, grp) if tr == 1 else (mode + "_nccl_sendrecv", grp)] = ((time.perf_counter() - g0) / g_steps, (mg.wire_bytes - w0) / g_steps)
+            # measurement aid: extra legs "mode:group:transport:trace_streams,..." from ORT_BENCH_GATHER_LEGS (quick mode prints them)
+            for leg in filter(None, os.environ.get("ORT_BENCH_GATHER_LEGS", "").split(",")):
+                mode, grp, tr, ts = leg.split(":")
+                mg.set_transport(int(tr)); mg.set_group(int(grp)); mg.set_trace_streams(int(ts))
+                gather_step(mode); mg.sync(); barrier()
+                g0 = time.perf_counter()
+                for _ in range(g_steps):
+                    gather_step(mode)
+                mg.sync(); barrier()
+                gather[(f"extra_{mode}_t{tr}_s{ts}", int(grp))] = ((time.perf_counter() - g0) / g_steps, 0.0)
+            if os.environ.get("ORT_BENCH_GATHER_LEGS"):
+                mg.set_trace_streams(8 if world > 4 else 4)
             mg.set_transport(1)
             mg.set_group(1)
             # one frame at a time, nothing in flight: the latency of "trace my strips + gather" for a single frame

@@ -112,6 +112,10 @@ class MultiGpu:
     def flush(self):
         self._ck(self.L.ort_mg_flush(self.h))
 
+    def set_trace_streams(self, n: int):
+        """Streams the strips of consecutive frames are traced on (1..8; default 4, 8 beyond four ranks)."""
+        self._ck(self.L.ort_mg_set_trace_streams(self.h, n))
+
     def set_transport(self, transport: int):
         """1: peer copies on the copy engines (CUDA IPC), 0: NCCL send / recv.  Collective; takes effect at the next frame."""
         self._ck(self.L.ort_mg_set_transport(self.h, transport))
