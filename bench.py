@@ -352,7 +352,10 @@ def run_product(args):
 
             g_steps = max(1, min(args.steps, 10))
             # (consumers, frames per wire operation): per-frame messages, and the whole step's strips as one NCCL group
-            for mode, grp, tr in (("round_robin", 1, 1), ("round_robin", len(step_cams), 1), ("rank0", len(step_cams), 1), ("round_robin", len(step_cams), 0)):
+            # frames per wire operation of the headline leg: a whole step up to 12 frames, half-steps of 12 beyond (8 GPUs, 24 frames
+            # per step: one operation per step 122, per 12 frames 139, per 8 frames 121 Grays/s; profiles/r2_n8_gather_legs.json)
+            G = min(len(step_cams), 12)
+            for mode, grp, tr in (("round_robin", 1, 1), ("round_robin", G, 1), ("rank0", G, 1), ("round_robin", G, 0), ("round_robin", len(step_cams), 1)):
                 mg.set_transport(tr)
                 mg.set_group(grp)
                 gather_step(mode)
@@ -554,15 +557,17 @@ def run_product(args):
 
     # max over ranks
     n_step_frames = len(step_cams)
-    g_rr, g_r0 = gather.get(("round_robin", n_step_frames), (0.0, 0.0)), gather.get(("rank0", n_step_frames), (0.0, 0.0))
+    G = min(n_step_frames, 12)
+    g_rr, g_r0 = gather.get(("round_robin", G), (0.0, 0.0)), gather.get(("rank0", G), (0.0, 0.0))
     g_rr1 = gather.get(("round_robin", 1), (0.0, 0.0))
-    g_rrn = gather.get(("round_robin_nccl_sendrecv", n_step_frames), (0.0, 0.0))
+    g_rrn = gather.get(("round_robin_nccl_sendrecv", G), (0.0, 0.0))
+    g_rrw = gather.get(("round_robin", n_step_frames), (0.0, 0.0))
     g_lat = max(gather.get("latency", [0.0]))
     d2h_sum = d2h_gbs_local
     if world > 1:
-        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1[0], g_rrn[0]], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([kernel_ms, warm_ms, e2e_s, wall, g_rr[0], g_r0[0], g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1[0], g_rrn[0], g_rrw[0]], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1_s, g_rrn_s = (float(x) for x in tt.tolist())
+        kernel_ms, warm_ms, e2e_s, wall, g_rr_s, g_r0_s, g_lat, rgba_s, e2e_sync_s, serial_ms, g_rr1_s, g_rrn_s, g_rrw_s = (float(x) for x in tt.tolist())
         cnt = torch.tensor([launches, bytes_per_step_local, pushes_per_step_local, d2h_gbs_local, g_rr[1], g_r0[1]], dtype=torch.float64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches_all = int(cnt[0].item())
@@ -575,7 +580,7 @@ def run_product(args):
     else:
         launches_all = launches
         pushes_per_ray_all = pushes_per_step_local / rays_per_step_local
-        g_rr_s = g_r0_s = g_rr1_s = g_rrn_s = 0.0
+        g_rr_s = g_r0_s = g_rr1_s = g_rrn_s = g_rrw_s = 0.0
         wire_rr = wire_r0 = ingest_r0 = 0.0
 
     result = None
@@ -690,12 +695,14 @@ def run_product(args):
                 "value": round(rays_per_step_total / g_rr_s / 1e6, 2), "unit": "Mrays/s",
                 "frac_of_no_gather": round(rays_per_step_total / g_rr_s / 1e6 / value_trace, 4),
                 "consumers": "round robin: frame k of the step is assembled on rank k mod N (N times the frames, N consumers)",
-                "wire": f"ort_mg_set_group({n_step_frames}): the strips of a step's {n_step_frames} frames leave in ONE wire operation that overlaps the next step's traces",
+                "wire": f"ort_mg_set_group({G}): the strips of {G} of a step's {n_step_frames} frames leave in ONE wire operation that overlaps the traces of the next frames",
                 "wire_bytes_per_step": int(wire_rr), "wire_gbs_aggregate": round(wire_rr / g_rr_s / 1e9, 1),
                 "transport": ("peer copies: every strip block moves with one cudaMemcpyAsync on the copy engines into the consumer's staging area (CUDA IPC mapping), one 4-byte ncclAllReduce per wire operation orders it"
                               if gather.get("transport") == 1 else "NCCL ncclSend / ncclRecv (CUDA IPC not available between the ranks)"),
                 "nccl_sendrecv_transport": {"value": round(rays_per_step_total / g_rrn_s / 1e6, 2), "unit": "Mrays/s",
                                             "note": "the same exchange with ort_mg_set_transport(0): NCCL's copy kernels share the SMs with the issue-bound trace kernels"},
+                "whole_step_per_operation": {"value": round(rays_per_step_total / g_rrw_s / 1e6, 2), "unit": "Mrays/s",
+                                             "note": f"ort_mg_set_group({n_step_frames}): all strips of a step in one wire operation (the same leg as the headline up to 12 frames per step)"},
                 "per_frame_messages": {"value": round(rays_per_step_total / g_rr1_s / 1e6, 2), "unit": "Mrays/s",
                                        "note": "ort_mg_set_group(1): every frame's strips leave as soon as they are traced (one wire operation per frame)"},
                 "api": "ort_mg_trace_frame_gather (inside libort_b200.so): strips traced into a ring of blocks on 4-8 trace streams, moved on the communicator's "

@@ -954,6 +954,12 @@ int ort_tree_load(ort_tree* t, const char* path)
 		std::fclose(f);
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: dump is h_octree<%d,%d>, tree is h_octree<%d,%d>", h.log2cap, h.depth, t->log2cap, t->depth);
 	}
+	if (h.root > t->cap || h.records > t->cap)
+	{
+		std::fclose(f);
+		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: '%s' is corrupt (root %u, %llu records for a table of %llu slots)", path, h.root,
+		                static_cast<unsigned long long>(h.records), static_cast<unsigned long long>(t->cap));
+	}
 	std::memset(t->tags, 0, t->cap);
 	std::vector<DumpRecord> buf(1 << 16);
 	uint64_t left = h.records;
@@ -973,6 +979,45 @@ int ort_tree_load(ort_tree* t, const char* path)
 		left -= n;
 	}
 	std::fclose(f);
+	// Nothing in the file is trusted: at(), set() and flatten() follow the root and the interior children as slot + 1
+	// indices.  Walk the DAG level by level from the root; every reference above the last level must name an occupied
+	// slot of this table.  (A slot can serve at several levels -- content addressing -- hence one visited bit per level.)
+	uint64_t occupied = 0, live = 0;
+	if (ok)
+	{
+		for (uint64_t s2 = 0; s2 < t->cap; ++s2)
+		{
+			occupied += t->tags[s2] != 0;
+			live += t->tags[s2] != 0 && t->refcounts[s2] != 0;       // (a gravestone keeps its tag, its count is 0)
+		}
+		ok = occupied == h.records && (h.root == 0 || (t->tags[h.root - 1] != 0 && t->refcounts[h.root - 1] != 0));
+	}
+	if (ok && h.root != 0 && t->depth > 1)
+	{
+		std::vector<uint16_t> seen(t->cap, 0);
+		std::vector<uint32_t> cur{ h.root - 1 }, nxt;
+		seen[h.root - 1] = 1;
+		for (int level = 1; level < t->depth && ok; ++level)
+		{
+			const uint16_t bit = static_cast<uint16_t>(1u << (level % 16));
+			nxt.clear();
+			for (const uint32_t slot : cur)
+			{
+				const uint32_t* ch = t->nodes + 8 * static_cast<size_t>(slot);
+				for (int k = 0; k < 8; ++k)
+				{
+					const uint32_t c = ch[k];
+					if (c == 0) continue;
+					if (c > t->cap || t->tags[c - 1] == 0 || t->refcounts[c - 1] == 0) { ok = false; break; }
+					if (seen[c - 1] & bit) continue;
+					seen[c - 1] |= bit;
+					nxt.push_back(c - 1);
+				}
+				if (!ok) break;
+			}
+			cur.swap(nxt);
+		}
+	}
 	if (!ok)
 	{
 		std::memset(t->tags, 0, t->cap);
@@ -980,7 +1025,8 @@ int ort_tree_load(ort_tree* t, const char* path)
 		t->invalidate_mirror();
 		return ort_fail(nullptr, ORT_ERR_INVALID, "ort_tree_load: '%s' is truncated or corrupt", path);
 	}
-	t->root = h.root; t->fillcnt = h.fillcnt; t->nodecnt = h.nodecnt; t->max_refcnt = h.max_refcnt;
+	// fillcnt counts the live slots: taken from the table, not from the header
+	t->root = h.root; t->fillcnt = static_cast<decltype(t->fillcnt)>(live); t->nodecnt = h.nodecnt; t->max_refcnt = h.max_refcnt;
 	t->table_full = false;
 	t->clear_dirty();
 	t->invalidate_mirror();

@@ -283,6 +283,39 @@ def test_table_dump_and_load_round_trip(ort, oc, tmp_path):
     bad.write_bytes(b"not a table")
     with pytest.raises(Exception):
         B.load(str(bad))
+    # a dump is not trusted: a root or an interior child that names no live slot of the table, a record count that
+    # does not match, a truncated file -- each is refused and leaves an empty, usable table behind
+    raw = bytearray(open(path, "rb").read())
+    hdr = 8 + 4 * 2 + 4 * 4 + 8                      # magic, log2cap, depth, root, fillcnt, nodecnt, max_refcnt, records
+    rec = 4 + 4 + 4 + 32                             # slot, refcount, tag (padded), children
+    assert (len(raw) - hdr) % rec == 0, "the test's idea of the dump layout is out of date"
+    cap = 1 << log2cap
+
+    def refused(mutate, what):
+        b = bytearray(raw)
+        mutate(b)
+        q = tmp_path / "corrupt.ort"
+        q.write_bytes(bytes(b))
+        D = ort.HOctree(log2cap, depth, device=None)
+        with pytest.raises(Exception):
+            D.load(str(q))
+        assert D.get_root() == 0 and D.get_fillcnt() == 0, what
+        D.set(1, 2, 3, 4)
+        assert D.at(1, 2, 3) == 4, what
+
+    import struct
+    refused(lambda b: struct.pack_into("<I", b, 16, cap + 7), "root beyond the table")
+    refused(lambda b: struct.pack_into("<Q", b, hdr - 8, (len(raw) - hdr) // rec + 1), "one record more than the file holds")
+    refused(lambda b: b.__delitem__(slice(len(b) - rec, len(b))), "truncated")
+    # the root's record: point one of its children outside the table, then at an empty slot
+    root = struct.unpack_from("<I", raw, 16)[0]
+    slots = np.frombuffer(bytes(raw[hdr:]), dtype=np.uint8).reshape(-1, rec)[:, :4].copy().view(np.uint32).ravel()
+    k = int(np.flatnonzero(slots == root - 1)[0])
+    off = hdr + k * rec + 12
+    child_k = next(i for i in range(8) if struct.unpack_from("<I", raw, off + 4 * i)[0] != 0)
+    refused(lambda b: struct.pack_into("<I", b, off + 4 * child_k, cap + 1), "interior child beyond the table")
+    empty = int(np.setdiff1d(np.arange(cap, dtype=np.uint32), slots)[0]) + 1
+    refused(lambda b: struct.pack_into("<I", b, off + 4 * child_k, empty), "interior child names an empty slot")
 
 
 @pytest.mark.parametrize("depth,log2cap", [(1, 8), (2, 8), (16, 18)])
