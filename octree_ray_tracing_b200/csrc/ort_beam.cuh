@@ -6,7 +6,7 @@
 // terrain.  Those rounds are the same for all rays of a tile, but SIMT already issues them once per warp -- only not
 // running them saves anything (tools/beam/beam_model.py: 19.7 / 30.3 / 37.6 rounds per ray -> 6.7 / 17.0 / 21.8).
 //
-// Two pieces.
+// Three pieces.
 //
 // (1) Re-entry (LeanWalker::start_at).  For a ray of the lean tier (no degenerate axis, no negative t, finite bias) let
 //     e_1 <= e_2 <= ... be the exit times the reference computes in its STEPs at the empty slots S_1, S_2, ... it visits
@@ -32,9 +32,9 @@
 //     its hit time the point o + t_hit d' lies within 2^-22 of the hit voxel (every entry plane of the voxel has t <=
 //     t_hit, every exit plane t >= t_hit).  Let R bound |d' - d_c| over the rays of a tile, d_c the direction through the
 //     tile's centre: R = (half diagonal of the tile in the image plane) / fov + eps_r + rounding.  A level-k grid cell has
-//     size s = 2^-k; take the largest k with t_max R + slack <= 0.7 s (t_max = 1.75 > sqrt(3): no ray stays longer in the
-//     cube).  Then, at equal parameter t, every ray of the tile is in one of the 27 cells around the cell of the
-//     central ray.  `skip` holds, for every level-k cell, 0 if any of its 27 neighbours contains a non-empty level-k cell
+//     size s = 2^-k; take the largest k with t_max R + slack <= 0.7 s (t_max = the distance from the origin to the farthest
+//     corner of the cube, widened by eps_r: no ray stays longer in it).  Then, at equal parameter t, every ray of the
+//     tile is in one of the 27 cells around the cell of the central ray.  `skip` holds, for every level-k cell, 0 if any of its 27 neighbours contains a non-empty level-k cell
 //     of the DAG ("dilated-occupied"), else the coarsest level j <= k whose cell around it is dilated-empty throughout.
 //     Marching the central ray through that grid (one load per step, the steps as large as the empty cells) gives the
 //     first parameter tau_c at which it is inside a dilated-occupied cell: no ray of the tile can hit anything before
@@ -46,8 +46,10 @@
 //     every ray of the tile has left it too: tau = +inf.  If all rays of the tile are certain to be lean-tier rays
 //     (beam_tile_start), the trace kernel writes 32 MISSes and is done -- no camera ray, no reciprocals.
 //
-// What this buys is measured in profiles/ (r2_beam_*); what it costs is one byte grid per DAG version (built lazily by
-// four small kernels, 8^k bytes) and one march per tile (a separate launch, one thread per tile).
+// What this buys is measured in profiles/ (r2_final_beam_ncu_full.md, r2_bench_n1.json) and argued in DESIGN.md 4b; what it
+// costs is one byte grid per DAG version and level in use (built lazily: occupancy, dilation, k - 1 pyramid levels, skip
+// levels; 8^k bytes) and one march per tile (a separate launch, one thread per tile).
+// Tested claim by claim: tests/test_beam.py (this header compiled for the host) and tests/test_gpu_beam.py.
 #pragma once
 
 #include <cmath>

@@ -386,7 +386,7 @@ int ort_mg_create(ort_mg** out, ort_ctx* ctx, int rank, int world, const void* i
 		m->peer_recv_base.assign(world, nullptr);
 		m->consumed.assign(world, 0);
 		if (const char* e = std::getenv("ORT_MG_TRANSPORT")) m->transport_pref = std::atoi(e) != 0;
-		m->n_trace_streams = world > 4 ? 8 : 4;
+		m->n_trace_streams = world > 2 ? 8 : 4;      // (4 GPUs: 8 streams 84.2, 4 streams 81.2 Grays/s with the gather)
 		for (int i = 0; i < ort_mg::kMaxTraceStreams; ++i)
 		{
 			ORT_CUDA(ctx, cudaStreamCreateWithFlags(&m->trace_stream[i], cudaStreamNonBlocking));

@@ -23,12 +23,13 @@ open(p, "w").write(s)
 PY
 cd "$SCRATCH"
 python -c "from octree_ray_tracing_b200 import build as b; b.build(force=True)"
-nm -D octree_ray_tracing_b200/libort_b200.so | grep -q __asan_ || { echo "library is not instrumented"; exit 2; }
+# (grep -c, not -q: with pipefail an early exit of grep would make nm's SIGPIPE look like a failure)
+[ "$(nm -D octree_ray_tracing_b200/libort_b200.so | grep -c __asan_)" -gt 0 ] || { echo "library is not instrumented"; exit 2; }
 export LD_PRELOAD="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 export ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=0
 export ORT_EMU_SANITIZE=1      # the host emulation of the device walkers too: their parent stacks are plain local arrays
 python -m pytest tests/test_host_tree.py tests/test_octree.py tests/test_shading.py tests/test_capi_symbols.py \
-       tests/test_fuzz_random_dags.py tests/test_multi_gpu_cpu.py tests/test_host_emu.py -q -s -m "not gpu" 2>&1 | tee sanitize.log | tail -3
+       tests/test_fuzz_random_dags.py tests/test_multi_gpu_cpu.py tests/test_host_emu.py tests/test_beam.py -q -s -m "not gpu" 2>&1 | tee sanitize.log | tail -3
 if grep -q "runtime error\|AddressSanitizer" sanitize.log; then
 	grep "runtime error\|AddressSanitizer" sanitize.log | sort | uniq -c | sort -rn | head -20
 	exit 1
