@@ -157,8 +157,9 @@ __device__ __forceinline__ float beam_march(const BeamGrid g, float ox, float oy
 			break;
 		// leave the level-s cell around the sample point (a virtual cell: that cell alone) through its nearest exit plane
 		const int sh = (cx == bx && cy == by && cz == bz) ? g.k - s : 0;
-		const float lx = __fmaf_rn(static_cast<float>((cx >> sh) << sh), cell, 1.0f), ly = __fmaf_rn(static_cast<float>((cy >> sh) << sh), cell, 1.0f),
-		            lz = __fmaf_rn(static_cast<float>((cz >> sh) << sh), cell, 1.0f);
+		const int keep = ~((1 << sh) - 1);                 // (a mask, not shifts: virtual cells have index -1)
+		const float lx = __fmaf_rn(static_cast<float>(cx & keep), cell, 1.0f), ly = __fmaf_rn(static_cast<float>(cy & keep), cell, 1.0f),
+		            lz = __fmaf_rn(static_cast<float>(cz & keep), cell, 1.0f);
 		const float w = static_cast<float>(1 << sh) * cell;
 		// Exit times of the three axes.  One that is not in the future (<= t) belongs to a plane the sample point sits on within
 		// rounding: the ray runs along it (or has just crossed it and the next sample will say so).  It is no exit; but while
