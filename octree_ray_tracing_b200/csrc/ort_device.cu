@@ -284,6 +284,17 @@ int beam_level(const ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& f
 	return k;
 }
 
+// the same for the experiment kernels that bring their own walker (ORT_EXPERIMENTS builds): the selected variant is not
+// the product's, everything else decides as above
+int beam_level_any_variant(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& fr, bool counting)
+{
+	const int keep = c->opt_variant;
+	c->opt_variant = ort::kLean;
+	const int k = beam_level(c, cam, fr, counting);
+	c->opt_variant = keep;
+	return k;
+}
+
 // Make the level-k grid describe the current DAG; on return the launch stream is ordered after the build.
 int beam_ensure_grid(ort_ctx* c, int k)
 {

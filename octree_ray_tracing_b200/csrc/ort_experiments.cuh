@@ -408,6 +408,82 @@ trace_frame_walker_kernel(const Dag g, Camera cam, FrameRows fr,
 	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
 }
 
+// Variants 24-27: the round-2 walkers and loop shapes again, now WITH the beam start (ort_beam.cuh) -- the product's frame
+// kernel with the walker and the loop as parameters.  The beam start removes the coherent rounds (all lanes descend, or all
+// advance), which are the ones the branchy round is cheap on; what is left is the split walk near the surface, where the
+// straight-line round (FlatWalker) and the other loop shapes might compare differently than they did in
+// profiles/r2_loop_shapes.json / r2_v14_straight_line_ncu_full.md.  LOOP: 0 one round() per iteration, 1 advance-while,
+// 2 descend-while (= the product).
+template<template<bool> class WALKER, bool COUNT, int LOOP>
+__global__ void __launch_bounds__(256, 6)
+trace_frame_walker_beam_kernel(const Dag g, Camera cam, FrameRows fr,
+                               uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* t, uint16_t* __restrict__ npush)
+{
+	extern __shared__ uint32_t s_stack[];
+	int x, r;
+	const bool inside = frame_pixel(fr, blockIdx.y, gridDim.y, x, r);
+	const float tau = read_tile_start(fr, t, x, r);
+	if (!inside) return;
+	const size_t i = static_cast<size_t>(r) * fr.W + x;
+	if (__float_as_uint(tau) == kBeamAllMissBits)
+	{
+		voxel[i] = 0u;
+		face[i] = 6;
+		t[i] = g.miss_t;
+		if (COUNT) npush[i] = 0;
+		return;
+	}
+	const int y = frame_row(fr, r);
+	float dx, dy, dz;
+	camera_ray(cam, x, y, dx, dy, dz);
+	const Ray ray = ray_setup_camera(g.rt, cam.ox, cam.oy, cam.oz, dx, dy, dz, cam.origin_flags);
+	Hit h;
+	if ((cam.origin_flags & kOriginInCube) != 0u && lean_path_ok(ray))
+	{
+		WALKER<COUNT> w;
+		const LeanStack<kLeanShift> st{ lean_stack_base(s_stack, g.depth) };
+		bool beam_used;
+		bool done = lean_start(w, g.root, ray, tau, g.miss_t, beam_used);
+		while (!done)
+		{
+			if (LOOP == 1)
+			{
+				for (;;)
+				{
+					uint32_t child;
+					bool end = false;
+					while ((child = w.load_child(g.base_biased)) == 0u)
+						if (w.advance(g.miss_t, st)) { end = true; break; }
+					if (end || w.descend(child, g.leaf_dimf, st)) break;
+				}
+			}
+			else if (LOOP == 2)
+			{
+				for (;;)
+				{
+					uint32_t child;
+					bool end = false;
+					while ((child = w.load_child(g.base_biased)) != 0u)
+						if (w.descend(child, g.leaf_dimf, st)) { end = true; break; }
+					if (end || w.advance(g.miss_t, st)) break;
+				}
+			}
+			else
+				while (!w.round(g.base_biased, g.leaf_dimf, g.miss_t, st)) {}
+			done = !(beam_used && w.mti == 8u);          // the beam guard (see walk_ray)
+			if (!done) { beam_used = false; w.start(g.root, ray); }
+		}
+		h = w.hit;
+	}
+	else
+		h = traverse_variant<1, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, cam.ox, cam.oy, cam.oz, ray);
+
+	voxel[i] = h.voxel;
+	face[i] = static_cast<uint8_t>(h.face);
+	t[i] = h.t;
+	if (COUNT) npush[i] = static_cast<uint16_t>(min(h.npush, 65535u));
+}
+
 }  // namespace ort
 
 // ------------------------------------------------------------------------------------------------
@@ -489,6 +565,32 @@ static int launch_frame_experiment(ort_ctx* c, const ort::Dag& g, const ort::Cam
 		       : v == 18 ? ORT_WALKER_KERNEL(ort::LeanWalker, 0, true, 1) : ORT_WALKER_KERNEL(ort::LeanWalker, 0, false, 6);
 #undef ORT_WALKER_KERNEL
 		k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
+	}
+	else if (v >= 24 && v <= 27 && lean_capable(c))
+	{
+		// 24 straight-line round, 25 plain round, 26 advance-while, 27 descend-while -- each with the beam start where the launch
+		// qualifies for one (else the same walker without: variants 14 / 19-like)
+		const int bk = beam_level_any_variant(c, cam, fr, npush != nullptr);
+		const size_t smem = ort::lean_smem_bytes(g.depth);
+		if (bk)
+		{
+			const int rc = beam_launch_march(c, bk, cam, fr, t);
+			if (rc != ORT_OK) return ORT_ERR_CUDA;
+#define ORT_BEAM_KERNEL(W, L) (npush ? ort::trace_frame_walker_beam_kernel<W, true, L> : ort::trace_frame_walker_beam_kernel<W, false, L>)
+			auto k = v == 24 ? ORT_BEAM_KERNEL(ort::FlatWalker, 0) : v == 25 ? ORT_BEAM_KERNEL(ort::LeanWalker, 0)
+			       : v == 26 ? ORT_BEAM_KERNEL(ort::LeanWalker, 1) : ORT_BEAM_KERNEL(ort::LeanWalker, 2);
+#undef ORT_BEAM_KERNEL
+			k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
+		}
+		else
+		{
+			// a launch without a beam level (PUSH counts of the reference walk, coarse pixels, ...): the same walker and loop from the origin
+#define ORT_WALKER_KERNEL(W, L) (npush ? ort::trace_frame_walker_kernel<W, true, L, false, 6> : ort::trace_frame_walker_kernel<W, false, L, false, 6>)
+			auto k = v == 24 ? ORT_WALKER_KERNEL(ort::FlatWalker, 0) : v == 25 ? ORT_WALKER_KERNEL(ort::LeanWalker, 0)
+			       : v == 26 ? ORT_WALKER_KERNEL(ort::LeanWalker, 1) : ORT_WALKER_KERNEL(ort::LeanWalker, 2);
+#undef ORT_WALKER_KERNEL
+			k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
+		}
 	}
 	else if (v == 1 && (c->opt_tile_shape != 0 || c->opt_block == 128 || c->opt_block == 64))
 	{

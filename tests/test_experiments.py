@@ -16,7 +16,8 @@ def test_the_product_library_carries_no_experiment_kernel(ort):
     from octree_ray_tracing_b200 import build
     build.build()
     names = ("trace_frame_tight_kernel", "trace_frame_pipe_kernel", "trace_frame_probe_kernel", "trace_frame_deferred_kernel",
-             "trace_frame_staged_kernel", "trace_frame_tiles_kernel", "trace_frame_shaped_kernel", "trace_frame_walker_kernel")
+             "trace_frame_staged_kernel", "trace_frame_tiles_kernel", "trace_frame_shaped_kernel", "trace_frame_walker_kernel",
+             "trace_frame_walker_beam_kernel")
     prod = subprocess.run(["nm", "-C", build.LIB], capture_output=True, text=True, check=True).stdout
     exp = subprocess.run(["nm", "-C", build.LIB_EXP], capture_output=True, text=True, check=True).stdout
     for n in names:
@@ -32,6 +33,9 @@ def test_experiment_kernels_equal_the_product_kernels():
                           "-k", "kernel_variants_agree or degenerate_rays_and_corner_cameras"], env=env, capture_output=True, text=True, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert "2 passed" in out.stdout, out.stdout[-500:]
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_beam.py"), "-x", "-q", "-m", "gpu",
+                          "-k", "beam_experiment_walkers"], env=env, capture_output=True, text=True, cwd=ROOT)
+    assert out.returncode == 0 and "1 passed" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
 
 
 @pytest.mark.gpu

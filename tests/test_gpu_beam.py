@@ -234,3 +234,33 @@ def test_band_schedule_changes_no_output(ort, oc):
     assert ctx.band_schedules == s1
     assert s1 >= s0
     ctx.close()
+
+
+def test_beam_experiment_walkers_equal_the_product(ort, oc):
+    """Measurement build only (ORT_B200_EXPERIMENTS=1; tests/test_experiments.py runs this in a child process): the walkers
+    and loop shapes of csrc/ort_experiments.cuh with the beam start (variants 24-27) against the product kernel."""
+    if b"experiments" not in ort.lib().ort_version():
+        pytest.skip("the product library carries no experiment kernels")
+    depth = 10
+    T = ort.HOctree(22, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=True)
+    T.sync()
+    ctx = T.ctx
+    W, H = 1920, 1080
+    for name, (pos, yaw, pitch) in POSES.items():
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        ctx.set_option("variant", 13)
+        want = ctx.trace_frame(pos, rot, fov, W, H)
+        ctx.set_option("count_beam", 1)
+        want_n = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)[3]
+        for v in (24, 25, 26, 27):
+            ctx.set_option("variant", v)
+            assert_same_hits(ctx.trace_frame(pos, rot, fov, W, H), want, f"pose {name}, variant {v}")
+            got = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=536, tile_rows=8, tile_step=2, want_npush=True)
+            ctx.set_option("variant", 13)
+            ref = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=536, tile_rows=8, tile_step=2, want_npush=True)
+            assert_same_hits(got, ref, f"pose {name}, variant {v}, strip")
+            assert np.array_equal(got[3], ref[3]), f"pose {name}, variant {v}: rounds differ from the product's"
+        ctx.set_option("count_beam", 0)
+        assert want_n.astype(np.int64).sum() > 0
+    ctx.close()
