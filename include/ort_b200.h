@@ -245,7 +245,9 @@ uint64_t ort_launch_count(const ort_ctx* ctx);
  * Beam start of camera frames (csrc/ort_beam.cuh): "beam" (1 = default: every 8 x 4 pixel tile of a frame launch starts
  * its rays at a lower bound of their hit times taken from a coarse grid of the DAG, and rays that provably leave the
  * cube unhindered end as a MISS without a round -- same outputs bit for bit, fewer PUSH rounds; 0 = every ray walks from
- * its origin like och_h_octree.h:292-447), "beam_level" (force a coarser grid level, measurement), "count_beam"
+ * its origin like och_h_octree.h:292-447), "beam_after" (default 2: a DAG version gets its grid once it has been traced
+ * that many times without one, so that a loop which edits the DAG every other frame never pays for grids it cannot use;
+ * 0 = build at the first frame), "beam_level" (force a coarser grid level, measurement), "count_beam"
  * (launches that return PUSH counts normally walk from the origin so that the counts are the reference's; 1 = they
  * use the beam start too and count the loads actually issued). */
 int ort_set_option(ort_ctx* ctx, const char* key, int value);

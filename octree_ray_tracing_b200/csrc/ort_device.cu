@@ -105,6 +105,11 @@ struct ort_ctx
 	int opt_beam = 1;                   // 1: camera frames of the lean tier start at their tile's beam bound
 	int opt_beam_level = 0;             // 0: the finest level the tile size allows; else forced (measurement)
 	int opt_count_beam = 0;             // 1: launches that return PUSH counts use the beam start too (counts = loads actually issued)
+	int opt_beam_after = 2;             // frame launches a DAG version must have seen before a grid is built for it (edit loops: see beam_level_for_launch)
+	int beam_dag_age = 0;               // frame calls that have met the current DAG version (saturating)
+	uint64_t frame_call_seq = 0;        // public frame calls so far (a host-buffer frame is one call, however many chunk launches it makes)
+	uint64_t beam_seen_seq = 0;
+	bool frame_call_nested = false;
 	uint64_t beam_builds = 0;
 
 	unsigned long long* d_counters = nullptr; // work counters of the persistent kernels: a ring, one per launch (kCounterRing)
@@ -236,6 +241,7 @@ void band_map_release(BandMap& m)
 inline void beam_invalidate(ort_ctx* c)
 {
 	for (int k = 0; k < 8; ++k) c->beam_valid[k] = false;
+	c->beam_dag_age = 0;
 }
 
 }  // namespace
@@ -284,13 +290,30 @@ int beam_level(const ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& f
 	return k;
 }
 
+// What a frame launch does.  A grid costs ~9 small launches per DAG version; a loop that edits the DAG every other frame
+// (BASELINE config 4: 1080p frames of 0.14 ms) would pay that again and again for frames too small to earn it back
+// (measured: 0.140 -> 0.187 ms per frame).  So a DAG version gets its grid only once it has been traced
+// by opt_beam_after frame calls without one: an edit loop never builds, a steady scene loses two frames.
+int beam_level_for_launch(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& fr, bool counting)
+{
+	const int k = beam_level(c, cam, fr, counting);
+	if (!k) return 0;
+	if (c->beam_valid[k]) return k;
+	if (c->beam_seen_seq != c->frame_call_seq)
+	{
+		c->beam_seen_seq = c->frame_call_seq;
+		if (c->beam_dag_age <= c->opt_beam_after) ++c->beam_dag_age;      // the current call included
+	}
+	return c->beam_dag_age > c->opt_beam_after ? k : 0;
+}
+
 // the same for the experiment kernels that bring their own walker (ORT_EXPERIMENTS builds): the selected variant is not
 // the product's, everything else decides as above
 int beam_level_any_variant(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& fr, bool counting)
 {
 	const int keep = c->opt_variant;
 	c->opt_variant = ort::kLean;
-	const int k = beam_level(c, cam, fr, counting);
+	const int k = beam_level_for_launch(c, cam, fr, counting);
 	c->opt_variant = keep;
 	return k;
 }
@@ -902,6 +925,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frame: bad arguments");
 	if (!rows) return ORT_OK;
 	DeviceGuard g(c->device);
+	if (!c->frame_call_nested) ++c->frame_call_seq;
 	const size_t n = static_cast<size_t>(rows) * W;
 	if (!c->has_root)
 		return launch_miss(c, n, voxel, face, t, npush);
@@ -934,7 +958,7 @@ int ort_trace_frame_async(ort_ctx* c, const float pos[3], const float rot[9], fl
 #endif
 	if (c->opt_variant != 0 && c->opt_variant != 1 && c->opt_variant != 2 && c->opt_variant != ort::kLean)
 		return bad_variant(c);
-	const int bk = beam_level(c, cam, fr, npush != nullptr);
+	const int bk = beam_level_for_launch(c, cam, fr, npush != nullptr);
 	if (bk)
 	{
 		const int rc = beam_launch_march(c, bk, cam, fr, t);
@@ -992,6 +1016,7 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 		return ort_fail(c, ORT_ERR_INVALID, "ort_trace_frames_async: the batched launch exists for variants 0, 1 and 13 (selected: %d)", c->opt_variant);
 	const ort::Dag dag = make_dag(c);
 	const size_t smem = ort::lean_smem_bytes(c->depth);
+	++c->frame_call_seq;
 	int i = 0;
 	while (i < n_jobs)
 	{
@@ -1021,7 +1046,7 @@ int ort_trace_frames_async(ort_ctx* c, const ort_frame_job* jobs, int n_jobs)
 		for (int k = 0; k < n && beam; ++k)
 		{
 			ort::FrameJob& d = batch.job[k];
-			d.beam_k = beam_level(c, d.cam, d.fr, count);
+			d.beam_k = beam_level_for_launch(c, d.cam, d.fr, count);
 			d.beam_min_comp = ort::beam_certify_min_comp(d.cam, ort::beam_tile_radius(d.cam, c->rcp_eps), c->rcp_sig_bits);
 			beam = d.beam_k != 0;
 			max_tiles = std::max(max_tiles, static_cast<unsigned>(((d.fr.W + 7) / 8) * ((d.fr.rows + 3) / 4)));
@@ -1126,6 +1151,8 @@ static int frame_to_host(ort_ctx* c, const float pos[3], const float rot[9], flo
 	}
 	const int n_streams = 3;
 	int launched = 0;
+	++c->frame_call_seq;                      // the chunks below are one frame call
+	struct Nested { ort_ctx* c; explicit Nested(ort_ctx* c_) : c(c_) { c->frame_call_nested = true; } ~Nested() { c->frame_call_nested = false; } } nested(c);
 	for (int k = 0; k < kChunks; ++k)
 	{
 		const int r0 = bounds[k], nr = bounds[k + 1] - bounds[k];
@@ -1320,7 +1347,7 @@ static int launch_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9],
 	const ort::Camera cam = make_camera(c, pos, rot, fov_factor, W, H);
 	const int rotate = c->opt_band_rotate >= 0 ? c->opt_band_rotate % ((rows + 15) / 16) : horizon_band(cam, W, y0, rows, tile_rows, tile_step);
 	const ort::FrameRows fr{ W, H, y0, rows, tile_rows, tile_step, 0, rotate, ort::tile_shift_of(tile_rows) };
-	const int bk = beam_level(c, cam, fr, false);
+	const int bk = beam_level_for_launch(c, cam, fr, false);
 	if (bk)
 	{
 		const int rc = beam_launch_march(c, bk, cam, fr, reinterpret_cast<float*>(d_rgba));
@@ -1349,11 +1376,15 @@ int ort_trace_frame_rgba(ort_ctx* c, const float pos[3], const float rot[9], flo
 	if (!rows) return ORT_OK;
 	DeviceGuard g(c->device);
 	if (is_device_ptr(rgba))
+	{
+		++c->frame_call_seq;
 		return launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, rgba);   // enqueue only
+	}
 
 	if (c->opt_zero_copy)
 		if (uint32_t* z = static_cast<uint32_t*>(mapped_host_alias(rgba)))
 		{
+			++c->frame_call_seq;
 			int rc = launch_frame_rgba(c, pos, rot, fov_factor, W, H, y0, rows, tile_rows, tile_step, z);
 			if (rc != ORT_OK) return rc;
 			ORT_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -1481,6 +1512,7 @@ int ort_set_option(ort_ctx* c, const char* key, int value)
 	else if (!std::strcmp(key, "beam")) c->opt_beam = value;
 	else if (!std::strcmp(key, "beam_level")) c->opt_beam_level = value;
 	else if (!std::strcmp(key, "count_beam")) c->opt_count_beam = value;
+	else if (!std::strcmp(key, "beam_after")) c->opt_beam_after = value;
 	else if (!std::strcmp(key, "defer_sync")) c->opt_defer_sync = value;
 	else if (!std::strcmp(key, "frame_chunks")) c->opt_frame_chunks = value;
 	else if (!std::strcmp(key, "rays_chunk")) c->opt_rays_chunk = value;

@@ -55,6 +55,7 @@ def test_bench_frames_beam_on_equals_beam_off_and_the_reference(ort, oc, emu):
     ort.harness.build_terrain(T)
     T.sync()
     ctx = T.ctx
+    ctx.set_option("beam_after", 0)          # a grid at the first frame of a DAG version (default: after two frames without)
     nodes8, root, _ = T.flatten()
     tab = emu.default_rcp_table()
     W, H = 3840, 2160
@@ -104,6 +105,7 @@ def test_strips_rgba_batched_launches_and_small_frames(ort, oc, emu):
     ort.harness.build_terrain(T, tunnels=True)
     T.sync()
     ctx = T.ctx
+    ctx.set_option("beam_after", 0)
     cols, _ = ort.harness.parse_voxels(ort.harness.DEMO_VOXELS)
     ctx.set_palette(cols)
     W, H = 1920, 1080
@@ -152,6 +154,7 @@ def test_strips_rgba_batched_launches_and_small_frames(ort, oc, emu):
     T.sync()
     pos, rot, fov = cams[1]
     assert T.ctx.beam_level(pos, rot, fov, 3840, 2160) == 7
+    T.ctx.set_option("beam_after", 0)
     T.ctx.set_option("beam", 0)
     a = T.ctx.trace_frame(pos, rot, fov, 3840, 2160)
     T.ctx.set_option("beam", 1)
@@ -171,6 +174,7 @@ def test_edit_loop_with_beam_start_vs_oracle(ort, oc, emu):
     rot, fov = oc.camera_coeffs(yaw, pitch)
     W, H = 1920, 1080
     assert T.ctx.beam_level(pos, rot, fov, W, H) > 0
+    T.ctx.set_option("beam_after", 0)
     d = oc.gen_rays(rot, fov, W, H)
     rs = np.random.RandomState(2)
     builds = T.ctx.beam_builds
@@ -246,6 +250,7 @@ def test_beam_experiment_walkers_equal_the_product(ort, oc):
     ort.harness.build_terrain(T, tunnels=True)
     T.sync()
     ctx = T.ctx
+    ctx.set_option("beam_after", 0)
     W, H = 1920, 1080
     for name, (pos, yaw, pitch) in POSES.items():
         rot, fov = oc.camera_coeffs(yaw, pitch)
@@ -264,3 +269,34 @@ def test_beam_experiment_walkers_equal_the_product(ort, oc):
         ctx.set_option("count_beam", 0)
         assert want_n.astype(np.int64).sum() > 0
     ctx.close()
+
+
+def test_an_edit_loop_never_builds_a_grid_and_a_steady_scene_does(ort, oc, emu):
+    """Default policy ("beam_after" = 2): a DAG version gets its grid at the third frame call that meets it.  Edits every
+    other frame (BASELINE config 4) therefore never build one; frames of an unchanged DAG do from the third on; either
+    way every frame equals the oracle."""
+    depth = 8
+    T = ort.HOctree(20, depth, device=0)
+    ort.harness.build_terrain(T, tunnels=False)
+    tab = emu.default_rcp_table()
+    pos, yaw, pitch = POSES["B"]
+    rot, fov = oc.camera_coeffs(yaw, pitch)
+    W, H = 1920, 1080
+    d = oc.gen_rays(rot, fov, W, H)
+
+    def check(what):
+        got = T.ctx.trace_frame(pos, rot, fov, W, H)            # a host-buffer frame: one call, several chunk launches
+        nodes8, root, _ = T.flatten()
+        assert_same_hits(got, oc.trace_rays(nodes8, root, depth, np.array(pos, np.float32), d, rcp_tab=tab, nthreads=NCPU), what)
+
+    T.sync()
+    for it in range(6):
+        T.set_box(60 + 20 * it, 80, 150 + 10 * (it % 3), 14, 2)
+        T.sync()
+        check(f"edit {it}, first frame")
+        check(f"edit {it}, second frame")
+    assert T.ctx.beam_builds == 0, "an edit every other frame must not build grids"
+    for k in range(4):
+        check(f"steady frame {k}")
+    assert T.ctx.beam_builds == 1
+    T.ctx.close()

@@ -213,8 +213,15 @@ def test_device_pointer_entry_points(ort, oc, golden):
     assert_same_hits(got, (g["rand_vox"], g["rand_face"], g["rand_t"]), "async rays")
     # one frame kernel + one rays kernel; with the beam start the frame also has its march and, once per DAG version, the
     # grid build (occupancy, dilation, k - 1 pyramid levels, skip levels)
+    # (default policy: the first two frame calls of a DAG version run without a grid, see ort_set_option "beam_after")
+    assert ctx.launch_count == 2
+    ctx.set_option("beam_after", 0)
     k = ctx.beam_level(g["poseB_pos"], g["poseB_rot"], float(g["poseB_fov"]), W, H)
-    assert ctx.launch_count == 2 + ((1 + 3 + (k - 1)) if k else 0)
+    ctx.trace_frame_async(g["poseB_pos"], g["poseB_rot"], float(g["poseB_fov"]), W, H, 0, H, 1, 1, dv, df, dt)
+    ctx.sync()
+    assert ctx.launch_count == 3 + ((1 + 3 + (k - 1)) if k else 0)
+    got = (dv.cpu().numpy().view(np.uint32), df.cpu().numpy(), dt.cpu().numpy())
+    assert_same_hits(got, (g["poseB_vox"], g["poseB_face"], g["poseB_t"]), "async frame with the beam start")
 
 
 def test_depth12_4k_properties(ort, oc, ncpu):

@@ -28,6 +28,9 @@ def config4(args):
     dim = 1 << depth
     n0, _ = tree.sync()
     ctx = tree.ctx
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     # camera 0.2 * (terrain amplitude) above the ground at the map centre, looking steeply down (t < 0.5 rule holds)
     pos = np.array([1.5, 1.5, 1.0 + (heights[dim // 2, dim // 2] + 0.05 * dim) / dim], np.float32)
     yaw, pitch = 0.4, -1.2
@@ -41,7 +44,7 @@ def config4(args):
     n_edits = delta_nodes = fulls = 0
     for frame in range(args.frames):
         face, vox, t = tree.sse_trace(pos, dir3)                       # pick ray (test_och_h_octree.cpp:535)
-        if frame % 2 == 1 and vox and t < 0.5:
+        if frame % 2 == 1 and vox and t < 0.5 and not args.no_edits:
             place = (frame // 2) % 2 == 0
             off = np.zeros(3, np.float32)
             if int(face) < 6:
@@ -74,6 +77,7 @@ def config4(args):
                       "delta_nodes_per_edit": round(delta_nodes / max(n_edits, 1), 1), "full_uploads_after_first": fulls,
                       "ms_per_frame_trace": round(t_trace / args.frames * 1e3, 4),
                       "Mrays_per_s_trace": round(W * H * args.frames / t_trace / 1e6, 1),
+                      "options": args.opt, "beam_level": ctx.beam_level(pos, rot, fov, W, H), "beam_grids_built": ctx.beam_builds,
                       "dag_nodes": tree.get_fillcnt(), "hits_last_frame": int((dv != 0).sum().item())}), flush=True)
 
 
@@ -85,6 +89,9 @@ def config5(args):
     depth, log2cap = args.depth, {12: 24, 13: 26, 14: 27}[args.depth]
     W, H, tr = 7680, 4320, 8
     ctx = ort.TraceContext(depth, device=local, node_capacity=1 << 16)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     t0 = time.time()
     update = None
     if rank == 0:
@@ -158,7 +165,8 @@ def config5(args):
         rays = W * H * len(cams)
         print(json.dumps({"config": 5, "depth": depth, "n_gpus": world, "resolution": [W, H], "frames_per_step": len(cams),
                           "dag_nodes": n_nodes, "dag_mib": round(n_nodes * 32 / 2**20, 1), "host_build_s": round(t_build, 1),
-                          "pushes_per_ray": round(float(pt[0] / pt[1]), 2),
+                          "pushes_per_ray": round(float(pt[0] / pt[1]), 2), "options": args.opt,
+                          "beam_level": ctx.beam_level(cams[0][0], cams[0][1], cams[0][2], W, H),
                           "Mrays_per_s_trace": round(rays / out["trace"] / 1e6, 1),
                           "Mrays_per_s_trace_plus_gather": round(rays / out["trace+gather"] / 1e6, 1),
                           "ms_per_frame_trace": round(out["trace"] / len(cams) * 1e3, 3),
@@ -176,6 +184,8 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--streams", type=int, default=3, help="config 5: frames in flight")
     ap.add_argument("--bulk", action="store_true", help="config 4: use the bulk box edit instead of the 64000-set() loop")
+    ap.add_argument("--opt", action="append", default=[], help="key=value passed to ort_set_option (e.g. beam=0)")
+    ap.add_argument("--no-edits", action="store_true", help="config 4: the same frames without the edits (a steady scene)")
     args = ap.parse_args()
     if args.depth is None:
         args.depth = 10 if args.config == 4 else 14
