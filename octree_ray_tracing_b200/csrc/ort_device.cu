@@ -794,12 +794,14 @@ int ort_upload_delta(ort_ctx* c, const uint32_t* ids, const uint32_t* nodes8, si
 		ORT_CUDA(c, cudaStreamSynchronize(c->stream));
 	}
 	c->n_nodes = max_id;
+	bool changed = n != 0;
 	if (c->index_base == 1)
 	{
+		changed = changed || c->root != root;
 		c->root = root;
 		c->has_root = root != 0;
 	}
-	beam_invalidate(c);
+	if (changed) beam_invalidate(c);            // (an empty delta -- a per-frame sync without edits -- leaves the grids alone)
 	return ORT_OK;
 }
 

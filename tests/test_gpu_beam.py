@@ -300,3 +300,38 @@ def test_an_edit_loop_never_builds_a_grid_and_a_steady_scene_does(ort, oc, emu):
         check(f"steady frame {k}")
     assert T.ctx.beam_builds == 1
     T.ctx.close()
+
+
+def test_pool_octree_frames_with_beam_start_vs_oracle(ort, oc):
+    """och::octree pool layout (raw rows, root = row 0, MISS time 0.0F) with the beam start, grids following the row deltas;
+    per-frame syncs without edits must not throw the grid away."""
+    from test_oracle import _builtin_table
+    rs = np.random.RandomState(11)
+    depth, cap = 7, 1 << 16
+    A, T = oc.OracleOctree(depth, cap), ort.Octree(depth, cap)
+    ops = []
+    for _ in range(30):
+        c = rs.randint(8, 120, 3)
+        e = rs.randint(2, 10)
+        ops += [(c[0] + x, c[1] + y, (c[2] + z) // 2, int(rs.randint(1, 6)), 0) for x in range(e) for y in range(e) for z in range(e)]
+    ops = np.array(ops, np.int32)
+    A.apply(ops); T.apply(ops)
+    T.sync()
+    T.ctx.set_option("beam_after", 0)
+    tab = _builtin_table()
+    pos, yaw, pitch = (1.5, 1.5, 1.9), 0.3, -1.1
+    rot, fov = oc.camera_coeffs(yaw, pitch)
+    W, H = 1280, 720
+    assert T.ctx.beam_level(pos, rot, fov, W, H) > 0
+    d = oc.gen_rays(rot, fov, W, H)
+    for step in range(3):
+        got = T.trace_frame(pos, yaw, pitch, W, H)
+        want = A.trace(np.array(pos, np.float32), d, rcp_tab=tab, nthreads=NCPU)
+        assert_same_hits(got, want, f"pool frame {step}")
+        b = T.ctx.beam_builds
+        assert_same_hits(T.trace_frame(pos, yaw, pitch, W, H), want, f"pool frame {step}, again")      # (trace_frame syncs first: an empty delta)
+        assert T.ctx.beam_builds == b and b == step + 1
+        more = np.array([(int(x), int(y), int(z), 3, 0) for x, y, z in rs.randint(20, 100, (200, 3))], np.int32)
+        A.apply(more); T.apply(more)
+        T.sync()
+    T.ctx.close()
