@@ -414,8 +414,10 @@ trace_frame_walker_kernel(const Dag g, Camera cam, FrameRows fr,
 // straight-line round (FlatWalker) and the other loop shapes might compare differently than they did in
 // profiles/r2_loop_shapes.json / r2_v14_straight_line_ncu_full.md.  LOOP: 0 one round() per iteration, 1 advance-while,
 // 2 descend-while (= the product).
-template<template<bool> class WALKER, bool COUNT, int LOOP>
-__global__ void __launch_bounds__(256, 6)
+// GUARD: 0 the product's retry loop around the walk, 1 a slow-path call after the walk (FastWalker from the origin), 2 no
+// guard at all (measurement only: what the guard costs).  MINB: resident blocks per SM the register budget allows for.
+template<template<bool> class WALKER, bool COUNT, int LOOP, int GUARD = 0, int MINB = 6>
+__global__ void __launch_bounds__(256, MINB)
 trace_frame_walker_beam_kernel(const Dag g, Camera cam, FrameRows fr,
                                uint32_t* __restrict__ voxel, uint8_t* __restrict__ face, float* t, uint16_t* __restrict__ npush)
 {
@@ -470,10 +472,12 @@ trace_frame_walker_beam_kernel(const Dag g, Camera cam, FrameRows fr,
 			}
 			else
 				while (!w.round(g.base_biased, g.leaf_dimf, g.miss_t, st)) {}
-			done = !(beam_used && w.mti == 8u);          // the beam guard (see walk_ray)
+			done = GUARD != 0 || !(beam_used && w.mti == 8u);          // the beam guard (see walk_ray)
 			if (!done) { beam_used = false; w.start(g.root, ray); }
 		}
 		h = w.hit;
+		if (GUARD == 1 && beam_used && w.mti == 8u)
+			h = traverse_variant<1, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, cam.ox, cam.oy, cam.oz, ray);
 	}
 	else
 		h = traverse_variant<1, COUNT>(g.nodes_m1, g.root, g.depth, g.miss_t, cam.ox, cam.oy, cam.oz, ray);
@@ -566,7 +570,7 @@ static int launch_frame_experiment(ort_ctx* c, const ort::Dag& g, const ort::Cam
 #undef ORT_WALKER_KERNEL
 		k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
 	}
-	else if (v >= 24 && v <= 27 && lean_capable(c))
+	else if (v >= 24 && v <= 31 && lean_capable(c))
 	{
 		// 24 straight-line round, 25 plain round, 26 advance-while, 27 descend-while -- each with the beam start where the launch
 		// qualifies for one (else the same walker without: variants 14 / 19-like)
@@ -577,8 +581,12 @@ static int launch_frame_experiment(ort_ctx* c, const ort::Dag& g, const ort::Cam
 			const int rc = beam_launch_march(c, bk, cam, fr, t);
 			if (rc != ORT_OK) return ORT_ERR_CUDA;
 #define ORT_BEAM_KERNEL(W, L) (npush ? ort::trace_frame_walker_beam_kernel<W, true, L> : ort::trace_frame_walker_beam_kernel<W, false, L>)
+			// 28-31: the product's walker and loop with the guard as a slow-path call / without a guard / other register budgets
+#define ORT_BEAM_KERNEL2(G, MB) (npush ? ort::trace_frame_walker_beam_kernel<ort::LeanWalker, true, 2, G, MB> : ort::trace_frame_walker_beam_kernel<ort::LeanWalker, false, 2, G, MB>)
 			auto k = v == 24 ? ORT_BEAM_KERNEL(ort::FlatWalker, 0) : v == 25 ? ORT_BEAM_KERNEL(ort::LeanWalker, 0)
-			       : v == 26 ? ORT_BEAM_KERNEL(ort::LeanWalker, 1) : ORT_BEAM_KERNEL(ort::LeanWalker, 2);
+			       : v == 26 ? ORT_BEAM_KERNEL(ort::LeanWalker, 1) : v == 27 ? ORT_BEAM_KERNEL(ort::LeanWalker, 2)
+			       : v == 28 ? ORT_BEAM_KERNEL2(1, 6) : v == 29 ? ORT_BEAM_KERNEL2(2, 6) : v == 30 ? ORT_BEAM_KERNEL2(0, 5) : ORT_BEAM_KERNEL2(0, 8);
+#undef ORT_BEAM_KERNEL2
 #undef ORT_BEAM_KERNEL
 			k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
 		}
@@ -587,7 +595,7 @@ static int launch_frame_experiment(ort_ctx* c, const ort::Dag& g, const ort::Cam
 			// a launch without a beam level (PUSH counts of the reference walk, coarse pixels, ...): the same walker and loop from the origin
 #define ORT_WALKER_KERNEL(W, L) (npush ? ort::trace_frame_walker_kernel<W, true, L, false, 6> : ort::trace_frame_walker_kernel<W, false, L, false, 6>)
 			auto k = v == 24 ? ORT_WALKER_KERNEL(ort::FlatWalker, 0) : v == 25 ? ORT_WALKER_KERNEL(ort::LeanWalker, 0)
-			       : v == 26 ? ORT_WALKER_KERNEL(ort::LeanWalker, 1) : ORT_WALKER_KERNEL(ort::LeanWalker, 2);
+			       : v == 26 ? ORT_WALKER_KERNEL(ort::LeanWalker, 1) : ORT_WALKER_KERNEL(ort::LeanWalker, 2);      // (27-31)
 #undef ORT_WALKER_KERNEL
 			k<<<grid, 256, smem, c->stream>>>(g, cam, fr, voxel, face, t, npush);
 		}
