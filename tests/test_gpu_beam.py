@@ -242,7 +242,8 @@ def test_band_schedule_changes_no_output(ort, oc):
 
 def test_beam_experiment_walkers_equal_the_product(ort, oc):
     """Measurement build only (ORT_B200_EXPERIMENTS=1; tests/test_experiments.py runs this in a child process): the walkers
-    and loop shapes of csrc/ort_experiments.cuh with the beam start (variants 24-27) against the product kernel."""
+    and loop shapes of csrc/ort_experiments.cuh with the beam start (variants 24-28, 30, 31; 29 runs without the guard and is
+    a measurement only) against the product kernel."""
     if b"experiments" not in ort.lib().ort_version():
         pytest.skip("the product library carries no experiment kernels")
     depth = 10
@@ -258,7 +259,7 @@ def test_beam_experiment_walkers_equal_the_product(ort, oc):
         want = ctx.trace_frame(pos, rot, fov, W, H)
         ctx.set_option("count_beam", 1)
         want_n = ctx.trace_frame(pos, rot, fov, W, H, want_npush=True)[3]
-        for v in (24, 25, 26, 27):
+        for v in (24, 25, 26, 27, 28, 30, 31):
             ctx.set_option("variant", v)
             assert_same_hits(ctx.trace_frame(pos, rot, fov, W, H), want, f"pose {name}, variant {v}")
             got = ctx.trace_frame(pos, rot, fov, W, H, y0=8, rows=536, tile_rows=8, tile_step=2, want_npush=True)
