@@ -43,6 +43,8 @@ struct BandMap
 	cudaEvent_t ev_order = nullptr;     // d_order[cur] has been uploaded
 	cudaEvent_t ev_read[2] = { nullptr, nullptr };   // last launch reading d_order[i]
 	bool     read_any[2] = { false, false };
+	cudaEvent_t ev_up[2] = { nullptr, nullptr };     // the upload of h_order's half i has been executed
+	bool     up_any[2] = { false, false };
 	int      cur = -1;                  // -1: no schedule yet (band_rotate rule)
 	bool     recording = false;
 	int      applied = 0;               // schedules uploaded so far
@@ -234,6 +236,7 @@ void band_map_release(BandMap& m)
 	if (m.ev_cost) cudaEventDestroy(m.ev_cost);
 	if (m.ev_order) cudaEventDestroy(m.ev_order);
 	for (int i = 0; i < 2; ++i) if (m.ev_read[i]) cudaEventDestroy(m.ev_read[i]);
+	for (int i = 0; i < 2; ++i) if (m.ev_up[i]) cudaEventDestroy(m.ev_up[i]);
 	m = BandMap{};
 }
 
@@ -405,6 +408,7 @@ BandMap* band_map_for(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& 
 		// the view that leaves may still have launches and copies in flight on its buffers
 		if (m.recording) cudaEventSynchronize(m.ev_cost);
 		for (int i = 0; i < 2; ++i) if (m.read_any[i]) cudaEventSynchronize(m.ev_read[i]);
+		for (int i = 0; i < 2; ++i) if (m.up_any[i]) cudaEventSynchronize(m.ev_up[i]);
 	}
 	if (!m.d_cost)
 	{
@@ -412,7 +416,8 @@ BandMap* band_map_for(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& 
 		          cudaMalloc(&m.d_cost, kBandCap * 4) == cudaSuccess && cudaHostAlloc(&m.h_cost, kBandCap * 4, cudaHostAllocDefault) == cudaSuccess &&
 		          cudaHostAlloc(&m.h_order, kBandCap * 4, cudaHostAllocDefault) == cudaSuccess &&
 		          cudaEventCreateWithFlags(&m.ev_cost, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m.ev_order, cudaEventDisableTiming) == cudaSuccess &&
-		          cudaEventCreateWithFlags(&m.ev_read[0], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m.ev_read[1], cudaEventDisableTiming) == cudaSuccess;
+		          cudaEventCreateWithFlags(&m.ev_read[0], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m.ev_read[1], cudaEventDisableTiming) == cudaSuccess &&
+		          cudaEventCreateWithFlags(&m.ev_up[0], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&m.ev_up[1], cudaEventDisableTiming) == cudaSuccess;
 		if (!ok)
 		{
 			cudaGetLastError();
@@ -426,6 +431,7 @@ BandMap* band_map_for(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& 
 	std::memcpy(m.geo, geo, sizeof geo);
 	m.bands = bands;
 	m.read_any[0] = m.read_any[1] = false;
+	m.up_any[0] = m.up_any[1] = false;
 	m.cur = -1;
 	m.recording = false;
 	m.applied = 0;
@@ -438,23 +444,27 @@ BandMap* band_map_for(ort_ctx* c, const ort::Camera& cam, const ort::FrameRows& 
 // records (fr.band_cost).  Costs are recorded by the first launches of a view and refreshed now and then.
 void band_map_before(ort_ctx* c, BandMap* m, ort::FrameRows& fr, bool may_record)
 {
-	if (m->recording && cudaEventQuery(m->ev_cost) == cudaSuccess)
+	// (the pinned half the next schedule is written to must have been read by its previous upload: a copy still queued on
+	// a stalled stream would otherwise pick up a half-written permutation)
+	const int nxt = m->cur == 0 ? 1 : 0;
+	if (m->recording && cudaEventQuery(m->ev_cost) == cudaSuccess && (!m->up_any[nxt] || cudaEventQuery(m->ev_up[nxt]) == cudaSuccess))
 	{
 		m->recording = false;
 		// most expensive band first (stable: equal costs keep the band_rotate order they were measured in)
-		const int nb = m->bands, nxt = m->cur == 0 ? 1 : 0;
+		const int nb = m->bands;
 		uint16_t* ho = m->h_order + static_cast<size_t>(nxt) * kBandCap;
 		std::vector<int> idx(nb);
 		for (int b = 0; b < nb; ++b) idx[b] = (b + fr.band_rotate) % nb;
 		std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return m->h_cost[a] > m->h_cost[b]; });
 		for (int b = 0; b < nb; ++b) ho[b] = static_cast<uint16_t>(idx[b]);
-		// the buffer may still be read by launches of two schedules ago; the upload waits for them
+		// the device buffer may still be read by launches of two schedules ago; the upload waits for them
 		bool fine = true;
 		if (m->read_any[nxt]) fine = cudaStreamWaitEvent(c->stream, m->ev_read[nxt], 0) == cudaSuccess;
 		fine = fine && cudaMemcpyAsync(m->d_order[nxt], ho, nb * 2, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
-		       cudaEventRecord(m->ev_order, c->stream) == cudaSuccess;
+		       cudaEventRecord(m->ev_up[nxt], c->stream) == cudaSuccess && cudaEventRecord(m->ev_order, c->stream) == cudaSuccess;
 		if (fine)
 		{
+			m->up_any[nxt] = true;
 			m->cur = nxt;
 			++m->applied;
 			++c->band_schedules;
@@ -626,6 +636,7 @@ int ort_destroy(ort_ctx* c)
 {
 	if (!c) return ORT_OK;
 	DeviceGuard g(c->device);
+	cudaDeviceSynchronize();                   // launches may be in flight on streams the caller handed over (ort_set_stream)
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
 	if (c->h2d_stream) cudaStreamSynchronize(c->h2d_stream);
