@@ -507,6 +507,23 @@ def run_product(args):
     barrier()
     e2e_s = time.perf_counter() - e0
     e2e_check = int((houts[(len(step_cams) - 1) % n_host][0] != 0).sum())
+    # measurement aid: the same with other numbers of launches per host-buffer frame (ORT_BENCH_E2E_CHUNKS="1,2,4")
+    e2e_chunk_legs = {}
+    for nck in filter(None, os.environ.get("ORT_BENCH_E2E_CHUNKS", "").split(",")):
+        ctx.set_option("frame_chunks", int(nck))
+        e2e_step()
+        barrier()
+        c0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        sec = time.perf_counter() - c0
+        if world > 1:
+            tsec = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tsec, op=dist.ReduceOp.MAX)
+            sec = float(tsec.item())
+        e2e_chunk_legs[f"frame_chunks={nck}"] = round(rays_per_step_total * e2e_steps / sec / 1e6, 2)
+    ctx.set_option("frame_chunks", 0)
 
     # the same, one synchronous call per frame (each call returns with its results on the host)
     def e2e_sync_step():
@@ -688,7 +705,7 @@ def run_product(args):
                     "host_ingest_note": f"measured in this run: all {world} rank(s) copy 256 MiB device -> pinned host at the same time (sum over ranks); "
                                         f"at 9 B per ray this caps e2e at {d2h_sum / 9 * 1e3:.0f} Mrays/s on this box",
                     "frac_of_host_ingest": round(e2e_val * 9 / 1e3 / d2h_sum, 4) if d2h_sum else None,
-                    "hits_last_frame": e2e_check},
+                    "hits_last_frame": e2e_check, **({"chunk_legs_Mrays/s": e2e_chunk_legs} if e2e_chunk_legs else {})},
             "e2e_rgba": {"value": round(rays_per_step_total * e2e_steps / rgba_s / 1e6, 2), "unit": "Mrays/s",
                          "d2h_bytes_per_step": frames_per_step * n_local * 4,
                          "api": "ort_trace_frame_rgba: trace_pixel's colour lookup fused into the kernel, one uint32 pixel per ray to pinned host memory"},
