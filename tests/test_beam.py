@@ -219,3 +219,81 @@ def test_beam_on_the_pool_octree_layout(emu, ort, oc):
     got = emu.trace_frame(pool, 0, depth, pos, rot, fov, W, H, walker=13, miss_t=0.0, pool=True, beam=grid, want_stats=True)
     assert_same_hits(got, want, "pool layout with beam start")
     assert got[3]["beam_rays"] + got[3]["beam_misses"] > 0 and got[3]["beam_guard"] == 0
+
+
+def test_beam_frames_on_random_dags(emu, ort, oc):
+    """The scenes of tests/test_fuzz_random_dags.py -- isolated voxels (the thing a non-conservative beam would fly past),
+    boxes, dense noise, a solid cube with holes (every ray starts inside: no beam start may happen) -- seen from random
+    cameras, on-grid origins included, at frame sizes that select every grid level: frames with the beam start equal the
+    oracle, the tile starts never exceed a hit time, the guard never fires, no tile is certified wrongly."""
+    from test_fuzz_random_dags import random_scene
+    tab = emu.default_rcp_table()
+    levels = set()
+    frames = tile_misses = beam_rays = 0
+    for seed in range(120):
+        depth, nodes8, root, _, _ = random_scene(ort, 5000 + seed, depth=3 + seed % 6)
+        if root == 0:
+            continue
+        rs = np.random.RandomState(seed)
+        grids = {}
+        for cam in range(3):
+            pos = rs.uniform(1.02, 1.98, 3).astype(np.float32)
+            if cam == 1:
+                q = 1 << int(rs.randint(1, depth + 1))
+                pos = (np.floor((pos - 1.0) * q) / q + 1.0 + (1.0 / q if rs.rand() < 0.5 else 0.0)).astype(np.float32)      # on some level's grid
+                pos = np.clip(pos, np.float32(1.0) + np.float32(1.0 / q), np.float32(2.0) - np.float32(1.0 / q))
+            rot, fov = oc.camera_coeffs(float(rs.uniform(-3.1, 3.1)), float(rs.uniform(-1.5, 1.5)))
+            W, H = [(256, 144), (640, 360), (1600, 900)][(seed + cam) % 3]
+            rows = min(H, 64)
+            y0 = int(rs.randint(0, H - rows + 1)) & ~3
+            k = emu.beam_level(pos, rot, fov, W, H, depth)
+            if k == 0:
+                continue
+            levels.add(k)
+            if k not in grids:
+                grids[k] = emu.beam_grid(nodes8, root, k)
+            d = oc.gen_rays(rot, fov, W, H, y0, y0 + rows)
+            want = oc.trace_rays(nodes8, root, depth, pos, d, rcp_tab=tab, nthreads=NCPU)
+            got = emu.trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=y0, rows=rows, walker=13, want_stats=True, beam=grids[k], want_tau=True)
+            what = f"seed {seed} (kind {(5000 + seed) % 4}, depth {depth}), camera {cam} at {pos.tolist()}, {W}x{H}, level {k}"
+            assert_same_hits(got, want, what)
+            st, tau = got[3], got[4]
+            assert st["beam_guard"] == 0 and st["beam_cert_wrong"] == 0, what
+            hit = want[0] != 0
+            assert (tau[hit] <= want[2][hit]).all(), f"{what}: a tile start later than a hit time of the tile"
+            frames += 1; tile_misses += st["beam_tile_misses"]; beam_rays += st["beam_rays"]
+    assert frames > 150 and len(levels) >= 3, (frames, levels)
+    assert tile_misses > 0 and beam_rays > 0
+
+
+def test_needles_and_sheets_are_not_flown_past(emu, ort, oc):
+    """What a beam bound must never do: start rays behind something thinner than the beam.  Depth 12, 4K pixels (grid level 7,
+    cells 32 voxels wide): single voxels floating in empty space at several distances, a wall one voxel thick and a
+    one-voxel-wide rod along the view direction, each seen by a handful of pixels at most."""
+    depth = 12
+    dim = 1 << depth
+    T = ort.HOctree(16, depth, device=None)
+    rs = np.random.RandomState(9)
+    needles = [(2100 + 37 * i, 2048 + int(rs.randint(-300, 300)), 2048 + int(rs.randint(-200, 200))) for i in range(40)]
+    for x, y, z in needles:
+        T.set(x, y, z, 1 + (x % 5))
+    T.fill_box((3500, 1000, 1000), (3501, 3000, 3000), 3)            # a sheet, one voxel thick, far away
+    T.fill_box((2300, 2047, 1500), (3400, 2048, 1501), 4)            # a rod along x
+    nodes8, root, _ = T.flatten()
+    tab = emu.default_rcp_table()
+    W, H = 3840, 2160
+    pos = np.array([1.5, 1.5, 1.5], np.float32)                      # voxel (2048, 2048, 2048): on every grid
+    for yaw, pitch in [(0.0, 0.0), (0.03, -0.12), (-0.05, 0.04)]:
+        rot, fov = oc.camera_coeffs(yaw, pitch)
+        k = emu.beam_level(pos, rot, fov, W, H, depth)
+        assert k == 7
+        grid = emu.beam_grid(nodes8, root, k)
+        y0, rows = 760, 640
+        d = oc.gen_rays(rot, fov, W, H, y0, y0 + rows)
+        want = oc.trace_rays(nodes8, root, depth, pos, d, rcp_tab=tab, nthreads=NCPU)
+        got = emu.trace_frame(nodes8, root, depth, pos, rot, fov, W, H, y0=y0, rows=rows, walker=13, want_stats=True, beam=grid, want_tau=True)
+        assert_same_hits(got, want, f"needles, yaw {yaw} pitch {pitch}")
+        hit = want[0] != 0
+        assert hit.sum() > 100 and len(np.unique(want[0][hit])) >= 4, "the scene should be visible: needles of several kinds, the sheet, the rod"
+        assert (got[4][hit] <= want[2][hit]).all()
+        assert got[3]["beam_guard"] == 0 and got[3]["beam_cert_wrong"] == 0 and got[3]["beam_tile_misses"] > 0
