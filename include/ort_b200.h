@@ -249,7 +249,10 @@ uint64_t ort_launch_count(const ort_ctx* ctx);
  * that many times without one, so that a loop which edits the DAG every other frame never pays for grids it cannot use;
  * 0 = build at the first frame), "beam_level" (force a coarser grid level, measurement), "count_beam"
  * (launches that return PUSH counts normally walk from the origin so that the counts are the reference's; 1 = they
- * use the beam start too and count the loads actually issued). */
+ * use the beam start too and count the loads actually issued).
+ * Band schedule: "band_order" (1 = default: a frame launch of a view that has been traced before -- same camera, same
+ * rows -- schedules its 16-row bands by what they cost last time, most expensive first, so that the long rays of a view
+ * start early; 0 = the "band_rotate" rule only).  Outputs never depend on it. */
 int ort_set_option(ort_ctx* ctx, const char* key, int value);
 
 /* Introspection of the beam start.  ort_beam_level: the grid level (3..7) frame launches of this camera geometry would
